@@ -1,0 +1,805 @@
+// drr_api.cu -- the C ABI of include/drr.h: context, asset upload, draw-list recording, column binning, launches.
+//
+// Data layout in HBM (all frames of a batch concatenated, see drr_device.cuh):
+//   views[frame] 24 B | segs[] 48 B | planes[] 12 B | colidx[frame][x] 8 B | spans[] 16 B | params[] 32 B (device scratch)
+//   framebuffers: max_views x (W*H*3 B, RGB24 row-major == Pixels.pixels, src/renderer/pixels.rs:5-14)
+//   assets: u16 texel pool (row-major, pow2 pitch, 0x8000 = None), u8 flat pool (4096 B per flat), float4 palette
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/drr.h"
+#include "drr_kernels.h"
+
+using namespace drr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct PinnedVec { // growable pinned staging buffer (cudaHostAlloc), so H2D copies are truly asynchronous
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = true; // false only in the CPU-test recording context (drr_test_ctx_create_host_only)
+    ~PinnedVec() { release(p); }
+    void release(T *q) {
+        if (!q) return;
+        if (pinned) cudaFreeHost(q); else free(q);
+    }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t nc = std::max<size_t>(want, cap ? cap * 2 : 1024);
+        T *q = nullptr;
+        if (pinned) {
+            if (cudaHostAlloc((void **)&q, nc * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+        } else if (!(q = (T *)malloc(nc * sizeof(T)))) {
+            return false;
+        }
+        if (n) memcpy(q, p, n * sizeof(T));
+        release(p);
+        p = q;
+        cap = nc;
+        return true;
+    }
+    bool push(const T &v) {
+        if (n == cap && !reserve(n + 1)) return false;
+        p[n++] = v;
+        return true;
+    }
+    void clear() { n = 0; }
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t nc = want + want / 4 + 16;
+        cudaError_t e = cudaMalloc((void **)&p, nc * sizeof(T));
+        if (e == cudaSuccess) cap = nc;
+        return e;
+    }
+};
+
+struct Entry { // one emitted column of one op, before resolving
+    uint32_t op;
+    uint8_t kind;
+    int16_t a, b; // inclusive rows, already clamped to the screen
+    int16_t top_y, bottom_y;
+};
+
+struct TmpSpan {
+    int16_t y0, y1;
+    uint32_t op;
+    uint8_t kind;
+    int16_t top_y, bottom_y;
+};
+
+inline bool kind_is_opaque(uint8_t k) { return k == KIND_WALL || k == KIND_FLAT || k == KIND_SKY; }
+
+// Remove rows [a, b] from every span of `list`, keeping list order (a split span's halves stay adjacent).
+void cut_rows(std::vector<TmpSpan> &list, std::vector<TmpSpan> &tmp, int a, int b) {
+    tmp.clear();
+    for (const TmpSpan &s : list) {
+        if (s.y1 < a || s.y0 > b) {
+            tmp.push_back(s);
+            continue;
+        }
+        if (s.y0 < a) {
+            TmpSpan l = s;
+            l.y1 = (int16_t)(a - 1);
+            tmp.push_back(l);
+        }
+        if (s.y1 > b) {
+            TmpSpan r = s;
+            r.y0 = (int16_t)(b + 1);
+            tmp.push_back(r);
+        }
+    }
+    list.swap(tmp);
+}
+
+// Turn the draw-ordered entries of ONE screen column into
+//   * opaque spans: pairwise disjoint, sorted by row -- an op that always writes (opaque bitmap, flat, opaque sky)
+//     erases whatever earlier ops put on the rows it covers, so those earlier rows can be dropped ("last writer wins",
+//     SURVEY.md 3.1), and
+//   * masked spans, in draw order: ops that may skip pixels (bitmaps with None texels).  They never erase anything
+//     here; on the device they are tested last-to-first and the first opaque texel wins, otherwise the opaque span
+//     below shows through.  A masked span survives only on rows where no LATER opaque op covers it.
+// The per-pixel result is identical to painting the entries in order.
+void resolve_column(const std::vector<Entry> &entries, std::vector<TmpSpan> &opq, std::vector<TmpSpan> &msk, std::vector<TmpSpan> &tmp) {
+    opq.clear();
+    msk.clear();
+    for (const Entry &e : entries) {
+        if (e.a > e.b) continue;
+        TmpSpan s{e.a, e.b, e.op, e.kind, e.top_y, e.bottom_y};
+        if (kind_is_opaque(e.kind)) {
+            cut_rows(opq, tmp, e.a, e.b);
+            if (!msk.empty()) cut_rows(msk, tmp, e.a, e.b);
+            opq.push_back(s);
+        } else {
+            msk.push_back(s);
+        }
+    }
+    std::sort(opq.begin(), opq.end(), [](const TmpSpan &l, const TmpSpan &r) { return l.y0 < r.y0; });
+}
+
+} // namespace
+
+struct drr_ctx {
+    int W = 0, H = 0, device = 0, max_views = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    float CFX, CFY, GCFX, ASPECT;
+
+    // assets (host mirror + device)
+    float4 pal[256];
+    bool have_pal = false, assets_dirty = true;
+    std::unordered_map<int, int> bitmap_slot, flat_slot;
+    std::vector<BitmapRec> bitmaps;
+    std::vector<uint16_t> texel_pool;
+    std::vector<uint8_t> flat_pool;
+    int sky_slot = -1;
+    DevBuf<uint16_t> d_texels;
+    DevBuf<uint8_t> d_flats;
+    DevBuf<BitmapRec> d_bitmaps;
+    DevBuf<float4> d_pal;
+
+    // recorded lists (pinned staging) and their device copies
+    PinnedVec<View> views;
+    PinnedVec<SegRec> segs;
+    PinnedVec<PlaneRec> planes;
+    PinnedVec<Span> spans;
+    PinnedVec<ColIdx> colidx;
+    PinnedVec<uint32_t> frame_span_base;
+    PinnedVec<uint32_t> frame_slot;
+    DevBuf<View> d_views;
+    DevBuf<SegRec> d_segs;
+    DevBuf<PlaneRec> d_planes;
+    DevBuf<Span> d_spans;
+    DevBuf<ColIdx> d_colidx;
+    DevBuf<uint32_t> d_frame_span_base, d_frame_slot;
+    DevBuf<SpanParams> d_params;
+    size_t uploaded_frames = 0, uploaded_spans = 0;
+    std::vector<int> slot_to_frame; // view slot -> recorded frame (or -1)
+
+    uint8_t *d_frames = nullptr;
+    uint64_t frame_stride = 0;
+    uint64_t *d_crc = nullptr;
+    PinnedVec<uint64_t> h_crc;
+
+    // frame being recorded
+    bool in_frame = false;
+    std::vector<std::vector<Entry>> cols;
+    std::vector<TmpSpan> opq, msk, tmp;
+
+    bool host_only = false; // CPU-test recording context: records and bins, can never draw
+    drr_stats stats{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+#define CTX_CHECK(ctx) \
+    if (!(ctx)) return DRR_E_INVALID
+#define CU(ctx, call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return e__ == cudaErrorMemoryAllocation ? DRR_E_NOMEM : DRR_E_CUDA;             \
+        }                                                                                   \
+    } while (0)
+
+static int fail(drr_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+extern "C" {
+
+const char *drr_error_name(int code) {
+    switch (code) {
+    case DRR_OK: return "DRR_OK";
+    case DRR_E_INVALID: return "DRR_E_INVALID";
+    case DRR_E_STATE: return "DRR_E_STATE";
+    case DRR_E_CUDA: return "DRR_E_CUDA";
+    case DRR_E_NOMEM: return "DRR_E_NOMEM";
+    case DRR_E_ASSET: return "DRR_E_ASSET";
+    case DRR_E_IO: return "DRR_E_IO";
+    case DRR_E_PANIC: return "DRR_E_PANIC";
+    default: return "DRR_E_UNKNOWN";
+    }
+}
+
+const char *drr_last_error(const drr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr_ctx **out) {
+    if (!out) return DRR_E_INVALID;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) {
+        g_create_error = "drr_ctx_create: bad width/height/max_views";
+        return DRR_E_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { // no CPU fallback, by design
+        g_create_error = std::string("drr_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); libdrr has no CPU path";
+        return DRR_E_CUDA;
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) {
+        g_create_error = "drr_ctx_create: bad device ordinal";
+        return DRR_E_INVALID;
+    }
+    e = cudaSetDevice(device_ordinal);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return DRR_E_CUDA;
+    }
+    drr_ctx *c = new drr_ctx();
+    c->W = width;
+    c->H = height;
+    c->device = device_ordinal;
+    c->max_views = max_views;
+    // src/renderer/constants.rs:7-17, same expressions, same evaluation order
+    c->ASPECT = 200.0f / 240.0f;
+    const float gsw = (float)(uint32_t)width / c->ASPECT;
+    c->GCFX = gsw / 2.0f;
+    c->CFX = (float)(uint32_t)width / 2.0f;
+    c->CFY = (float)(uint32_t)height / 2.0f;
+    c->cols.resize(width);
+    c->slot_to_frame.assign(max_views, -1);
+    c->frame_stride = ((uint64_t)width * height * 3 + 255) / 256 * 256;
+    auto bail = [&](const char *what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        drr_ctx_destroy(c);
+        return ce == cudaErrorMemoryAllocation ? DRR_E_NOMEM : DRR_E_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    c->own_stream = true;
+    if ((e = cudaMalloc((void **)&c->d_frames, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMalloc(framebuffers)", e);
+    if ((e = cudaMalloc((void **)&c->d_crc, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMalloc(crc)", e);
+    if ((e = cudaMemset(c->d_frames, 0, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
+    if ((e = cudaMemset(c->d_crc, 0, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
+    for (auto &ev : c->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    *out = c;
+    return DRR_OK;
+}
+
+void drr_ctx_destroy(drr_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->host_only) {
+        delete ctx;
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->d_frames) cudaFree(ctx->d_frames);
+    if (ctx->d_crc) cudaFree(ctx->d_crc);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int drr_set_stream(drr_ctx *ctx, void *cuda_stream) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    if (!cuda_stream) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return DRR_OK;
+}
+void *drr_get_stream(drr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ---- assets ------------------------------------------------------------------------------------------------------
+int drr_upload_palette(drr_ctx *ctx, const uint8_t rgb[768]) {
+    CTX_CHECK(ctx);
+    if (!rgb) return fail(ctx, DRR_E_INVALID, "drr_upload_palette: null");
+    for (int i = 0; i < 256; i++) {
+        const uint32_t r = rgb[i * 3], g = rgb[i * 3 + 1], b = rgb[i * 3 + 2];
+        const uint32_t packed = r | (g << 8) | (b << 16);
+        float w;
+        memcpy(&w, &packed, 4);
+        ctx->pal[i] = make_float4((float)r, (float)g, (float)b, w); // `color.r as f32` (bitmap_render.rs:204)
+    }
+    ctx->have_pal = true;
+    ctx->assets_dirty = true;
+    return DRR_OK;
+}
+
+int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels) {
+    CTX_CHECK(ctx);
+    if (!texels || w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: bad size (the reference divides by width and height)");
+    if (ctx->bitmap_slot.count(id)) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: id already uploaded");
+    uint32_t pitch = 1;
+    while (pitch < (uint32_t)w) pitch <<= 1;
+    BitmapRec r;
+    r.base = (uint32_t)ctx->texel_pool.size();
+    r.w = (int16_t)w;
+    r.h = (int16_t)h;
+    r.opaque = 1;
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * h, 0x8000);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int16_t t = texels[(size_t)y * w + x];
+            if (t < 0 || t > 255) {
+                if (t != -1) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
+                r.opaque = 0;
+                ctx->texel_pool[r.base + (size_t)y * pitch + x] = 0x8000;
+            } else {
+                ctx->texel_pool[r.base + (size_t)y * pitch + x] = (uint16_t)t;
+            }
+        }
+    ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
+    ctx->bitmaps.push_back(r);
+    ctx->assets_dirty = true;
+    return DRR_OK;
+}
+
+int drr_upload_flat(drr_ctx *ctx, int id, const uint8_t px[4096]) {
+    CTX_CHECK(ctx);
+    if (!px) return fail(ctx, DRR_E_INVALID, "drr_upload_flat: null");
+    if (ctx->flat_slot.count(id)) return fail(ctx, DRR_E_INVALID, "drr_upload_flat: id already uploaded");
+    if (ctx->flat_slot.size() >= 32767) return fail(ctx, DRR_E_INVALID, "drr_upload_flat: too many flats");
+    ctx->flat_slot[id] = (int)(ctx->flat_pool.size() / 4096);
+    ctx->flat_pool.insert(ctx->flat_pool.end(), px, px + 4096);
+    ctx->assets_dirty = true;
+    return DRR_OK;
+}
+
+int drr_set_sky(drr_ctx *ctx, int bitmap_id) {
+    CTX_CHECK(ctx);
+    auto it = ctx->bitmap_slot.find(bitmap_id);
+    if (it == ctx->bitmap_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_set_sky: unknown bitmap id");
+    const BitmapRec &r = ctx->bitmaps[it->second];
+    // draw_sky hard-codes 256x128 (visplanes.rs:49-50); a smaller texture would index out of bounds in the reference
+    if (r.w != 256 || r.h != 128) return fail(ctx, DRR_E_ASSET, "drr_set_sky: sky bitmap must be 256x128");
+    ctx->sky_slot = it->second;
+    return DRR_OK;
+}
+
+static int upload_assets(drr_ctx *ctx) {
+    if (!ctx->assets_dirty) return DRR_OK;
+    if (!ctx->have_pal) return fail(ctx, DRR_E_ASSET, "palette not uploaded");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, ctx->d_pal.reserve(256));
+    CU(ctx, cudaMemcpy(ctx->d_pal.p, ctx->pal, sizeof(ctx->pal), cudaMemcpyHostToDevice));
+    CU(ctx, ctx->d_texels.reserve(std::max<size_t>(ctx->texel_pool.size(), 1)));
+    if (!ctx->texel_pool.empty())
+        CU(ctx, cudaMemcpy(ctx->d_texels.p, ctx->texel_pool.data(), ctx->texel_pool.size() * 2, cudaMemcpyHostToDevice));
+    CU(ctx, ctx->d_flats.reserve(std::max<size_t>(ctx->flat_pool.size(), 1)));
+    if (!ctx->flat_pool.empty()) CU(ctx, cudaMemcpy(ctx->d_flats.p, ctx->flat_pool.data(), ctx->flat_pool.size(), cudaMemcpyHostToDevice));
+    CU(ctx, ctx->d_bitmaps.reserve(std::max<size_t>(ctx->bitmaps.size(), 1)));
+    if (!ctx->bitmaps.empty())
+        CU(ctx, cudaMemcpy(ctx->d_bitmaps.p, ctx->bitmaps.data(), ctx->bitmaps.size() * sizeof(BitmapRec), cudaMemcpyHostToDevice));
+    ctx->assets_dirty = false;
+    return DRR_OK;
+}
+
+// ---- recording ---------------------------------------------------------------------------------------------------
+int drr_reset(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
+    ctx->views.clear();
+    ctx->segs.clear();
+    ctx->planes.clear();
+    ctx->spans.clear();
+    ctx->colidx.clear();
+    ctx->frame_span_base.clear();
+    ctx->frame_slot.clear();
+    ctx->uploaded_frames = ctx->uploaded_spans = 0;
+    std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
+    const uint64_t launches = ctx->stats.kernel_launches;
+    ctx->stats = drr_stats{};
+    ctx->stats.kernel_launches = launches;
+    return DRR_OK;
+}
+
+int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
+    CTX_CHECK(ctx);
+    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_begin: previous frame not ended");
+    if (!view || view_idx < 0 || view_idx >= ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: bad view index");
+    if (ctx->slot_to_frame[view_idx] >= 0) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
+    View v{view->pos_x, view->pos_y, view->floor_height, view->angle, view->cos_angle, view->sin_angle};
+    if (!ctx->views.push(v) || !ctx->frame_slot.push((uint32_t)view_idx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    if (ctx->frame_span_base.n == 0 && !ctx->frame_span_base.push(0)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    ctx->slot_to_frame[view_idx] = (int)ctx->views.n - 1;
+    for (auto &c : ctx->cols) c.clear();
+    ctx->in_frame = true;
+    return DRR_OK;
+}
+
+int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, int n) {
+    CTX_CHECK(ctx);
+    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_emit_columns outside a frame");
+    if (!hdr || n < 0 || (n > 0 && !cols)) return fail(ctx, DRR_E_INVALID, "drr_emit_columns: null");
+    auto it = ctx->bitmap_slot.find(hdr->bitmap_id);
+    if (it == ctx->bitmap_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_emit_columns: unknown bitmap id");
+    SegRec r;
+    r.bitmap_slot = (uint32_t)it->second;
+    r.light_level = hdr->light_level;
+    r.phase = hdr->phase;
+    r.lsx = hdr->line_start_x;
+    r.lsy = hdr->line_start_y;
+    r.lex = hdr->line_end_x;
+    r.ley = hdr->line_end_y;
+    r.start_offset = hdr->start_offset;
+    r.start_x = hdr->start_x;
+    r.end_x = hdr->end_x;
+    r.bottom_height = hdr->bottom_height;
+    r.top_height = hdr->top_height;
+    r.offset_x = hdr->offset_x;
+    r.offset_y = hdr->offset_y;
+    const uint32_t op = (uint32_t)ctx->segs.n;
+    if (!ctx->segs.push(r)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    const uint8_t kind = ctx->bitmaps[it->second].opaque ? KIND_WALL : KIND_WALL_HOLES;
+    const int H = ctx->H, W = ctx->W;
+    for (int i = 0; i < n; i++) {
+        const drr_col &c = cols[i];
+        // Pixels::set ignores x >= W and y > H (pixels.rs:23); negative values become huge usize and are ignored too
+        if (c.x < 0 || c.x >= W) continue;
+        const int a = std::max<int>(c.clipped_top_y, 0), b = std::min<int>(c.clipped_bottom_y, H - 1);
+        if (a > b) continue;
+        ctx->cols[c.x].push_back(Entry{op, kind, (int16_t)a, (int16_t)b, c.top_y, c.bottom_y});
+    }
+    ctx->stats.seg_headers++;
+    ctx->stats.column_records += (uint64_t)n;
+    return DRR_OK;
+}
+
+int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom) {
+    CTX_CHECK(ctx);
+    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_emit_visplane outside a frame");
+    if (!hdr || !top || !bottom) return fail(ctx, DRR_E_INVALID, "drr_emit_visplane: null");
+    const int W = ctx->W, H = ctx->H;
+    // the reference indexes [i16; SCREEN_WIDTH] arrays with x (visplanes.rs:61,95): out-of-range x panics there
+    if (hdr->left < 0 || hdr->right >= W) return fail(ctx, DRR_E_INVALID, "drr_emit_visplane: left/right outside the screen");
+    PlaneRec p;
+    uint8_t kind;
+    if (hdr->flat_id == DRR_FLAT_SKY) {
+        if (ctx->sky_slot < 0) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: sky not set");
+        p.flat_slot = -1;
+        kind = ctx->bitmaps[ctx->sky_slot].opaque ? KIND_SKY : KIND_SKY_HOLES;
+    } else {
+        auto it = ctx->flat_slot.find(hdr->flat_id);
+        if (it == ctx->flat_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: unknown flat id");
+        p.flat_slot = (int16_t)it->second;
+        kind = KIND_FLAT;
+    }
+    p.height = hdr->height;
+    p.light_level = hdr->light_level;
+    p.left = hdr->left;
+    p.right = hdr->right;
+    p.reserved = 0;
+    const uint32_t op = (uint32_t)ctx->planes.n;
+    if (!ctx->planes.push(p)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    for (int x = hdr->left; x <= hdr->right; x++) {
+        const int16_t t = std::max<int16_t>(top[x - hdr->left], 0);                  // visplanes.rs:61 / :95
+        const int16_t b = std::min<int16_t>(bottom[x - hdr->left], (int16_t)(H - 1)); // :62 / :96
+        if (kind == KIND_FLAT && (int16_t)(b - t) <= 1) continue;                    // :99-101 (not applied to sky)
+        if (t > b) continue;
+        ctx->cols[x].push_back(Entry{op, kind, t, b, 0, 0});
+    }
+    ctx->stats.visplanes++;
+    if (hdr->right >= hdr->left) ctx->stats.visplane_columns += (uint64_t)(hdr->right - hdr->left + 1);
+    return DRR_OK;
+}
+
+int drr_frame_end(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_end outside a frame");
+    ctx->in_frame = false;
+    for (int x = 0; x < ctx->W; x++) {
+        ColIdx ci;
+        ci.first = (uint32_t)ctx->spans.n;
+        ci.n_opaque = ci.n_masked = 0;
+        if (!ctx->cols[x].empty()) {
+            resolve_column(ctx->cols[x], ctx->opq, ctx->msk, ctx->tmp);
+            if (ctx->opq.size() > 65535 || ctx->msk.size() > 65535) return fail(ctx, DRR_E_INVALID, "too many spans in one column");
+            ci.n_opaque = (uint16_t)ctx->opq.size();
+            ci.n_masked = (uint16_t)ctx->msk.size();
+            if (!ctx->spans.reserve(ctx->spans.n + ctx->opq.size() + ctx->msk.size())) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+            for (const auto *list : {&ctx->opq, &ctx->msk})
+                for (const TmpSpan &s : *list) {
+                    Span d;
+                    d.y0 = (uint16_t)s.y0;
+                    d.y1 = (uint16_t)s.y1;
+                    d.x = (uint16_t)x;
+                    d.kind = s.kind;
+                    d.pad = 0;
+                    d.op = s.op;
+                    d.top_y = s.top_y;
+                    d.bottom_y = s.bottom_y;
+                    ctx->spans.push(d);
+                }
+        }
+        if (!ctx->colidx.push(ci)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    }
+    if (!ctx->frame_span_base.push((uint32_t)ctx->spans.n)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    ctx->stats.frames++;
+    return DRR_OK;
+}
+
+// ---- execution ---------------------------------------------------------------------------------------------------
+int drr_upload_lists(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
+    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_upload_lists inside a frame");
+    int rc = upload_assets(ctx);
+    if (rc) return rc;
+    const size_t nf = ctx->views.n;
+    if (nf == 0) {
+        ctx->uploaded_frames = 0;
+        return DRR_OK;
+    }
+    CU(ctx, ctx->d_views.reserve(nf));
+    CU(ctx, ctx->d_segs.reserve(std::max<size_t>(ctx->segs.n, 1)));
+    CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
+    CU(ctx, ctx->d_spans.reserve(std::max<size_t>(ctx->spans.n, 1)));
+    CU(ctx, ctx->d_params.reserve(std::max<size_t>(ctx->spans.n, 1)));
+    CU(ctx, ctx->d_colidx.reserve(ctx->colidx.n));
+    CU(ctx, ctx->d_frame_span_base.reserve(nf + 1));
+    CU(ctx, ctx->d_frame_slot.reserve(nf));
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemcpyAsync(ctx->d_views.p, ctx->views.p, nf * sizeof(View), cudaMemcpyHostToDevice, st));
+    if (ctx->segs.n) CU(ctx, cudaMemcpyAsync(ctx->d_segs.p, ctx->segs.p, ctx->segs.n * sizeof(SegRec), cudaMemcpyHostToDevice, st));
+    if (ctx->planes.n) CU(ctx, cudaMemcpyAsync(ctx->d_planes.p, ctx->planes.p, ctx->planes.n * sizeof(PlaneRec), cudaMemcpyHostToDevice, st));
+    if (ctx->spans.n) CU(ctx, cudaMemcpyAsync(ctx->d_spans.p, ctx->spans.p, ctx->spans.n * sizeof(Span), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_colidx.p, ctx->colidx.p, ctx->colidx.n * sizeof(ColIdx), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_span_base.p, ctx->frame_span_base.p, (nf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    ctx->uploaded_frames = nf;
+    ctx->uploaded_spans = ctx->spans.n;
+    return DRR_OK;
+}
+
+static int make_args(drr_ctx *ctx, DrawArgs &a) {
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
+    if (ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "nothing uploaded (call drr_upload_lists)");
+    a.W = ctx->W;
+    a.H = ctx->H;
+    a.nframes = (int)ctx->uploaded_frames;
+    a.CFX = ctx->CFX;
+    a.CFY = ctx->CFY;
+    a.GCFX = ctx->GCFX;
+    a.ASPECT = ctx->ASPECT;
+    a.Wf = (float)(uint32_t)ctx->W;
+    a.Hf = (float)(uint32_t)ctx->H;
+    a.views = ctx->d_views.p;
+    a.segs = ctx->d_segs.p;
+    a.planes = ctx->d_planes.p;
+    a.spans = ctx->d_spans.p;
+    a.frame_span_base = ctx->d_frame_span_base.p;
+    a.frame_slot = ctx->d_frame_slot.p;
+    a.colidx = ctx->d_colidx.p;
+    a.params = ctx->d_params.p;
+    a.texels = ctx->d_texels.p;
+    a.flats = ctx->d_flats.p;
+    a.bitmaps = ctx->d_bitmaps.p;
+    a.palette = ctx->d_pal.p;
+    a.sky_base = ctx->sky_slot >= 0 ? ctx->bitmaps[ctx->sky_slot].base : 0;
+    a.frames = ctx->d_frames;
+    a.frame_stride = ctx->frame_stride;
+    a.crc = ctx->d_crc;
+    return DRR_OK;
+}
+
+static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march) {
+    if (setup) {
+        CU(ctx, launch_span_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream));
+        if (ctx->uploaded_spans) ctx->stats.kernel_launches++;
+    }
+    if (march) {
+        CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+        int launches = 0;
+        CU(ctx, launch_march(a, ctx->stream, &launches));
+        ctx->stats.kernel_launches += (uint64_t)launches;
+    }
+    return DRR_OK;
+}
+
+int drr_draw(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    DrawArgs a;
+    int rc = make_args(ctx, a);
+    if (rc) return rc;
+    return draw_once(ctx, a, true, true);
+}
+
+int drr_submit(drr_ctx *ctx) {
+    int rc = drr_upload_lists(ctx);
+    if (rc) return rc;
+    if (ctx->uploaded_frames == 0) return DRR_OK;
+    return drr_draw(ctx);
+}
+
+int drr_sync(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DRR_OK;
+}
+
+int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    if (!out || view_idx < 0 || view_idx >= ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_read_framebuffer: bad view index");
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_frames + (uint64_t)view_idx * ctx->frame_stride, (size_t)ctx->W * ctx->H * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DRR_OK;
+}
+
+int drr_read_checksums(drr_ctx *ctx, int first, int count, uint64_t *out) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    if (!out || first < 0 || count < 0 || first + count > ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_read_checksums: bad range");
+    if (count == 0) return DRR_OK;
+    if (!ctx->h_crc.reserve((size_t)count)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    CU(ctx, cudaMemcpyAsync(ctx->h_crc.p, ctx->d_crc + first, sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_crc.p, sizeof(uint64_t) * (size_t)count);
+    return DRR_OK;
+}
+
+uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes) {
+    uint64_t acc = 0;
+    const uint64_t nwords = (nbytes + 3) / 4;
+    for (uint64_t i = 0; i < nwords; i++) {
+        uint32_t w = 0;
+        for (int k = 0; k < 4; k++)
+            if (i * 4 + k < nbytes) w |= (uint32_t)rgb24[i * 4 + k] << (8 * k);
+        acc += checksum_term(w, i);
+    }
+    return acc;
+}
+
+int drr_get_stats(drr_ctx *ctx, drr_stats *out) {
+    CTX_CHECK(ctx);
+    if (!out) return DRR_E_INVALID;
+    drr_stats s = ctx->stats;
+    s.spans = ctx->spans.n;
+    s.drawlist_bytes_algorithmic = 24 * s.frames + 48 * s.seg_headers + 10 * s.column_records + 12 * s.visplanes + 4 * s.visplane_columns;
+    s.device_list_bytes = ctx->views.n * sizeof(View) + ctx->segs.n * sizeof(SegRec) + ctx->planes.n * sizeof(PlaneRec) +
+                          ctx->spans.n * sizeof(Span) + ctx->colidx.n * sizeof(ColIdx) + ctx->frame_span_base.n * 4 + ctx->frame_slot.n * 4;
+    *out = s;
+    return DRR_OK;
+}
+
+int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, float *march_ms) {
+    CTX_CHECK(ctx);
+    if (iters <= 0) return fail(ctx, DRR_E_INVALID, "drr_time_draw: iters");
+    DrawArgs a;
+    int rc = make_args(ctx, a);
+    if (rc) return rc;
+    struct { bool s, m; float *out; } legs[3] = {{true, true, total_ms}, {true, false, setup_ms}, {false, true, march_ms}};
+    for (auto &leg : legs) {
+        if (!leg.out) continue;
+        CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        for (int i = 0; i < iters; i++)
+            if ((rc = draw_once(ctx, a, leg.s, leg.m))) return rc;
+        CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(ctx, cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0;
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        *leg.out = ms / (float)iters;
+    }
+    return DRR_OK;
+}
+
+// ---- CPU-testable internals (no CUDA needed) ---------------------------------------------------------------------------
+// A context that can RECORD and BIN draw lists without a GPU (plain malloc staging) so the host logic is testable in
+// the CPU-only container.  It has no framebuffers and every execution entry point fails with DRR_E_CUDA.
+int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx **out) {
+    if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) return DRR_E_INVALID;
+    drr_ctx *c = new drr_ctx();
+    c->host_only = true;
+    c->W = width;
+    c->H = height;
+    c->max_views = max_views;
+    c->ASPECT = 200.0f / 240.0f;
+    c->GCFX = ((float)(uint32_t)width / c->ASPECT) / 2.0f;
+    c->CFX = (float)(uint32_t)width / 2.0f;
+    c->CFY = (float)(uint32_t)height / 2.0f;
+    c->cols.resize(width);
+    c->slot_to_frame.assign(max_views, -1);
+    c->views.pinned = c->segs.pinned = c->planes.pinned = c->spans.pinned = c->colidx.pinned = false;
+    c->frame_span_base.pinned = c->frame_slot.pinned = c->h_crc.pinned = false;
+    *out = c;
+    return DRR_OK;
+}
+// Raw views of the staged (binned) lists: which = 0 views, 1 segs, 2 planes, 3 spans, 4 colidx, 5 frame_span_base, 6 frame_slot
+const void *drr_test_list(drr_ctx *ctx, int which, uint64_t *count, uint64_t *elem_size) {
+    if (!ctx || !count || !elem_size) return nullptr;
+    switch (which) {
+    case 0: *count = ctx->views.n; *elem_size = sizeof(View); return ctx->views.p;
+    case 1: *count = ctx->segs.n; *elem_size = sizeof(SegRec); return ctx->segs.p;
+    case 2: *count = ctx->planes.n; *elem_size = sizeof(PlaneRec); return ctx->planes.p;
+    case 3: *count = ctx->spans.n; *elem_size = sizeof(Span); return ctx->spans.p;
+    case 4: *count = ctx->colidx.n; *elem_size = sizeof(ColIdx); return ctx->colidx.p;
+    case 5: *count = ctx->frame_span_base.n; *elem_size = 4; return ctx->frame_span_base.p;
+    case 6: *count = ctx->frame_slot.n; *elem_size = 4; return ctx->frame_slot.p;
+    default: return nullptr;
+    }
+}
+// bitmap slot -> (w, h, opaque); flat_slot/bitmap_slot resolve ids the way the device tables do
+int drr_test_bitmap_info(drr_ctx *ctx, int slot, int *w, int *h, int *opaque) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->bitmaps.size()) return DRR_E_INVALID;
+    *w = ctx->bitmaps[slot].w;
+    *h = ctx->bitmaps[slot].h;
+    *opaque = (int)ctx->bitmaps[slot].opaque;
+    return DRR_OK;
+}
+int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major w*h, -1 = None (decoded back from the device pool layout)
+    if (!ctx || slot < 0 || slot >= (int)ctx->bitmaps.size()) return DRR_E_INVALID;
+    const BitmapRec &r = ctx->bitmaps[slot];
+    uint32_t pitch = 1;
+    while (pitch < (uint32_t)r.w) pitch <<= 1;
+    for (int y = 0; y < r.h; y++)
+        for (int x = 0; x < r.w; x++) {
+            const uint16_t t = ctx->texel_pool[r.base + (size_t)y * pitch + x];
+            out[(size_t)y * r.w + x] = (t & 0x8000) ? (int16_t)-1 : (int16_t)t;
+        }
+    return DRR_OK;
+}
+int drr_test_flat_texels(drr_ctx *ctx, int slot, uint8_t *out4096) {
+    if (!ctx || slot < 0 || (size_t)(slot + 1) * 4096 > ctx->flat_pool.size()) return DRR_E_INVALID;
+    memcpy(out4096, ctx->flat_pool.data() + (size_t)slot * 4096, 4096);
+    return DRR_OK;
+}
+int drr_test_palette(drr_ctx *ctx, uint8_t *out768) {
+    if (!ctx || !ctx->have_pal) return DRR_E_INVALID;
+    for (int i = 0; i < 256; i++) {
+        out768[i * 3] = (uint8_t)ctx->pal[i].x;
+        out768[i * 3 + 1] = (uint8_t)ctx->pal[i].y;
+        out768[i * 3 + 2] = (uint8_t)ctx->pal[i].z;
+    }
+    return DRR_OK;
+}
+int drr_test_sky_slot(drr_ctx *ctx) { return ctx ? ctx->sky_slot : -1; }
+int drr_test_bitmap_id_of_slot(drr_ctx *ctx, int slot) {
+    for (auto &kv : ctx->bitmap_slot)
+        if (kv.second == slot) return kv.first;
+    return -1;
+}
+int drr_test_flat_id_of_slot(drr_ctx *ctx, int slot) {
+    for (auto &kv : ctx->flat_slot)
+        if (kv.second == slot) return kv.first;
+    return -1;
+}
+
+// ---- column resolver on raw entries: used by tests/ to check the column resolver against a painter -----------
+// entries: n x 4 ints {kind, a, b, tag}; out: up to cap x 4 ints {kind, y0, y1, tag}; returns n_opaque | n_masked << 16, or -1.
+int drr_test_resolve_column(const int32_t *entries, int n, int32_t *out, int cap) {
+    std::vector<Entry> e;
+    for (int i = 0; i < n; i++) e.push_back(Entry{(uint32_t)entries[i * 4 + 3], (uint8_t)entries[i * 4], (int16_t)entries[i * 4 + 1], (int16_t)entries[i * 4 + 2], 0, 0});
+    std::vector<TmpSpan> opq, msk, tmp;
+    resolve_column(e, opq, msk, tmp);
+    if ((int)(opq.size() + msk.size()) > cap) return -1;
+    int k = 0;
+    for (const auto *list : {&opq, &msk})
+        for (const TmpSpan &s : *list) {
+            out[k * 4] = s.kind;
+            out[k * 4 + 1] = s.y0;
+            out[k * 4 + 2] = s.y1;
+            out[k * 4 + 3] = (int32_t)s.op;
+            k++;
+        }
+    return (int)opq.size() | ((int)msk.size() << 16);
+}
+
+} // extern "C"

@@ -1,0 +1,125 @@
+// drr_device.cuh -- device data layout and exact-arithmetic helpers shared by the kernels.
+//
+// Arithmetic contract: every f32 operation of the reference is reproduced with an explicitly
+// rounded intrinsic (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn), which nvcc never contracts into an FMA and
+// never reassociates, regardless of -fmad / -use_fast_math.  Float->int casts follow Rust `as` (truncate, saturate,
+// NaN -> 0); i16 arithmetic wraps (release build).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace drr {
+
+// ---- span kinds -------------------------------------------------------------------------------------------------
+enum : uint32_t {
+    KIND_WALL = 0,       // wall / sprite column whose bitmap has no transparent texel (always writes)
+    KIND_WALL_HOLES = 1, // bitmap with None texels (masked mid-textures, sprites, holey walls): may skip pixels
+    KIND_FLAT = 2,       // floor / ceiling
+    KIND_SKY = 3,        // sky, opaque sky bitmap
+    KIND_SKY_HOLES = 4,  // sky bitmap with None texels
+};
+
+// Resolved span of one screen column, produced by the host-side binning (drr_api.cu). 16 bytes.
+struct Span {
+    uint16_t y0, y1; // inclusive screen rows this span still owns after later opaque spans were cut out
+    uint16_t x;      // screen column
+    uint8_t kind;
+    uint8_t pad;
+    uint32_t op;     // index into segs[] (wall kinds) or planes[] (flat / sky kinds), global over the batch
+    int16_t top_y, bottom_y; // BitmapColumn.top_y / bottom_y (wall kinds only)
+};
+static_assert(sizeof(Span) == 16, "Span layout");
+
+// Device copy of drr_seg_hdr with the bitmap id resolved to a slot. 48 bytes.
+struct SegRec {
+    uint32_t bitmap_slot;
+    int16_t light_level;
+    int16_t phase;
+    float lsx, lsy, lex, ley;
+    float start_offset;
+    int32_t start_x, end_x;
+    float bottom_height, top_height;
+    int16_t offset_x, offset_y;
+};
+static_assert(sizeof(SegRec) == 48, "SegRec layout");
+
+struct PlaneRec { // 12 bytes
+    int16_t flat_slot; // -1 = sky
+    int16_t height;
+    int16_t light_level;
+    int16_t left, right;
+    int16_t reserved;
+};
+static_assert(sizeof(PlaneRec) == 12, "PlaneRec layout");
+
+struct ColIdx { // per (frame, screen column). 8 bytes
+    uint32_t first; // first span (global index); opaque spans sorted by y first, then masked spans in draw order
+    uint16_t n_opaque, n_masked;
+};
+static_assert(sizeof(ColIdx) == 8, "ColIdx layout");
+
+struct BitmapRec { // 12 bytes
+    uint32_t base; // index into the u16 texel pool (row-major, 0x8000 bit = None)
+    int16_t w, h;
+    uint32_t opaque;
+};
+
+struct View { // == drr_view, 24 bytes
+    float pos_x, pos_y, floor_height, angle, cos_a, sin_a;
+};
+
+// Per-span parameters written by the setup kernel and consumed by the march kernel. 32 bytes.
+//   wall kinds: a.x = y0|y1<<16, a.y = texel index of (row 0, column tx), a.z = w|h<<16, a.w = top_y|bottom_y<<16
+//               b.x = uy1 bits,  b.y = light factor bits,                 b.z = off_y(u16)|kind<<16, b.w = mod magic
+//   flat:       a.x = y0|y1<<16, a.y = flat base (byte index),            a.z = wz bits,  a.w = light/255 bits
+//               b.x = GCFX*wz bits, b.z = kind<<16
+//   sky kinds:  a.x = y0|y1<<16, a.y = texel index of (row 0, column tx), b.z = kind<<16
+struct SpanParams {
+    uint4 a, b;
+};
+static_assert(sizeof(SpanParams) == 32, "SpanParams layout");
+
+// ---- Rust scalar semantics ----------------------------------------------------------------------------------------
+// `f as i16`: cvt.rzi saturates to the destination range and maps NaN to 0 (PTX ISA, cvt: "float-to-integer
+// conversions ... clamped to the destination range; NaN -> 0").
+__device__ __forceinline__ int sat_i16(float f) {
+    short r;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(f));
+    return (int)r;
+}
+__device__ __forceinline__ uint32_t sat_u8(float f) { // `f as u8`
+    uint32_t r = __float2uint_rz(f);                  // saturates below at 0, NaN -> 0
+    return r > 255u ? 255u : r;
+}
+__device__ __forceinline__ int wrap16(int v) { return (int)(short)v; } // i16 wrapping result of an i32 computation
+
+// The reference's idiom for a non-negative remainder (bitmap_render.rs:245-248, 260-263, visplanes.rs:56-58):
+//     if t < 0 { t += n * (1 - t / n) }  t %= n;       all in wrapping i16
+__device__ __forceinline__ int rust_wrap_mod16(int t, int n) {
+    if (t < 0) {
+        int q = wrap16(1 - t / n);
+        t = wrap16(t + wrap16(n * q));
+    }
+    return t % n; // may be negative after an i16 overflow: the reference would index out of bounds and panic
+}
+
+// diminish_color's factor (bitmap_render.rs:190-201): light/255 - dist * (1/4096), clamped below at 0.
+__device__ __forceinline__ float light_factor(float light_over_255, int dist_i16) {
+    float f = __fsub_rn(light_over_255, __fmul_rn((float)dist_i16, 0.000244140625f));
+    return f < 0.0f ? 0.0f : f;
+}
+// (c as f32 * factor) as u8 per channel (bitmap_render.rs:203-207), packed 0x00BBGGRR. pal = (r, g, b) as floats.
+__device__ __forceinline__ uint32_t lit_rgb(float4 pal, float factor) {
+    uint32_t r = sat_u8(__fmul_rn(pal.x, factor));
+    uint32_t g = sat_u8(__fmul_rn(pal.y, factor));
+    uint32_t b = sat_u8(__fmul_rn(pal.z, factor));
+    return r | (g << 8) | (b << 16);
+}
+
+// Position-weighted linear checksum (drr.h: drr_read_checksums)
+__host__ __device__ __forceinline__ uint64_t checksum_term(uint32_t word, uint64_t index) {
+    uint32_t k = ((uint32_t)(index + 1u) * 0x9E3779B1u) | 1u;
+    return (uint64_t)word * (uint64_t)k;
+}
+
+} // namespace drr

@@ -1,0 +1,34 @@
+// drr_kernels.h -- kernel argument block and launchers (shared by drr_kernels.cu and drr_api.cu)
+#pragma once
+#include "drr_device.cuh"
+
+namespace drr {
+
+static constexpr int MARCH_THREADS = 128;
+
+struct DrawArgs {
+    int W, H, nframes;
+    // src/renderer/constants.rs:7-17 derived from W, H with the reference's own expressions (see make_constants())
+    float CFX, CFY, GCFX, ASPECT, Wf, Hf;
+    const View *views;
+    const SegRec *segs;
+    const PlaneRec *planes;
+    const Span *spans;
+    const uint32_t *frame_span_base; // nframes + 1 entries
+    const uint32_t *frame_slot;      // framebuffer slot (view index) of each recorded frame
+    const ColIdx *colidx;            // nframes * W entries
+    SpanParams *params;              // one per span
+    const uint16_t *texels;          // bitmap pool, row-major, power-of-two row pitch, 0x8000 = None
+    const uint8_t *flats;            // 4096 bytes per flat slot
+    const BitmapRec *bitmaps;
+    const float4 *palette;           // 256 x (r, g, b as f32, packed 0x00BBGGRR bits)
+    uint32_t sky_base;               // texel index of the 256x128 sky bitmap
+    uint8_t *frames;                 // framebuffers, frame_stride bytes apart, RGB24 row-major
+    uint64_t frame_stride;
+    uint64_t *crc;                   // per-frame checksum accumulators (zeroed before the launch)
+};
+
+cudaError_t launch_span_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st);
+cudaError_t launch_march(const DrawArgs &a, cudaStream_t st, int *launches);
+
+} // namespace drr

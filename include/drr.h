@@ -1,0 +1,160 @@
+/* drr.h -- C ABI of libdrr.so: the B200 (sm_100a) replacement for the per-pixel back-end of
+ * freewilll/doom-rust-renderer.
+ *
+ * The reference has no FFI of its own; its renderer API is the Rust call
+ *     Renderer::new(&mut Pixels, &Map, &MapObjects, &mut Textures, &mut Sprites, sky, &mut Flats, &Palette, &Player, timestamp).render()
+ * (src/renderer/mod.rs:37-59,118-136; only call site src/game.rs:505-519) whose one observable effect is filling
+ * Pixels.pixels (RGB24, src/renderer/pixels.rs:5-30).  The seam this library plugs into is the set of three leaf call
+ * sites of the per-pixel drawers:
+ *     src/renderer/segs.rs:234           -> render_vertical_bitmap_line   (solid / lower / upper wall columns)
+ *     src/renderer/bitmap_render.rs:109  -> render_vertical_bitmap_line   (masked mid-textures and sprites)
+ *     src/renderer/mod.rs:108            -> draw_visplane / draw_sky      (floors, ceilings, sky)
+ * At those sites the host, instead of drawing, appends to a per-frame list (drr_emit_*); the list order is the draw
+ * order and "last writer wins, transparent texels do not write" is preserved per pixel.  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the three one-line call-site changes.
+ *
+ * Conventions: every function returns 0 on success or a negative DRR_E_* code (never aborts, never unwinds);
+ * drr_last_error(ctx) gives a message.  The caller owns every input buffer, the library copies before returning;
+ * output buffers are caller-allocated.  One context = one caller thread and one GPU (the reference is single-threaded,
+ * its types are !Send); distinct contexts may be driven from distinct threads / processes, one per GPU.
+ * No CPU fallback exists: without a CUDA device drr_ctx_create fails with DRR_E_CUDA.
+ */
+#ifndef DRR_H
+#define DRR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRR_OK 0
+#define DRR_E_INVALID (-1)   /* bad argument */
+#define DRR_E_STATE (-2)     /* call out of sequence (e.g. emit outside frame_begin/frame_end) */
+#define DRR_E_CUDA (-3)      /* CUDA runtime error (message in drr_last_error) */
+#define DRR_E_NOMEM (-4)     /* host or device allocation failed */
+#define DRR_E_ASSET (-5)     /* unknown bitmap / flat id, sky not set, palette missing */
+#define DRR_E_IO (-6)        /* scene loader: file / WAD format problem */
+#define DRR_E_PANIC (-7)     /* scene front-end: the reference would have panicked on this input */
+
+typedef struct drr_ctx drr_ctx;
+
+/* Player (src/game.rs:41-45) plus cos/sin of `angle` evaluated by the HOST libm (the same sinf/cosf the reference's
+ * Vertex::rotate calls, src/map/vertexes.rs:20-25), so the device never evaluates a transcendental. 24 bytes. */
+typedef struct {
+    float pos_x, pos_y;
+    float floor_height;
+    float angle;
+    float cos_angle, sin_angle;
+} drr_view;
+
+#define DRR_PHASE_WALL 0   /* drawn immediately, src/renderer/segs.rs:234 */
+#define DRR_PHASE_MASKED 2 /* deferred masked mid-texture or sprite, src/renderer/bitmap_render.rs:109 */
+
+/* Per-seg arguments of render_vertical_bitmap_line (src/renderer/bitmap_render.rs:213-224); the same fields the
+ * reference keeps in BitmapRender (bitmap_render.rs:29-45). 48 bytes. */
+typedef struct {
+    int32_t bitmap_id;   /* handle given to drr_upload_bitmap */
+    int16_t light_level; /* sector light level */
+    int16_t phase;       /* DRR_PHASE_* (informational; list order is what defines the result) */
+    float line_start_x, line_start_y, line_end_x, line_end_y; /* ClippedLine.line, view space */
+    float start_offset;                                        /* ClippedLine.start_offset */
+    int32_t start_x, end_x;                                    /* screen x of the clipped line ends */
+    float bottom_height, top_height;
+    int16_t offset_x, offset_y;
+} drr_seg_hdr;
+
+/* Per-column arguments (bitmap_render.rs:225-229) == BitmapColumn (bitmap_render.rs:19-25); the reference widens
+ * i16 to i32 when it stores them (add_column, :84-99), so i16 is lossless. 10 bytes. */
+typedef struct {
+    int16_t x;
+    int16_t clipped_top_y, clipped_bottom_y;
+    int16_t bottom_y, top_y;
+} drr_col;
+
+#define DRR_FLAT_SKY (-1)
+
+/* Visplane (src/renderer/visplanes.rs:17-26) minus its arrays. 12 bytes. */
+typedef struct {
+    int16_t flat_id; /* handle given to drr_upload_flat, or DRR_FLAT_SKY when the flat's name contains "SKY" (visplanes.rs:89) */
+    int16_t height;
+    int16_t light_level;
+    int16_t left, right;
+    int16_t reserved;
+} drr_visplane_hdr;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* width/height play the role of SCREEN_WIDTH/SCREEN_HEIGHT (src/game.rs:28-29); the f32 projection constants of
+ * src/renderer/constants.rs:7-17 are derived from them exactly as the reference does.  max_views = number of
+ * framebuffers kept resident in HBM (width*height*3 bytes each). */
+int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr_ctx **out);
+void drr_ctx_destroy(drr_ctx *ctx);
+const char *drr_last_error(const drr_ctx *ctx); /* ctx may be NULL: last creation error of this thread */
+const char *drr_error_name(int code);
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all copies and launches; NULL = own stream. */
+int drr_set_stream(drr_ctx *ctx, void *cuda_stream);
+void *drr_get_stream(drr_ctx *ctx);
+
+/* ---- assets (uploaded once, device resident) ------------------------------------------------------------------ */
+int drr_upload_palette(drr_ctx *ctx, const uint8_t rgb[768]);                                   /* Palette::new, src/graphics/palette.rs:11-28 */
+int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels_rowmajor);       /* Bitmap, src/graphics/bitmap.rs:11-15; -1 == None */
+int drr_upload_flat(drr_ctx *ctx, int id, const uint8_t px[4096]);                               /* Flat, src/graphics/flats.rs:19-22 */
+int drr_set_sky(drr_ctx *ctx, int bitmap_id);                                                    /* sky_texture, src/renderer/mod.rs:32 (must be 256x128) */
+
+/* ---- recording one frame == one Renderer::render() ------------------------------------------------------------ */
+int drr_reset(drr_ctx *ctx); /* forget all recorded frames */
+int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view);
+int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, int n);          /* replaces n calls of render_vertical_bitmap_line */
+int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom);
+/* top/bottom point at the entries for x = hdr->left .. hdr->right (right-left+1 values each), passed through
+ * UNCLAMPED exactly as the reference stores them (quirk Q3, visplanes.rs:36-37,60-64). */
+int drr_frame_end(drr_ctx *ctx);
+
+/* ---- execution ---------------------------------------------------------------------------------------------- */
+int drr_upload_lists(drr_ctx *ctx); /* async H2D of everything recorded since drr_reset (from pinned staging) */
+int drr_draw(drr_ctx *ctx);         /* async: render every uploaded frame into its framebuffer (+ per-frame checksum) */
+int drr_submit(drr_ctx *ctx);       /* drr_upload_lists + drr_draw */
+int drr_sync(drr_ctx *ctx);
+int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out_rgb24);    /* width*height*3 bytes, row-major RGB24 == Pixels.pixels */
+int drr_read_checksums(drr_ctx *ctx, int first_view, int count, uint64_t *out);
+/* Per-frame checksum: sum over little-endian u32 words w_i of the frame of  w_i * (((i+1)*0x9E3779B1 mod 2^32) | 1),
+ * mod 2^64.  drr_checksum_host computes the same on a host buffer. */
+uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes);
+
+/* ---- introspection for benchmarks ----------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t frames;              /* frames recorded */
+    uint64_t seg_headers;         /* drr_emit_columns calls */
+    uint64_t column_records;      /* drr_col records */
+    uint64_t visplanes;           /* drr_emit_visplane calls */
+    uint64_t visplane_columns;    /* sum of right-left+1 */
+    uint64_t drawlist_bytes_algorithmic; /* 24*frames + 48*seg_headers + 10*column_records + 12*visplanes + 4*visplane_columns */
+    uint64_t device_list_bytes;   /* bytes of the column-binned device representation actually uploaded */
+    uint64_t spans;               /* resolved spans (opaque + masked) */
+    uint64_t kernel_launches;     /* kernels launched by this context so far */
+} drr_stats;
+int drr_get_stats(drr_ctx *ctx, drr_stats *out);
+/* Time `iters` back-to-back drr_draw() passes with CUDA events on the context's stream; returns average milliseconds of
+ * the whole pass and of the two kernels separately (setup_ms, march_ms may be NULL). */
+int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, float *march_ms);
+
+/* ---- host front-end: the reference's Renderer for a WAD map, emitting through the functions above -------------- */
+/* Mirrors Game::new's asset/map loading (src/game.rs:118-196) without SDL. */
+typedef struct drr_scene drr_scene;
+int drr_scene_load(const char *wad_path, const char *map_name, int width, int height, drr_scene **out);
+void drr_scene_free(drr_scene *scene);
+const char *drr_scene_last_error(const drr_scene *scene); /* scene may be NULL */
+int drr_scene_upload_assets(drr_scene *scene, drr_ctx *ctx); /* palette, every bitmap/flat the map can reference, sky */
+int drr_scene_player_start(drr_scene *scene, float out_xya[3]); /* Player1Start, src/game.rs:151-157 */
+#define DRR_PHASES_WALLS 1
+#define DRR_PHASES_PLANES 2
+#define DRR_PHASES_MASKED 4
+#define DRR_PHASES_ALL 7
+/* One Renderer::new(..., player, timestamp).render() for the player at (x, y, angle): frame_begin, emits, frame_end.
+ * `phases` gates which leaf call sites emit (config 3's walls-only / flats-only split). */
+int drr_scene_emit_view(drr_scene *scene, drr_ctx *ctx, int view_idx, float x, float y, float angle, float timestamp, int phases);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRR_H */

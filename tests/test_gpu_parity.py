@@ -1,0 +1,323 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.  Bit-exact (byte for byte) RGB24.
+
+Tolerance: none.  The path is f32 + integer work whose every rounding is specified, so the bar
+is equality of every byte of every frame, plus equality of the device checksum with the host checksum of the oracle frame.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import pytest
+
+import common
+from common import drr, orc, synth_wad
+
+pytestmark = pytest.mark.gpu
+
+
+def _libm():
+    m = ctypes.CDLL("libm.so.6")
+    for f in (m.cosf, m.sinf):
+        f.restype = ctypes.c_float
+        f.argtypes = [ctypes.c_float]
+    return m
+
+
+def _compare(ctx, k, ref, what):
+    got = ctx.read_framebuffer(k)
+    diff = (got != ref).any(2)
+    if diff.any():
+        ys, xs = np.nonzero(diff)
+        msg = "%s: %d pixels differ; first at x=%d y=%d got=%s want=%s" % (what, int(diff.sum()), xs[0], ys[0], got[ys[0], xs[0]], ref[ys[0], xs[0]])
+        raise AssertionError(msg)
+
+
+# ---- whole frames through the product front-end -----------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,n", [(320, 200, 48), (640, 400, 12), (1280, 800, 6), (1024, 768, 3), (1920, 1200, 2), (200, 120, 6), (324, 200, 3)])
+def test_scene_frames_match_oracle(W, H, n):
+    path, gm = common.wad("e1m1")
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[:: max(1, 4096 // (n + 4))], n)
+    assert len(views) == n
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views) == []
+    ctx.submit()
+    ctx.sync()
+    crcs = ctx.read_checksums(0, n)
+    for k, v in enumerate(views):
+        ref = game.render(float(v[0]), float(v[1]), float(v[2]))
+        _compare(ctx, k, ref, "%dx%d view %d %s" % (W, H, k, v))
+        assert int(crcs[k]) == drr.checksum_numpy(ref)
+
+
+def test_config1_spawn_viewpoint():
+    """BASELINE config 1: the Player1Start viewpoint at 320x200, timestamp 0."""
+    path, _ = common.wad("e1m1")
+    game = orc.Game(path, "E1M1", 320, 200)
+    x, y, a = game.player_start()
+    ctx = drr.Context(320, 200, 0, 1)
+    scene = drr.Scene(path, "E1M1", 320, 200)
+    assert scene.player_start() == (x, y, a)
+    scene.upload_assets(ctx)
+    scene.emit_view(ctx, 0, x, y, a)
+    ctx.submit()
+    ctx.sync()
+    _compare(ctx, 0, game.render(x, y, a), "spawn view")
+
+
+@pytest.mark.parametrize("phases", [1, 2, 4, 3, 6])
+def test_phase_isolation(phases):
+    """BASELINE config 3: walls-only / flats-only (/ masked-only) isolation."""
+    path, gm = common.wad("e1m1")
+    W, H = 640, 400
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[100::700], 5)
+    ctx = drr.Context(W, H, 0, len(views))
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views, phases=phases) == []
+    ctx.submit()
+    ctx.sync()
+    for k, v in enumerate(views):
+        _compare(ctx, k, game.render(float(v[0]), float(v[1]), float(v[2]), phases=phases), "phases=%d view %d" % (phases, k))
+
+
+@pytest.mark.parametrize("timestamp", [0.0, 0.4, 0.7, 12.5])
+def test_animated_flats(timestamp):
+    path, gm = common.wad("e1m1")
+    W, H = 320, 200
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[50::400], 10)
+    ctx = drr.Context(W, H, 0, len(views))
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views, timestamp=timestamp) == []
+    ctx.submit()
+    ctx.sync()
+    for k, v in enumerate(views):
+        _compare(ctx, k, game.render(float(v[0]), float(v[1]), float(v[2]), timestamp=timestamp), "t=%g view %d" % (timestamp, k))
+
+
+def test_stress_map():
+    """BASELINE config 5's map (open sectors, many visplanes, tall columns), a few viewpoints."""
+    path, gm = common.wad("stress")
+    W, H = 640, 400
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.scatter_viewpoints(gm, 64), 6)
+    ctx = drr.Context(W, H, 0, len(views))
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views) == []
+    ctx.submit()
+    ctx.sync()
+    for k, v in enumerate(views):
+        _compare(ctx, k, game.render(float(v[0]), float(v[1]), float(v[2])), "stress view %d" % k)
+
+
+# ---- kernels alone: the oracle's own leaf-call trace fed through the C ABI --------------------------------------------
+def test_oracle_trace_through_c_abi():
+    path, gm = common.wad("e1m1")
+    W, H = 320, 200
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[7::500], 8)
+    # render once so that every lazily composed texture exists before the assets are exported
+    refs = [game.render(float(v[0]), float(v[1]), float(v[2])) for v in views]
+    ctx = drr.Context(W, H, 0, len(views))
+    common.upload_oracle_assets(ctx, game)
+    for k, v in enumerate(views):
+        game.render(float(v[0]), float(v[1]), float(v[2]), trace=True)
+        common.emit_trace(ctx, game, k, float(v[0]), float(v[1]), float(v[2]), game.trace())
+    ctx.submit()
+    ctx.sync()
+    for k in range(len(views)):
+        _compare(ctx, k, refs[k], "trace view %d" % k)
+
+
+# ---- fuzz: arbitrary (also nonsensical) leaf arguments -----------------------------------------------------------------
+def _fuzz_assets(rng, n_bitmaps=10):
+    pal = rng.integers(0, 256, 768, dtype=np.uint8)
+    bitmaps = []
+    for i in range(n_bitmaps):
+        w = int(rng.choice([1, 3, 8, 16, 41, 64, 128, 200]))
+        h = int(rng.choice([1, 2, 7, 16, 56, 72, 96, 128, 130]))
+        t = rng.integers(0, 256, (h, w)).astype(np.int16)
+        if i % 2:
+            t[rng.random((h, w)) < 0.35] = -1
+        bitmaps.append(t)
+    sky = rng.integers(0, 256, (128, 256)).astype(np.int16)
+    flats = [rng.integers(0, 256, 4096, dtype=np.uint8) for _ in range(4)]
+    return pal, bitmaps, sky, flats
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("W,H", [(320, 200), (96, 64)])
+def test_fuzz_columns(seed, W, H):
+    """Random render_vertical_bitmap_line arguments, including degenerate ones (zero-height columns, bottom_y == top_y,
+    huge offsets, NaN / inf line ends, negative light, transparent texels, overlapping columns in draw order)."""
+    rng = np.random.default_rng(seed)
+    pal, bitmaps, sky, flats = _fuzz_assets(rng)
+    nviews = 4
+    ctx = drr.Context(W, H, 0, nviews)
+    ctx.upload_palette(pal)
+    for i, b in enumerate(bitmaps):
+        ctx.upload_bitmap(100 + i, b)
+    ctx.upload_bitmap(99, sky)
+    ctx.set_sky(99)
+    leaf = orc.Leaf(W, H, pal)
+    refs = []
+    special = [np.float32(v) for v in (0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, 3e38)]
+    for v in range(nviews):
+        ref = np.zeros((H, W, 3), np.uint8)
+        ctx.frame_begin(v, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+        for _ in range(120):
+            bi = int(rng.integers(0, len(bitmaps)))
+            line = rng.uniform(0.5, 900, 4).astype(np.float32)
+            line[1] = rng.uniform(-600, 600)
+            line[3] = rng.uniform(-600, 600)
+            so = np.float32(rng.uniform(0, 300))
+            bh, th = np.float32(rng.uniform(-200, 50)), np.float32(rng.uniform(-50, 400))
+            if rng.random() < 0.08:
+                line[int(rng.integers(0, 4))] = rng.choice(special)
+            if rng.random() < 0.05:
+                bh = rng.choice(special)
+            if rng.random() < 0.05:
+                so = rng.choice(special)
+            sx = int(rng.integers(-20, W))
+            ex = sx + int(rng.integers(0, 80))
+            light = int(rng.integers(-40, 300))
+            ox, oy = int(rng.integers(-400, 400)), int(rng.integers(-400, 400))
+            if rng.random() < 0.05:
+                oy = int(rng.choice([-32768, 32767, -32000, 32000]))
+            if rng.random() < 0.05:
+                ox = int(rng.choice([-32768, 32767]))
+            cols = []
+            for x in range(max(sx, -2), min(ex + 1, W + 2)):
+                if rng.random() < 0.3:
+                    continue
+                top_y = int(rng.integers(-300, H))
+                bottom_y = top_y + int(rng.integers(0, 500)) if rng.random() > 0.05 else top_y
+                ct = max(top_y, int(rng.integers(-5, H)))
+                cb = min(bottom_y, int(rng.integers(0, H + 5)))
+                cols.append((x, ct, cb, bottom_y, top_y))
+            hdr = drr.DrrSegHdr(100 + bi, light, 0, line[0], line[1], line[2], line[3], so, sx, ex, bh, th, ox, oy)
+            ctx.emit_columns(hdr, np.array(cols, dtype=drr.COL_DTYPE))
+            for (x, ct, cb, by, ty) in cols:
+                if 0 <= x < W:  # Pixels::set ignores x >= W; rows are clamped like the reference's y > H check
+                    try:
+                        leaf.column(ref, bitmaps[bi], light, line, so, sx, ex, bh, th, ox, oy, x, min(cb, H - 1), max(ct, 0), by, ty)
+                    except orc.OracleError:
+                        pytest.fail("oracle panicked on fuzz input (generator must avoid panics)")
+        ctx.frame_end()
+        refs.append(ref)
+    ctx.submit()
+    ctx.sync()
+    for v in range(nviews):
+        _compare(ctx, v, refs[v], "fuzz columns seed %d view %d" % (seed, v))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("W,H", [(320, 200), (96, 64)])
+def test_fuzz_visplanes(seed, W, H):
+    """Random draw_visplane / draw_sky arguments: planes crossing the horizon (vy == 0 row, negative distances -> factor > 1),
+    (0,0) columns (quirk Q3), 1-pixel columns (Q4), unclamped top/bottom, overlapping planes in draw order, any angle."""
+    rng = np.random.default_rng(1000 + seed)
+    pal, bitmaps, sky, flats = _fuzz_assets(rng, 1)
+    if seed == 3:
+        sky[rng.random(sky.shape) < 0.2] = -1  # sky with holes
+    m = _libm()
+    nviews = 4
+    ctx = drr.Context(W, H, 0, nviews)
+    ctx.upload_palette(pal)
+    ctx.upload_bitmap(99, sky)
+    ctx.set_sky(99)
+    for i, f in enumerate(flats):
+        ctx.upload_flat(10 + i, f)
+    leaf = orc.Leaf(W, H, pal)
+    refs = []
+    for v in range(nviews):
+        ref = np.zeros((H, W, 3), np.uint8)
+        px, py = np.float32(rng.uniform(-3000, 3000)), np.float32(rng.uniform(-3000, 3000))
+        fh = np.float32(rng.integers(-10, 10) * 8)
+        ang = np.float32(rng.uniform(-7, 7))
+        ctx.frame_begin(v, px, py, fh, ang, m.cosf(float(ang)), m.sinf(float(ang)))
+        for _ in range(40):
+            left = int(rng.integers(0, W))
+            right = min(W - 1, left + int(rng.integers(0, 120)))
+            top = np.zeros(W, np.int16)
+            bottom = np.zeros(W, np.int16)
+            t0 = int(rng.integers(-30, H))
+            for x in range(left, right + 1):
+                if rng.random() < 0.1:
+                    continue  # stays (0, 0)
+                t0 += int(rng.integers(-3, 4))
+                top[x] = t0
+                bottom[x] = t0 + int(rng.integers(-2, 90))
+            is_sky = rng.random() < 0.25
+            fi = int(rng.integers(0, len(flats)))
+            height = int(rng.integers(-30, 60) * 8)
+            light = int(rng.integers(0, 256))
+            hdr = drr.DrrVisplaneHdr(drr.FLAT_SKY if is_sky else 10 + fi, height, light, left, right, 0)
+            ctx.emit_visplane(hdr, top[left:right + 1], bottom[left:right + 1])
+            leaf.visplane(ref, flats[fi], sky, top, bottom, 1 if is_sky else 0, height, light, left, right, px, py, fh, ang)
+        ctx.frame_end()
+        refs.append(ref)
+    ctx.submit()
+    ctx.sync()
+    for v in range(nviews):
+        _compare(ctx, v, refs[v], "fuzz visplanes seed %d view %d" % (seed, v))
+
+
+def test_empty_and_black_frames():
+    """A frame with no ops is all zeros (Pixels::new), and re-drawing a slot overwrites the previous contents."""
+    W, H = 320, 200
+    ctx = drr.Context(W, H, 0, 2)
+    ctx.upload_palette(np.arange(768, dtype=np.uint8))
+    for rep in range(2):
+        ctx.reset()
+        ctx.frame_begin(0, 0, 0, 0, 0, 1, 0)
+        ctx.frame_end()
+        ctx.frame_begin(1, 0, 0, 0, 0, 1, 0)
+        ctx.frame_end()
+        ctx.submit()
+        ctx.sync()
+        assert not ctx.read_framebuffer(0).any() and not ctx.read_framebuffer(1).any()
+        assert list(ctx.read_checksums(0, 2)) == [0, 0]
+
+
+def test_redraw_is_idempotent_and_checksum_of_checksums():
+    path, gm = common.wad("e1m1")
+    W, H = 320, 200
+    n = 64
+    views = synth_wad.walk_viewpoints(gm, n)
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    scene.emit_views(ctx, views)
+    ctx.submit()
+    ctx.sync()
+    c1 = ctx.read_checksums(0, n)
+    ctx.draw()
+    ctx.sync()
+    c2 = ctx.read_checksums(0, n)
+    assert (c1 == c2).all()
+    host = np.array([drr.checksum_numpy(ctx.read_framebuffer(k)) for k in range(n)], np.uint64)
+    assert (host == c1).all()
+    with np.errstate(over="ignore"):
+        assert int(host.sum(dtype=np.uint64)) == int(c1.sum(dtype=np.uint64))
+
+
+def test_error_paths():
+    ctx = drr.Context(64, 32, 0, 1)
+    with pytest.raises(drr.DrrError):
+        ctx.frame_end()  # not in a frame
+    with pytest.raises(drr.DrrError):
+        ctx.set_sky(5)  # unknown bitmap
+    ctx.frame_begin(0, 0, 0, 0, 0, 1, 0)
+    with pytest.raises(drr.DrrError):
+        ctx.emit_columns(drr.DrrSegHdr(7, 0, 0, 1, 1, 1, 1, 0, 0, 1, 0, 1, 0, 0), np.zeros(0, drr.COL_DTYPE))  # unknown bitmap id
+    ctx.frame_end()
+    with pytest.raises(drr.DrrError):
+        ctx.submit()  # palette missing

@@ -1,0 +1,207 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports what include/drr.h declares, the column
+resolver equals a painter, and the host front-end + binning reproduce the oracle frame when replayed on the CPU.
+No compute call needs a GPU here; drawing without CUDA must fail loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import common
+from common import drr, orc, synth_wad
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(common.ROOT, "include", "drr.h")).read()
+    declared = set(re.findall(r"\b(drr_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"drr_ctx", "drr_scene"}
+    L = ctypes.CDLL(drr.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(drr.EXPORTED_SYMBOLS) <= declared
+    assert len(declared) >= 30
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(drr.DrrView) == 24
+    assert ctypes.sizeof(drr.DrrSegHdr) == 48
+    assert ctypes.sizeof(drr.DrrVisplaneHdr) == 12
+    assert drr.COL_DTYPE.itemsize == 10
+    assert drr.DrrSegHdr.start_x.offset == 28 and drr.DrrSegHdr.offset_y.offset == 46
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device context creation fails with DRR_E_CUDA; the recording-only test context cannot draw."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(drr.DrrError) as e:
+        drr.Context(320, 200, 0, 1)
+    assert e.value.code == -3
+    ctx = drr.Context(64, 64, 0, 1, _host_only=True)
+    ctx.upload_palette(np.zeros(768, np.uint8))
+    ctx.frame_begin(0, 0, 0, 0, 0, 1, 0)
+    ctx.frame_end()
+    for fn in (ctx.submit, ctx.draw, ctx.upload_lists, ctx.sync, lambda: ctx.read_framebuffer(0)):
+        with pytest.raises(drr.DrrError) as e:
+            fn()
+        assert e.value.code == -3
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never load, import or execute anything under oracle/."""
+    pkg = os.path.join(common.ROOT, "doom_rust_renderer_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                src = open(os.path.join(root, f), errors="replace").read()
+                assert "oracle" not in src.lower().replace("oracle-free", ""), os.path.join(root, f)
+
+
+def _paint(entries, H):
+    """Reference painter for one column: ops in order, opaque kinds always write, masked kinds write where `mask` says."""
+    owner = -np.ones(H, np.int64)
+    for i, (kind, a, b, tag) in enumerate(entries):
+        if a > b:
+            continue
+        if kind in (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY):
+            owner[a:b + 1] = tag
+        else:
+            rows = np.arange(a, b + 1)
+            hit = ((rows * 7 + tag * 13) % 3) != 0  # deterministic pseudo transparency per (row, op)
+            owner[rows[hit]] = tag
+    return owner
+
+
+def test_resolve_column_equals_painter():
+    rng = np.random.default_rng(5)
+    H = 200
+    L = drr._lib()
+    for trial in range(300):
+        n = int(rng.integers(0, 14))
+        entries = []
+        for i in range(n):
+            a = int(rng.integers(0, H))
+            b = min(H - 1, a + int(rng.integers(-3, 80)))
+            entries.append((int(rng.choice([0, 1, 2, 3, 4])), a, b, i))
+        want = _paint(entries, H)
+        e = np.array(entries, np.int32).reshape(-1, 4)
+        out = np.zeros((256, 4), np.int32)
+        rc = L.drr_test_resolve_column(e.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p), 256)
+        assert rc >= 0
+        n_op, n_ms = rc & 0xFFFF, rc >> 16
+        got = -np.ones(H, np.int64)
+        prev = -1
+        for (kind, y0, y1, tag) in out[:n_op]:
+            assert y0 > prev and y1 >= y0
+            prev = y1
+            got[y0:y1 + 1] = tag
+        # device rule: masked spans are tested last-to-first, first hit wins, else the opaque span below
+        for y in range(H):
+            for (kind, y0, y1, tag) in out[n_op:n_op + n_ms][::-1]:
+                if y0 <= y <= y1 and ((y * 7 + tag * 13) % 3) != 0:
+                    got[y] = tag
+                    break
+        assert (got == want).all(), (trial, entries)
+
+
+@pytest.mark.parametrize("W,H,kind,n", [(160, 100, "e1m1", 10), (320, 200, "e1m1", 3), (96, 64, "tiny", 6), (200, 120, "stress", 2)])
+def test_front_end_and_binning_replay_equals_oracle(W, H, kind, n):
+    """Closure on the CPU: product front-end -> C ABI -> column-binned spans, replayed span by span with the oracle's
+    leaf drawers, equals the oracle's direct render of the same viewpoint."""
+    path, gm = common.wad(kind)
+    game = orc.Game(path, "E1M1", W, H)
+    src = synth_wad.walk_viewpoints(gm, 512) if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, 64)
+    views = common.usable_views(game, src[:: max(1, len(src) // (n + 2))], n)
+    ctx = drr.Context(W, H, 0, len(views), _host_only=True)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views) == []
+    for k, v in enumerate(views):
+        ref = game.render(float(v[0]), float(v[1]), float(v[2]))
+        got = common.replay_binned_frame(ctx, k)
+        assert (got == ref).all(), "view %d: %d pixels differ" % (k, int((got != ref).any(2).sum()))
+
+
+def test_front_end_emits_the_oracles_leaf_calls():
+    """The product front-end must make the same leaf calls, in the same order, with the same arguments as the oracle's
+    restatement of the reference (bitmap handles differ, so they are compared through their texel contents)."""
+    path, gm = common.wad("e1m1")
+    W, H = 320, 200
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 512)[3::60], 5)
+    scene = drr.Scene(path, "E1M1", W, H)
+    for v in views:
+        game.render(float(v[0]), float(v[1]), float(v[2]), trace=True)
+        trace = game.trace()
+        # oracle trace through the ABI
+        ctx_a = drr.Context(W, H, 0, 1, _host_only=True)
+        common.upload_oracle_assets(ctx_a, game)
+        common.emit_trace(ctx_a, game, 0, float(v[0]), float(v[1]), float(v[2]), trace)
+        # product front-end through the ABI
+        ctx_b = drr.Context(W, H, 0, 1, _host_only=True)
+        scene.upload_assets(ctx_b)
+        scene.emit_view(ctx_b, 0, float(v[0]), float(v[1]), float(v[2]))
+        sa, sb = ctx_a.stats(), ctx_b.stats()
+        for key in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans"):
+            assert sa[key] == sb[key], (key, sa[key], sb[key])
+        assets_a, assets_b = common.AssetsFromCtx(ctx_a), common.AssetsFromCtx(ctx_b)
+        segs_a, segs_b = ctx_a._list(1, drr.SEG_DTYPE), ctx_b._list(1, drr.SEG_DTYPE)
+        for ga, gb in zip(segs_a, segs_b):
+            for f in drr.SEG_DTYPE.names[1:]:
+                assert ga[f].tobytes() == gb[f].tobytes(), f
+            assert (assets_a.bitmap(int(ga["bitmap_slot"])) == assets_b.bitmap(int(gb["bitmap_slot"]))).all()
+        pa, pb = ctx_a._list(2, drr.PLANE_DTYPE), ctx_b._list(2, drr.PLANE_DTYPE)
+        for qa, qb in zip(pa, pb):
+            for f in ("height", "light_level", "left", "right"):
+                assert qa[f] == qb[f]
+            assert (qa["flat_slot"] < 0) == (qb["flat_slot"] < 0)
+            if qa["flat_slot"] >= 0:
+                assert (assets_a.flat(int(qa["flat_slot"])) == assets_b.flat(int(qb["flat_slot"]))).all()
+        spa, spb = ctx_a._list(3, drr.SPAN_DTYPE), ctx_b._list(3, drr.SPAN_DTYPE)
+        assert spa.tobytes() == spb.tobytes()
+        assert ctx_a._list(0, drr.VIEW_DTYPE).tobytes() == ctx_b._list(0, drr.VIEW_DTYPE).tobytes()
+
+
+def test_recording_state_machine_and_validation():
+    ctx = drr.Context(64, 32, 0, 2, _host_only=True)
+    ctx.upload_palette(np.zeros(768, np.uint8))
+    ctx.upload_bitmap(1, np.zeros((4, 4), np.int16))
+    with pytest.raises(drr.DrrError):
+        ctx.upload_bitmap(1, np.zeros((4, 4), np.int16))  # duplicate id
+    with pytest.raises(drr.DrrError):
+        ctx.upload_bitmap(2, np.full((2, 2), 300, np.int16))  # texel out of range
+    with pytest.raises(drr.DrrError):
+        ctx.set_sky(1)  # not 256x128
+    with pytest.raises(drr.DrrError):
+        ctx.emit_visplane(drr.DrrVisplaneHdr(0, 0, 0, 0, 0, 0), np.zeros(1, np.int16), np.zeros(1, np.int16))  # outside a frame
+    ctx.frame_begin(0, 0, 0, 0, 0, 1, 0)
+    with pytest.raises(drr.DrrError):
+        ctx.frame_begin(1, 0, 0, 0, 0, 1, 0)  # nested
+    with pytest.raises(drr.DrrError):
+        ctx.emit_visplane(drr.DrrVisplaneHdr(5, 0, 0, 0, 0, 0), np.zeros(1, np.int16), np.zeros(1, np.int16))  # unknown flat
+    with pytest.raises(drr.DrrError):
+        ctx.emit_visplane(drr.DrrVisplaneHdr(-1, 0, 0, 0, 0, 0), np.zeros(1, np.int16), np.zeros(1, np.int16))  # sky not set
+    # columns outside the screen are dropped like Pixels::set drops them; ragged / empty inputs are fine
+    cols = np.array([(-3, 0, 5, 5, 0), (64, 0, 5, 5, 0), (5, 10, 3, 3, 10), (6, -4, 40, 40, -4)], dtype=drr.COL_DTYPE)
+    ctx.emit_columns(drr.DrrSegHdr(1, 100, 0, 1, 1, 2, -1, 0, 0, 10, -8, 8, 0, 0), cols)
+    ctx.emit_columns(drr.DrrSegHdr(1, 100, 0, 1, 1, 2, -1, 0, 0, 10, -8, 8, 0, 0), np.zeros(0, drr.COL_DTYPE))
+    ctx.frame_end()
+    with pytest.raises(drr.DrrError):
+        ctx.frame_begin(0, 0, 0, 0, 0, 1, 0)  # slot already recorded
+    spans = ctx._list(3, drr.SPAN_DTYPE)
+    assert len(spans) == 1 and spans[0]["x"] == 6 and spans[0]["y0"] == 0 and spans[0]["y1"] == 31
+    st = ctx.stats()
+    assert st["drawlist_bytes_algorithmic"] == 24 + 2 * 48 + 4 * 10
+    ctx.reset()
+    assert ctx.stats()["frames"] == 0
+
+
+def test_checksum_definitions_agree():
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 3, 4, 5, 192000, 1000 * 3):
+        b = rng.integers(0, 256, n, dtype=np.uint8)
+        assert drr.checksum_host(b) == drr.checksum_numpy(b)

@@ -1,0 +1,184 @@
+"""CPU tests of the oracle itself.
+
+The reference ships no tests, golden vectors or fixtures for this path, so the oracle is "parity
+unpinned" by the reference; what can be pinned is (a) the Rust scalar semantics it relies on, checked here against
+independent numpy/python restatements, and (b) its own output on the deterministic synthetic WAD, frozen as golden
+checksums in tests/golden/ (regenerate with tools/make_golden.py)."""
+from __future__ import annotations
+
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import common
+from common import drr, orc, synth_wad
+
+GOLDEN = os.path.join(common.ROOT, "tests", "golden", "oracle_frames.json")
+
+
+def test_synthetic_wad_is_deterministic():
+    data, gm, stats = synth_wad.build_wad("e1m1")
+    data2, _, _ = synth_wad.build_wad("e1m1")
+    assert data == data2
+    gold = json.load(open(GOLDEN))
+    assert zlib.crc32(data) == gold["wad_crc32"]["e1m1"]
+    assert stats["sectors"] >= 85 and stats["segs"] >= 730 and stats["things"] >= 130
+
+
+def test_oracle_frames_match_golden():
+    gold = json.load(open(GOLDEN))
+    path, gm = common.wad("e1m1")
+    views = synth_wad.walk_viewpoints(gm, 4096)
+    for case in gold["frames"]:
+        W, H = case["W"], case["H"]
+        game = orc.Game(path, "E1M1", W, H)
+        for item in case["views"]:
+            if item["index"] == "spawn":
+                x, y, a = game.player_start()
+            else:
+                x, y, a = (float(t) for t in views[item["index"]])
+            img = game.render(x, y, a, timestamp=item.get("timestamp", 0.0), phases=item.get("phases", 7))
+            assert zlib.crc32(img.tobytes()) == item["crc32"], (W, H, item)
+            assert drr.checksum_numpy(img) == int(item["checksum"]), (W, H, item)
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+def test_diminish_color_against_numpy_float32():
+    """bitmap_render.rs:190-208 restated independently with numpy float32 scalars."""
+    rng = np.random.default_rng(3)
+    for _ in range(4000):
+        rgb = [int(v) for v in rng.integers(0, 256, 3)]
+        light = int(rng.integers(-50, 400))
+        dist = int(rng.choice([rng.integers(-32768, 32768), rng.integers(-200, 3000)]))
+        factor = _f32(light) / _f32(255.0)
+        factor = _f32(factor - _f32(_f32(dist) * _f32(1.0 / 4096.0)))
+        if factor < 0:
+            factor = _f32(0)
+        want = []
+        for c in rgb:
+            v = _f32(_f32(c) * factor)
+            want.append(0 if not (v > 0) else 255 if v >= 255 else int(v))
+        assert orc.diminish_color(rgb, light, dist) == tuple(want)
+
+
+def test_wrap_mod_idiom_is_floormod():
+    """`if t < 0 { t += n * (1 - t / n) } t %= n` in wrapping i16 equals the mathematical floor-mod for every i16 t and
+    every n in 1..=32767 the kernels can meet (the device code relies on this identity, drr_kernels.cu: wall_ty)."""
+    t = np.arange(-32768, 32768, dtype=np.int64)
+    for n in list(range(1, 300)) + [511, 512, 1000, 4096, 30000, 32767]:
+        q = np.trunc(t / n).astype(np.int64)  # i16 division truncates toward zero
+        one_minus = ((1 - q + 32768) % 65536) - 32768
+        prod = ((n * one_minus + 32768) % 65536) - 32768
+        fixed = np.where(t < 0, ((t + prod + 32768) % 65536) - 32768, t)
+        res = np.fmod(fixed, n).astype(np.int64)  # remainder takes the dividend's sign
+        assert (res == np.mod(t, n)).all(), n
+
+
+def test_leaf_column_matches_python_restatement():
+    """render_vertical_bitmap_line restated in python/numpy float32 for one seg, compared pixel by pixel."""
+    W, H = 64, 48
+    rng = np.random.default_rng(11)
+    pal = rng.integers(0, 256, 768, dtype=np.uint8)
+    tex = rng.integers(0, 256, (72, 40)).astype(np.int16)
+    tex[rng.random(tex.shape) < 0.2] = -1
+    leaf = orc.Leaf(W, H, pal)
+    line = (np.float32(100.0), np.float32(40.0), np.float32(180.5), np.float32(-30.25))
+    so, bh, th = np.float32(12.5), np.float32(-41.0), np.float32(87.0)
+    sx, ex, light, ox, oy = 3, 60, 200, 17, -9
+    img = np.zeros((H, W, 3), np.uint8)
+    want = np.zeros((H, W, 3), np.uint8)
+    f = np.float32
+    for x in range(sx, ex + 1):
+        top_y, bottom_y = 5 - x // 8, 40 + x // 6
+        ct, cb = max(top_y, 0), min(bottom_y, H - 1)
+        leaf.column(img, tex, light, line, so, sx, ex, bh, th, ox, oy, x, cb, ct, bottom_y, top_y)
+        ln = f(np.sqrt(f(f(f(line[0] - line[2]) ** 2) + f(f(line[1] - line[3]) ** 2))))
+        ax = f(f(x - sx) / f(ex - sx))
+        num = f(f(f(1 - ax) * f(f(0) / line[0])) + f(ax * f(ln / line[2])))
+        den = f(f(f(1 - ax) * f(f(1) / line[0])) + f(ax * f(f(1) / line[2])))
+        tx = int(f(num / den)) + int(so) + ox
+        tx %= tex.shape[1]
+        z = int(f(f(f(1 - ax) + ax) / den))
+        fac = f(f(f(light) / f(255)) - f(f(z) * f(1 / 4096)))
+        fac = f(max(fac, f(0)))
+        for y in range(ct, cb + 1):
+            ay = f(f(y - top_y) / f(bottom_y - top_y))
+            ty = int(f(f(tex.shape[0]) + f(ay * f(th - bh)))) + oy
+            ty %= tex.shape[0]
+            t = int(tex[ty, tx])
+            if t >= 0:
+                want[y, x] = [min(255, int(f(f(pal[3 * t + c]) * fac))) for c in range(3)]
+    assert (img == want).all()
+
+
+def test_leaf_visplane_matches_python_restatement():
+    W, H = 64, 48
+    rng = np.random.default_rng(12)
+    pal = rng.integers(0, 256, 768, dtype=np.uint8)
+    flat = rng.integers(0, 256, 4096, dtype=np.uint8)
+    leaf = orc.Leaf(W, H, pal)
+    f = np.float32
+    px, py, fh, ang = f(-1503.5), f(977.25), f(32.0), f(0.6)
+    top = np.full(W, 30, np.int16)
+    bottom = np.full(W, 47, np.int16)
+    img = np.zeros((H, W, 3), np.uint8)
+    leaf.visplane(img, flat, None, top, bottom, 0, 32, 180, 2, 61, px, py, fh, ang)
+    import ctypes
+    m = ctypes.CDLL("libm.so.6")
+    m.cosf.restype = m.sinf.restype = ctypes.c_float
+    m.cosf.argtypes = m.sinf.argtypes = [ctypes.c_float]
+    ca, sa = f(m.cosf(float(ang))), f(m.sinf(float(ang)))
+    aspect = f(f(200.0) / f(240.0))
+    gcfx = f(f(f(W) / aspect) / f(2))
+    want = np.zeros((H, W, 3), np.uint8)
+
+    def i16(v):
+        v = float(v)
+        return 0 if v != v else max(-32768, min(32767, int(v)))
+    for x in range(2, 62):
+        for y in range(30, 48):
+            vx = f(f(f(W / 2) - f(x)) / aspect)
+            vy = f(f(H / 2) - f(y))
+            wz = f(f(f(32) - fh) - f(41))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                wx = f(f(gcfx * wz) / vy)
+                wy = f(f(wz * vx) / vy)
+            rx = f(f(wx * ca) - f(wy * sa))
+            ry = f(f(wy * ca) + f(wx * sa))
+            tx = (i16(rx) + i16(px)) & 63
+            ty = (i16(ry) + i16(py)) & 63
+            fac = f(f(f(180) / f(255)) - f(f(i16(wx)) * f(1 / 4096)))
+            fac = f(max(fac, f(0)))
+            t = int(flat[ty * 64 + tx])
+            want[y, x] = [min(255, int(f(f(pal[3 * t + c]) * fac))) for c in range(3)]
+    assert (img == want).all()
+
+
+def test_trace_replay_closure_on_cpu():
+    """direct render == the recorded leaf calls replayed in order (oracle self-consistency)."""
+    path, gm = common.wad("e1m1")
+    W, H = 160, 100
+    game = orc.Game(path, "E1M1", W, H)
+    v = common.usable_views(game, synth_wad.walk_viewpoints(gm, 64)[5::9], 3)
+    for x, y, a in v:
+        ref = game.render(float(x), float(y), float(a), trace=True)
+        tr = game.trace()
+        leaf = orc.Leaf(W, H, game.palette())
+        img = np.zeros((H, W, 3), np.uint8)
+        fh = game.floor_height_at(float(x), float(y))
+        sky = game.bitmap(game.sky_bitmap_id())
+        for t in tr:
+            if t["kind"] == 0:
+                leaf.column(img, game.bitmap(t["asset"]), t["light_level"], t["line"], t["start_offset"], t["start_x"], t["end_x"],
+                            t["bottom_height"], t["top_height"], t["offset_x"], t["offset_y"], t["x"], t["clipped_bottom_y"],
+                            t["clipped_top_y"], t["bottom_y"], t["top_y"])
+            else:
+                leaf.visplane(img, game.flat(t["asset"]), sky, t["top"], t["bottom"], t["is_sky"], t["height"], t["light_level"],
+                              t["left"], t["right"], x, y, fh, a)
+        assert (img == ref).all()
