@@ -180,9 +180,14 @@ struct drr_ctx {
 
     // frame being recorded
     bool in_frame = false;
+    size_t segs_n0 = 0, planes_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
+    drr_stats stats0{};
+    int cur_slot = -1;
     std::vector<std::vector<Entry>> cols;
     std::vector<TmpSpan> opq, msk, tmp;
 
+    std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
+    int prof_steps = 0;
     bool host_only = false; // CPU-test recording context: records and bins, can never draw
     drr_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -420,7 +425,26 @@ int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
     if (ctx->frame_span_base.n == 0 && !ctx->frame_span_base.push(0)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     ctx->slot_to_frame[view_idx] = (int)ctx->views.n - 1;
     for (auto &c : ctx->cols) c.clear();
+    ctx->segs_n0 = ctx->segs.n;
+    ctx->planes_n0 = ctx->planes.n;
+    ctx->stats0 = ctx->stats;
+    ctx->cur_slot = view_idx;
     ctx->in_frame = true;
+    return DRR_OK;
+}
+
+int drr_frame_abort(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_abort outside a frame");
+    ctx->in_frame = false;
+    ctx->views.n--;
+    ctx->frame_slot.n--;
+    ctx->segs.n = ctx->segs_n0;
+    ctx->planes.n = ctx->planes_n0;
+    ctx->slot_to_frame[ctx->cur_slot] = -1;
+    const uint64_t launches = ctx->stats.kernel_launches;
+    ctx->stats = ctx->stats0;
+    ctx->stats.kernel_launches = launches;
     return DRR_OK;
 }
 
@@ -599,7 +623,9 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     return DRR_OK;
 }
 
-static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march) {
+static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march, bool profile = false) {
+    const bool prof = profile && (size_t)(ctx->prof_steps + 1) * 3 <= ctx->prof_ev.size();
+    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3], ctx->stream));
     if (setup) {
         CU(ctx, launch_span_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream));
         if (ctx->uploaded_spans) ctx->stats.kernel_launches++;
@@ -607,8 +633,13 @@ static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march) {
     if (march) {
         CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
         int launches = 0;
+        if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], ctx->stream));
         CU(ctx, launch_march(a, ctx->stream, &launches));
         ctx->stats.kernel_launches += (uint64_t)launches;
+        if (prof) {
+            CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], ctx->stream));
+            ctx->prof_steps++;
+        }
     }
     return DRR_OK;
 }
@@ -618,7 +649,42 @@ int drr_draw(drr_ctx *ctx) {
     DrawArgs a;
     int rc = make_args(ctx, a);
     if (rc) return rc;
-    return draw_once(ctx, a, true, true);
+    return draw_once(ctx, a, true, true, true);
+}
+
+// Per-kernel device times of the drr_draw() calls made since drr_profile_begin, from CUDA events recorded on the
+// context's stream around each kernel (the memset of the checksum array is counted with the setup leg).
+int drr_profile_begin(drr_ctx *ctx, int max_steps) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    if (max_steps < 0 || max_steps > 4096) return fail(ctx, DRR_E_INVALID, "drr_profile_begin: max_steps");
+    while (ctx->prof_ev.size() < (size_t)max_steps * 3) {
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreate(&e));
+        ctx->prof_ev.push_back(e);
+    }
+    ctx->prof_steps = 0;
+    return DRR_OK;
+}
+int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *march_ms_total) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    float s = 0, m = 0;
+    for (int i = 0; i < ctx->prof_steps; i++) {
+        float a = 0, b = 0;
+        CU(ctx, cudaEventElapsedTime(&a, ctx->prof_ev[i * 3], ctx->prof_ev[i * 3 + 1]));
+        CU(ctx, cudaEventElapsedTime(&b, ctx->prof_ev[i * 3 + 1], ctx->prof_ev[i * 3 + 2]));
+        s += a;
+        m += b;
+    }
+    if (steps) *steps = ctx->prof_steps;
+    if (setup_ms_total) *setup_ms_total = s;
+    if (march_ms_total) *march_ms_total = m;
+    ctx->prof_steps = 0;
+    for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+    ctx->prof_ev.clear();
+    return DRR_OK;
 }
 
 int drr_submit(drr_ctx *ctx) {

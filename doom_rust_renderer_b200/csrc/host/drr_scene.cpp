@@ -999,7 +999,7 @@ struct drr_scene {
             map_objects();                                  // C
             for (Render &r : renders) render_deferred(r, colpool.data()); // D: segs.rs:593-597
         } catch (...) {
-            drr_frame_end(ctx);
+            drr_frame_abort(ctx); // the reference would have panicked: nothing is recorded for this view
             throw;
         }
         chk(drr_frame_end(ctx));

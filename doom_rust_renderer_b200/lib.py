@@ -71,11 +71,12 @@ def _lib() -> C.CDLL:
             "drr_upload_palette": (i, [vp, vp]), "drr_upload_bitmap": (i, [vp, i, i, i, vp]), "drr_upload_flat": (i, [vp, i, vp]),
             "drr_set_sky": (i, [vp, i]), "drr_reset": (i, [vp]), "drr_frame_begin": (i, [vp, i, C.POINTER(DrrView)]),
             "drr_emit_columns": (i, [vp, C.POINTER(DrrSegHdr), vp, i]),
-            "drr_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_frame_end": (i, [vp]),
+            "drr_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_frame_end": (i, [vp]), "drr_frame_abort": (i, [vp]),
             "drr_upload_lists": (i, [vp]), "drr_draw": (i, [vp]), "drr_submit": (i, [vp]), "drr_sync": (i, [vp]),
             "drr_read_framebuffer": (i, [vp, i, vp]), "drr_read_checksums": (i, [vp, i, i, vp]),
             "drr_checksum_host": (C.c_uint64, [vp, C.c_uint64]), "drr_get_stats": (i, [vp, C.POINTER(DrrStats)]),
             "drr_time_draw": (i, [vp, i, C.POINTER(f), C.POINTER(f), C.POINTER(f)]),
+            "drr_profile_begin": (i, [vp, i]), "drr_profile_end": (i, [vp, C.POINTER(i), C.POINTER(f), C.POINTER(f)]),
             "drr_scene_load": (i, [C.c_char_p, C.c_char_p, i, i, C.POINTER(vp)]), "drr_scene_free": (None, [vp]),
             "drr_scene_last_error": (C.c_char_p, [vp]), "drr_scene_upload_assets": (i, [vp, vp]),
             "drr_scene_player_start": (i, [vp, vp]), "drr_scene_emit_view": (i, [vp, vp, i, f, f, f, f, i]),
@@ -98,8 +99,9 @@ def _lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "drr_ctx_create", "drr_ctx_destroy", "drr_last_error", "drr_error_name", "drr_set_stream", "drr_get_stream",
     "drr_upload_palette", "drr_upload_bitmap", "drr_upload_flat", "drr_set_sky", "drr_reset", "drr_frame_begin",
-    "drr_emit_columns", "drr_emit_visplane", "drr_frame_end", "drr_upload_lists", "drr_draw", "drr_submit", "drr_sync",
+    "drr_emit_columns", "drr_emit_visplane", "drr_frame_end", "drr_frame_abort", "drr_upload_lists", "drr_draw", "drr_submit", "drr_sync",
     "drr_read_framebuffer", "drr_read_checksums", "drr_checksum_host", "drr_get_stats", "drr_time_draw",
+    "drr_profile_begin", "drr_profile_end",
     "drr_scene_load", "drr_scene_free", "drr_scene_last_error", "drr_scene_upload_assets", "drr_scene_player_start",
     "drr_scene_emit_view",
 ]
@@ -196,6 +198,9 @@ class Context:
     def frame_end(self):
         self._ck(self.L.drr_frame_end(self.h))
 
+    def frame_abort(self):
+        self._ck(self.L.drr_frame_abort(self.h))
+
     # ---- execution
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.drr_set_stream(self.h, C.c_void_p(cuda_stream)))
@@ -231,6 +236,15 @@ class Context:
         t, s, m = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.drr_time_draw(self.h, iters, C.byref(t), C.byref(s), C.byref(m)))
         return t.value, s.value, m.value
+
+    def profile_begin(self, max_steps: int):
+        self._ck(self.L.drr_profile_begin(self.h, max_steps))
+
+    def profile_end(self):
+        """(steps, setup_ms_total, march_ms_total) of the draws since profile_begin."""
+        n, s, m = C.c_int(), C.c_float(), C.c_float()
+        self._ck(self.L.drr_profile_end(self.h, C.byref(n), C.byref(s), C.byref(m)))
+        return n.value, s.value, m.value
 
     # ---- test-only views of the binned lists (CPU-testable host logic)
     def _list(self, which: int, dtype) -> np.ndarray:
@@ -294,7 +308,7 @@ class Scene:
 
     def emit_views(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = PHASES_ALL, first_slot: int = 0):
         """views: float32 [n][3] = (x, y, angle).  Returns the list of view indices the reference would have panicked on
-        (those frames are recorded empty, i.e. black)."""
+        (nothing is recorded for those; their framebuffer slots keep their previous contents)."""
         bad = []
         for k, (x, y, a) in enumerate(np.asarray(views, np.float32)):
             rc = self.L.drr_scene_emit_view(self.h, ctx.h, first_slot + k, float(x), float(y), float(a), timestamp, phases)

@@ -109,6 +109,7 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
 /* top/bottom point at the entries for x = hdr->left .. hdr->right (right-left+1 values each), passed through
  * UNCLAMPED exactly as the reference stores them (quirk Q3, visplanes.rs:36-37,60-64). */
 int drr_frame_end(drr_ctx *ctx);
+int drr_frame_abort(drr_ctx *ctx); /* discard the frame being recorded (the view index becomes free again) */
 
 /* ---- execution ---------------------------------------------------------------------------------------------- */
 int drr_upload_lists(drr_ctx *ctx); /* async H2D of everything recorded since drr_reset (from pinned staging) */
@@ -137,6 +138,11 @@ int drr_get_stats(drr_ctx *ctx, drr_stats *out);
 /* Time `iters` back-to-back drr_draw() passes with CUDA events on the context's stream; returns average milliseconds of
  * the whole pass and of the two kernels separately (setup_ms, march_ms may be NULL). */
 int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, float *march_ms);
+
+/* Per-kernel device times of the drr_draw()/drr_submit() calls made between begin and end (CUDA events on the context's
+ * stream around each kernel; at most max_steps draws are profiled).  Totals in milliseconds. */
+int drr_profile_begin(drr_ctx *ctx, int max_steps);
+int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *march_ms_total);
 
 /* ---- host front-end: the reference's Renderer for a WAD map, emitting through the functions above -------------- */
 /* Mirrors Game::new's asset/map loading (src/game.rs:118-196) without SDL. */
