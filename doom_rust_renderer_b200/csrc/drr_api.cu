@@ -848,6 +848,28 @@ int drr_test_flat_id_of_slot(drr_ctx *ctx, int slot) {
     return -1;
 }
 
+// Device self-check of the hoisted-reciprocal division used by the march kernel (drr_kernels.cu: fast_div) against
+// __fdiv_rn.  mode 0: a in [-amax, amax] (n0 = 2*amax+1 values), b = all non-zero integers in [-n1/2, n1/2];
+// mode 1: a = floats with bit patterns lo + k*stride (k < n0), b = CFY - y for y < n1 (H = n1).  Returns mismatches.
+int drr_test_fastdiv(drr_ctx *ctx, int mode, long long n0, long long n1, float CFY, uint32_t lo, uint32_t stride, unsigned long long *bad,
+                     float *first2) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    unsigned long long *d_bad = nullptr;
+    float *d_first = nullptr;
+    CU(ctx, cudaMalloc((void **)&d_bad, 8));
+    CU(ctx, cudaMalloc((void **)&d_first, 8));
+    CU(ctx, cudaMemsetAsync(d_bad, 0, 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_first, 0, 8, ctx->stream));
+    CU(ctx, launch_fastdiv_check(mode, n0, n1, CFY, (int)n1, lo, stride, d_bad, d_first, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(first2, d_first, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bad);
+    cudaFree(d_first);
+    return DRR_OK;
+}
+
 // ---- column resolver on raw entries: used by tests/ to check the column resolver against a painter -----------
 // entries: n x 4 ints {kind, a, b, tag}; out: up to cap x 4 ints {kind, y0, y1, tag}; returns n_opaque | n_masked << 16, or -1.
 int drr_test_resolve_column(const int32_t *entries, int n, int32_t *out, int cap) {

@@ -5,6 +5,10 @@
 namespace drr {
 
 static constexpr int MARCH_THREADS = 128;
+#ifndef DRR_MARCH_MIN_BLOCKS
+#define DRR_MARCH_MIN_BLOCKS 6
+#endif
+static constexpr int MARCH_MIN_BLOCKS = DRR_MARCH_MIN_BLOCKS; // occupancy target: 6 CTAs x 4 warps per SM (<= 80 registers)
 
 struct DrawArgs {
     int W, H, nframes;
@@ -30,5 +34,7 @@ struct DrawArgs {
 
 cudaError_t launch_span_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st);
 cudaError_t launch_march(const DrawArgs &a, cudaStream_t st, int *launches);
+cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
+                                 unsigned long long *d_bad, float *d_first, cudaStream_t st);
 
 } // namespace drr

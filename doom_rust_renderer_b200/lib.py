@@ -87,6 +87,7 @@ def _lib() -> C.CDLL:
             "drr_test_sky_slot": (i, [vp]),
             "drr_test_bitmap_id_of_slot": (i, [vp, i]), "drr_test_flat_id_of_slot": (i, [vp, i]),
             "drr_test_resolve_column": (i, [vp, i, vp, i]),
+            "drr_test_fastdiv": (i, [vp, i, C.c_longlong, C.c_longlong, f, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -245,6 +246,13 @@ class Context:
         n, s, m = C.c_int(), C.c_float(), C.c_float()
         self._ck(self.L.drr_profile_end(self.h, C.byref(n), C.byref(s), C.byref(m)))
         return n.value, s.value, m.value
+
+    def test_fastdiv(self, mode: int, n0: int, n1: int, cfy: float = 0.0, lo: int = 0, stride: int = 1):
+        """Device self-check of the hoisted-reciprocal division against __fdiv_rn; returns (mismatches, first offending pair)."""
+        bad = C.c_ulonglong()
+        first = np.zeros(2, np.float32)
+        self._ck(self.L.drr_test_fastdiv(self.h, mode, n0, n1, cfy, lo, stride, C.byref(bad), _ptr(first)))
+        return bad.value, (float(first[0]), float(first[1]))
 
     # ---- test-only views of the binned lists (CPU-testable host logic)
     def _list(self, which: int, dtype) -> np.ndarray:

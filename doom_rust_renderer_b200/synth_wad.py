@@ -190,8 +190,10 @@ def make_graphics(rng: PCG32):
         x = -rng.rng(0, 12)
         while x < w:
             pw = rng.choice([32, 64, 128])
-            p = add_patch(_pattern(rng, pw, h if i % 4 else rng.choice([128, 96]), rng.below(5), rng.below(200)))
-            plist.append((x, rng.rng(-8, 8) if i % 3 == 0 else 0, p))
+            # patches are taller than the texture and start at or above its top edge: composite WALLS stay fully opaque, as
+            # in real IWADs (holes only occur in the dedicated HOLEY00 / PARTIAL0 / GRATExx textures below)
+            p = add_patch(_pattern(rng, pw, h + 16, rng.below(5), rng.below(200)))
+            plist.append((x, -rng.rng(0, 16) if i % 3 == 0 else 0, p))
             x += pw - (rng.rng(0, 10) if i % 2 else 0)
         textures.append(TextureDef("COMP%02d" % i, w, h, plist))
     # 3) a wall whose LAST patch has transparent texels: they punch holes into the earlier patch (quirk Q1)

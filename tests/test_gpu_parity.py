@@ -321,3 +321,25 @@ def test_error_paths():
     ctx.frame_end()
     with pytest.raises(drr.DrrError):
         ctx.submit()  # palette missing
+
+
+# ---- the hoisted-reciprocal division of the march kernel is the correctly rounded quotient ---------------------------------
+def test_fast_division_walls_exhaustive():
+    """bitmap_render.rs:256: ay = (y - top_y) as f32 / (bottom_y - top_y) as f32.  y in [0, H), top_y/bottom_y are i16, so the
+    numerator is an integer in [-32767-H, 32768+H] and the denominator a non-zero integer in [-65535, 65535]: all
+    ~1.8e10 pairs are compared bitwise with __fdiv_rn on the device."""
+    ctx = drr.Context(64, 64, 0, 1)
+    amax = 32768 + 2048
+    bad, first = ctx.test_fastdiv(0, 2 * amax + 1, 2 * 65535)
+    assert bad == 0, first
+
+
+@pytest.mark.parametrize("H", [200, 400, 768, 800, 1200, 201])
+def test_fast_division_flats_sampled(H):
+    """visplanes.rs:113-114: wx = GCFX*wz / vy, wy = wz*vx / vy with vy = H/2 - y.  Every row's denominator against 2^25
+    numerators spread over the whole float range (those outside [2^-60, 2^60] take __fdiv_rn in the kernel and are
+    skipped here), including both signs."""
+    ctx = drr.Context(64, 64, 0, 1)
+    for lo in (0x00000000, 0x80000000, 0x3F800000 - (1 << 24), 0x12345678):
+        bad, first = ctx.test_fastdiv(1, 1 << 23, H, H / 2.0, lo, 255)
+        assert bad == 0, (H, lo, first)
