@@ -83,9 +83,9 @@ static_assert(sizeof(SpanParams) == 32, "SpanParams layout");
 // `f as i16`: cvt.rzi saturates to the destination range and maps NaN to 0 (PTX ISA, cvt: "float-to-integer
 // conversions ... clamped to the destination range; NaN -> 0").
 __device__ __forceinline__ int sat_i16(float f) {
-    short r;
-    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(f));
-    return (int)r;
+    int r; // 32-bit destination: the s16 result arrives sign-extended (F2I.S16), no widening instruction needed
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
 }
 __device__ __forceinline__ uint32_t sat_u8(float f) { // `f as u8`
     uint32_t r = __float2uint_rz(f);                  // saturates below at 0, NaN -> 0

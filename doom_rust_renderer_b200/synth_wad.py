@@ -307,8 +307,9 @@ def _carve(gm: GridMap, cx0, cy0, cx1, cy1, sector: int):
     gm.cells[cy0:cy1, cx0:cx1] = sector
 
 
-WALL_POOL = ["WALL%02d" % i for i in range(16)] + ["COMP%02d" % i for i in range(12)] + ["HOLEY00", "PARTIAL0"] + \
-            ["FILL%02d" % i for i in range(35, 40)]
+# opaque wall textures used at random; the two holey ones (HOLEY00, PARTIAL0) are assigned to a few specific sectors below,
+# like the rare see-through walls of real maps, so that they are exercised without dominating the workload
+WALL_POOL = ["WALL%02d" % i for i in range(16)] + ["COMP%02d" % i for i in range(12)] + ["FILL%02d" % i for i in range(35, 40)]
 FLOOR_POOL = ["FLOOR%02d" % i for i in range(12)]
 CEIL_POOL = ["CEIL%02d" % i for i in range(8)]
 GRATES = ["GRATE00", "GRATE01", "GRATE02", "GRATE03"]
@@ -345,6 +346,10 @@ def build_e1m1_class(rng: PCG32) -> GridMap:
             _carve(gm, cx0, cy0, cx0 + w, cy0 + h, s)
             rooms.append((cx0, cy0, cx0 + w, cy0 + h, s))
     gm.rooms = rooms
+
+    gm.sectors[rooms[7][4]].wall_tex = "HOLEY00"
+    gm.sectors[rooms[13][4]].wall_tex = "PARTIAL0"
+    gm.sectors[rooms[18][4]].step_tex = "HOLEY00"
 
     # --- corridors: lattice neighbours, L-shaped, some as staircases -------------------------------------
     def corridor(a, b, stairs: bool):
