@@ -6,6 +6,7 @@
 //   assets: u16 texel pool (row-major, pow2 pitch, 0x8000 = None), u8 flat pool (4096 B per flat), float4 palette
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -188,6 +189,10 @@ struct drr_ctx {
 
     std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
     int prof_steps = 0;
+    // Kernel selection (A/B switch, read once from the environment at context creation):
+    //   DRR_KERNEL=tile  (default) span-per-warp kernel with a shared-memory tile, column-major texel pool
+    //   DRR_KERNEL=march           lane-per-column scanline march, row-major texel pool
+    bool use_tile = true;
     bool host_only = false; // CPU-test recording context: records and bins, can never draw
     drr_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -260,6 +265,7 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     c->GCFX = gsw / 2.0f;
     c->CFX = (float)(uint32_t)width / 2.0f;
     c->CFY = (float)(uint32_t)height / 2.0f;
+    if (const char *k = getenv("DRR_KERNEL")) c->use_tile = std::string(k) != "march";
     c->cols.resize(width);
     c->slot_to_frame.assign(max_views, -1);
     c->frame_stride = ((uint64_t)width * height * 3 + 255) / 256 * 256;
@@ -331,23 +337,28 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     CTX_CHECK(ctx);
     if (!texels || w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: bad size (the reference divides by width and height)");
     if (ctx->bitmap_slot.count(id)) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: id already uploaded");
+    // pool layout: column-major [x][y] with pitch = next pow2 >= h (tile kernel) or row-major [y][x] with pitch = next
+    // pow2 >= w (march kernel); the setup kernel computes the matching base + tx offset
+    const bool cm = ctx->use_tile;
     uint32_t pitch = 1;
-    while (pitch < (uint32_t)w) pitch <<= 1;
+    while (pitch < (uint32_t)(cm ? h : w)) pitch <<= 1;
     BitmapRec r;
     r.base = (uint32_t)ctx->texel_pool.size();
     r.w = (int16_t)w;
     r.h = (int16_t)h;
     r.opaque = 1;
-    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * h, 0x8000);
+    for (size_t i = 0; i < (size_t)w * h; i++)
+        if (texels[i] < -1 || texels[i] > 255) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * (cm ? w : h), 0x8000);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const int16_t t = texels[(size_t)y * w + x];
-            if (t < 0 || t > 255) {
-                if (t != -1) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
+            const size_t at = r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x);
+            if (t < 0) {
                 r.opaque = 0;
-                ctx->texel_pool[r.base + (size_t)y * pitch + x] = 0x8000;
+                ctx->texel_pool[at] = 0x8000;
             } else {
-                ctx->texel_pool[r.base + (size_t)y * pitch + x] = (uint16_t)t;
+                ctx->texel_pool[at] = (uint16_t)t;
             }
         }
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
@@ -598,6 +609,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     a.W = ctx->W;
     a.H = ctx->H;
     a.nframes = (int)ctx->uploaded_frames;
+    a.colmajor = ctx->use_tile ? 1 : 0;
     a.CFX = ctx->CFX;
     a.CFY = ctx->CFY;
     a.GCFX = ctx->GCFX;
@@ -634,7 +646,7 @@ static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march, bo
         CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
         int launches = 0;
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], ctx->stream));
-        CU(ctx, launch_march(a, ctx->stream, &launches));
+        CU(ctx, ctx->use_tile ? launch_tile(a, ctx->stream, &launches) : launch_march(a, ctx->stream, &launches));
         ctx->stats.kernel_launches += (uint64_t)launches;
         if (prof) {
             CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], ctx->stream));
@@ -774,6 +786,7 @@ int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx 
     if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) return DRR_E_INVALID;
     drr_ctx *c = new drr_ctx();
     c->host_only = true;
+    if (const char *k = getenv("DRR_KERNEL")) c->use_tile = std::string(k) != "march";
     c->W = width;
     c->H = height;
     c->max_views = max_views;
@@ -813,11 +826,12 @@ int drr_test_bitmap_info(drr_ctx *ctx, int slot, int *w, int *h, int *opaque) {
 int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major w*h, -1 = None (decoded back from the device pool layout)
     if (!ctx || slot < 0 || slot >= (int)ctx->bitmaps.size()) return DRR_E_INVALID;
     const BitmapRec &r = ctx->bitmaps[slot];
+    const bool cm = ctx->use_tile;
     uint32_t pitch = 1;
-    while (pitch < (uint32_t)r.w) pitch <<= 1;
+    while (pitch < (uint32_t)(cm ? r.h : r.w)) pitch <<= 1;
     for (int y = 0; y < r.h; y++)
         for (int x = 0; x < r.w; x++) {
-            const uint16_t t = ctx->texel_pool[r.base + (size_t)y * pitch + x];
+            const uint16_t t = ctx->texel_pool[r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x)];
             out[(size_t)y * r.w + x] = (t & 0x8000) ? (int16_t)-1 : (int16_t)t;
         }
     return DRR_OK;

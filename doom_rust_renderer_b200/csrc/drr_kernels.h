@@ -10,8 +10,15 @@ static constexpr int MARCH_THREADS = 128;
 #endif
 static constexpr int MARCH_MIN_BLOCKS = DRR_MARCH_MIN_BLOCKS; // occupancy target: 6 CTAs x 4 warps per SM (<= 80 registers)
 
+static constexpr int TILE_THREADS = 256;
+#ifndef DRR_TILE_MIN_BLOCKS
+#define DRR_TILE_MIN_BLOCKS 4
+#endif
+static constexpr int TILE_MIN_BLOCKS = DRR_TILE_MIN_BLOCKS;
+
 struct DrawArgs {
     int W, H, nframes;
+    int colmajor; // texel pool layout: 1 = column-major (tile kernel), 0 = row-major (march kernel)
     // src/renderer/constants.rs:7-17 derived from W, H with the reference's own expressions (see make_constants())
     float CFX, CFY, GCFX, ASPECT, Wf, Hf;
     const View *views;
@@ -34,6 +41,7 @@ struct DrawArgs {
 
 cudaError_t launch_span_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st);
 cudaError_t launch_march(const DrawArgs &a, cudaStream_t st, int *launches);
+cudaError_t launch_tile(const DrawArgs &a, cudaStream_t st, int *launches);
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);
 
