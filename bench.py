@@ -53,11 +53,15 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU.  Started before the warm-up (NVML start-up takes longer than a
+    short timed region); result() reports the samples that fall inside [mark_start, mark_end] and, when the region was
+    too short to catch three of them, the samples of the surrounding loaded period (warm-up included), saying which."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.stop_flag, self.max_mhz = index, [], False, None
+        self.t0 = self.t1 = None
+        self.error = None
 
     def run(self):
         try:
@@ -65,25 +69,39 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                t = time.perf_counter()
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, n in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-                time.sleep(0.02)
+                self.samples.append((t, mhz, r))
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
-            self.reasons.add("sampler_error:%s" % type(e).__name__)
+            self.error = "%s: %s" % (type(e).__name__, e)
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def result(self):
         self.stop_flag = True
         self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [s for s in self.samples if self.t0 is not None and self.t0 - 0.25 <= s[0] <= self.t1 + 0.01]
+            window = "timed region + preceding warm-up (region shorter than 3 sampling periods)"
+        mhz = sorted(s[1] for s in inside)
+        reasons = sorted({n for s in inside for bit, n in names.items() if s[2] & bit})
+        out = {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside), "window": window}
+        if self.error:
+            out["sampler_error"] = self.error
+        return out
 
 
 def make_wad(kind: str):
@@ -125,8 +143,10 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
     if args.views:
         n_views = args.views
     path, gm = make_wad(kind)
+    from doom_rust_renderer_b200 import shard
     all_views = viewpoints(gm, kind, n_views * world)
-    mine = all_views[rank * n_views:(rank + 1) * n_views]
+    lo, hi = shard.shard_range(len(all_views), rank, world)  # contiguous viewpoint range of this GPU
+    mine = all_views[lo:hi]
 
     ctx = drr.Context(W, H, local_rank, n_views)
     scene = drr.Scene(path, "E1M1", W, H)
@@ -154,20 +174,27 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         return float(t.item())
 
     # ---- device-resident lists: `value` ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx.upload_lists()
     for _ in range(args.warmup):
         ctx.draw()
+    ctx.sync()
+    t_wait = time.perf_counter()
+    while not sampler.samples and sampler.error is None and time.perf_counter() - t_wait < 3.0:
+        ctx.draw()  # keep the GPU loaded until NVML delivers its first sample (untimed)
+        ctx.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.stats()["kernel_launches"]
     ctx.profile_begin(args.steps)
+    sampler.mark_start()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             ctx.draw()
         e1.record(stream)
     e1.synchronize()
+    sampler.mark_end()
     barrier()
     clocks = sampler.result()
     prof_steps, setup_ms_tot, march_ms_tot = ctx.profile_end()
@@ -194,16 +221,10 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
     assert (crc_e2e == crc_dev).all(), "checksums changed between device-resident and end-to-end passes"
 
     # host-side gather of the per-frame checksums (8 B/frame), off the timed path: checksum of checksums
-    with np.errstate(over="ignore"):
-        coc = int(crc_dev.sum(dtype=np.uint64))
-    if world > 1:
-        t = torch.tensor([coc & 0x7FFFFFFF, coc >> 31 & 0x7FFFFFFF, coc >> 62], dtype=torch.int64, device="cuda")
-        parts = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        vals = [int(p[0]) | (int(p[1]) << 31) | (int(p[2]) << 62) for p in parts]
-        coc = sum(vals) & 0xFFFFFFFFFFFFFFFF
+    coc = shard.checksum_of_checksums(shard.gather_checksums(crc_dev, device="cuda") if world > 1 else crc_dev)
 
     st = ctx.stats()
+    kernel_name = ctx.kernel_name()
     frames_total = n_views * world
     px_total = W * H * frames_total
     alg_bytes_launch = 3 * W * H * n_views + st["drawlist_bytes_algorithmic"]  # per GPU per launch
@@ -217,11 +238,11 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         "e2e_value": px_total / (ms_e2e * 1e-3) / 1e6, "e2e_ms_per_step": ms_e2e, "e2e_frames_per_s": frames_total / (ms_e2e * 1e-3),
         "h2d_bytes_per_step": st["device_list_bytes"], "d2h_bytes_per_step": 8 * n_views,
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "drr_march_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes_per_launch": alg_bytes_launch, "framebuffer_bytes_per_launch": 3 * W * H * n_views,
-                     "drawlist_bytes_per_launch": st["drawlist_bytes_algorithmic"], "march_ms": march_ms, "setup_ms": setup_ms,
-                     "march_share_of_step": march_ms / (march_ms + setup_ms) if march_ms + setup_ms > 0 else None},
+                     "drawlist_bytes_per_launch": st["drawlist_bytes_algorithmic"], "kernel_ms": march_ms, "setup_ms": setup_ms,
+                     "kernel_share_of_step": march_ms / (march_ms + setup_ms) if march_ms + setup_ms > 0 else None},
         "lists": {k: st[k] for k in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans", "device_list_bytes")},
         "host_build_s": host_build_s, "checksum_of_checksums": "%016x" % coc,
     }
@@ -324,7 +345,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="walk320", choices=sorted(WORKLOADS))

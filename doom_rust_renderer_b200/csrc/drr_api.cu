@@ -189,9 +189,10 @@ struct drr_ctx {
 
     std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
     int prof_steps = 0;
-    // Kernel selection (A/B switch, read once from the environment at context creation):
-    //   DRR_KERNEL=tile  (default) span-per-warp kernel with a shared-memory tile, column-major texel pool
-    //   DRR_KERNEL=march           lane-per-column scanline march, row-major texel pool
+    // Kernel selection, fixed at context creation (the texel pool layout depends on it):
+    //   tile  : span-per-warp kernel with a shared-memory tile, column-major texel pool -- wins when spans are long (H >= 400)
+    //   march : lane-per-column scanline march, row-major texel pool                   -- wins when spans are short (H < 400)
+    // DRR_KERNEL=tile|march overrides the automatic choice (A/B measurements, profiles/).
     bool use_tile = true;
     bool host_only = false; // CPU-test recording context: records and bins, can never draw
     drr_stats stats{};
@@ -265,7 +266,11 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     c->GCFX = gsw / 2.0f;
     c->CFX = (float)(uint32_t)width / 2.0f;
     c->CFY = (float)(uint32_t)height / 2.0f;
-    if (const char *k = getenv("DRR_KERNEL")) c->use_tile = std::string(k) != "march";
+    c->use_tile = height >= 400;
+    if (const char *k = getenv("DRR_KERNEL")) {
+        if (std::string(k) == "march") c->use_tile = false;
+        if (std::string(k) == "tile") c->use_tile = true;
+    }
     c->cols.resize(width);
     c->slot_to_frame.assign(max_views, -1);
     c->frame_stride = ((uint64_t)width * height * 3 + 255) / 256 * 256;
@@ -786,7 +791,11 @@ int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx 
     if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) return DRR_E_INVALID;
     drr_ctx *c = new drr_ctx();
     c->host_only = true;
-    if (const char *k = getenv("DRR_KERNEL")) c->use_tile = std::string(k) != "march";
+    c->use_tile = height >= 400;
+    if (const char *k = getenv("DRR_KERNEL")) {
+        if (std::string(k) == "march") c->use_tile = false;
+        if (std::string(k) == "tile") c->use_tile = true;
+    }
     c->W = width;
     c->H = height;
     c->max_views = max_views;
@@ -851,6 +860,7 @@ int drr_test_palette(drr_ctx *ctx, uint8_t *out768) {
     return DRR_OK;
 }
 int drr_test_sky_slot(drr_ctx *ctx) { return ctx ? ctx->sky_slot : -1; }
+int drr_test_uses_tile_kernel(drr_ctx *ctx) { return ctx && ctx->use_tile ? 1 : 0; }
 int drr_test_bitmap_id_of_slot(drr_ctx *ctx, int slot) {
     for (auto &kv : ctx->bitmap_slot)
         if (kv.second == slot) return kv.first;

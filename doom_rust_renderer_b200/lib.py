@@ -84,7 +84,7 @@ def _lib() -> C.CDLL:
             "drr_test_list": (vp, [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "drr_test_bitmap_info": (i, [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "drr_test_bitmap_texels": (i, [vp, i, vp]), "drr_test_flat_texels": (i, [vp, i, vp]), "drr_test_palette": (i, [vp, vp]),
-            "drr_test_sky_slot": (i, [vp]),
+            "drr_test_sky_slot": (i, [vp]), "drr_test_uses_tile_kernel": (i, [vp]),
             "drr_test_bitmap_id_of_slot": (i, [vp, i]), "drr_test_flat_id_of_slot": (i, [vp, i]),
             "drr_test_resolve_column": (i, [vp, i, vp, i]),
             "drr_test_fastdiv": (i, [vp, i, C.c_longlong, C.c_longlong, f, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), vp]),
@@ -237,6 +237,9 @@ class Context:
         t, s, m = C.c_float(), C.c_float(), C.c_float()
         self._ck(self.L.drr_time_draw(self.h, iters, C.byref(t), C.byref(s), C.byref(m)))
         return t.value, s.value, m.value
+
+    def kernel_name(self) -> str:
+        return "drr_tile_kernel" if self.L.drr_test_uses_tile_kernel(self.h) else "drr_march_kernel"
 
     def profile_begin(self, max_steps: int):
         self._ck(self.L.drr_profile_begin(self.h, max_steps))

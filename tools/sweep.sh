@@ -10,7 +10,7 @@ for knob in "$@"; do
 import json, sys
 d = json.load(open("/tmp/sweep.json"))
 s = d["secondary"][0]
-print("%-40s %-20s walk320 march %.4f ms frac %.4f | walk1280 march %.4f ms frac %.4f" % (sys.argv[1], sys.argv[2], d["roofline"]["march_ms"], d["roofline"]["frac"], s["roofline"]["march_ms"], s["roofline"]["frac"]))
+print("%-40s %-20s walk320 march %.4f ms frac %.4f | walk1280 march %.4f ms frac %.4f" % (sys.argv[1], sys.argv[2], d["roofline"]["kernel_ms"], d["roofline"]["frac"], s["roofline"]["kernel_ms"], s["roofline"]["frac"]))
 PY
 done
 touch doom_rust_renderer_b200/csrc/drr_kernels.cu doom_rust_renderer_b200/csrc/drr_api.cu
