@@ -621,6 +621,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     a.ASPECT = ctx->ASPECT;
     a.Wf = (float)(uint32_t)ctx->W;
     a.Hf = (float)(uint32_t)ctx->H;
+    a.one = 1.0f;
     a.views = ctx->d_views.p;
     a.segs = ctx->d_segs.p;
     a.planes = ctx->d_planes.p;

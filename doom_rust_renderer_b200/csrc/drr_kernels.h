@@ -21,6 +21,7 @@ struct DrawArgs {
     int colmajor; // texel pool layout: 1 = column-major (tile kernel), 0 = row-major (march kernel)
     // src/renderer/constants.rs:7-17 derived from W, H with the reference's own expressions (see make_constants())
     float CFX, CFY, GCFX, ASPECT, Wf, Hf;
+    float one; // always 1.0f, but opaque to ptxas: see add2_nofuse() in drr_kernels.cu
     const View *views;
     const SegRec *segs;
     const PlaneRec *planes;
