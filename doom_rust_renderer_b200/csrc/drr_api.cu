@@ -171,6 +171,8 @@ struct drr_ctx {
     DevBuf<ColIdx> d_colidx;
     DevBuf<uint32_t> d_frame_span_base, d_frame_slot;
     DevBuf<SpanParams> d_params;
+    DevBuf<uint4> d_tparams; // 4 x uint4 per span (tile kernel)
+    uint8_t *d_sky_rows = nullptr;
     size_t uploaded_frames = 0, uploaded_spans = 0;
     std::vector<int> slot_to_frame; // view slot -> recorded frame (or -1)
 
@@ -283,6 +285,8 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     c->own_stream = true;
     if ((e = cudaMalloc((void **)&c->d_frames, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMalloc(framebuffers)", e);
     if ((e = cudaMalloc((void **)&c->d_crc, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMalloc(crc)", e);
+    if ((e = cudaMalloc((void **)&c->d_sky_rows, (size_t)height)) != cudaSuccess) return bail("cudaMalloc(sky rows)", e);
+    if ((e = launch_sky_rows(c->d_sky_rows, height, c->stream)) != cudaSuccess) return bail("sky rows kernel", e);
     if ((e = cudaMemset(c->d_frames, 0, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
     if ((e = cudaMemset(c->d_crc, 0, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
     for (auto &ev : c->ev)
@@ -303,6 +307,7 @@ void drr_ctx_destroy(drr_ctx *ctx) {
         if (ev) cudaEventDestroy(ev);
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
+    if (ctx->d_sky_rows) cudaFree(ctx->d_sky_rows);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -354,17 +359,15 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     r.opaque = 1;
     for (size_t i = 0; i < (size_t)w * h; i++)
         if (texels[i] < -1 || texels[i] > 255) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
-    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * (cm ? w : h), 0x8000);
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * (cm ? w : h), cm ? 4096 : 0x8000);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const int16_t t = texels[(size_t)y * w + x];
             const size_t at = r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x);
-            if (t < 0) {
-                r.opaque = 0;
-                ctx->texel_pool[at] = 0x8000;
-            } else {
-                ctx->texel_pool[at] = (uint16_t)t;
-            }
+            if (t < 0) r.opaque = 0;
+            // tile kernel: the palette BYTE offset (index * 16; 256 * 16 = None); march kernel: the index (0x8000 = None)
+            if (cm) ctx->texel_pool[at] = (uint16_t)(t < 0 ? 4096 : t * 16);
+            else ctx->texel_pool[at] = (uint16_t)(t < 0 ? 0x8000 : t);
         }
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
     ctx->bitmaps.push_back(r);
@@ -591,7 +594,8 @@ int drr_upload_lists(drr_ctx *ctx) {
     CU(ctx, ctx->d_segs.reserve(std::max<size_t>(ctx->segs.n, 1)));
     CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
     CU(ctx, ctx->d_spans.reserve(std::max<size_t>(ctx->spans.n, 1)));
-    CU(ctx, ctx->d_params.reserve(std::max<size_t>(ctx->spans.n, 1)));
+    if (ctx->use_tile) CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->spans.n, 1) * 4));
+    else CU(ctx, ctx->d_params.reserve(std::max<size_t>(ctx->spans.n, 1)));
     CU(ctx, ctx->d_colidx.reserve(ctx->colidx.n));
     CU(ctx, ctx->d_frame_span_base.reserve(nf + 1));
     CU(ctx, ctx->d_frame_slot.reserve(nf));
@@ -630,6 +634,8 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     a.frame_slot = ctx->d_frame_slot.p;
     a.colidx = ctx->d_colidx.p;
     a.params = ctx->d_params.p;
+    a.tparams = ctx->d_tparams.p;
+    a.sky_rows = ctx->d_sky_rows;
     a.texels = ctx->d_texels.p;
     a.flats = ctx->d_flats.p;
     a.bitmaps = ctx->d_bitmaps.p;
@@ -645,7 +651,7 @@ static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march, bo
     const bool prof = profile && (size_t)(ctx->prof_steps + 1) * 3 <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3], ctx->stream));
     if (setup) {
-        CU(ctx, launch_span_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream));
+        CU(ctx, ctx->use_tile ? launch_tile_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream) : launch_span_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream));
         if (ctx->uploaded_spans) ctx->stats.kernel_launches++;
     }
     if (march) {
@@ -842,7 +848,7 @@ int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major 
     for (int y = 0; y < r.h; y++)
         for (int x = 0; x < r.w; x++) {
             const uint16_t t = ctx->texel_pool[r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x)];
-            out[(size_t)y * r.w + x] = (t & 0x8000) ? (int16_t)-1 : (int16_t)t;
+            out[(size_t)y * r.w + x] = cm ? (t == 4096 ? (int16_t)-1 : (int16_t)(t / 16)) : ((t & 0x8000) ? (int16_t)-1 : (int16_t)t);
         }
     return DRR_OK;
 }

@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t lit_rgb(float4 pal, float factor) {
 
 // Position-weighted linear checksum (drr.h: drr_read_checksums)
 __host__ __device__ __forceinline__ uint64_t checksum_term(uint32_t word, uint64_t index) {
-    uint32_t k = ((uint32_t)(index + 1u) * 0x9E3779B1u) | 1u;
+    uint32_t k = (uint32_t)(index + 1u) * 0x9E3779B1u; // never 0 for index + 1 < 2^32 (the multiplier is odd)
     return (uint64_t)word * (uint64_t)k;
 }
 

@@ -29,8 +29,11 @@ struct DrawArgs {
     const uint32_t *frame_span_base; // nframes + 1 entries
     const uint32_t *frame_slot;      // framebuffer slot (view index) of each recorded frame
     const ColIdx *colidx;            // nframes * W entries
-    SpanParams *params;              // one per span
-    const uint16_t *texels;          // bitmap pool, row-major, power-of-two row pitch, 0x8000 = None
+    SpanParams *params;              // one per span (march kernel)
+    void *tparams;                   // one 64-byte decoded record per span (tile kernel, drr_tile.cu)
+    const uint8_t *sky_rows;         // sky texture row of every screen row (tile kernel)
+    const uint16_t *texels;          // bitmap pool: march = row-major, pow2 row pitch, palette index, 0x8000 = None;
+                                     //              tile  = column-major, pow2 column pitch, palette byte offset (index*16), 4096 = None
     const uint8_t *flats;            // 4096 bytes per flat slot
     const BitmapRec *bitmaps;
     const float4 *palette;           // 256 x (r, g, b as f32, packed 0x00BBGGRR bits)
@@ -43,6 +46,10 @@ struct DrawArgs {
 cudaError_t launch_span_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st);
 cudaError_t launch_march(const DrawArgs &a, cudaStream_t st, int *launches);
 cudaError_t launch_tile(const DrawArgs &a, cudaStream_t st, int *launches);
+cudaError_t launch_tile_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st);
+cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
+cudaError_t launch_checksum_pass(const DrawArgs &a, cudaStream_t st, int *launches);
+void tile_config(int W, int H, int *tc, int *lpg);
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);
 

@@ -1,0 +1,493 @@
+// drr_tile.cu -- the tile draw kernel (sm_100a) and its span-setup kernel.
+//
+//   drr_tile_setup_kernel : one thread per resolved span.  Everything of render_vertical_bitmap_line that depends on the
+//                           column only (src/renderer/bitmap_render.rs:233-251), the per-visplane constants of
+//                           draw_visplane (src/renderer/visplanes.rs:108,112-114) and draw_sky's tx (visplanes.rs:54-66),
+//                           decoded all the way into the register values the pixel loops use (64 B per span), so that
+//                           the draw kernel spends no instructions on decoding.
+//   drr_tile_kernel       : one CTA per (frame, TC screen columns, band of rows; the band is the whole column for
+//                           H <= 800).  A span belongs to one screen column, so all of its parameters are uniform over
+//                           the lanes that work on it: a group of LPG lanes (the whole warp for tall screens, 16 or 8 lanes
+//                           for short ones, so that short spans still fill the warp) takes a span, each lane takes TWO rows
+//                           (y and y + LPG) at a time and evaluates them with Blackwell's packed FP32 instructions
+//                           (FFMA2 / FMUL2 / FADD2: two independent IEEE f32 results per issue slot).  The per-PIXEL part:
+//                           wall/sprite ty + texel + diminish_color (bitmap_render.rs:253-275, 190-208), flat inverse
+//                           projection (visplanes.rs:103-128), sky (visplanes.rs:65-77).  Pixels go to a column-major u32
+//                           tile in shared memory (consecutive lanes -> consecutive words: conflict-free); a column's
+//                           spans are drawn by ONE lane group in list order (opaque spans, which are pairwise disjoint,
+//                           then masked spans in draw order), and finally the tile is written out row by row as 16-byte
+//                           vectors of the row-major RGB24 framebuffer (Pixels::set, src/renderer/pixels.rs:22-30) while
+//                           the per-frame checksum is accumulated.  Column sets are handed to warps dynamically (shared
+//                           counter), so a warp that drew short columns takes more of them.
+#include "drr_device.cuh"
+#include "drr_kernels.h"
+#include "drr_math.cuh"
+#include <algorithm>
+
+namespace drr {
+
+// Decoded span record, 64 bytes.  Word layout (a.x .. d.w):
+//   all kinds : a.x = y0 | y1 << 16     a.y = kind | flags << 8      a.z = texel index / flat byte offset of the column
+//   wall kinds: a.w = K1   b.x = mask   b.y = K2   b.z = magic   b.w = -h      (ty = ((tyr + K1) & mask) + K2, then mod h)
+//               c.x = -top_y (f32)   c.y = -(bottom_y - top_y) (f32)   c.z = refined 1/(bottom_y - top_y)   c.w = uy1
+//               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
+//   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
+enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10 };
+
+__global__ void __launch_bounds__(256) drr_tile_setup_kernel(DrawArgs a, uint32_t nspans) {
+    __shared__ int s_f0;
+    const uint32_t s0 = blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) { // frame of the block's first span: upper_bound(frame_span_base, s0) - 1
+        int lo = 0, hi = a.nframes;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (a.frame_span_base[mid] <= s0) lo = mid + 1; else hi = mid;
+        }
+        s_f0 = lo - 1;
+    }
+    __syncthreads();
+    const uint32_t s = s0 + threadIdx.x;
+    if (s >= nspans) return;
+    int f = s_f0;
+    while (s >= a.frame_span_base[f + 1]) ++f;
+
+    const Span sp = a.spans[s];
+    uint4 ra = make_uint4((uint32_t)sp.y0 | ((uint32_t)sp.y1 << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
+    uint32_t kind = sp.kind;
+
+    if (kind == KIND_WALL || kind == KIND_WALL_HOLES) {
+        const SegRec g = a.segs[sp.op];
+        const BitmapRec bm = a.bitmaps[g.bitmap_slot];
+        const uint32_t h = (uint32_t)bm.h;
+        const WallColumn wc = wall_column(g, bm.w, sp.x);
+        if (wc.tx < 0) kind = KIND_NONE; // reference: negative index -> panic
+        const uint32_t lp = ilog2_ceil(h); // column-major texel pool: one texture column = 1 << lp consecutive texels
+        ra.z = bm.base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
+        uint32_t flags = 0;
+        if ((h & (h - 1u)) == 0u) {
+            // floormod(wrap16(tyr + off_y), 2^k) == (tyr + off_y) & (2^k - 1): the i16 wrap only touches bits >= 16
+            flags |= TS_POW2;
+            ra.w = (uint32_t)(int)g.offset_y;
+            rb.x = h - 1u;
+        } else {
+            // floormod(v, h) for v in i16 via u = v + M (M = multiple of h >= 32768), q = umulhi(u, magic), r = u - q*h;
+            // wrap16(t + off) + M == ((t + off + 32768) & 0xffff) + (M - 32768)
+            const uint32_t M = h * ((32768u + h - 1u) / h);
+            ra.w = (uint32_t)((int)g.offset_y + 32768);
+            rb.x = 0xffffu;
+            rb.y = M - 32768u;
+            rb.z = (uint32_t)(0x100000000ull / h) + 1u;
+            rb.w = 0u - h;
+        }
+        const int den = (int)sp.bottom_y - (int)sp.top_y;
+        const float denF = (float)den;
+        rc.x = __float_as_uint(-(float)sp.top_y);
+        rc.y = __float_as_uint(-denF);
+        rc.z = __float_as_uint(den != 0 ? refined_rcp(denF) : 0.0f);
+        rc.w = __float_as_uint(wc.uy1);
+        // bottom_y == top_y: ay is NaN or +-inf, (1.0 - ay) * 0.0 is NaN, the sum is NaN and `NaN as i16` is 0
+        rd.x = den != 0 ? __float_as_uint((float)h) : 0x7fc00000u;
+        rd.y = __float_as_uint(wc.factor);
+        if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
+        ra.y = kind | flags;
+    } else if (kind == KIND_FLAT) {
+        const PlaneRec p = a.planes[sp.op];
+        const View vw = a.views[f];
+        // visplanes.rs:112  wz = visplane.height as f32 - player.floor_height - PLAYER_EYE_HEIGHT
+        const float wz = __fsub_rn(__fsub_rn((float)p.height, vw.floor_height), 41.0f);
+        // visplanes.rs:108  vx = (CAMERA_FOCUS_X - x as f32) / ASPECT_RATIO_CORRECTION
+        const float vx = __fdiv_rn(__fsub_rn(a.CFX, (float)sp.x), a.ASPECT);
+        const float wzvx = __fmul_rn(wz, vx);    // left operand of visplanes.rs:114
+        const float gwz = __fmul_rn(a.GCFX, wz); // left operand of visplanes.rs:113
+        ra.z = (uint32_t)p.flat_slot * 4096u;
+        rc.x = __float_as_uint(wzvx);
+        rc.y = __float_as_uint(gwz);
+        rc.z = __float_as_uint(__fdiv_rn((float)p.light_level, 255.0f)); // bitmap_render.rs:191
+        ra.y = kind | ((fast_div_operand_ok(wzvx) && fast_div_operand_ok(gwz)) ? TS_FASTDIV : 0u);
+    } else { // sky kinds
+        const View vw = a.views[f];
+        int tx = sky_tx(vw.angle, (int)(short)sp.x, a.Wf);
+        if (tx < 0) { kind = KIND_NONE; tx = 0; }
+        ra.z = a.sky_base + ((uint32_t)tx << 7);
+        ra.y = kind;
+    }
+    uint4 *out = reinterpret_cast<uint4 *>(a.tparams) + (size_t)s * 4;
+    out[0] = ra;
+    out[1] = rb;
+    out[2] = rc;
+    out[3] = rd;
+}
+
+// sky ty of every screen row (visplanes.rs:68-72: depends on the row only), computed once per context
+__global__ void drr_sky_rows_kernel(uint8_t *rows, int H, float Hf) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y < H) rows[y] = (uint8_t)sky_ty(y, Hf);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pixel loops
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// ---- Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2: two independent IEEE f32 operations per instruction, same rounding
+// as the scalar forms) ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+// ptxas (CUDA 12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 even though both carry an explicit .rn
+// and -fmad=false is given (the scalar forms are left alone).  A product that feeds a sum is therefore added with
+// fma(p, one, c) where `one` is 1.0f read from the kernel arguments: round(p * 1 + c) == round(p + c), and ptxas cannot
+// fold a multiplier it does not know.  tests/test_host.py checks the SASS for it.
+__device__ __forceinline__ float2 add2_nofuse(float2 prod, float2 c, float one) { return __ffma2_rn(prod, f2(one), c); }
+__device__ __forceinline__ float2 fast_div2(float2 a, float2 negb, float2 r) { // a / b with r = refined 1/b, negb = -b
+    const float2 q0 = __fmul2_rn(a, r);
+    const float2 rem = __ffma2_rn(negb, q0, a);
+    return __ffma2_rn(r, rem, q0);
+}
+// one pixel's lit colour for 0 <= factor <= 1 (see lit_rgb_unit): (r, g) as a packed pair, b scalar
+__device__ __forceinline__ uint32_t lit_rgb_unit_p(float4 p, float factor) {
+    const float2 rg = __fadd2_rz(__fmul2_rn(f2(p.x, p.y), f2(factor)), f2(8388608.0f));
+    const float b = __fadd_rz(__fmul_rn(p.z, factor), 8388608.0f);
+    return __byte_perm(__byte_perm(__float_as_uint(rg.x), __float_as_uint(rg.y), 0x0040), __float_as_uint(b), 0x5410);
+}
+
+static constexpr uint32_t TEXEL_HOLE = 4096u; // texel pool values are palette byte offsets (index * 16); 256 * 16 = None
+
+// bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows
+template <bool POW2>
+__device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, const uint4 rc, float hF, float2 yt, float one,
+                                             const uint16_t *__restrict__ texels, uint32_t &t0, uint32_t &t1) {
+    const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));   // :256
+    // :257 with uy0 == 0.0: (1.0 - ay) * 0.0 is +-0.0 for finite ay and h + (+-0.0) == h, so the middle term drops out
+    const float2 sum = add2_nofuse(__fmul2_rn(ay, f2(__uint_as_float(rc.w))), f2(hF), one);
+    uint32_t u0 = ((uint32_t)sat_i16(sum.x) + ra.w) & rb.x; // :259
+    uint32_t u1 = ((uint32_t)sat_i16(sum.y) + ra.w) & rb.x;
+    if (!POW2) { // :260-263 == floormod (identity checked in tests/: test_wrap_mod_idiom_is_floormod)
+        u0 += rb.y;
+        u1 += rb.y;
+        u0 = __umulhi(u0, rb.z) * rb.w + u0;
+        u1 = __umulhi(u1, rb.z) * rb.w + u1;
+    }
+    t0 = texels[ra.z + u0];
+    t1 = texels[ra.z + u1];
+}
+
+template <int LPG, bool HOLES, bool POW2>
+__device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
+                                               uint32_t col_addr, const uint16_t *__restrict__ texels, uint32_t pal_addr, float one) {
+    const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
+    int y = ya + li;
+    uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
+    float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + LPG), __uint_as_float(rc.x)));
+    if (!(ra.y & TS_BRIGHT)) {
+#pragma unroll 2
+        for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
+            uint32_t t0, t1;
+            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, texels, t0, t1);
+            const uint32_t rgb0 = lit_rgb_unit_p(lds_f4(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(lds_f4(pal_addr + t1), factor);
+            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, rgb0);
+            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, rgb1);
+        }
+    } else {
+        for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
+            uint32_t t0, t1;
+            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, texels, t0, t1);
+            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(lds_f4(pal_addr + t0), factor));
+            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(lds_f4(pal_addr + t1), factor));
+        }
+    }
+}
+
+// visplanes.rs:103-128 for one pixel of a flat span, every division IEEE
+__device__ __forceinline__ uint32_t flat_pixel_slow(float vy, float gwz, float wzvx, float lf, float cos_a, float sin_a, int px16, int py16,
+                                                    const uint8_t *__restrict__ flat, uint32_t pal_addr) {
+    const float wx = __fdiv_rn(gwz, vy), wy = __fdiv_rn(wzvx, vy);
+    const float rx = __fsub_rn(__fmul_rn(wx, cos_a), __fmul_rn(wy, sin_a)); // vertexes.rs:20-25
+    const float ry = __fadd_rn(__fmul_rn(wy, cos_a), __fmul_rn(wx, sin_a));
+    const uint32_t tx = (uint32_t)(sat_i16(rx) + px16); // i16 wrap does not reach the low 6 bits
+    const uint32_t ty = (uint32_t)(sat_i16(ry) + py16);
+    const uint32_t texel = flat[((ty << 6) & 0xfc0u) | (tx & 63u)];
+    return lit_rgb_any(lds_f4(pal_addr + texel * 16u), light_factor(lf, sat_i16(wx)));
+}
+
+template <int LPG>
+__device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, int ya, int yb, int b0, int li, uint32_t col_addr, float CFY,
+                                               float cos_a, float sin_a, int px16, int py16, const uint8_t *__restrict__ flats,
+                                               uint32_t pal_addr, float one) {
+    const float wzvx = __uint_as_float(rc.x), gwz = __uint_as_float(rc.y), lf = __uint_as_float(rc.z);
+    const uint8_t *__restrict__ flat = flats + ra.z;
+    int y = ya + li;
+    uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
+    if (ra.y & TS_FASTDIV) {
+        // rows y and y + LPG of this lane together (visplanes.rs:109-128, twice).  The row with vy == 0 (y == H/2 for even H)
+        // divides by zero: the loop leaves garbage there (no fault), it is redone below with the IEEE division.
+        float2 vy = f2(__fsub_rn(CFY, (float)y), __fsub_rn(CFY, (float)(y + LPG)));
+        for (; y <= yb; y += 2 * LPG, vy = __fadd2_rn(vy, f2((float)(-2 * LPG))), addr += 8u * LPG) {
+            float2 r0;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.y) : "f"(vy.y));
+            const float2 nvy = f2(-vy.x, -vy.y);
+            const float2 r = __ffma2_rn(r0, __ffma2_rn(nvy, r0, f2(1.0f)), r0); // refined_rcp, twice
+            const float2 wx = fast_div2(f2(gwz), nvy, r);                       // :113
+            const float2 wy = fast_div2(f2(wzvx), nvy, r);                      // :114
+            const float2 rx = add2_nofuse(__fmul2_rn(wx, f2(cos_a)), __fmul2_rn(wy, f2(-sin_a)), one); // wx*cos - wy*sin (vertexes.rs:20-25)
+            const float2 ry = add2_nofuse(__fmul2_rn(wy, f2(cos_a)), __fmul2_rn(wx, f2(sin_a)), one);
+            const uint32_t tx0 = (uint32_t)(sat_i16(rx.x) + px16), ty0 = (uint32_t)(sat_i16(ry.x) + py16);
+            const uint32_t tx1 = (uint32_t)(sat_i16(rx.y) + px16), ty1 = (uint32_t)(sat_i16(ry.y) + py16);
+            const uint32_t t0 = flat[((ty0 << 6) & 0xfc0u) | (tx0 & 63u)];
+            const uint32_t t1 = flat[((ty1 << 6) & 0xfc0u) | (tx1 & 63u)];
+            // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
+            const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
+            float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), one);
+            fac.x = fac.x < 0.0f ? 0.0f : fac.x;
+            fac.y = fac.y < 0.0f ? 0.0f : fac.y;
+            const float4 p0 = lds_f4(pal_addr + t0 * 16u), p1 = lds_f4(pal_addr + t1 * 16u);
+            uint32_t rgb0, rgb1;
+            if (fac.x <= 1.0f && fac.y <= 1.0f) {
+                rgb0 = lit_rgb_unit_p(p0, fac.x);
+                rgb1 = lit_rgb_unit_p(p1, fac.y);
+            } else {
+                rgb0 = lit_rgb_any(p0, fac.x);
+                rgb1 = lit_rgb_any(p1, fac.y);
+            }
+            sts_u32(addr, rgb0);
+            if (y + LPG <= yb) sts_u32(addr + 4u * LPG, rgb1);
+        }
+        const int ym = (int)CFY; // exact integer when H is even
+        if ((float)ym == CFY && ym >= ya && ym <= yb && li == ((ym - ya) % LPG))
+            sts_u32(col_addr + 4u * (uint32_t)(ym - b0), flat_pixel_slow(0.0f, gwz, wzvx, lf, cos_a, sin_a, px16, py16, flat, pal_addr));
+    } else {
+        float vy = __fsub_rn(CFY, (float)y);
+        for (; y <= yb; y += LPG, vy -= (float)LPG, addr += 4u * LPG)
+            sts_u32(addr, flat_pixel_slow(vy, gwz, wzvx, lf, cos_a, sin_a, px16, py16, flat, pal_addr));
+    }
+}
+
+template <int LPG, bool HOLES>
+__device__ __forceinline__ void tile_sky_span(const uint4 ra, int ya, int yb, int b0, int li, uint32_t col_addr,
+                                              const uint8_t *__restrict__ sky_rows, const uint16_t *__restrict__ texels, uint32_t pal_addr) {
+    uint32_t addr = col_addr + 4u * (uint32_t)(ya + li - b0);
+    for (int y = ya + li; y <= yb; y += LPG, addr += 4u * LPG) {
+        const uint32_t texel = texels[ra.z + sky_rows[y]]; // column-major sky: base + tx*128 + ty
+        if (HOLES && texel == TEXEL_HOLE) continue;
+        sts_u32(addr, lds_u32(pal_addr + texel + 12u)); // no lighting (visplanes.rs:74-77)
+    }
+}
+
+// PRMT selector that assembles an output word starting at channel `ph` of pixel a: bytes a[ph..2] then b[0..]
+__device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph == 1 ? 0x5421u : 0x6542u; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------------
+// TC  = screen columns per tile (16: 48-byte row segments, 3 lanes x 10 rows per write-out step; 32: 96 bytes, 6 lanes x 5 rows)
+// LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
+// RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
+template <int TC, int LPG, bool FAST_STORE>
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int band_rows, int nbands, int RP) {
+    extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
+    __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
+    __shared__ int s_next;
+    constexpr int G = 32 / LPG;          // columns per warp step
+    constexpr int NSETS = TC / G;
+    constexpr int NW = TILE_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gpf = (a.W + TC - 1) / TC;
+    const unsigned bid = blockIdx.x;
+    const int band = (int)(bid % (unsigned)nbands);
+    const int g = (int)((bid / (unsigned)nbands) % (unsigned)gpf);
+    const int f = (int)(bid / ((unsigned)nbands * (unsigned)gpf));
+    const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
+
+    for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
+    for (int i = threadIdx.x; i < (TC * RP + 3) / 4; i += TILE_THREADS) reinterpret_cast<uint4 *>(s_tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) s_next = NW;
+    __syncthreads();
+    const uint32_t pal_addr = (uint32_t)__cvta_generic_to_shared(s_pal);
+    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(s_tile);
+    const uint16_t *__restrict__ texels = a.texels;
+    const uint8_t *__restrict__ flats = a.flats;
+    const View vw = a.views[f];
+    const int px16 = sat_i16(vw.pos_x), py16 = sat_i16(vw.pos_y); // visplanes.rs:119-120 `player.position.x as i16`
+    const int grp = lane / LPG, li = lane % LPG;
+
+    // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
+    // list in order: opaque spans (pairwise disjoint), then masked spans in draw order
+    for (int cs = warp; cs < NSETS;) {
+        const int c = cs * G + grp, x = g * TC + c;
+        ColIdx ci;
+        ci.first = 0; ci.n_opaque = 0; ci.n_masked = 0;
+        if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
+        const int n = ci.n_opaque + ci.n_masked;
+        const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
+        const uint32_t col_addr = tile_addr + 4u * (uint32_t)(c * RP);
+        for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
+            __syncwarp(); // a masked span may overwrite what another lane of the group stored for an earlier span
+            if (j < n) {
+                const uint4 ra = P[4 * j];
+                const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
+                const uint32_t kind = ra.y & 0xffu;
+                if (ya <= yb && kind != KIND_NONE) {
+                    if (kind == KIND_FLAT) {
+                        tile_flat_span<LPG>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
+                    } else if (kind == KIND_WALL) {
+                        const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
+                        if (ra.y & TS_POW2) tile_wall_span<LPG, false, true>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        else tile_wall_span<LPG, false, false>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                    } else if (kind == KIND_WALL_HOLES) {
+                        const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
+                        if (ra.y & TS_POW2) tile_wall_span<LPG, true, true>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        else tile_wall_span<LPG, true, false>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                    } else if (kind == KIND_SKY) {
+                        tile_sky_span<LPG, false>(ra, ya, yb, b0, li, col_addr, a.sky_rows, texels, pal_addr);
+                    } else if (kind == KIND_SKY_HOLES) {
+                        tile_sky_span<LPG, true>(ra, ya, yb, b0, li, col_addr, a.sky_rows, texels, pal_addr);
+                    }
+                }
+            }
+        }
+        int nx = 0;
+        if (lane == 0) nx = atomicAdd(&s_next, 1);
+        cs = __shfl_sync(0xffffffffu, nx, 0);
+    }
+    __syncthreads(); // every span of the tile is in before the write-out
+
+    // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x).  A row of the tile is TC*3 bytes = LPR 16-byte
+    // vectors; a warp step covers RPI rows with LPR lanes each.  Vector j of a row holds bytes 16j .. 16j+15, i.e. pixels
+    // (16j)/3 .. (16j+15)/3 of the tile row, starting at channel j % 3 of the first one.
+    const uint32_t slot = a.frame_slot[f];
+    const size_t pitch = (size_t)a.W * 3;
+    uint8_t *base = a.frames + (size_t)slot * a.frame_stride + (size_t)g * (TC * 3);
+    const int nrows = b1 - b0 + 1;
+    if (FAST_STORE) {
+        constexpr int LPR = TC * 3 / 16, RPI = 32 / LPR;
+        const int rl = lane / LPR, j = lane % LPR, ph = j % 3;
+        uint64_t acc = 0;
+        if (lane < LPR * RPI) {
+            const int cb = (16 * j) / 3;
+            // word m of the vector starts at byte 16j + 4m of the row: pixel q(m), channel (ph + m) % 3 -> selector; the pixel
+            // pairs are (0,1) (1,2)|(2,3) (2,3)|(3,4) (4,5) relative to cb, depending on the phase
+            const uint32_t s0 = wsel(ph), s1 = wsel((ph + 1) % 3), s2 = wsel((ph + 2) % 3), s3 = s0;
+            const uint32_t pw = (uint32_t)(pitch >> 2);
+            int r = warp * RPI + rl;
+            uint32_t ta = tile_addr + 4u * (uint32_t)(cb * RP + r);
+            uint32_t *wp = reinterpret_cast<uint32_t *>(base) + (size_t)(b0 + r) * pw + 4 * j;
+            // checksum weight of word i is (i + 1) * C mod 2^32 (drr.h); this lane's words are i0 .. i0+3, i0 advancing by a row step
+            const uint32_t C = 0x9E3779B1u;
+            uint32_t k0 = ((uint32_t)(b0 + r) * pw + (uint32_t)g * (TC * 3 / 4) + 4u * (uint32_t)j + 1u) * C;
+            const uint32_t kstep = (uint32_t)(NW * RPI) * pw * C;
+            const size_t wstep = (size_t)(NW * RPI) * pw;
+#pragma unroll 2
+            for (; r < nrows; r += NW * RPI) {
+                const uint32_t p0 = lds_u32(ta), p1 = lds_u32(ta + 4u * RP), p2 = lds_u32(ta + 8u * RP), p3 = lds_u32(ta + 12u * RP),
+                               p4 = lds_u32(ta + 16u * RP), p5 = lds_u32(ta + 20u * RP);
+                uint4 v;
+                v.x = __byte_perm(p0, p1, s0);
+                v.y = __byte_perm(ph == 2 ? p2 : p1, ph == 2 ? p3 : p2, s1);
+                v.z = __byte_perm(ph == 0 ? p2 : p3, ph == 0 ? p3 : p4, s2);
+                v.w = __byte_perm(p4, p5, s3);
+                *reinterpret_cast<uint4 *>(wp) = v;
+                acc += (uint64_t)v.x * k0 + (uint64_t)v.y * (k0 + C) + (uint64_t)v.z * (k0 + 2u * C) + (uint64_t)v.w * (k0 + 3u * C);
+                ta += 4u * (NW * RPI);
+                wp += wstep;
+                k0 += kstep;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long *>(a.crc + slot), (unsigned long long)acc);
+    } else {
+        for (int i = threadIdx.x; i < TC * nrows; i += TILE_THREADS) { // generic widths: bytewise; the checksum is a separate pass
+            const int c = i % TC, r = i / TC, x = g * TC + c;
+            if (x >= a.W) continue;
+            const uint32_t rgb = s_tile[c * RP + r];
+            uint8_t *p = base + (size_t)(b0 + r) * pitch + c * 3;
+            p[0] = (uint8_t)rgb;
+            p[1] = (uint8_t)(rgb >> 8);
+            p[2] = (uint8_t)(rgb >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------------
+cudaError_t launch_tile_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st) {
+    if (nspans == 0) return cudaSuccess;
+    drr_tile_setup_kernel<<<(nspans + 255) / 256, 256, 0, st>>>(a, nspans);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
+    drr_sky_rows_kernel<<<(H + 255) / 256, 256, 0, st>>>(rows, H, (float)(uint32_t)H);
+    return cudaGetLastError();
+}
+
+void tile_config(int W, int H, int *tc, int *lpg) {
+    // tall screens: long spans, a whole warp per span and 16-column tiles (two full-height tiles per SM); short screens:
+    // 8 or 16 lanes per span so that short spans still fill the warp, 32-column tiles
+    *tc = H >= 400 ? 16 : 32;
+    *lpg = H >= 600 ? 32 : H >= 300 ? 16 : 8;
+    if (const char *e = getenv("DRR_TILE_COLS")) {
+        const int v = atoi(e);
+        if (v == 16 || v == 32) *tc = v;
+    }
+    if (const char *e = getenv("DRR_TILE_LPG")) {
+        const int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) *lpg = v;
+    }
+}
+
+template <int TC, int LPG>
+static cudaError_t launch_tile_t(const DrawArgs &a, cudaStream_t st, int *launches) {
+    const int gpf = (a.W + TC - 1) / TC;
+    // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
+    const int max_rows = 820;
+    const int nbands = (a.H + max_rows - 1) / max_rows;
+    const int band_rows = (a.H + nbands - 1) / nbands;
+    const int want = TC == 16 ? 2 : 1;
+    int RP = band_rows;
+    while (RP % 32 != want) ++RP;
+    const long long blocks = (long long)a.nframes * gpf * nbands;
+    if (blocks == 0) return cudaSuccess;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const size_t dyn = ((size_t)TC * RP * 4 + 15) / 16 * 16;
+    const bool fast = (a.W % TC) == 0;
+    *launches = 1;
+    cudaError_t e;
+    if (fast) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(drr_tile_kernel<TC, LPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        drr_tile_kernel<TC, LPG, true><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, band_rows, nbands, RP);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(drr_tile_kernel<TC, LPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        drr_tile_kernel<TC, LPG, false><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, band_rows, nbands, RP);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch_checksum_pass(a, st, launches);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile(const DrawArgs &a, cudaStream_t st, int *launches) {
+    int tc, lpg;
+    tile_config(a.W, a.H, &tc, &lpg);
+    if (tc == 16) {
+        if (lpg == 32) return launch_tile_t<16, 32>(a, st, launches);
+        if (lpg == 16) return launch_tile_t<16, 16>(a, st, launches);
+        return launch_tile_t<16, 8>(a, st, launches);
+    }
+    if (lpg == 32) return launch_tile_t<32, 32>(a, st, launches);
+    if (lpg == 16) return launch_tile_t<32, 16>(a, st, launches);
+    return launch_tile_t<32, 8>(a, st, launches);
+}
+
+} // namespace drr

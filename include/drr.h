@@ -118,7 +118,7 @@ int drr_submit(drr_ctx *ctx);       /* drr_upload_lists + drr_draw */
 int drr_sync(drr_ctx *ctx);
 int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out_rgb24);    /* width*height*3 bytes, row-major RGB24 == Pixels.pixels */
 int drr_read_checksums(drr_ctx *ctx, int first_view, int count, uint64_t *out);
-/* Per-frame checksum: sum over little-endian u32 words w_i of the frame of  w_i * (((i+1)*0x9E3779B1 mod 2^32) | 1),
+/* Per-frame checksum: sum over little-endian u32 words w_i of the frame of  w_i * ((i+1)*0x9E3779B1 mod 2^32),
  * mod 2^64.  drr_checksum_host computes the same on a host buffer. */
 uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes);
 
