@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-One "step" = one pass of the hot path (span-setup kernel + scanline-march kernel) over one batch of viewpoints whose
+One "step" = one pass of the hot path (column-binning kernel + tile draw kernel) over one batch of viewpoints whose
 draw lists were produced beforehand by the host front-end (doom_rust_renderer_b200/csrc/host/drr_scene.cpp).
 
   value  : whole-job Mpixels/s (screen pixels W*H*frames / time) with draw lists resident in HBM, CUDA events on the
@@ -204,15 +204,13 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
 
     # ---- host lists every step: `e2e` ----
     for _ in range(max(1, args.warmup // 2)):
-        ctx.upload_lists()
-        ctx.draw()
+        ctx.submit()
         ctx.read_checksums(0, n_views)
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
-            ctx.upload_lists()
-            ctx.draw()
+            ctx.submit()  # pinned host lists -> H2D (chunked, overlapped with the kernels) -> bin + draw
             crc_e2e = ctx.read_checksums(0, n_views)
         e1.record(stream)
     e1.synchronize()

@@ -1,9 +1,11 @@
-// drr_api.cu -- the C ABI of include/drr.h: context, asset upload, draw-list recording, column binning, launches.
+// drr_api.cu -- the C ABI of include/drr.h: context, asset upload, draw-list recording, upload and launches.
 //
 // Data layout in HBM (all frames of a batch concatenated, see drr_device.cuh):
-//   views[frame] 24 B | segs[] 48 B | planes[] 12 B | colidx[frame][x] 8 B | spans[] 16 B | params[] 32 B (device scratch)
+//   as emitted:  views[frame] 24 B | ops[] 4 B (call order) | segs[] 64 B | cols[] 10 B | planes[] 16 B | (top, bottom) pairs 4 B
+//   device scratch: colidx[frame][x] 8 B and one decoded 64-byte record per (op, column), both written by the bin kernel
 //   framebuffers: max_views x (W*H*3 B, RGB24 row-major == Pixels.pixels, src/renderer/pixels.rs:5-14)
-//   assets: u16 texel pool (row-major, pow2 pitch, 0x8000 = None), u8 flat pool (4096 B per flat), float4 palette
+//   assets: u16 texel pool (column-major, pow2 column pitch, palette byte offsets, 4096 = None), u8 flat pool (4096 B per
+//           flat), float4 palette
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -71,69 +73,6 @@ struct DevBuf {
     }
 };
 
-struct Entry { // one emitted column of one op, before resolving
-    uint32_t op;
-    uint8_t kind;
-    int16_t a, b; // inclusive rows, already clamped to the screen
-    int16_t top_y, bottom_y;
-};
-
-struct TmpSpan {
-    int16_t y0, y1;
-    uint32_t op;
-    uint8_t kind;
-    int16_t top_y, bottom_y;
-};
-
-inline bool kind_is_opaque(uint8_t k) { return k == KIND_WALL || k == KIND_FLAT || k == KIND_SKY; }
-
-// Remove rows [a, b] from every span of `list`, keeping list order (a split span's halves stay adjacent).
-void cut_rows(std::vector<TmpSpan> &list, std::vector<TmpSpan> &tmp, int a, int b) {
-    tmp.clear();
-    for (const TmpSpan &s : list) {
-        if (s.y1 < a || s.y0 > b) {
-            tmp.push_back(s);
-            continue;
-        }
-        if (s.y0 < a) {
-            TmpSpan l = s;
-            l.y1 = (int16_t)(a - 1);
-            tmp.push_back(l);
-        }
-        if (s.y1 > b) {
-            TmpSpan r = s;
-            r.y0 = (int16_t)(b + 1);
-            tmp.push_back(r);
-        }
-    }
-    list.swap(tmp);
-}
-
-// Turn the draw-ordered entries of ONE screen column into
-//   * opaque spans: pairwise disjoint, sorted by row -- an op that always writes (opaque bitmap, flat, opaque sky)
-//     erases whatever earlier ops put on the rows it covers, so those earlier rows can be dropped ("last writer wins",
-//     SURVEY.md 3.1), and
-//   * masked spans, in draw order: ops that may skip pixels (bitmaps with None texels).  They never erase anything
-//     here; on the device they are tested last-to-first and the first opaque texel wins, otherwise the opaque span
-//     below shows through.  A masked span survives only on rows where no LATER opaque op covers it.
-// The per-pixel result is identical to painting the entries in order.
-void resolve_column(const std::vector<Entry> &entries, std::vector<TmpSpan> &opq, std::vector<TmpSpan> &msk, std::vector<TmpSpan> &tmp) {
-    opq.clear();
-    msk.clear();
-    for (const Entry &e : entries) {
-        if (e.a > e.b) continue;
-        TmpSpan s{e.a, e.b, e.op, e.kind, e.top_y, e.bottom_y};
-        if (kind_is_opaque(e.kind)) {
-            cut_rows(opq, tmp, e.a, e.b);
-            if (!msk.empty()) cut_rows(msk, tmp, e.a, e.b);
-            opq.push_back(s);
-        } else {
-            msk.push_back(s);
-        }
-    }
-    std::sort(opq.begin(), opq.end(), [](const TmpSpan &l, const TmpSpan &r) { return l.y0 < r.y0; });
-}
-
 } // namespace
 
 struct drr_ctx {
@@ -156,24 +95,27 @@ struct drr_ctx {
     DevBuf<BitmapRec> d_bitmaps;
     DevBuf<float4> d_pal;
 
-    // recorded lists (pinned staging) and their device copies
+    // recorded lists (pinned staging, exactly what the host emitted, all frames concatenated) and their device copies
     PinnedVec<View> views;
-    PinnedVec<SegRec> segs;
-    PinnedVec<PlaneRec> planes;
-    PinnedVec<Span> spans;
-    PinnedVec<ColIdx> colidx;
-    PinnedVec<uint32_t> frame_span_base;
+    PinnedVec<uint32_t> ops;            // per frame, call order: bit 31 = visplane, low bits = index into planes / segs
+    PinnedVec<uint32_t> frame_op_base;  // frames + 1
+    PinnedVec<uint32_t> frame_rec_base; // frames + 1: records (columns that survive clipping) before each frame
     PinnedVec<uint32_t> frame_slot;
+    PinnedVec<SegRec> segs;
+    PinnedVec<ColRec> cols;
+    PinnedVec<PlaneRec> planes;
+    PinnedVec<uint32_t> parr;           // (top, bottom) i16 pairs
+    std::vector<uint32_t> frame_seg_base, frame_col_base, frame_plane_base, frame_parr_base; // frames + 1 each (chunked upload)
     DevBuf<View> d_views;
+    DevBuf<uint32_t> d_ops, d_frame_op_base, d_frame_rec_base, d_frame_slot, d_parr, d_frame_cursor;
     DevBuf<SegRec> d_segs;
+    DevBuf<uint16_t> d_cols; // ColRec is 10 bytes, 2-byte aligned
     DevBuf<PlaneRec> d_planes;
-    DevBuf<Span> d_spans;
     DevBuf<ColIdx> d_colidx;
-    DevBuf<uint32_t> d_frame_span_base, d_frame_slot;
-    DevBuf<SpanParams> d_params;
-    DevBuf<uint4> d_tparams; // 4 x uint4 per span (tile kernel)
+    DevBuf<uint4> d_tparams; // 4 x uint4 per record
     uint8_t *d_sky_rows = nullptr;
-    size_t uploaded_frames = 0, uploaded_spans = 0;
+    size_t uploaded_frames = 0;
+    uint64_t rec_count = 0; // records of all frames recorded so far
     std::vector<int> slot_to_frame; // view slot -> recorded frame (or -1)
 
     uint8_t *d_frames = nullptr;
@@ -183,19 +125,21 @@ struct drr_ctx {
 
     // frame being recorded
     bool in_frame = false;
-    size_t segs_n0 = 0, planes_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
+    size_t ops_n0 = 0, segs_n0 = 0, cols_n0 = 0, planes_n0 = 0, parr_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
+    uint64_t rec0 = 0;
     drr_stats stats0{};
     int cur_slot = -1;
-    std::vector<std::vector<Entry>> cols;
-    std::vector<TmpSpan> opq, msk, tmp;
+
+    // host-side reference binning (test infrastructure: drr_test_list which = 3, 4), computed on demand
+    std::vector<Span> t_spans;
+    std::vector<ColIdx> t_colidx;
+
+    cudaStream_t cstream = nullptr;      // copy stream of the pipelined drr_submit
+    std::vector<cudaEvent_t> chunk_ev;   // "chunk uploaded" events
+    cudaEvent_t ev_lists_free = nullptr; // recorded on `stream` after the last kernel that reads the device lists
 
     std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
     int prof_steps = 0;
-    // Kernel selection, fixed at context creation (the texel pool layout depends on it):
-    //   tile  : span-per-warp kernel with a shared-memory tile, column-major texel pool -- wins when spans are long (H >= 400)
-    //   march : lane-per-column scanline march, row-major texel pool                   -- wins when spans are short (H < 400)
-    // DRR_KERNEL=tile|march overrides the automatic choice (A/B measurements, profiles/).
-    bool use_tile = true;
     bool host_only = false; // CPU-test recording context: records and bins, can never draw
     drr_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -268,12 +212,6 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     c->GCFX = gsw / 2.0f;
     c->CFX = (float)(uint32_t)width / 2.0f;
     c->CFY = (float)(uint32_t)height / 2.0f;
-    c->use_tile = height >= 400;
-    if (const char *k = getenv("DRR_KERNEL")) {
-        if (std::string(k) == "march") c->use_tile = false;
-        if (std::string(k) == "tile") c->use_tile = true;
-    }
-    c->cols.resize(width);
     c->slot_to_frame.assign(max_views, -1);
     c->frame_stride = ((uint64_t)width * height * 3 + 255) / 256 * 256;
     auto bail = [&](const char *what, cudaError_t ce) {
@@ -291,6 +229,8 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     if ((e = cudaMemset(c->d_crc, 0, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
     for (auto &ev : c->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(copy)", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_lists_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
     return DRR_OK;
 }
@@ -303,8 +243,13 @@ void drr_ctx_destroy(drr_ctx *ctx) {
     }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->cstream) cudaStreamSynchronize(ctx->cstream);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->prof_ev) cudaEventDestroy(ev);
+    if (ctx->ev_lists_free) cudaEventDestroy(ctx->ev_lists_free);
+    if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_sky_rows) cudaFree(ctx->d_sky_rows);
@@ -347,11 +292,10 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     CTX_CHECK(ctx);
     if (!texels || w <= 0 || h <= 0 || w > 32767 || h > 32767) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: bad size (the reference divides by width and height)");
     if (ctx->bitmap_slot.count(id)) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: id already uploaded");
-    // pool layout: column-major [x][y] with pitch = next pow2 >= h (tile kernel) or row-major [y][x] with pitch = next
-    // pow2 >= w (march kernel); the setup kernel computes the matching base + tx offset
-    const bool cm = ctx->use_tile;
+    // pool layout: column-major [x][y] with column pitch = next pow2 >= h (one screen column walks ONE texture column, i.e. a
+    // contiguous run of texels); values are palette BYTE offsets (index * 16; 256 * 16 = None)
     uint32_t pitch = 1;
-    while (pitch < (uint32_t)(cm ? h : w)) pitch <<= 1;
+    while (pitch < (uint32_t)h) pitch <<= 1;
     BitmapRec r;
     r.base = (uint32_t)ctx->texel_pool.size();
     r.w = (int16_t)w;
@@ -359,15 +303,12 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     r.opaque = 1;
     for (size_t i = 0; i < (size_t)w * h; i++)
         if (texels[i] < -1 || texels[i] > 255) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
-    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * (cm ? w : h), cm ? 4096 : 0x8000);
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * w, 4096);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const int16_t t = texels[(size_t)y * w + x];
-            const size_t at = r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x);
             if (t < 0) r.opaque = 0;
-            // tile kernel: the palette BYTE offset (index * 16; 256 * 16 = None); march kernel: the index (0x8000 = None)
-            if (cm) ctx->texel_pool[at] = (uint16_t)(t < 0 ? 4096 : t * 16);
-            else ctx->texel_pool[at] = (uint16_t)(t < 0 ? 0x8000 : t);
+            ctx->texel_pool[r.base + (size_t)x * pitch + y] = (uint16_t)(t < 0 ? 4096 : t * 16);
         }
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
     ctx->bitmaps.push_back(r);
@@ -416,17 +357,36 @@ static int upload_assets(drr_ctx *ctx) {
 }
 
 // ---- recording ---------------------------------------------------------------------------------------------------
+// Recording is appending: the lists go to the device exactly as emitted (SURVEY 8d's algorithmic bytes plus indices);
+// turning per-op lists into per-column lists ("column binning") is the bin kernel's job (drr_tile.cu).
+static bool push_frame_bases(drr_ctx *ctx) {
+    ctx->frame_seg_base.push_back((uint32_t)ctx->segs.n);
+    ctx->frame_col_base.push_back((uint32_t)ctx->cols.n);
+    ctx->frame_plane_base.push_back((uint32_t)ctx->planes.n);
+    ctx->frame_parr_base.push_back((uint32_t)ctx->parr.n);
+    return ctx->frame_op_base.push((uint32_t)ctx->ops.n) && ctx->frame_rec_base.push((uint32_t)ctx->rec_count);
+}
+
 int drr_reset(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
     ctx->views.clear();
-    ctx->segs.clear();
-    ctx->planes.clear();
-    ctx->spans.clear();
-    ctx->colidx.clear();
-    ctx->frame_span_base.clear();
+    ctx->ops.clear();
+    ctx->frame_op_base.clear();
+    ctx->frame_rec_base.clear();
     ctx->frame_slot.clear();
-    ctx->uploaded_frames = ctx->uploaded_spans = 0;
+    ctx->segs.clear();
+    ctx->cols.clear();
+    ctx->planes.clear();
+    ctx->parr.clear();
+    ctx->frame_seg_base.clear();
+    ctx->frame_col_base.clear();
+    ctx->frame_plane_base.clear();
+    ctx->frame_parr_base.clear();
+    ctx->t_spans.clear();
+    ctx->t_colidx.clear();
+    ctx->rec_count = 0;
+    ctx->uploaded_frames = 0;
     std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
     const uint64_t launches = ctx->stats.kernel_launches;
     ctx->stats = drr_stats{};
@@ -439,16 +399,21 @@ int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_begin: previous frame not ended");
     if (!view || view_idx < 0 || view_idx >= ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: bad view index");
     if (ctx->slot_to_frame[view_idx] >= 0) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
+    if (ctx->frame_op_base.n == 0 && !push_frame_bases(ctx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     View v{view->pos_x, view->pos_y, view->floor_height, view->angle, view->cos_angle, view->sin_angle};
     if (!ctx->views.push(v) || !ctx->frame_slot.push((uint32_t)view_idx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    if (ctx->frame_span_base.n == 0 && !ctx->frame_span_base.push(0)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     ctx->slot_to_frame[view_idx] = (int)ctx->views.n - 1;
-    for (auto &c : ctx->cols) c.clear();
+    ctx->ops_n0 = ctx->ops.n;
     ctx->segs_n0 = ctx->segs.n;
+    ctx->cols_n0 = ctx->cols.n;
     ctx->planes_n0 = ctx->planes.n;
+    ctx->parr_n0 = ctx->parr.n;
+    ctx->rec0 = ctx->rec_count;
     ctx->stats0 = ctx->stats;
     ctx->cur_slot = view_idx;
     ctx->in_frame = true;
+    ctx->t_spans.clear();
+    ctx->t_colidx.clear();
     return DRR_OK;
 }
 
@@ -458,8 +423,12 @@ int drr_frame_abort(drr_ctx *ctx) {
     ctx->in_frame = false;
     ctx->views.n--;
     ctx->frame_slot.n--;
+    ctx->ops.n = ctx->ops_n0;
     ctx->segs.n = ctx->segs_n0;
+    ctx->cols.n = ctx->cols_n0;
     ctx->planes.n = ctx->planes_n0;
+    ctx->parr.n = ctx->parr_n0;
+    ctx->rec_count = ctx->rec0;
     ctx->slot_to_frame[ctx->cur_slot] = -1;
     const uint64_t launches = ctx->stats.kernel_launches;
     ctx->stats = ctx->stats0;
@@ -488,17 +457,29 @@ int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, 
     r.top_height = hdr->top_height;
     r.offset_x = hdr->offset_x;
     r.offset_y = hdr->offset_y;
-    const uint32_t op = (uint32_t)ctx->segs.n;
-    if (!ctx->segs.push(r)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    const uint8_t kind = ctx->bitmaps[it->second].opaque ? KIND_WALL : KIND_WALL_HOLES;
+    r.pad = 0;
+    static_assert(sizeof(drr_col) == sizeof(ColRec), "drr_col layout");
+    if (!ctx->cols.reserve(ctx->cols.n + (size_t)n)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     const int H = ctx->H, W = ctx->W;
-    for (int i = 0; i < n; i++) {
-        const drr_col &c = cols[i];
-        // Pixels::set ignores x >= W and y > H (pixels.rs:23); negative values become huge usize and are ignored too
-        if (c.x < 0 || c.x >= W) continue;
-        const int a = std::max<int>(c.clipped_top_y, 0), b = std::min<int>(c.clipped_bottom_y, H - 1);
-        if (a > b) continue;
-        ctx->cols[c.x].push_back(Entry{op, kind, (int16_t)a, (int16_t)b, c.top_y, c.bottom_y});
+    // the bin kernel finds a seg's record for screen column x by index, which needs x strictly increasing within one
+    // SegRec: the reference emits x = start_x .. end_x in order; anything else is split into increasing runs
+    for (int i = 0; i < n;) {
+        int j = i + 1;
+        while (j < n && cols[j].x > cols[j - 1].x) ++j;
+        r.cols_first = (uint32_t)ctx->cols.n;
+        r.n = (uint32_t)(j - i);
+        r.x0 = cols[i].x;
+        r.x1 = cols[j - 1].x;
+        memcpy(ctx->cols.p + ctx->cols.n, cols + i, sizeof(ColRec) * (size_t)(j - i));
+        ctx->cols.n += (size_t)(j - i);
+        for (int k = i; k < j; k++) {
+            const drr_col &c = cols[k];
+            // Pixels::set ignores x >= W and y > H (pixels.rs:23); negative values become huge usize and are ignored too
+            if (c.x < 0 || c.x >= W) continue;
+            if (std::max<int>(c.clipped_top_y, 0) <= std::min<int>(c.clipped_bottom_y, H - 1)) ctx->rec_count++;
+        }
+        if (!ctx->ops.push((uint32_t)ctx->segs.n) || !ctx->segs.push(r)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+        i = j;
     }
     ctx->stats.seg_headers++;
     ctx->stats.column_records += (uint64_t)n;
@@ -513,72 +494,96 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
     // the reference indexes [i16; SCREEN_WIDTH] arrays with x (visplanes.rs:61,95): out-of-range x panics there
     if (hdr->left < 0 || hdr->right >= W) return fail(ctx, DRR_E_INVALID, "drr_emit_visplane: left/right outside the screen");
     PlaneRec p;
-    uint8_t kind;
     if (hdr->flat_id == DRR_FLAT_SKY) {
         if (ctx->sky_slot < 0) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: sky not set");
         p.flat_slot = -1;
-        kind = ctx->bitmaps[ctx->sky_slot].opaque ? KIND_SKY : KIND_SKY_HOLES;
+        p.kind = (int16_t)(ctx->bitmaps[ctx->sky_slot].opaque ? KIND_SKY : KIND_SKY_HOLES);
     } else {
         auto it = ctx->flat_slot.find(hdr->flat_id);
         if (it == ctx->flat_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: unknown flat id");
         p.flat_slot = (int16_t)it->second;
-        kind = KIND_FLAT;
+        p.kind = (int16_t)KIND_FLAT;
     }
     p.height = hdr->height;
     p.light_level = hdr->light_level;
     p.left = hdr->left;
     p.right = hdr->right;
-    p.reserved = 0;
-    const uint32_t op = (uint32_t)ctx->planes.n;
-    if (!ctx->planes.push(p)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    for (int x = hdr->left; x <= hdr->right; x++) {
-        const int16_t t = std::max<int16_t>(top[x - hdr->left], 0);                  // visplanes.rs:61 / :95
-        const int16_t b = std::min<int16_t>(bottom[x - hdr->left], (int16_t)(H - 1)); // :62 / :96
-        if (kind == KIND_FLAT && (int16_t)(b - t) <= 1) continue;                    // :99-101 (not applied to sky)
-        if (t > b) continue;
-        ctx->cols[x].push_back(Entry{op, kind, t, b, 0, 0});
+    p.arr_first = (uint32_t)ctx->parr.n;
+    const int ncols = hdr->right >= hdr->left ? hdr->right - hdr->left + 1 : 0;
+    if (!ctx->parr.reserve(ctx->parr.n + (size_t)ncols)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    for (int i = 0; i < ncols; i++) {
+        ctx->parr.p[ctx->parr.n++] = (uint32_t)(uint16_t)top[i] | ((uint32_t)(uint16_t)bottom[i] << 16); // unclamped, as stored (quirk Q3)
+        const int t = std::max<int>(top[i], 0);            // visplanes.rs:61 / :95
+        const int b = std::min<int>(bottom[i], H - 1);     // :62 / :96
+        if (p.kind == (int16_t)KIND_FLAT && (int16_t)(b - t) <= 1) continue; // :99-101 (not applied to sky)
+        if (t <= b) ctx->rec_count++;
     }
+    if (ncols > 0 && (!ctx->ops.push(0x80000000u | (uint32_t)ctx->planes.n) || !ctx->planes.push(p))) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     ctx->stats.visplanes++;
-    if (hdr->right >= hdr->left) ctx->stats.visplane_columns += (uint64_t)(hdr->right - hdr->left + 1);
+    ctx->stats.visplane_columns += (uint64_t)ncols;
     return DRR_OK;
 }
 
 int drr_frame_end(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_end outside a frame");
-    ctx->in_frame = false;
-    for (int x = 0; x < ctx->W; x++) {
-        ColIdx ci;
-        ci.first = (uint32_t)ctx->spans.n;
-        ci.n_opaque = ci.n_masked = 0;
-        if (!ctx->cols[x].empty()) {
-            resolve_column(ctx->cols[x], ctx->opq, ctx->msk, ctx->tmp);
-            if (ctx->opq.size() > 65535 || ctx->msk.size() > 65535) return fail(ctx, DRR_E_INVALID, "too many spans in one column");
-            ci.n_opaque = (uint16_t)ctx->opq.size();
-            ci.n_masked = (uint16_t)ctx->msk.size();
-            if (!ctx->spans.reserve(ctx->spans.n + ctx->opq.size() + ctx->msk.size())) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-            for (const auto *list : {&ctx->opq, &ctx->msk})
-                for (const TmpSpan &s : *list) {
-                    Span d;
-                    d.y0 = (uint16_t)s.y0;
-                    d.y1 = (uint16_t)s.y1;
-                    d.x = (uint16_t)x;
-                    d.kind = s.kind;
-                    d.pad = 0;
-                    d.op = s.op;
-                    d.top_y = s.top_y;
-                    d.bottom_y = s.bottom_y;
-                    ctx->spans.push(d);
-                }
-        }
-        if (!ctx->colidx.push(ci)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    if (ctx->rec_count > 0xffffffffull || ctx->cols.n > 0xffffffffull || ctx->parr.n > 0xffffffffull) {
+        drr_frame_abort(ctx);
+        return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 column records");
     }
-    if (!ctx->frame_span_base.push((uint32_t)ctx->spans.n)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    ctx->in_frame = false;
+    if (!push_frame_bases(ctx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     ctx->stats.frames++;
     return DRR_OK;
 }
 
 // ---- execution ---------------------------------------------------------------------------------------------------
+static int reserve_device_lists(drr_ctx *ctx) {
+    const size_t nf = ctx->views.n;
+    CU(ctx, ctx->d_views.reserve(nf));
+    CU(ctx, ctx->d_ops.reserve(std::max<size_t>(ctx->ops.n, 1)));
+    CU(ctx, ctx->d_frame_op_base.reserve(nf + 1));
+    CU(ctx, ctx->d_frame_rec_base.reserve(nf + 1));
+    CU(ctx, ctx->d_frame_slot.reserve(nf));
+    CU(ctx, ctx->d_frame_cursor.reserve(nf));
+    CU(ctx, ctx->d_segs.reserve(std::max<size_t>(ctx->segs.n, 1)));
+    CU(ctx, ctx->d_cols.reserve(std::max<size_t>(ctx->cols.n, 1) * 5));
+    CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
+    CU(ctx, ctx->d_parr.reserve(std::max<size_t>(ctx->parr.n, 1)));
+    CU(ctx, ctx->d_colidx.reserve(nf * (size_t)ctx->W));
+    CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->rec_count, 1) * 4));
+    return DRR_OK;
+}
+
+// H2D of the per-frame tables (small) -- always whole
+static int upload_tables(drr_ctx *ctx, cudaStream_t st) {
+    const size_t nf = ctx->views.n;
+    CU(ctx, cudaMemcpyAsync(ctx->d_views.p, ctx->views.p, nf * sizeof(View), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_op_base.p, ctx->frame_op_base.p, (nf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_rec_base.p, ctx->frame_rec_base.p, (nf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    return DRR_OK;
+}
+
+// H2D of the draw lists of frames [f0, f1) (contiguous slices: frames are recorded one after the other)
+static int upload_frames(drr_ctx *ctx, size_t f0, size_t f1, cudaStream_t st) {
+    auto slice = [&](void *dst, const void *src, size_t elem, size_t lo, size_t hi) -> cudaError_t {
+        if (hi <= lo) return cudaSuccess;
+        return cudaMemcpyAsync((char *)dst + lo * elem, (const char *)src + lo * elem, (hi - lo) * elem, cudaMemcpyHostToDevice, st);
+    };
+    CU(ctx, slice(ctx->d_ops.p, ctx->ops.p, 4, ctx->frame_op_base.p[f0], ctx->frame_op_base.p[f1]));
+    CU(ctx, slice(ctx->d_segs.p, ctx->segs.p, sizeof(SegRec), ctx->frame_seg_base[f0], ctx->frame_seg_base[f1]));
+    CU(ctx, slice(ctx->d_cols.p, ctx->cols.p, sizeof(ColRec), ctx->frame_col_base[f0], ctx->frame_col_base[f1]));
+    CU(ctx, slice(ctx->d_planes.p, ctx->planes.p, sizeof(PlaneRec), ctx->frame_plane_base[f0], ctx->frame_plane_base[f1]));
+    CU(ctx, slice(ctx->d_parr.p, ctx->parr.p, 4, ctx->frame_parr_base[f0], ctx->frame_parr_base[f1]));
+    return DRR_OK;
+}
+
+static uint64_t list_bytes(const drr_ctx *ctx) {
+    return ctx->views.n * sizeof(View) + ctx->ops.n * 4 + ctx->frame_op_base.n * 4 + ctx->frame_rec_base.n * 4 + ctx->frame_slot.n * 4 +
+           ctx->segs.n * sizeof(SegRec) + ctx->cols.n * sizeof(ColRec) + ctx->planes.n * sizeof(PlaneRec) + ctx->parr.n * 4;
+}
+
 int drr_upload_lists(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
@@ -586,39 +591,21 @@ int drr_upload_lists(drr_ctx *ctx) {
     int rc = upload_assets(ctx);
     if (rc) return rc;
     const size_t nf = ctx->views.n;
-    if (nf == 0) {
-        ctx->uploaded_frames = 0;
-        return DRR_OK;
-    }
-    CU(ctx, ctx->d_views.reserve(nf));
-    CU(ctx, ctx->d_segs.reserve(std::max<size_t>(ctx->segs.n, 1)));
-    CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
-    CU(ctx, ctx->d_spans.reserve(std::max<size_t>(ctx->spans.n, 1)));
-    if (ctx->use_tile) CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->spans.n, 1) * 4));
-    else CU(ctx, ctx->d_params.reserve(std::max<size_t>(ctx->spans.n, 1)));
-    CU(ctx, ctx->d_colidx.reserve(ctx->colidx.n));
-    CU(ctx, ctx->d_frame_span_base.reserve(nf + 1));
-    CU(ctx, ctx->d_frame_slot.reserve(nf));
-    cudaStream_t st = ctx->stream;
-    CU(ctx, cudaMemcpyAsync(ctx->d_views.p, ctx->views.p, nf * sizeof(View), cudaMemcpyHostToDevice, st));
-    if (ctx->segs.n) CU(ctx, cudaMemcpyAsync(ctx->d_segs.p, ctx->segs.p, ctx->segs.n * sizeof(SegRec), cudaMemcpyHostToDevice, st));
-    if (ctx->planes.n) CU(ctx, cudaMemcpyAsync(ctx->d_planes.p, ctx->planes.p, ctx->planes.n * sizeof(PlaneRec), cudaMemcpyHostToDevice, st));
-    if (ctx->spans.n) CU(ctx, cudaMemcpyAsync(ctx->d_spans.p, ctx->spans.p, ctx->spans.n * sizeof(Span), cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(ctx->d_colidx.p, ctx->colidx.p, ctx->colidx.n * sizeof(ColIdx), cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(ctx->d_frame_span_base.p, ctx->frame_span_base.p, (nf + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    ctx->uploaded_frames = 0;
+    if (nf == 0) return DRR_OK;
+    if ((rc = reserve_device_lists(ctx))) return rc;
+    if ((rc = upload_tables(ctx, ctx->stream))) return rc;
+    if ((rc = upload_frames(ctx, 0, nf, ctx->stream))) return rc;
     ctx->uploaded_frames = nf;
-    ctx->uploaded_spans = ctx->spans.n;
     return DRR_OK;
 }
 
-static int make_args(drr_ctx *ctx, DrawArgs &a) {
+static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
-    if (ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "nothing uploaded (call drr_upload_lists)");
+    if (nframes == 0) return fail(ctx, DRR_E_STATE, "nothing uploaded (call drr_upload_lists)");
     a.W = ctx->W;
     a.H = ctx->H;
-    a.nframes = (int)ctx->uploaded_frames;
-    a.colmajor = ctx->use_tile ? 1 : 0;
+    a.nframes = (int)nframes;
     a.CFX = ctx->CFX;
     a.CFY = ctx->CFY;
     a.GCFX = ctx->GCFX;
@@ -627,19 +614,22 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     a.Hf = (float)(uint32_t)ctx->H;
     a.one = 1.0f;
     a.views = ctx->d_views.p;
-    a.segs = ctx->d_segs.p;
-    a.planes = ctx->d_planes.p;
-    a.spans = ctx->d_spans.p;
-    a.frame_span_base = ctx->d_frame_span_base.p;
+    a.ops = ctx->d_ops.p;
+    a.frame_op_base = ctx->d_frame_op_base.p;
+    a.frame_rec_base = ctx->d_frame_rec_base.p;
     a.frame_slot = ctx->d_frame_slot.p;
+    a.segs = ctx->d_segs.p;
+    a.cols = reinterpret_cast<const ColRec *>(ctx->d_cols.p);
+    a.planes = ctx->d_planes.p;
+    a.parr = ctx->d_parr.p;
+    a.frame_cursor = ctx->d_frame_cursor.p;
     a.colidx = ctx->d_colidx.p;
-    a.params = ctx->d_params.p;
     a.tparams = ctx->d_tparams.p;
-    a.sky_rows = ctx->d_sky_rows;
     a.texels = ctx->d_texels.p;
     a.flats = ctx->d_flats.p;
     a.bitmaps = ctx->d_bitmaps.p;
     a.palette = ctx->d_pal.p;
+    a.sky_rows = ctx->d_sky_rows;
     a.sky_base = ctx->sky_slot >= 0 ? ctx->bitmaps[ctx->sky_slot].base : 0;
     a.frames = ctx->d_frames;
     a.frame_stride = ctx->frame_stride;
@@ -647,23 +637,23 @@ static int make_args(drr_ctx *ctx, DrawArgs &a) {
     return DRR_OK;
 }
 
-static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march, bool profile = false) {
+// bin kernel + tile kernel over frames [f0, f0 + n) on the context's stream
+static int draw_range(drr_ctx *ctx, const DrawArgs &a, int f0, int n, bool bin, bool tile, bool profile = false) {
     const bool prof = profile && (size_t)(ctx->prof_steps + 1) * 3 <= ctx->prof_ev.size();
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3], ctx->stream));
-    if (setup) {
-        CU(ctx, ctx->use_tile ? launch_tile_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream) : launch_span_setup(a, (uint32_t)ctx->uploaded_spans, ctx->stream));
-        if (ctx->uploaded_spans) ctx->stats.kernel_launches++;
+    if (bin) {
+        CU(ctx, launch_bin(a, f0, n, ctx->stream));
+        ctx->stats.kernel_launches++;
     }
-    if (march) {
-        CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], ctx->stream));
+    if (tile) {
         int launches = 0;
-        if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], ctx->stream));
-        CU(ctx, ctx->use_tile ? launch_tile(a, ctx->stream, &launches) : launch_march(a, ctx->stream, &launches));
+        CU(ctx, launch_tile(a, f0, n, ctx->stream, &launches));
         ctx->stats.kernel_launches += (uint64_t)launches;
-        if (prof) {
-            CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], ctx->stream));
-            ctx->prof_steps++;
-        }
+    }
+    if (prof) {
+        CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], ctx->stream));
+        ctx->prof_steps++;
     }
     return DRR_OK;
 }
@@ -671,13 +661,14 @@ static int draw_once(drr_ctx *ctx, const DrawArgs &a, bool setup, bool march, bo
 int drr_draw(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     DrawArgs a;
-    int rc = make_args(ctx, a);
+    int rc = make_args(ctx, a, ctx->uploaded_frames);
     if (rc) return rc;
-    return draw_once(ctx, a, true, true, true);
+    CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+    return draw_range(ctx, a, 0, a.nframes, true, true, true);
 }
 
 // Per-kernel device times of the drr_draw() calls made since drr_profile_begin, from CUDA events recorded on the
-// context's stream around each kernel (the memset of the checksum array is counted with the setup leg).
+// context's stream around each kernel.
 int drr_profile_begin(drr_ctx *ctx, int max_steps) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
@@ -711,11 +702,41 @@ int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *marc
     return DRR_OK;
 }
 
+// drr_submit: upload and draw, pipelined.  The batch is cut into chunks of frames; chunk k+1's lists travel over PCIe
+// on the copy stream while chunk k is binned and drawn on the context's stream.
 int drr_submit(drr_ctx *ctx) {
-    int rc = drr_upload_lists(ctx);
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
+    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_submit inside a frame");
+    int rc = upload_assets(ctx);
     if (rc) return rc;
-    if (ctx->uploaded_frames == 0) return DRR_OK;
-    return drr_draw(ctx);
+    const size_t nf = ctx->views.n;
+    ctx->uploaded_frames = 0;
+    if (nf == 0) return DRR_OK;
+    if ((rc = reserve_device_lists(ctx))) return rc;
+    size_t nchunks = std::min<size_t>({(size_t)16, nf, (size_t)(list_bytes(ctx) / (2u << 20)) + 1});
+    if (const char *e = getenv("DRR_SUBMIT_CHUNKS")) nchunks = std::min<size_t>(nf, (size_t)std::max(1, atoi(e)));
+    while (ctx->chunk_ev.size() < nchunks) {
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+    }
+    DrawArgs a;
+    if ((rc = make_args(ctx, a, nf))) return rc;
+    // the copies overwrite lists that kernels already queued on the context's stream may still read
+    CU(ctx, cudaEventRecord(ctx->ev_lists_free, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->cstream, ctx->ev_lists_free, 0));
+    CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+    if ((rc = upload_tables(ctx, ctx->cstream))) return rc;
+    for (size_t c = 0; c < nchunks; c++) {
+        const size_t f0 = nf * c / nchunks, f1 = nf * (c + 1) / nchunks;
+        if ((rc = upload_frames(ctx, f0, f1, ctx->cstream))) return rc;
+        CU(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->cstream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        if ((rc = draw_range(ctx, a, (int)f0, (int)(f1 - f0), true, true))) return rc;
+    }
+    ctx->uploaded_frames = nf;
+    return DRR_OK;
 }
 
 int drr_sync(drr_ctx *ctx) {
@@ -762,10 +783,9 @@ int drr_get_stats(drr_ctx *ctx, drr_stats *out) {
     CTX_CHECK(ctx);
     if (!out) return DRR_E_INVALID;
     drr_stats s = ctx->stats;
-    s.spans = ctx->spans.n;
+    s.spans = ctx->rec_count;
     s.drawlist_bytes_algorithmic = 24 * s.frames + 48 * s.seg_headers + 10 * s.column_records + 12 * s.visplanes + 4 * s.visplane_columns;
-    s.device_list_bytes = ctx->views.n * sizeof(View) + ctx->segs.n * sizeof(SegRec) + ctx->planes.n * sizeof(PlaneRec) +
-                          ctx->spans.n * sizeof(Span) + ctx->colidx.n * sizeof(ColIdx) + ctx->frame_span_base.n * 4 + ctx->frame_slot.n * 4;
+    s.device_list_bytes = list_bytes(ctx);
     *out = s;
     return DRR_OK;
 }
@@ -774,14 +794,16 @@ int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, flo
     CTX_CHECK(ctx);
     if (iters <= 0) return fail(ctx, DRR_E_INVALID, "drr_time_draw: iters");
     DrawArgs a;
-    int rc = make_args(ctx, a);
+    int rc = make_args(ctx, a, ctx->uploaded_frames);
     if (rc) return rc;
     struct { bool s, m; float *out; } legs[3] = {{true, true, total_ms}, {true, false, setup_ms}, {false, true, march_ms}};
     for (auto &leg : legs) {
         if (!leg.out) continue;
         CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        for (int i = 0; i < iters; i++)
-            if ((rc = draw_once(ctx, a, leg.s, leg.m))) return rc;
+        for (int i = 0; i < iters; i++) {
+            if (leg.m) CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+            if ((rc = draw_range(ctx, a, 0, a.nframes, leg.s, leg.m))) return rc;
+        }
         CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
         CU(ctx, cudaEventSynchronize(ctx->ev[1]));
         float ms = 0;
@@ -792,17 +814,12 @@ int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, flo
 }
 
 // ---- CPU-testable internals (no CUDA needed) ---------------------------------------------------------------------------
-// A context that can RECORD and BIN draw lists without a GPU (plain malloc staging) so the host logic is testable in
-// the CPU-only container.  It has no framebuffers and every execution entry point fails with DRR_E_CUDA.
+// A context that can RECORD draw lists without a GPU (plain malloc staging) so the host logic is testable in the CPU-only
+// container.  It has no framebuffers and every execution entry point fails with DRR_E_CUDA.
 int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx **out) {
     if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) return DRR_E_INVALID;
     drr_ctx *c = new drr_ctx();
     c->host_only = true;
-    c->use_tile = height >= 400;
-    if (const char *k = getenv("DRR_KERNEL")) {
-        if (std::string(k) == "march") c->use_tile = false;
-        if (std::string(k) == "tile") c->use_tile = true;
-    }
     c->W = width;
     c->H = height;
     c->max_views = max_views;
@@ -810,26 +827,85 @@ int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx 
     c->GCFX = ((float)(uint32_t)width / c->ASPECT) / 2.0f;
     c->CFX = (float)(uint32_t)width / 2.0f;
     c->CFY = (float)(uint32_t)height / 2.0f;
-    c->cols.resize(width);
     c->slot_to_frame.assign(max_views, -1);
-    c->views.pinned = c->segs.pinned = c->planes.pinned = c->spans.pinned = c->colidx.pinned = false;
-    c->frame_span_base.pinned = c->frame_slot.pinned = c->h_crc.pinned = false;
+    c->views.pinned = c->segs.pinned = c->planes.pinned = c->cols.pinned = c->parr.pinned = c->ops.pinned = false;
+    c->frame_op_base.pinned = c->frame_rec_base.pinned = c->frame_slot.pinned = c->h_crc.pinned = false;
     *out = c;
     return DRR_OK;
 }
-// Raw views of the staged (binned) lists: which = 0 views, 1 segs, 2 planes, 3 spans, 4 colidx, 5 frame_span_base, 6 frame_slot
+
+// Host restatement of the bin kernel's column binning (drr_tile.cu: walk_column), op by op in call order: the per-column
+// span lists the device is expected to build.  Test infrastructure only (tests/ compare the device's lists with these,
+// and replay them on the CPU with the reference restatement's leaf drawers); the product never draws from them.
+static void host_reference_binning(drr_ctx *ctx) {
+    const size_t nf = ctx->frame_op_base.n ? ctx->frame_op_base.n - 1 : 0;
+    const int W = ctx->W, H = ctx->H;
+    ctx->t_spans.clear();
+    ctx->t_colidx.assign(nf * (size_t)W, ColIdx{0, 0});
+    std::vector<std::vector<Span>> percol(W);
+    for (size_t f = 0; f < nf; f++) {
+        for (auto &v : percol) v.clear();
+        for (uint32_t o = ctx->frame_op_base.p[f]; o < ctx->frame_op_base.p[f + 1]; o++) {
+            const uint32_t op = ctx->ops.p[o];
+            if (op & 0x80000000u) {
+                const PlaneRec &p = ctx->planes.p[op & 0x7fffffffu];
+                for (int x = p.left; x <= p.right; x++) {
+                    const uint32_t tb = ctx->parr.p[p.arr_first + (uint32_t)(x - p.left)];
+                    const int t = std::max<int>((int16_t)(tb & 0xffffu), 0), b = std::min<int>((int16_t)(tb >> 16), H - 1);
+                    if (p.kind == (int16_t)KIND_FLAT && (int16_t)(b - t) <= 1) continue;
+                    if (t > b) continue;
+                    percol[x].push_back(Span{(uint16_t)t, (uint16_t)b, (uint16_t)x, (uint8_t)p.kind, 0, op & 0x7fffffffu, 0, 0});
+                }
+            } else {
+                const SegRec &g = ctx->segs.p[op];
+                const uint8_t kind = ctx->bitmaps[g.bitmap_slot].opaque ? KIND_WALL : KIND_WALL_HOLES;
+                for (uint32_t i = 0; i < g.n; i++) {
+                    const ColRec &c = ctx->cols.p[g.cols_first + i];
+                    if (c.x < 0 || c.x >= W) continue;
+                    const int a = std::max<int>(c.clipped_top_y, 0), b = std::min<int>(c.clipped_bottom_y, H - 1);
+                    if (a > b) continue;
+                    percol[c.x].push_back(Span{(uint16_t)a, (uint16_t)b, (uint16_t)c.x, kind, 0, op, c.top_y, c.bottom_y});
+                }
+            }
+        }
+        for (int x = 0; x < W; x++) {
+            ctx->t_colidx[f * (size_t)W + x] = ColIdx{(uint32_t)ctx->t_spans.size(), (uint32_t)percol[x].size()};
+            ctx->t_spans.insert(ctx->t_spans.end(), percol[x].begin(), percol[x].end());
+        }
+    }
+}
+
+// Raw views of the recorded lists: which = 0 views, 1 segs, 2 planes, 3 spans and 4 colidx of the host reference binning,
+// 5 frame_rec_base, 6 frame_slot, 7 column records, 8 visplane (top, bottom) pairs, 9 ops, 10 frame_op_base
 const void *drr_test_list(drr_ctx *ctx, int which, uint64_t *count, uint64_t *elem_size) {
     if (!ctx || !count || !elem_size) return nullptr;
+    if ((which == 3 || which == 4) && ctx->t_colidx.empty() && !ctx->in_frame) host_reference_binning(ctx);
     switch (which) {
     case 0: *count = ctx->views.n; *elem_size = sizeof(View); return ctx->views.p;
     case 1: *count = ctx->segs.n; *elem_size = sizeof(SegRec); return ctx->segs.p;
     case 2: *count = ctx->planes.n; *elem_size = sizeof(PlaneRec); return ctx->planes.p;
-    case 3: *count = ctx->spans.n; *elem_size = sizeof(Span); return ctx->spans.p;
-    case 4: *count = ctx->colidx.n; *elem_size = sizeof(ColIdx); return ctx->colidx.p;
-    case 5: *count = ctx->frame_span_base.n; *elem_size = 4; return ctx->frame_span_base.p;
+    case 3: *count = ctx->t_spans.size(); *elem_size = sizeof(Span); return ctx->t_spans.data();
+    case 4: *count = ctx->t_colidx.size(); *elem_size = sizeof(ColIdx); return ctx->t_colidx.data();
+    case 5: *count = ctx->frame_rec_base.n; *elem_size = 4; return ctx->frame_rec_base.p;
     case 6: *count = ctx->frame_slot.n; *elem_size = 4; return ctx->frame_slot.p;
+    case 7: *count = ctx->cols.n; *elem_size = sizeof(ColRec); return ctx->cols.p;
+    case 8: *count = ctx->parr.n; *elem_size = 4; return ctx->parr.p;
+    case 9: *count = ctx->ops.n; *elem_size = 4; return ctx->ops.p;
+    case 10: *count = ctx->frame_op_base.n; *elem_size = 4; return ctx->frame_op_base.p;
     default: return nullptr;
     }
+}
+// What the bin kernel produced for the uploaded batch: colidx_out = nframes * W (first, n) pairs, recs_out = two words per
+// record (y0 | y1 << 16, kind | flags), indexed by the `first` values of colidx_out.
+int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
+    if (ctx->rec_count)
+        CU(ctx, cudaMemcpy2D(recs_out, 8, ctx->d_tparams.p, 64, 8, (size_t)ctx->rec_count, cudaMemcpyDeviceToHost));
+    return DRR_OK;
 }
 // bitmap slot -> (w, h, opaque); flat_slot/bitmap_slot resolve ids the way the device tables do
 int drr_test_bitmap_info(drr_ctx *ctx, int slot, int *w, int *h, int *opaque) {
@@ -842,13 +918,12 @@ int drr_test_bitmap_info(drr_ctx *ctx, int slot, int *w, int *h, int *opaque) {
 int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major w*h, -1 = None (decoded back from the device pool layout)
     if (!ctx || slot < 0 || slot >= (int)ctx->bitmaps.size()) return DRR_E_INVALID;
     const BitmapRec &r = ctx->bitmaps[slot];
-    const bool cm = ctx->use_tile;
     uint32_t pitch = 1;
-    while (pitch < (uint32_t)(cm ? r.h : r.w)) pitch <<= 1;
+    while (pitch < (uint32_t)r.h) pitch <<= 1;
     for (int y = 0; y < r.h; y++)
         for (int x = 0; x < r.w; x++) {
-            const uint16_t t = ctx->texel_pool[r.base + (cm ? (size_t)x * pitch + y : (size_t)y * pitch + x)];
-            out[(size_t)y * r.w + x] = cm ? (t == 4096 ? (int16_t)-1 : (int16_t)(t / 16)) : ((t & 0x8000) ? (int16_t)-1 : (int16_t)t);
+            const uint16_t t = ctx->texel_pool[r.base + (size_t)x * pitch + y];
+            out[(size_t)y * r.w + x] = t == 4096 ? (int16_t)-1 : (int16_t)(t / 16);
         }
     return DRR_OK;
 }
@@ -867,7 +942,11 @@ int drr_test_palette(drr_ctx *ctx, uint8_t *out768) {
     return DRR_OK;
 }
 int drr_test_sky_slot(drr_ctx *ctx) { return ctx ? ctx->sky_slot : -1; }
-int drr_test_uses_tile_kernel(drr_ctx *ctx) { return ctx && ctx->use_tile ? 1 : 0; }
+int drr_test_tile_config(drr_ctx *ctx, int *tc, int *lpg) {
+    if (!ctx || !tc || !lpg) return DRR_E_INVALID;
+    tile_config(ctx->W, ctx->H, tc, lpg);
+    return DRR_OK;
+}
 int drr_test_bitmap_id_of_slot(drr_ctx *ctx, int slot) {
     for (auto &kv : ctx->bitmap_slot)
         if (kv.second == slot) return kv.first;
@@ -879,7 +958,7 @@ int drr_test_flat_id_of_slot(drr_ctx *ctx, int slot) {
     return -1;
 }
 
-// Device self-check of the hoisted-reciprocal division used by the march kernel (drr_kernels.cu: fast_div) against
+// Device self-check of the hoisted-reciprocal division used by the pixel loops (drr_math.cuh: fast_div) against
 // __fdiv_rn.  mode 0: a in [-amax, amax] (n0 = 2*amax+1 values), b = all non-zero integers in [-n1/2, n1/2];
 // mode 1: a = floats with bit patterns lo + k*stride (k < n0), b = CFY - y for y < n1 (H = n1).  Returns mismatches.
 int drr_test_fastdiv(drr_ctx *ctx, int mode, long long n0, long long n1, float CFY, uint32_t lo, uint32_t stride, unsigned long long *bad,
@@ -899,26 +978,6 @@ int drr_test_fastdiv(drr_ctx *ctx, int mode, long long n0, long long n1, float C
     cudaFree(d_bad);
     cudaFree(d_first);
     return DRR_OK;
-}
-
-// ---- column resolver on raw entries: used by tests/ to check the column resolver against a painter -----------
-// entries: n x 4 ints {kind, a, b, tag}; out: up to cap x 4 ints {kind, y0, y1, tag}; returns n_opaque | n_masked << 16, or -1.
-int drr_test_resolve_column(const int32_t *entries, int n, int32_t *out, int cap) {
-    std::vector<Entry> e;
-    for (int i = 0; i < n; i++) e.push_back(Entry{(uint32_t)entries[i * 4 + 3], (uint8_t)entries[i * 4], (int16_t)entries[i * 4 + 1], (int16_t)entries[i * 4 + 2], 0, 0});
-    std::vector<TmpSpan> opq, msk, tmp;
-    resolve_column(e, opq, msk, tmp);
-    if ((int)(opq.size() + msk.size()) > cap) return -1;
-    int k = 0;
-    for (const auto *list : {&opq, &msk})
-        for (const TmpSpan &s : *list) {
-            out[k * 4] = s.kind;
-            out[k * 4 + 1] = s.y0;
-            out[k * 4 + 2] = s.y1;
-            out[k * 4 + 3] = (int32_t)s.op;
-            k++;
-        }
-    return (int)opq.size() | ((int)msk.size() << 16);
 }
 
 } // extern "C"

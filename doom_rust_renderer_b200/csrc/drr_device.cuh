@@ -19,9 +19,11 @@ enum : uint32_t {
     KIND_SKY_HOLES = 4,  // sky bitmap with None texels
 };
 
-// Resolved span of one screen column, produced by the host-side binning (drr_api.cu). 16 bytes.
+// One emitted column of one op after clipping to the screen, in draw order (what the bin kernel turns into a TileSpan).
+// On the device it only ever exists in registers; this struct is the host-side mirror used by the CPU tests
+// (drr_test_list) to check the device binning. 16 bytes.
 struct Span {
-    uint16_t y0, y1; // inclusive screen rows this span still owns after later opaque spans were cut out
+    uint16_t y0, y1; // inclusive screen rows
     uint16_t x;      // screen column
     uint8_t kind;
     uint8_t pad;
@@ -30,7 +32,7 @@ struct Span {
 };
 static_assert(sizeof(Span) == 16, "Span layout");
 
-// Device copy of drr_seg_hdr with the bitmap id resolved to a slot. 48 bytes.
+// Device copy of drr_seg_hdr (bitmap id resolved to a slot) plus where its column records are. 64 bytes.
 struct SegRec {
     uint32_t bitmap_slot;
     int16_t light_level;
@@ -40,26 +42,37 @@ struct SegRec {
     int32_t start_x, end_x;
     float bottom_height, top_height;
     int16_t offset_x, offset_y;
+    uint32_t cols_first; // index of the first ColRec; the records' x is strictly increasing (drr_emit_columns splits otherwise)
+    uint32_t n;          // number of ColRec
+    int16_t x0, x1;      // x of the first / last record
+    uint32_t pad;
 };
-static_assert(sizeof(SegRec) == 48, "SegRec layout");
+static_assert(sizeof(SegRec) == 64, "SegRec layout");
 
-struct PlaneRec { // 12 bytes
+// == drr_col (BitmapColumn, bitmap_render.rs:19-25). 10 bytes, 2-byte aligned.
+struct ColRec {
+    int16_t x, clipped_top_y, clipped_bottom_y, bottom_y, top_y;
+};
+static_assert(sizeof(ColRec) == 10, "ColRec layout");
+
+struct PlaneRec { // 16 bytes
     int16_t flat_slot; // -1 = sky
     int16_t height;
     int16_t light_level;
     int16_t left, right;
-    int16_t reserved;
+    int16_t kind;       // KIND_FLAT / KIND_SKY / KIND_SKY_HOLES
+    uint32_t arr_first; // index into the (top, bottom) i16 pair pool of the entry for x == left
 };
-static_assert(sizeof(PlaneRec) == 12, "PlaneRec layout");
+static_assert(sizeof(PlaneRec) == 16, "PlaneRec layout");
 
 struct ColIdx { // per (frame, screen column). 8 bytes
-    uint32_t first; // first span (global index); opaque spans sorted by y first, then masked spans in draw order
-    uint16_t n_opaque, n_masked;
+    uint32_t first; // first TileSpan of the column (global index); the column's spans follow in draw order
+    uint32_t n;
 };
 static_assert(sizeof(ColIdx) == 8, "ColIdx layout");
 
 struct BitmapRec { // 12 bytes
-    uint32_t base; // index into the u16 texel pool (row-major, 0x8000 bit = None)
+    uint32_t base; // index into the u16 texel pool (column-major, pow2 column pitch, palette byte offsets, 4096 = None)
     int16_t w, h;
     uint32_t opaque;
 };
@@ -67,17 +80,6 @@ struct BitmapRec { // 12 bytes
 struct View { // == drr_view, 24 bytes
     float pos_x, pos_y, floor_height, angle, cos_a, sin_a;
 };
-
-// Per-span parameters written by the setup kernel and consumed by the march kernel. 32 bytes.
-//   wall kinds: a.x = y0|y1<<16, a.y = texel index of (row 0, column tx), a.z = w|h<<16, a.w = top_y|bottom_y<<16
-//               b.x = uy1 bits,  b.y = light factor bits,                 b.z = off_y(u16)|kind<<16, b.w = mod magic
-//   flat:       a.x = y0|y1<<16, a.y = flat base (byte index),            a.z = wz bits,  a.w = light/255 bits
-//               b.x = GCFX*wz bits, b.z = kind<<16
-//   sky kinds:  a.x = y0|y1<<16, a.y = texel index of (row 0, column tx), b.z = kind<<16
-struct SpanParams {
-    uint4 a, b;
-};
-static_assert(sizeof(SpanParams) == 32, "SpanParams layout");
 
 // ---- Rust scalar semantics ----------------------------------------------------------------------------------------
 // `f as i16`: cvt.rzi saturates to the destination range and maps NaN to 0 (PTX ISA, cvt: "float-to-integer

@@ -1,8 +1,10 @@
-// drr_tile.cu -- the tile draw kernel (sm_100a) and its span-setup kernel.
+// drr_tile.cu -- the two sm_100a kernels of the draw path: column binning + span setup, and the tile draw kernel.
 //
-//   drr_tile_setup_kernel : one thread per resolved span.  Everything of render_vertical_bitmap_line that depends on the
-//                           column only (src/renderer/bitmap_render.rs:233-251), the per-visplane constants of
-//                           draw_visplane (src/renderer/visplanes.rs:108,112-114) and draw_sky's tx (visplanes.rs:54-66),
+//   drr_bin_kernel        : one thread per (frame, screen column).  Walks the frame's ops in call order ("column binning":
+//                           the emitted lists are per op, the draw kernel wants them per column) and writes, for every
+//                           (op, column) that survives clipping, everything of render_vertical_bitmap_line that depends on
+//                           the column only (src/renderer/bitmap_render.rs:233-251), the per-visplane constants of
+//                           draw_visplane (src/renderer/visplanes.rs:108,112-114) or draw_sky's tx (visplanes.rs:54-66),
 //                           decoded all the way into the register values the pixel loops use (64 B per span), so that
 //                           the draw kernel spends no instructions on decoding.
 //   drr_tile_kernel       : one CTA per (frame, TC screen columns, band of rows; the band is the whole column for
@@ -14,8 +16,8 @@
 //                           wall/sprite ty + texel + diminish_color (bitmap_render.rs:253-275, 190-208), flat inverse
 //                           projection (visplanes.rs:103-128), sky (visplanes.rs:65-77).  Pixels go to a column-major u32
 //                           tile in shared memory (consecutive lanes -> consecutive words: conflict-free); a column's
-//                           spans are drawn by ONE lane group in list order (opaque spans, which are pairwise disjoint,
-//                           then masked spans in draw order), and finally the tile is written out row by row as 16-byte
+//                           spans are drawn by ONE lane group in draw order (the kinds that always write overwrite, the
+//                           kinds with None texels skip them), and finally the tile is written out row by row as 16-byte
 //                           vectors of the row-major RGB24 framebuffer (Pixels::set, src/renderer/pixels.rs:22-30) while
 //                           the per-frame checksum is accumulated.  Column sets are handed to warps dynamically (shared
 //                           counter), so a warp that drew short columns takes more of them.
@@ -34,88 +36,141 @@ namespace drr {
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
 enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10 };
 
-__global__ void __launch_bounds__(256) drr_tile_setup_kernel(DrawArgs a, uint32_t nspans) {
-    __shared__ int s_f0;
-    const uint32_t s0 = blockIdx.x * blockDim.x;
-    if (threadIdx.x == 0) { // frame of the block's first span: upper_bound(frame_span_base, s0) - 1
-        int lo = 0, hi = a.nframes;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (a.frame_span_base[mid] <= s0) lo = mid + 1; else hi = mid;
-        }
-        s_f0 = lo - 1;
+// Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
+__device__ __forceinline__ void wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
+    const BitmapRec bm = a.bitmaps[g.bitmap_slot];
+    const uint32_t h = (uint32_t)bm.h;
+    uint32_t kind = bm.opaque ? KIND_WALL : KIND_WALL_HOLES;
+    uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
+    const WallColumn wc = wall_column(g, bm.w, x);
+    if (wc.tx < 0) kind = KIND_NONE; // reference: negative index -> panic
+    const uint32_t lp = ilog2_ceil(h); // column-major texel pool: one texture column = 1 << lp consecutive texels
+    ra.z = bm.base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
+    uint32_t flags = 0;
+    if ((h & (h - 1u)) == 0u) {
+        // floormod(wrap16(tyr + off_y), 2^k) == (tyr + off_y) & (2^k - 1): the i16 wrap only touches bits >= 16
+        flags |= TS_POW2;
+        ra.w = (uint32_t)(int)g.offset_y;
+        rb.x = h - 1u;
+    } else {
+        // floormod(v, h) for v in i16 via u = v + M (M = multiple of h >= 32768), q = umulhi(u, magic), r = u - q*h;
+        // wrap16(t + off) + M == ((t + off + 32768) & 0xffff) + (M - 32768)
+        const uint32_t M = h * ((32768u + h - 1u) / h);
+        ra.w = (uint32_t)((int)g.offset_y + 32768);
+        rb.x = 0xffffu;
+        rb.y = M - 32768u;
+        rb.z = (uint32_t)(0x100000000ull / h) + 1u;
+        rb.w = 0u - h;
     }
-    __syncthreads();
-    const uint32_t s = s0 + threadIdx.x;
-    if (s >= nspans) return;
-    int f = s_f0;
-    while (s >= a.frame_span_base[f + 1]) ++f;
+    const int den = bottom_y - top_y;
+    const float denF = (float)den;
+    rc.x = __float_as_uint(-(float)top_y);
+    rc.y = __float_as_uint(-denF);
+    rc.z = __float_as_uint(den != 0 ? refined_rcp(denF) : 0.0f);
+    rc.w = __float_as_uint(wc.uy1);
+    // bottom_y == top_y: ay is NaN or +-inf, (1.0 - ay) * 0.0 is NaN, the sum is NaN and `NaN as i16` is 0
+    rd.x = den != 0 ? __float_as_uint((float)h) : 0x7fc00000u;
+    rd.y = __float_as_uint(wc.factor);
+    if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
+    ra.y = kind | flags;
+    out[0] = ra;
+    out[1] = rb;
+    out[2] = rc;
+    out[3] = rd;
+}
 
-    const Span sp = a.spans[s];
-    uint4 ra = make_uint4((uint32_t)sp.y0 | ((uint32_t)sp.y1 << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
-    uint32_t kind = sp.kind;
-
-    if (kind == KIND_WALL || kind == KIND_WALL_HOLES) {
-        const SegRec g = a.segs[sp.op];
-        const BitmapRec bm = a.bitmaps[g.bitmap_slot];
-        const uint32_t h = (uint32_t)bm.h;
-        const WallColumn wc = wall_column(g, bm.w, sp.x);
-        if (wc.tx < 0) kind = KIND_NONE; // reference: negative index -> panic
-        const uint32_t lp = ilog2_ceil(h); // column-major texel pool: one texture column = 1 << lp consecutive texels
-        ra.z = bm.base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
-        uint32_t flags = 0;
-        if ((h & (h - 1u)) == 0u) {
-            // floormod(wrap16(tyr + off_y), 2^k) == (tyr + off_y) & (2^k - 1): the i16 wrap only touches bits >= 16
-            flags |= TS_POW2;
-            ra.w = (uint32_t)(int)g.offset_y;
-            rb.x = h - 1u;
-        } else {
-            // floormod(v, h) for v in i16 via u = v + M (M = multiple of h >= 32768), q = umulhi(u, magic), r = u - q*h;
-            // wrap16(t + off) + M == ((t + off + 32768) & 0xffff) + (M - 32768)
-            const uint32_t M = h * ((32768u + h - 1u) / h);
-            ra.w = (uint32_t)((int)g.offset_y + 32768);
-            rb.x = 0xffffu;
-            rb.y = M - 32768u;
-            rb.z = (uint32_t)(0x100000000ull / h) + 1u;
-            rb.w = 0u - h;
-        }
-        const int den = (int)sp.bottom_y - (int)sp.top_y;
-        const float denF = (float)den;
-        rc.x = __float_as_uint(-(float)sp.top_y);
-        rc.y = __float_as_uint(-denF);
-        rc.z = __float_as_uint(den != 0 ? refined_rcp(denF) : 0.0f);
-        rc.w = __float_as_uint(wc.uy1);
-        // bottom_y == top_y: ay is NaN or +-inf, (1.0 - ay) * 0.0 is NaN, the sum is NaN and `NaN as i16` is 0
-        rd.x = den != 0 ? __float_as_uint((float)h) : 0x7fc00000u;
-        rd.y = __float_as_uint(wc.factor);
-        if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
-        ra.y = kind | flags;
-    } else if (kind == KIND_FLAT) {
-        const PlaneRec p = a.planes[sp.op];
-        const View vw = a.views[f];
+// Decoded record of a visplane column: the per-plane and per-column constants of draw_visplane / draw_sky
+__device__ __forceinline__ void plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb, uint4 *out) {
+    uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rc = make_uint4(0u, 0u, 0u, 0u);
+    if (p.kind == KIND_FLAT) {
         // visplanes.rs:112  wz = visplane.height as f32 - player.floor_height - PLAYER_EYE_HEIGHT
         const float wz = __fsub_rn(__fsub_rn((float)p.height, vw.floor_height), 41.0f);
         // visplanes.rs:108  vx = (CAMERA_FOCUS_X - x as f32) / ASPECT_RATIO_CORRECTION
-        const float vx = __fdiv_rn(__fsub_rn(a.CFX, (float)sp.x), a.ASPECT);
+        const float vx = __fdiv_rn(__fsub_rn(a.CFX, (float)x), a.ASPECT);
         const float wzvx = __fmul_rn(wz, vx);    // left operand of visplanes.rs:114
         const float gwz = __fmul_rn(a.GCFX, wz); // left operand of visplanes.rs:113
         ra.z = (uint32_t)p.flat_slot * 4096u;
         rc.x = __float_as_uint(wzvx);
         rc.y = __float_as_uint(gwz);
         rc.z = __float_as_uint(__fdiv_rn((float)p.light_level, 255.0f)); // bitmap_render.rs:191
-        ra.y = kind | ((fast_div_operand_ok(wzvx) && fast_div_operand_ok(gwz)) ? TS_FASTDIV : 0u);
+        ra.y = KIND_FLAT | ((fast_div_operand_ok(wzvx) && fast_div_operand_ok(gwz)) ? TS_FASTDIV : 0u);
     } else { // sky kinds
-        const View vw = a.views[f];
-        int tx = sky_tx(vw.angle, (int)(short)sp.x, a.Wf);
+        uint32_t kind = (uint32_t)p.kind;
+        int tx = sky_tx(vw.angle, x, a.Wf);
         if (tx < 0) { kind = KIND_NONE; tx = 0; }
         ra.z = a.sky_base + ((uint32_t)tx << 7);
         ra.y = kind;
     }
-    uint4 *out = reinterpret_cast<uint4 *>(a.tparams) + (size_t)s * 4;
     out[0] = ra;
-    out[1] = rb;
+    out[1] = make_uint4(0u, 0u, 0u, 0u);
     out[2] = rc;
-    out[3] = rd;
+    out[3] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// Walk the ops of frame f in call order and visit what each of them draws in screen column x.  EMIT = false only counts;
+// EMIT = true writes the decoded records to out[0], out[4], ...  The clipping rules are Pixels::set's (pixels.rs:23: x >= W
+// is ignored, rows are clipped to the screen by the callers) and draw_visplane's (visplanes.rs:95-101).  Returns the count.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, int wx0, int wx1, const View &vw, uint4 *out) {
+    uint32_t n = 0;
+    const uint32_t o0 = a.frame_op_base[f], o1 = a.frame_op_base[f + 1];
+    for (uint32_t o = o0; o < o1; ++o) {
+        const uint32_t op = a.ops[o];
+        if (op & 0x80000000u) {
+            const PlaneRec p = a.planes[op & 0x7fffffffu];
+            if (p.right < wx0 || p.left > wx1) continue; // not in this warp's columns (warp-uniform)
+            if (x < p.left || x > p.right) continue;
+            const uint32_t tb = a.parr[p.arr_first + (uint32_t)(x - p.left)];
+            const int t = max((int)(short)(tb & 0xffffu), 0);                // visplanes.rs:61 / :95
+            const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
+            if (p.kind == KIND_FLAT && (int)(short)(b - t) <= 1) continue;   // :99-101 (not applied to sky)
+            if (t > b) continue;
+            if (EMIT) plane_record(a, p, vw, x, t, b, out + 4 * n);
+            ++n;
+        } else {
+            const SegRec g = a.segs[op];
+            if (g.n == 0 || g.x1 < wx0 || g.x0 > wx1) continue;
+            if (x < g.x0 || x > g.x1) continue;
+            // the records' x is strictly increasing: usually x0, x0+1, ... (direct index), otherwise binary search
+            uint32_t i = (uint32_t)(x - g.x0);
+            if ((uint32_t)(g.x1 - g.x0) + 1u != g.n) {
+                uint32_t lo = 0, hi = g.n;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (a.cols[g.cols_first + mid].x < x) lo = mid + 1; else hi = mid;
+                }
+                if (lo >= g.n || a.cols[g.cols_first + lo].x != x) continue;
+                i = lo;
+            }
+            const ColRec c = a.cols[g.cols_first + i];
+            const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
+            if (ya > yb) continue;
+            if (EMIT) wall_record(a, g, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n);
+            ++n;
+        }
+    }
+    return n;
+}
+
+// drr_bin_kernel: one thread per (frame, screen column).  Counts what the frame's ops draw in the column, reserves that
+// many records of the frame's range with one atomic, then writes the records in draw order ("column binning").
+__global__ void __launch_bounds__(128) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
+    const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
+    const int x = (int)(blockIdx.x % (unsigned)bpf) * 128 + (int)threadIdx.x;
+    const int wx0 = x & ~31, wx1 = wx0 + 31;
+    if (wx0 >= a.W) return;
+    const View vw = a.views[f];
+    const bool live = x < a.W;
+    const uint32_t n = live ? walk_column<false>(a, f, x, wx0, wx1, vw, nullptr) : 0u;
+    uint32_t first = a.frame_rec_base[f];
+    if (n) first += atomicAdd(a.frame_cursor + f, n);
+    if (live) {
+        ColIdx ci;
+        ci.first = first;
+        ci.n = n;
+        a.colidx[(size_t)f * a.W + x] = ci;
+        if (n) walk_column<true>(a, f, x, wx0, wx1, vw, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4);
+    }
 }
 
 // sky ty of every screen row (visplanes.rs:68-72: depends on the row only), computed once per context
@@ -283,7 +338,7 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
 template <int TC, int LPG, bool FAST_STORE>
-__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int band_rows, int nbands, int RP) {
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
     __shared__ int s_next;
@@ -295,7 +350,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel
     const unsigned bid = blockIdx.x;
     const int band = (int)(bid % (unsigned)nbands);
     const int g = (int)((bid / (unsigned)nbands) % (unsigned)gpf);
-    const int f = (int)(bid / ((unsigned)nbands * (unsigned)gpf));
+    const int f = frame0 + (int)(bid / ((unsigned)nbands * (unsigned)gpf));
     const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
 
     for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
@@ -311,17 +366,18 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel
     const int grp = lane / LPG, li = lane % LPG;
 
     // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
-    // list in order: opaque spans (pairwise disjoint), then masked spans in draw order
+    // list in draw order ("last writer wins, transparent texels do not write"): the kinds that always write
+    // simply overwrite, the HOLES kinds skip their None texels
     for (int cs = warp; cs < NSETS;) {
         const int c = cs * G + grp, x = g * TC + c;
         ColIdx ci;
-        ci.first = 0; ci.n_opaque = 0; ci.n_masked = 0;
+        ci.first = 0; ci.n = 0;
         if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
-        const int n = ci.n_opaque + ci.n_masked;
+        const int n = (int)ci.n;
         const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
         const uint32_t col_addr = tile_addr + 4u * (uint32_t)(c * RP);
         for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
-            __syncwarp(); // a masked span may overwrite what another lane of the group stored for an earlier span
+            __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
             if (j < n) {
                 const uint4 ra = P[4 * j];
                 const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
@@ -410,9 +466,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel
 // ------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------
-cudaError_t launch_tile_setup(const DrawArgs &a, uint32_t nspans, cudaStream_t st) {
-    if (nspans == 0) return cudaSuccess;
-    drr_tile_setup_kernel<<<(nspans + 255) / 256, 256, 0, st>>>(a, nspans);
+cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t st) {
+    if (nframes <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.frame_cursor + frame0, 0, sizeof(uint32_t) * (size_t)nframes, st);
+    if (e != cudaSuccess) return e;
+    const int bpf = (a.W + 127) / 128;
+    const long long blocks = (long long)nframes * bpf;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    drr_bin_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, frame0, bpf);
     return cudaGetLastError();
 }
 
@@ -422,10 +483,10 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
 }
 
 void tile_config(int W, int H, int *tc, int *lpg) {
-    // tall screens: long spans, a whole warp per span and 16-column tiles (two full-height tiles per SM); short screens:
-    // 8 or 16 lanes per span so that short spans still fill the warp, 32-column tiles
+    // measured (tools/sweep_tile.sh, profiles/r1_tile_geometry.md): 16-column full-height tiles with 16 lanes per span at
+    // 1280x800, 32-column tiles with 8 lanes per span at 320x200 -- short lane groups keep the warp full on short spans
     *tc = H >= 400 ? 16 : 32;
-    *lpg = H >= 600 ? 32 : H >= 300 ? 16 : 8;
+    *lpg = H >= 600 ? 16 : 8;
     if (const char *e = getenv("DRR_TILE_COLS")) {
         const int v = atoi(e);
         if (v == 16 || v == 32) *tc = v;
@@ -437,7 +498,7 @@ void tile_config(int W, int H, int *tc, int *lpg) {
 }
 
 template <int TC, int LPG>
-static cudaError_t launch_tile_t(const DrawArgs &a, cudaStream_t st, int *launches) {
+static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
     const int gpf = (a.W + TC - 1) / TC;
     // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
     const int max_rows = 820;
@@ -446,7 +507,7 @@ static cudaError_t launch_tile_t(const DrawArgs &a, cudaStream_t st, int *launch
     const int want = TC == 16 ? 2 : 1;
     int RP = band_rows;
     while (RP % 32 != want) ++RP;
-    const long long blocks = (long long)a.nframes * gpf * nbands;
+    const long long blocks = (long long)nframes * gpf * nbands;
     if (blocks == 0) return cudaSuccess;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t dyn = ((size_t)TC * RP * 4 + 15) / 16 * 16;
@@ -460,7 +521,7 @@ static cudaError_t launch_tile_t(const DrawArgs &a, cudaStream_t st, int *launch
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
-        drr_tile_kernel<TC, LPG, true><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, band_rows, nbands, RP);
+        drr_tile_kernel<TC, LPG, true><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, frame0, band_rows, nbands, RP);
     } else {
         static bool attr_done = false;
         if (!attr_done) {
@@ -468,26 +529,26 @@ static cudaError_t launch_tile_t(const DrawArgs &a, cudaStream_t st, int *launch
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
-        drr_tile_kernel<TC, LPG, false><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, band_rows, nbands, RP);
+        drr_tile_kernel<TC, LPG, false><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, frame0, band_rows, nbands, RP);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        e = launch_checksum_pass(a, st, launches);
+        e = launch_checksum_pass(a, frame0, nframes, st, launches);
         if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile(const DrawArgs &a, cudaStream_t st, int *launches) {
+cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
     int tc, lpg;
     tile_config(a.W, a.H, &tc, &lpg);
     if (tc == 16) {
-        if (lpg == 32) return launch_tile_t<16, 32>(a, st, launches);
-        if (lpg == 16) return launch_tile_t<16, 16>(a, st, launches);
-        return launch_tile_t<16, 8>(a, st, launches);
+        if (lpg == 32) return launch_tile_t<16, 32>(a, frame0, nframes, st, launches);
+        if (lpg == 16) return launch_tile_t<16, 16>(a, frame0, nframes, st, launches);
+        return launch_tile_t<16, 8>(a, frame0, nframes, st, launches);
     }
-    if (lpg == 32) return launch_tile_t<32, 32>(a, st, launches);
-    if (lpg == 16) return launch_tile_t<32, 16>(a, st, launches);
-    return launch_tile_t<32, 8>(a, st, launches);
+    if (lpg == 32) return launch_tile_t<32, 32>(a, frame0, nframes, st, launches);
+    if (lpg == 16) return launch_tile_t<32, 16>(a, frame0, nframes, st, launches);
+    return launch_tile_t<32, 8>(a, frame0, nframes, st, launches);
 }
 
 } // namespace drr

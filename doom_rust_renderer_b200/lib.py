@@ -84,9 +84,9 @@ def _lib() -> C.CDLL:
             "drr_test_list": (vp, [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "drr_test_bitmap_info": (i, [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "drr_test_bitmap_texels": (i, [vp, i, vp]), "drr_test_flat_texels": (i, [vp, i, vp]), "drr_test_palette": (i, [vp, vp]),
-            "drr_test_sky_slot": (i, [vp]), "drr_test_uses_tile_kernel": (i, [vp]),
+            "drr_test_sky_slot": (i, [vp]), "drr_test_tile_config": (i, [vp, C.POINTER(i), C.POINTER(i)]),
             "drr_test_bitmap_id_of_slot": (i, [vp, i]), "drr_test_flat_id_of_slot": (i, [vp, i]),
-            "drr_test_resolve_column": (i, [vp, i, vp, i]),
+            "drr_test_device_bins": (i, [vp, vp, vp]),
             "drr_test_fastdiv": (i, [vp, i, C.c_longlong, C.c_longlong, f, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), vp]),
         }
         for name, (res, args) in sig.items():
@@ -239,7 +239,16 @@ class Context:
         return t.value, s.value, m.value
 
     def kernel_name(self) -> str:
-        return "drr_tile_kernel" if self.L.drr_test_uses_tile_kernel(self.h) else "drr_march_kernel"
+        tc, lpg = C.c_int(), C.c_int()
+        self._ck(self.L.drr_test_tile_config(self.h, C.byref(tc), C.byref(lpg)))
+        return "drr_tile_kernel<%d,%d>" % (tc.value, lpg.value)
+
+    def device_bins(self, nframes: int):
+        """(colidx [nframes*W] of COLIDX_DTYPE, recs [n][2] u32 = (y0 | y1 << 16, kind | flags)) as the bin kernel wrote them."""
+        ci = np.zeros(nframes * self.W, COLIDX_DTYPE)
+        recs = np.zeros((max(1, self.stats()["spans"]), 2), np.uint32)
+        self._ck(self.L.drr_test_device_bins(self.h, _ptr(ci), _ptr(recs)))
+        return ci, recs
 
     def profile_begin(self, max_steps: int):
         self._ck(self.L.drr_profile_begin(self.h, max_steps))
@@ -272,10 +281,12 @@ class Context:
 VIEW_DTYPE = np.dtype([("pos_x", "<f4"), ("pos_y", "<f4"), ("floor_height", "<f4"), ("angle", "<f4"), ("cos_a", "<f4"), ("sin_a", "<f4")])
 SEG_DTYPE = np.dtype([("bitmap_slot", "<u4"), ("light_level", "<i2"), ("phase", "<i2"), ("lsx", "<f4"), ("lsy", "<f4"), ("lex", "<f4"),
                       ("ley", "<f4"), ("start_offset", "<f4"), ("start_x", "<i4"), ("end_x", "<i4"), ("bottom_height", "<f4"),
-                      ("top_height", "<f4"), ("offset_x", "<i2"), ("offset_y", "<i2")])
-PLANE_DTYPE = np.dtype([("flat_slot", "<i2"), ("height", "<i2"), ("light_level", "<i2"), ("left", "<i2"), ("right", "<i2"), ("reserved", "<i2")])
+                      ("top_height", "<f4"), ("offset_x", "<i2"), ("offset_y", "<i2"), ("cols_first", "<u4"), ("n", "<u4"),
+                      ("x0", "<i2"), ("x1", "<i2"), ("pad", "<u4")])
+PLANE_DTYPE = np.dtype([("flat_slot", "<i2"), ("height", "<i2"), ("light_level", "<i2"), ("left", "<i2"), ("right", "<i2"), ("kind", "<i2"),
+                        ("arr_first", "<u4")])
 SPAN_DTYPE = np.dtype([("y0", "<u2"), ("y1", "<u2"), ("x", "<u2"), ("kind", "u1"), ("pad", "u1"), ("op", "<u4"), ("top_y", "<i2"), ("bottom_y", "<i2")])
-COLIDX_DTYPE = np.dtype([("first", "<u4"), ("n_opaque", "<u2"), ("n_masked", "<u2")])
+COLIDX_DTYPE = np.dtype([("first", "<u4"), ("n", "<u4")])
 KIND_WALL, KIND_WALL_HOLES, KIND_FLAT, KIND_SKY, KIND_SKY_HOLES = 0, 1, 2, 3, 4
 
 

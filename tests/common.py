@@ -137,8 +137,8 @@ class AssetsFromCtx:
 
 
 def replay_binned_frame(ctx: drr.Context, frame: int) -> np.ndarray:
-    """CPU replay of ONE recorded frame from the column-binned lists (what the GPU consumes), span by span, using the
-    oracle's leaf drawers.  Used to validate the host-side binning / resolving without a GPU."""
+    """CPU replay of ONE recorded frame from the column-binned lists (the host restatement of what the bin kernel builds),
+    span by span in draw order, using the oracle's leaf drawers.  Validates recording + binning without a GPU."""
     W, H = ctx.W, ctx.H
     assets = AssetsFromCtx(ctx)
     leaf = orc.Leaf(W, H, assets.palette)
@@ -155,12 +155,7 @@ def replay_binned_frame(ctx: drr.Context, frame: int) -> np.ndarray:
     bottom = np.zeros(W, np.int16)
     for x in range(W):
         ci = colidx[frame * W + x]
-        lst = spans[ci["first"]:ci["first"] + ci["n_opaque"] + ci["n_masked"]]
-        # opaque spans must be disjoint and sorted
-        prev = -1
-        for s in lst[:ci["n_opaque"]]:
-            assert s["y0"] > prev and s["y1"] >= s["y0"], "opaque spans must be disjoint, sorted, non-empty"
-            prev = s["y1"]
+        lst = spans[ci["first"]:ci["first"] + ci["n"]]  # the column's spans in draw order
         for s in lst:
             assert s["x"] == x
             y0, y1 = int(s["y0"]), int(s["y1"])

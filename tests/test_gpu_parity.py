@@ -53,6 +53,37 @@ def test_scene_frames_match_oracle(W, H, n):
         assert int(crcs[k]) == drr.checksum_numpy(ref)
 
 
+@pytest.mark.parametrize("W,H,kind", [(320, 200, "e1m1"), (200, 120, "stress"), (1280, 800, "e1m1")])
+def test_device_binning_equals_host_restatement(W, H, kind):
+    """The bin kernel's per-column span lists (rows, kind, draw order) equal the host restatement of the binning rule."""
+    path, gm = common.wad(kind)
+    game = orc.Game(path, "E1M1", W, H)
+    src = synth_wad.walk_viewpoints(gm, 512) if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, 64)
+    views = common.usable_views(game, src[:: max(1, len(src) // 8)], 5)
+    ctx = drr.Context(W, H, 0, len(views))
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views) == []
+    ctx.submit()
+    ctx.sync()
+    ci_dev, recs = ctx.device_bins(len(views))
+    spans, ci_host = ctx._list(3, drr.SPAN_DTYPE), ctx._list(4, drr.COLIDX_DTYPE)
+    assert len(ci_dev) == len(ci_host) == len(views) * W
+    assert (ci_dev["n"] == ci_host["n"]).all()
+    assert int(ci_host["n"].sum()) == ctx.stats()["spans"] == len(spans)
+    # every device range lies inside its frame's record range and ranges do not overlap
+    order = np.argsort(ci_dev["first"], kind="stable")
+    nz = order[ci_dev["n"][order] > 0]
+    ends = ci_dev["first"][nz].astype(np.int64) + ci_dev["n"][nz]
+    assert (ends[:-1] <= ci_dev["first"][nz][1:]).all() and ends[-1] <= len(spans)
+    for i in np.nonzero(ci_host["n"])[0]:
+        h = spans[ci_host["first"][i]:ci_host["first"][i] + ci_host["n"][i]]
+        d = recs[ci_dev["first"][i]:ci_dev["first"][i] + ci_dev["n"][i]]
+        assert ((d[:, 0] & 0xFFFF) == h["y0"]).all() and ((d[:, 0] >> 16) == h["y1"]).all(), i
+        kind_d = d[:, 1] & 0xFF
+        assert ((kind_d == h["kind"]) | (kind_d == 7)).all(), i  # 7 = column the reference would have panicked on
+
+
 def test_config1_spawn_viewpoint():
     """BASELINE config 1: the Player1Start viewpoint at 320x200, timestamp 0."""
     path, _ = common.wad("e1m1")
