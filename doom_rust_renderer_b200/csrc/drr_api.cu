@@ -135,6 +135,8 @@ struct drr_ctx {
     std::vector<ColIdx> t_colidx;
 
     cudaStream_t cstream = nullptr;      // copy stream of the pipelined drr_submit
+    cudaStream_t stream2 = nullptr;      // second compute stream: odd chunks run here so that a chunk's bin kernel overlaps the previous chunk's draw tail
+    cudaEvent_t ev_stream2 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;   // "chunk uploaded" events
     cudaEvent_t ev_lists_free = nullptr; // recorded on `stream` after the last kernel that reads the device lists
 
@@ -231,6 +233,8 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(copy)", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_lists_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(2)", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_stream2, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
     return DRR_OK;
 }
@@ -250,6 +254,8 @@ void drr_ctx_destroy(drr_ctx *ctx) {
     for (auto &ev : ctx->prof_ev) cudaEventDestroy(ev);
     if (ctx->ev_lists_free) cudaEventDestroy(ctx->ev_lists_free);
     if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2), cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_stream2) cudaEventDestroy(ctx->ev_stream2);
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_sky_rows) cudaFree(ctx->d_sky_rows);
@@ -638,21 +644,22 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
 }
 
 // bin kernel + tile kernel over frames [f0, f0 + n) on the context's stream
-static int draw_range(drr_ctx *ctx, const DrawArgs &a, int f0, int n, bool bin, bool tile, bool profile = false) {
+static int draw_range(drr_ctx *ctx, const DrawArgs &a, int f0, int n, bool bin, bool tile, bool profile = false, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
     const bool prof = profile && (size_t)(ctx->prof_steps + 1) * 3 <= ctx->prof_ev.size();
-    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3], ctx->stream));
+    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3], st));
     if (bin) {
-        CU(ctx, launch_bin(a, f0, n, ctx->stream));
+        CU(ctx, launch_bin(a, f0, n, st));
         ctx->stats.kernel_launches++;
     }
-    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], ctx->stream));
+    if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], st));
     if (tile) {
         int launches = 0;
-        CU(ctx, launch_tile(a, f0, n, ctx->stream, &launches));
+        CU(ctx, launch_tile(a, f0, n, st, &launches));
         ctx->stats.kernel_launches += (uint64_t)launches;
     }
     if (prof) {
-        CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 2], st));
         ctx->prof_steps++;
     }
     return DRR_OK;
@@ -714,7 +721,8 @@ int drr_submit(drr_ctx *ctx) {
     ctx->uploaded_frames = 0;
     if (nf == 0) return DRR_OK;
     if ((rc = reserve_device_lists(ctx))) return rc;
-    size_t nchunks = std::min<size_t>({(size_t)16, nf, (size_t)(list_bytes(ctx) / (2u << 20)) + 1});
+    // ~4 MB of lists per chunk, at most 8 chunks (measured: tools/sweep_submit.sh; more chunks cost more in launches than they hide)
+    size_t nchunks = std::min<size_t>({(size_t)8, nf, (size_t)(list_bytes(ctx) / (4u << 20)) + 1});
     if (const char *e = getenv("DRR_SUBMIT_CHUNKS")) nchunks = std::min<size_t>(nf, (size_t)std::max(1, atoi(e)));
     while (ctx->chunk_ev.size() < nchunks) {
         cudaEvent_t e;
@@ -727,15 +735,45 @@ int drr_submit(drr_ctx *ctx) {
     CU(ctx, cudaEventRecord(ctx->ev_lists_free, ctx->stream));
     CU(ctx, cudaStreamWaitEvent(ctx->cstream, ctx->ev_lists_free, 0));
     CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
+    const bool two = nchunks > 1 && !getenv("DRR_SUBMIT_ONE_STREAM");
+    if (two) { // stream2's first kernel must come after the checksum memset queued on the context's stream
+        CU(ctx, cudaEventRecord(ctx->ev_stream2, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_stream2, 0));
+    }
     if ((rc = upload_tables(ctx, ctx->cstream))) return rc;
+    // DRR_SUBMIT_TRACE=1: print when each chunk's copy and draw finished (device time since the start of the call)
+    const bool trace = getenv("DRR_SUBMIT_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(1 + 2 * nchunks);
+        for (auto &e : tev) CU(ctx, cudaEventCreate(&e));
+        CU(ctx, cudaEventRecord(tev[0], ctx->cstream));
+    }
     for (size_t c = 0; c < nchunks; c++) {
         const size_t f0 = nf * c / nchunks, f1 = nf * (c + 1) / nchunks;
         if ((rc = upload_frames(ctx, f0, f1, ctx->cstream))) return rc;
         CU(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->cstream));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
-        if ((rc = draw_range(ctx, a, (int)f0, (int)(f1 - f0), true, true))) return rc;
+        if (trace) CU(ctx, cudaEventRecord(tev[1 + 2 * c], ctx->cstream));
+        cudaStream_t st = (two && (c & 1)) ? ctx->stream2 : ctx->stream;
+        CU(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+        if ((rc = draw_range(ctx, a, (int)f0, (int)(f1 - f0), true, true, false, st))) return rc;
+        if (trace) CU(ctx, cudaEventRecord(tev[2 + 2 * c], st));
+    }
+    if (two) { // everything is complete when the context's stream is
+        CU(ctx, cudaEventRecord(ctx->ev_stream2, ctx->stream2));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_stream2, 0));
     }
     ctx->uploaded_frames = nf;
+    if (trace) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t c = 0; c < nchunks; c++) {
+            float tc = 0, td = 0;
+            cudaEventElapsedTime(&tc, tev[0], tev[1 + 2 * c]);
+            cudaEventElapsedTime(&td, tev[0], tev[2 + 2 * c]);
+            fprintf(stderr, "drr_submit chunk %zu/%zu: copy done %.3f ms, draw done %.3f ms\n", c, nchunks, tc, td);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return DRR_OK;
 }
 

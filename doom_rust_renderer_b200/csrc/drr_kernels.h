@@ -8,7 +8,11 @@ static constexpr int TILE_THREADS = 256;
 #ifndef DRR_TILE_MIN_BLOCKS
 #define DRR_TILE_MIN_BLOCKS 4
 #endif
-static constexpr int TILE_MIN_BLOCKS = DRR_TILE_MIN_BLOCKS;
+static constexpr int TILE_MIN_BLOCKS = DRR_TILE_MIN_BLOCKS; // 16-column full-height tiles (tall screens): shared memory allows 4 CTAs per SM
+#ifndef DRR_TILE_MIN_BLOCKS_SHORT
+#define DRR_TILE_MIN_BLOCKS_SHORT 6
+#endif
+static constexpr int TILE_MIN_BLOCKS_SHORT = DRR_TILE_MIN_BLOCKS_SHORT; // 32-column tiles (short screens): small tiles, more CTAs hide latency (tools/sweep.sh)
 
 struct DrawArgs {
     int W, H, nframes;

@@ -34,7 +34,7 @@ namespace drr {
 //               c.x = -top_y (f32)   c.y = -(bottom_y - top_y) (f32)   c.z = refined 1/(bottom_y - top_y)   c.w = uy1
 //               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
-enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10 };
+enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11 };
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
 __device__ __forceinline__ void wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
@@ -92,8 +92,18 @@ __device__ __forceinline__ void plane_record(const DrawArgs &a, const PlaneRec &
         ra.z = (uint32_t)p.flat_slot * 4096u;
         rc.x = __float_as_uint(wzvx);
         rc.y = __float_as_uint(gwz);
-        rc.z = __float_as_uint(__fdiv_rn((float)p.light_level, 255.0f)); // bitmap_render.rs:191
-        ra.y = KIND_FLAT | ((fast_div_operand_ok(wzvx) && fast_div_operand_ok(gwz)) ? TS_FASTDIV : 0u);
+        const float lf = __fdiv_rn((float)p.light_level, 255.0f);
+        rc.z = __float_as_uint(lf); // bitmap_render.rs:191
+        uint32_t flags = (fast_div_operand_ok(wzvx) && fast_div_operand_ok(gwz)) ? TS_FASTDIV : 0u;
+        // Is the light factor <= 1 on every row of the span?  wx = GCFX*wz / (CFY - y) is monotonic in y on either side of the
+        // horizon and so is factor = light/255 - (wx as i16)/4096 (every step is a monotonic function), so the rows ya and yb
+        // bound it when the span does not touch the horizon row; then the pixel loop needs no saturating path.
+        const float vya = __fsub_rn(a.CFY, (float)ya), vyb = __fsub_rn(a.CFY, (float)yb);
+        if ((vya > 0.0f) == (vyb > 0.0f) && vya != 0.0f && vyb != 0.0f) {
+            const float fa = light_factor(lf, sat_i16(__fdiv_rn(gwz, vya))), fb = light_factor(lf, sat_i16(__fdiv_rn(gwz, vyb)));
+            if (fa <= 1.0f && fb <= 1.0f) flags |= TS_UNIT;
+        }
+        ra.y = KIND_FLAT | flags;
     } else { // sky kinds
         uint32_t kind = (uint32_t)p.kind;
         int tx = sky_tx(vw.angle, x, a.Wf);
@@ -110,16 +120,32 @@ __device__ __forceinline__ void plane_record(const DrawArgs &a, const PlaneRec &
 // Walk the ops of frame f in call order and visit what each of them draws in screen column x.  EMIT = false only counts;
 // EMIT = true writes the decoded records to out[0], out[4], ...  The clipping rules are Pixels::set's (pixels.rs:23: x >= W
 // is ignored, rows are clipped to the screen by the callers) and draw_visplane's (visplanes.rs:95-101).  Returns the count.
+// s_tab holds, per op of the frame, (x0 | x1 << 16, op word): the x test runs on shared memory, the op's record is only
+// loaded on a hit.  Ops beyond the table's capacity are read from global memory.
+static constexpr int BIN_THREADS = 128;
+static constexpr int BIN_TAB = 512;
+
+__device__ __forceinline__ uint2 op_range(const DrawArgs &a, uint32_t op) { // (x0 | x1 << 16, op); an empty op gets x0 > x1
+    if (op & 0x80000000u) {
+        const PlaneRec p = a.planes[op & 0x7fffffffu];
+        return make_uint2((uint32_t)(uint16_t)p.left | ((uint32_t)(uint16_t)p.right << 16), op);
+    }
+    const SegRec *g = a.segs + op;
+    const uint32_t n = g->n;
+    const int x0 = n ? g->x0 : 1, x1 = n ? g->x1 : 0;
+    return make_uint2((uint32_t)(uint16_t)x0 | ((uint32_t)(uint16_t)x1 << 16), op);
+}
+
 template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, int wx0, int wx1, const View &vw, uint4 *out) {
+__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, uint4 *out) {
     uint32_t n = 0;
-    const uint32_t o0 = a.frame_op_base[f], o1 = a.frame_op_base[f + 1];
-    for (uint32_t o = o0; o < o1; ++o) {
-        const uint32_t op = a.ops[o];
+    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
+    for (uint32_t k = 0; k < nops; ++k) {
+        const uint2 e = k < (uint32_t)BIN_TAB ? s_tab[k] : op_range(a, a.ops[o0 + k]);
+        if (x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) continue;
+        const uint32_t op = e.y;
         if (op & 0x80000000u) {
             const PlaneRec p = a.planes[op & 0x7fffffffu];
-            if (p.right < wx0 || p.left > wx1) continue; // not in this warp's columns (warp-uniform)
-            if (x < p.left || x > p.right) continue;
             const uint32_t tb = a.parr[p.arr_first + (uint32_t)(x - p.left)];
             const int t = max((int)(short)(tb & 0xffffu), 0);                // visplanes.rs:61 / :95
             const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
@@ -128,24 +154,24 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             if (EMIT) plane_record(a, p, vw, x, t, b, out + 4 * n);
             ++n;
         } else {
-            const SegRec g = a.segs[op];
-            if (g.n == 0 || g.x1 < wx0 || g.x0 > wx1) continue;
-            if (x < g.x0 || x > g.x1) continue;
+            const SegRec *gp = a.segs + op;
+            const uint32_t gn = gp->n, cols_first = gp->cols_first;
+            const int gx0 = gp->x0, gx1 = gp->x1;
             // the records' x is strictly increasing: usually x0, x0+1, ... (direct index), otherwise binary search
-            uint32_t i = (uint32_t)(x - g.x0);
-            if ((uint32_t)(g.x1 - g.x0) + 1u != g.n) {
-                uint32_t lo = 0, hi = g.n;
+            uint32_t i = (uint32_t)(x - gx0);
+            if ((uint32_t)(gx1 - gx0) + 1u != gn) {
+                uint32_t lo = 0, hi = gn;
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi) >> 1;
-                    if (a.cols[g.cols_first + mid].x < x) lo = mid + 1; else hi = mid;
+                    if (a.cols[cols_first + mid].x < x) lo = mid + 1; else hi = mid;
                 }
-                if (lo >= g.n || a.cols[g.cols_first + lo].x != x) continue;
+                if (lo >= gn || a.cols[cols_first + lo].x != x) continue;
                 i = lo;
             }
-            const ColRec c = a.cols[g.cols_first + i];
+            const ColRec c = a.cols[cols_first + i];
             const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
             if (ya > yb) continue;
-            if (EMIT) wall_record(a, g, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n);
+            if (EMIT) wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n);
             ++n;
         }
     }
@@ -154,23 +180,23 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
 
 // drr_bin_kernel: one thread per (frame, screen column).  Counts what the frame's ops draw in the column, reserves that
 // many records of the frame's range with one atomic, then writes the records in draw order ("column binning").
-__global__ void __launch_bounds__(128) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
+__global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
+    __shared__ uint2 s_tab[BIN_TAB];
     const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
-    const int x = (int)(blockIdx.x % (unsigned)bpf) * 128 + (int)threadIdx.x;
-    const int wx0 = x & ~31, wx1 = wx0 + 31;
-    if (wx0 >= a.W) return;
+    const int x = (int)(blockIdx.x % (unsigned)bpf) * BIN_THREADS + (int)threadIdx.x;
+    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
+    for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += BIN_THREADS) s_tab[k] = op_range(a, a.ops[o0 + k]);
+    __syncthreads();
+    if (x >= a.W) return;
     const View vw = a.views[f];
-    const bool live = x < a.W;
-    const uint32_t n = live ? walk_column<false>(a, f, x, wx0, wx1, vw, nullptr) : 0u;
+    const uint32_t n = walk_column<false>(a, f, x, vw, s_tab, nullptr);
     uint32_t first = a.frame_rec_base[f];
     if (n) first += atomicAdd(a.frame_cursor + f, n);
-    if (live) {
-        ColIdx ci;
-        ci.first = first;
-        ci.n = n;
-        a.colidx[(size_t)f * a.W + x] = ci;
-        if (n) walk_column<true>(a, f, x, wx0, wx1, vw, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4);
-    }
+    ColIdx ci;
+    ci.first = first;
+    ci.n = n;
+    a.colidx[(size_t)f * a.W + x] = ci;
+    if (n) walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4);
 }
 
 // sky ty of every screen row (visplanes.rs:68-72: depends on the row only), computed once per context
@@ -222,14 +248,15 @@ __device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, con
         u0 = __umulhi(u0, rb.z) * rb.w + u0;
         u1 = __umulhi(u1, rb.z) * rb.w + u1;
     }
-    t0 = texels[ra.z + u0];
-    t1 = texels[ra.z + u1];
+    t0 = texels[u0]; // `texels` already points at the span's texture column
+    t1 = texels[u1];
 }
 
 template <int LPG, bool HOLES, bool POW2>
 __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
                                                uint32_t col_addr, const uint16_t *__restrict__ texels, uint32_t pal_addr, float one) {
     const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
+    const uint16_t *__restrict__ col = texels + ra.z;
     int y = ya + li;
     uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + LPG), __uint_as_float(rc.x)));
@@ -237,7 +264,7 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
 #pragma unroll 2
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
-            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, texels, t0, t1);
+            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
             const uint32_t rgb0 = lit_rgb_unit_p(lds_f4(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(lds_f4(pal_addr + t1), factor);
             if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, rgb0);
             if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, rgb1);
@@ -245,7 +272,7 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
     } else {
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
-            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, texels, t0, t1);
+            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
             if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(lds_f4(pal_addr + t0), factor));
             if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(lds_f4(pal_addr + t1), factor));
         }
@@ -264,7 +291,7 @@ __device__ __forceinline__ uint32_t flat_pixel_slow(float vy, float gwz, float w
     return lit_rgb_any(lds_f4(pal_addr + texel * 16u), light_factor(lf, sat_i16(wx)));
 }
 
-template <int LPG>
+template <int LPG, bool UNIT>
 __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, int ya, int yb, int b0, int li, uint32_t col_addr, float CFY,
                                                float cos_a, float sin_a, int px16, int py16, const uint8_t *__restrict__ flats,
                                                uint32_t pal_addr, float one) {
@@ -293,11 +320,12 @@ __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, i
             // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
             const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
             float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), one);
-            fac.x = fac.x < 0.0f ? 0.0f : fac.x;
-            fac.y = fac.y < 0.0f ? 0.0f : fac.y;
+            // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
+            fac.x = fmaxf(fac.x, 0.0f);
+            fac.y = fmaxf(fac.y, 0.0f);
             const float4 p0 = lds_f4(pal_addr + t0 * 16u), p1 = lds_f4(pal_addr + t1 * 16u);
             uint32_t rgb0, rgb1;
-            if (fac.x <= 1.0f && fac.y <= 1.0f) {
+            if (UNIT || (fac.x <= 1.0f && fac.y <= 1.0f)) {
                 rgb0 = lit_rgb_unit_p(p0, fac.x);
                 rgb1 = lit_rgb_unit_p(p1, fac.y);
             } else {
@@ -308,7 +336,7 @@ __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, i
             if (y + LPG <= yb) sts_u32(addr + 4u * LPG, rgb1);
         }
         const int ym = (int)CFY; // exact integer when H is even
-        if ((float)ym == CFY && ym >= ya && ym <= yb && li == ((ym - ya) % LPG))
+        if (!UNIT && (float)ym == CFY && ym >= ya && ym <= yb && li == ((ym - ya) % LPG)) // (a UNIT span does not touch that row)
             sts_u32(col_addr + 4u * (uint32_t)(ym - b0), flat_pixel_slow(0.0f, gwz, wzvx, lf, cos_a, sin_a, px16, py16, flat, pal_addr));
     } else {
         float vy = __fsub_rn(CFY, (float)y);
@@ -338,7 +366,7 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
 template <int TC, int LPG, bool FAST_STORE>
-__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
+__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
     __shared__ int s_next;
@@ -384,7 +412,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_BLOCKS) drr_tile_kernel
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
                     if (kind == KIND_FLAT) {
-                        tile_flat_span<LPG>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
+                        // a span clipped to a band stays inside the rows its flags were computed for
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV))
+                            tile_flat_span<LPG, true>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
+                        else
+                            tile_flat_span<LPG, false>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
                     } else if (kind == KIND_WALL) {
                         const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
                         if (ra.y & TS_POW2) tile_wall_span<LPG, false, true>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
@@ -470,10 +502,10 @@ cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t 
     if (nframes <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(a.frame_cursor + frame0, 0, sizeof(uint32_t) * (size_t)nframes, st);
     if (e != cudaSuccess) return e;
-    const int bpf = (a.W + 127) / 128;
+    const int bpf = (a.W + BIN_THREADS - 1) / BIN_THREADS;
     const long long blocks = (long long)nframes * bpf;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    drr_bin_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, frame0, bpf);
+    drr_bin_kernel<<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a, frame0, bpf);
     return cudaGetLastError();
 }
 
