@@ -34,10 +34,11 @@ namespace drr {
 //               c.x = -top_y (f32)   c.y = -(bottom_y - top_y) (f32)   c.z = refined 1/(bottom_y - top_y)   c.w = uy1
 //               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
+static constexpr uint32_t COL_COVERED = 0x80000000u; // ColIdx.n flag: the column's always-writing spans cover every row
 enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11 };
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
-__device__ __forceinline__ void wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
+__device__ __forceinline__ uint32_t wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
     const BitmapRec bm = a.bitmaps[g.bitmap_slot];
     const uint32_t h = (uint32_t)bm.h;
     uint32_t kind = bm.opaque ? KIND_WALL : KIND_WALL_HOLES;
@@ -77,10 +78,11 @@ __device__ __forceinline__ void wall_record(const DrawArgs &a, const SegRec &g, 
     out[1] = rb;
     out[2] = rc;
     out[3] = rd;
+    return kind;
 }
 
 // Decoded record of a visplane column: the per-plane and per-column constants of draw_visplane / draw_sky
-__device__ __forceinline__ void plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb, uint4 *out) {
+__device__ __forceinline__ uint32_t plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb, uint4 *out) {
     uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rc = make_uint4(0u, 0u, 0u, 0u);
     if (p.kind == KIND_FLAT) {
         // visplanes.rs:112  wz = visplane.height as f32 - player.floor_height - PLAYER_EYE_HEIGHT
@@ -115,6 +117,7 @@ __device__ __forceinline__ void plane_record(const DrawArgs &a, const PlaneRec &
     out[1] = make_uint4(0u, 0u, 0u, 0u);
     out[2] = rc;
     out[3] = make_uint4(0u, 0u, 0u, 0u);
+    return ra.y & 0xffu;
 }
 
 // Walk the ops of frame f in call order and visit what each of them draws in screen column x.  EMIT = false only counts;
@@ -136,8 +139,42 @@ __device__ __forceinline__ uint2 op_range(const DrawArgs &a, uint32_t op) { // (
     return make_uint2((uint32_t)(uint16_t)x0 | ((uint32_t)(uint16_t)x1 << 16), op);
 }
 
+// Coverage of a column by the spans that always write (wall / flat / sky without None texels): when their union is the
+// whole column, every pixel is written at least once and the tile kernel need not clear the column first.  (In the
+// reference's lists a wall and the flat next to it usually share their boundary row, so overlaps are the normal case.)
+// Up to COVER_MAX such spans are tracked; more just means "clear it".
+static constexpr int COVER_MAX = 6;
+struct Cover {
+    uint32_t iv[COVER_MAX];
+    int n = 0;
+    bool overflow = false;
+    __device__ __forceinline__ void add(int ya, int yb) {
+        if (n < COVER_MAX) {
+#pragma unroll
+            for (int i = 0; i < COVER_MAX; ++i)
+                if (i == n) iv[i] = (uint32_t)ya | ((uint32_t)yb << 16);
+            ++n;
+        } else {
+            overflow = true;
+        }
+    }
+    __device__ __forceinline__ bool covers(int H) const { // sweep: extend the covered prefix [0, cur) until it stops growing
+        if (overflow) return false;
+        int cur = 0;
+        for (int pass = 0; pass < COVER_MAX && cur < H; ++pass) {
+            int reach = cur;
+#pragma unroll
+            for (int i = 0; i < COVER_MAX; ++i)
+                if (i < n && (int)(iv[i] & 0xffffu) <= cur) reach = max(reach, (int)(iv[i] >> 16) + 1);
+            if (reach == cur) break;
+            cur = reach;
+        }
+        return cur >= H;
+    }
+};
+
 template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, uint4 *out) {
+__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, uint4 *out, Cover *cover) {
     uint32_t n = 0;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
     for (uint32_t k = 0; k < nops; ++k) {
@@ -151,7 +188,10 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
             if (p.kind == KIND_FLAT && (int)(short)(b - t) <= 1) continue;   // :99-101 (not applied to sky)
             if (t > b) continue;
-            if (EMIT) plane_record(a, p, vw, x, t, b, out + 4 * n);
+            if (EMIT) {
+                const uint32_t k = plane_record(a, p, vw, x, t, b, out + 4 * n);
+                if (k == KIND_FLAT || k == KIND_SKY) cover->add(t, b);
+            }
             ++n;
         } else {
             const SegRec *gp = a.segs + op;
@@ -171,7 +211,9 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             const ColRec c = a.cols[cols_first + i];
             const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
             if (ya > yb) continue;
-            if (EMIT) wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n);
+            if (EMIT) {
+                if (wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n) == KIND_WALL) cover->add(ya, yb);
+            }
             ++n;
         }
     }
@@ -189,14 +231,15 @@ __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int fr
     __syncthreads();
     if (x >= a.W) return;
     const View vw = a.views[f];
-    const uint32_t n = walk_column<false>(a, f, x, vw, s_tab, nullptr);
+    const uint32_t n = walk_column<false>(a, f, x, vw, s_tab, nullptr, nullptr);
     uint32_t first = a.frame_rec_base[f];
     if (n) first += atomicAdd(a.frame_cursor + f, n);
+    Cover cover;
+    if (n) walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
     ColIdx ci;
     ci.first = first;
-    ci.n = n;
+    ci.n = n | (cover.covers(a.H) ? COL_COVERED : 0u);
     a.colidx[(size_t)f * a.W + x] = ci;
-    if (n) walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4);
 }
 
 // sky ty of every screen row (visplanes.rs:68-72: depends on the row only), computed once per context
@@ -366,7 +409,7 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
 template <int TC, int LPG, bool FAST_STORE>
-__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
+__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, unsigned ntiles, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
     __shared__ int s_next;
@@ -375,35 +418,40 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
     constexpr int NW = TILE_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gpf = (a.W + TC - 1) / TC;
-    const unsigned bid = blockIdx.x;
-    const int band = (int)(bid % (unsigned)nbands);
-    const int g = (int)((bid / (unsigned)nbands) % (unsigned)gpf);
-    const int f = frame0 + (int)(bid / ((unsigned)nbands * (unsigned)gpf));
-    const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
-
-    for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
-    for (int i = threadIdx.x; i < (TC * RP + 3) / 4; i += TILE_THREADS) reinterpret_cast<uint4 *>(s_tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x == 0) s_next = NW;
-    __syncthreads();
+    const int grp = lane / LPG, li = lane % LPG;
     const uint32_t pal_addr = (uint32_t)__cvta_generic_to_shared(s_pal);
     const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(s_tile);
     const uint16_t *__restrict__ texels = a.texels;
     const uint8_t *__restrict__ flats = a.flats;
+
+    // the palette is staged once per CTA; the CTA then draws tile bid (and bid + gridDim.x, ... when launched persistent)
+    for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
+    if (threadIdx.x == 0) s_next = NW;
+    for (unsigned bid = blockIdx.x; bid < ntiles; bid += gridDim.x) {
+    __syncthreads(); // palette / s_next visible; the previous tile's write-out has finished reading the tile
+    const int band = (int)(bid % (unsigned)nbands);
+    const int g = (int)((bid / (unsigned)nbands) % (unsigned)gpf);
+    const int f = frame0 + (int)(bid / ((unsigned)nbands * (unsigned)gpf));
+    const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
     const View vw = a.views[f];
     const int px16 = sat_i16(vw.pos_x), py16 = sat_i16(vw.pos_y); // visplanes.rs:119-120 `player.position.x as i16`
-    const int grp = lane / LPG, li = lane % LPG;
 
     // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
     // list in draw order ("last writer wins, transparent texels do not write"): the kinds that always write
     // simply overwrite, the HOLES kinds skip their None texels
     for (int cs = warp; cs < NSETS;) {
-        const int c = cs * G + grp, x = g * TC + c;
+        // the G columns of a set are NSETS apart: their lane groups then store to disjoint bank ranges when they sit on the same rows
+        const int c = grp * NSETS + cs, x = g * TC + c;
         ColIdx ci;
         ci.first = 0; ci.n = 0;
         if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
-        const int n = (int)ci.n;
+        const int n = (int)(ci.n & ~COL_COVERED);
         const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
         const uint32_t col_addr = tile_addr + 4u * (uint32_t)(c * RP);
+        // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
+        // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
+        if (!(ci.n & COL_COVERED))
+            for (int r = li; r <= b1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
         for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
             __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
             if (j < n) {
@@ -438,6 +486,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
         cs = __shfl_sync(0xffffffffu, nx, 0);
     }
     __syncthreads(); // every span of the tile is in before the write-out
+    if (threadIdx.x == 0) s_next = NW; // nobody reads it again before the barrier at the top of the next tile
 
     // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x).  A row of the tile is TC*3 bytes = LPR 16-byte
     // vectors; a warp step covers RPI rows with LPR lanes each.  Vector j of a row holds bytes 16j .. 16j+15, i.e. pixels
@@ -493,6 +542,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
             p[2] = (uint8_t)(rgb >> 16);
         }
     }
+    } // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -533,7 +583,8 @@ template <int TC, int LPG>
 static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
     const int gpf = (a.W + TC - 1) / TC;
     // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
-    const int max_rows = 820;
+    int max_rows = 820;
+    if (const char *e = getenv("DRR_TILE_MAX_ROWS")) max_rows = std::max(32, atoi(e));
     const int nbands = (a.H + max_rows - 1) / max_rows;
     const int band_rows = (a.H + nbands - 1) / nbands;
     const int want = TC == 16 ? 2 : 1;
@@ -542,26 +593,39 @@ static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cud
     const long long blocks = (long long)nframes * gpf * nbands;
     if (blocks == 0) return cudaSuccess;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    const size_t dyn = ((size_t)TC * RP * 4 + 15) / 16 * 16;
+    size_t dyn = ((size_t)TC * RP * 4 + 15) / 16 * 16;
+    if (const char *e = getenv("DRR_TILE_SMEM_PAD_KB")) dyn += (size_t)atoi(e) * 1024; // A/B: fewer CTAs per SM, more L1
     const bool fast = (a.W % TC) == 0;
     *launches = 1;
     cudaError_t e;
+    // one CTA per tile by default; DRR_TILE_PERSISTENT=1 launches only as many CTAs as fit on the device at once, each
+    // walking tiles with that stride
+    auto grid_for = [&](auto kernel, unsigned *grid) -> cudaError_t {
+        static size_t dyn_done = (size_t)-1;
+        static int per_sm = 0, sms = 0;
+        if (dyn_done != dyn) {
+            cudaError_t ee = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (ee != cudaSuccess) return ee;
+            if ((ee = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_THREADS, dyn)) != cudaSuccess) return ee;
+            int dev = 0;
+            if ((ee = cudaGetDevice(&dev)) != cudaSuccess) return ee;
+            if ((ee = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return ee;
+            dyn_done = dyn;
+        }
+        long long cap = (long long)std::max(1, per_sm) * std::max(1, sms);
+        // measured (gpurun_out/sweep: 0.79 vs 0.71 ms at 320x200, 1.53 vs 1.17 ms at 1280x800): one CTA per tile wins, because the
+        // hardware hands tiles to SMs as they free up while a static stride waits for the unluckiest CTA; kept as an A/B knob
+        if (!getenv("DRR_TILE_PERSISTENT")) cap = blocks;
+        *grid = (unsigned)std::min<long long>(blocks, cap);
+        return cudaSuccess;
+    };
+    unsigned grid = 0;
     if (fast) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(drr_tile_kernel<TC, LPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        drr_tile_kernel<TC, LPG, true><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, frame0, band_rows, nbands, RP);
+        if ((e = grid_for(drr_tile_kernel<TC, LPG, true>, &grid)) != cudaSuccess) return e;
+        drr_tile_kernel<TC, LPG, true><<<grid, TILE_THREADS, dyn, st>>>(a, frame0, (unsigned)blocks, band_rows, nbands, RP);
     } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(drr_tile_kernel<TC, LPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        drr_tile_kernel<TC, LPG, false><<<(unsigned)blocks, TILE_THREADS, dyn, st>>>(a, frame0, band_rows, nbands, RP);
+        if ((e = grid_for(drr_tile_kernel<TC, LPG, false>, &grid)) != cudaSuccess) return e;
+        drr_tile_kernel<TC, LPG, false><<<grid, TILE_THREADS, dyn, st>>>(a, frame0, (unsigned)blocks, band_rows, nbands, RP);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         e = launch_checksum_pass(a, frame0, nframes, st, launches);

@@ -69,7 +69,10 @@ def test_device_binning_equals_host_restatement(W, H, kind):
     ci_dev, recs = ctx.device_bins(len(views))
     spans, ci_host = ctx._list(3, drr.SPAN_DTYPE), ctx._list(4, drr.COLIDX_DTYPE)
     assert len(ci_dev) == len(ci_host) == len(views) * W
+    covered = (ci_dev["n"] >> 31).astype(bool)  # bin kernel's flag: the always-writing spans cover every row of the column
+    ci_dev["n"] &= 0x7FFFFFFF
     assert (ci_dev["n"] == ci_host["n"]).all()
+    assert kind != "e1m1" or covered.mean() > 0.5
     assert int(ci_host["n"].sum()) == ctx.stats()["spans"] == len(spans)
     # every device range lies inside its frame's record range and ranges do not overlap
     order = np.argsort(ci_dev["first"], kind="stable")
@@ -82,6 +85,14 @@ def test_device_binning_equals_host_restatement(W, H, kind):
         assert ((d[:, 0] & 0xFFFF) == h["y0"]).all() and ((d[:, 0] >> 16) == h["y1"]).all(), i
         kind_d = d[:, 1] & 0xFF
         assert ((kind_d == h["kind"]) | (kind_d == 7)).all(), i  # 7 = column the reference would have panicked on
+        rows = np.zeros(H, np.int32)
+        for k, sp in zip(kind_d, h):
+            if k in (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY):
+                rows[sp["y0"]:sp["y1"] + 1] += 1
+        if covered[i]:
+            assert (rows >= 1).all(), i
+        elif int(np.isin(kind_d, (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY)).sum()) <= 6:
+            assert not (rows >= 1).all(), i
 
 
 def test_config1_spawn_viewpoint():
