@@ -115,7 +115,8 @@ struct drr_ctx {
     DevBuf<uint4> d_tparams; // 4 x uint4 per record
     uint8_t *d_sky_rows = nullptr;
     size_t uploaded_frames = 0;
-    uint64_t rec_count = 0; // records of all frames recorded so far
+    uint64_t rec_count = 0; // columns that survive clipping, all frames recorded so far (statistics)
+    uint64_t rec_cap = 0;   // screen columns inside the x ranges of all ops recorded so far: what the bin kernel may reserve (>= rec_count)
     std::vector<int> slot_to_frame; // view slot -> recorded frame (or -1)
 
     uint8_t *d_frames = nullptr;
@@ -126,7 +127,7 @@ struct drr_ctx {
     // frame being recorded
     bool in_frame = false;
     size_t ops_n0 = 0, segs_n0 = 0, cols_n0 = 0, planes_n0 = 0, parr_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
-    uint64_t rec0 = 0;
+    uint64_t rec0 = 0, cap0 = 0;
     drr_stats stats0{};
     int cur_slot = -1;
 
@@ -370,7 +371,7 @@ static bool push_frame_bases(drr_ctx *ctx) {
     ctx->frame_col_base.push_back((uint32_t)ctx->cols.n);
     ctx->frame_plane_base.push_back((uint32_t)ctx->planes.n);
     ctx->frame_parr_base.push_back((uint32_t)ctx->parr.n);
-    return ctx->frame_op_base.push((uint32_t)ctx->ops.n) && ctx->frame_rec_base.push((uint32_t)ctx->rec_count);
+    return ctx->frame_op_base.push((uint32_t)ctx->ops.n) && ctx->frame_rec_base.push((uint32_t)ctx->rec_cap);
 }
 
 int drr_reset(drr_ctx *ctx) {
@@ -391,7 +392,7 @@ int drr_reset(drr_ctx *ctx) {
     ctx->frame_parr_base.clear();
     ctx->t_spans.clear();
     ctx->t_colidx.clear();
-    ctx->rec_count = 0;
+    ctx->rec_count = ctx->rec_cap = 0;
     ctx->uploaded_frames = 0;
     std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
     const uint64_t launches = ctx->stats.kernel_launches;
@@ -415,6 +416,7 @@ int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
     ctx->planes_n0 = ctx->planes.n;
     ctx->parr_n0 = ctx->parr.n;
     ctx->rec0 = ctx->rec_count;
+    ctx->cap0 = ctx->rec_cap;
     ctx->stats0 = ctx->stats;
     ctx->cur_slot = view_idx;
     ctx->in_frame = true;
@@ -435,6 +437,7 @@ int drr_frame_abort(drr_ctx *ctx) {
     ctx->planes.n = ctx->planes_n0;
     ctx->parr.n = ctx->parr_n0;
     ctx->rec_count = ctx->rec0;
+    ctx->rec_cap = ctx->cap0;
     ctx->slot_to_frame[ctx->cur_slot] = -1;
     const uint64_t launches = ctx->stats.kernel_launches;
     ctx->stats = ctx->stats0;
@@ -484,6 +487,8 @@ int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, 
             if (c.x < 0 || c.x >= W) continue;
             if (std::max<int>(c.clipped_top_y, 0) <= std::min<int>(c.clipped_bottom_y, H - 1)) ctx->rec_count++;
         }
+        // the bin kernel reserves one record slot per screen column inside the run's x range (its records may be sparser)
+        ctx->rec_cap += (uint64_t)std::max(0, std::min<int>(r.x1, W - 1) - std::max<int>(r.x0, 0) + 1);
         if (!ctx->ops.push((uint32_t)ctx->segs.n) || !ctx->segs.push(r)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
         i = j;
     }
@@ -524,6 +529,7 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
         if (p.kind == (int16_t)KIND_FLAT && (int16_t)(b - t) <= 1) continue; // :99-101 (not applied to sky)
         if (t <= b) ctx->rec_count++;
     }
+    ctx->rec_cap += (uint64_t)ncols;
     if (ncols > 0 && (!ctx->ops.push(0x80000000u | (uint32_t)ctx->planes.n) || !ctx->planes.push(p))) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
     ctx->stats.visplanes++;
     ctx->stats.visplane_columns += (uint64_t)ncols;
@@ -533,7 +539,7 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
 int drr_frame_end(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_end outside a frame");
-    if (ctx->rec_count > 0xffffffffull || ctx->cols.n > 0xffffffffull || ctx->parr.n > 0xffffffffull) {
+    if (ctx->rec_cap > 0xffffffffull || ctx->cols.n > 0xffffffffull || ctx->parr.n > 0xffffffffull) {
         drr_frame_abort(ctx);
         return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 column records");
     }
@@ -557,7 +563,7 @@ static int reserve_device_lists(drr_ctx *ctx) {
     CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
     CU(ctx, ctx->d_parr.reserve(std::max<size_t>(ctx->parr.n, 1)));
     CU(ctx, ctx->d_colidx.reserve(nf * (size_t)ctx->W));
-    CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->rec_count, 1) * 4));
+    CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->rec_cap, 1) * 4));
     return DRR_OK;
 }
 
@@ -934,15 +940,15 @@ const void *drr_test_list(drr_ctx *ctx, int which, uint64_t *count, uint64_t *el
     }
 }
 // What the bin kernel produced for the uploaded batch: colidx_out = nframes * W (first, n) pairs, recs_out = two words per
-// record (y0 | y1 << 16, kind | flags), indexed by the `first` values of colidx_out.
+// record slot (y0 | y1 << 16, kind | flags), indexed by the `first` values of colidx_out; *nrec = number of slots.
 int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
-    if (ctx->rec_count)
-        CU(ctx, cudaMemcpy2D(recs_out, 8, ctx->d_tparams.p, 64, 8, (size_t)ctx->rec_count, cudaMemcpyDeviceToHost));
+    if (ctx->rec_cap)
+        CU(ctx, cudaMemcpy2D(recs_out, 8, ctx->d_tparams.p, 64, 8, (size_t)ctx->rec_cap, cudaMemcpyDeviceToHost));
     return DRR_OK;
 }
 // bitmap slot -> (w, h, opaque); flat_slot/bitmap_slot resolve ids the way the device tables do

@@ -23,7 +23,7 @@ struct DrawArgs {
     const View *views;               // [nframes]
     const uint32_t *ops;             // per frame, in call order: bit 31 = visplane, low bits = index into planes[] / segs[]
     const uint32_t *frame_op_base;   // [nframes + 1]
-    const uint32_t *frame_rec_base;  // [nframes + 1] first TileSpan of each frame (exact: the host counts valid columns at emit time)
+    const uint32_t *frame_rec_base;  // [nframes + 1] first record slot of each frame (one slot per emitted column: an upper bound)
     const uint32_t *frame_slot;      // framebuffer slot (view index) of each recorded frame
     const SegRec *segs;
     const ColRec *cols;

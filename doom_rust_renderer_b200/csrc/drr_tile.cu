@@ -231,11 +231,17 @@ __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int fr
     __syncthreads();
     if (x >= a.W) return;
     const View vw = a.views[f];
-    const uint32_t n = walk_column<false>(a, f, x, vw, s_tab, nullptr, nullptr);
+    // reserve one record per op whose x range contains the column (an upper bound of what survives clipping; the frame's
+    // record range is sized by the host from the same bound): this pass touches shared memory only
+    uint32_t cap = 0;
+    for (uint32_t k = 0; k < nops; ++k) {
+        const uint32_t r = k < (uint32_t)BIN_TAB ? s_tab[k].x : op_range(a, a.ops[o0 + k]).x;
+        cap += (x >= (int)(short)(r & 0xffffu) && x <= (int)(short)(r >> 16)) ? 1u : 0u;
+    }
     uint32_t first = a.frame_rec_base[f];
-    if (n) first += atomicAdd(a.frame_cursor + f, n);
+    if (cap) first += atomicAdd(a.frame_cursor + f, cap);
     Cover cover;
-    if (n) walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
+    const uint32_t n = cap ? walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover) : 0u;
     ColIdx ci;
     ci.first = first;
     ci.n = n | (cover.covers(a.H) ? COL_COVERED : 0u);

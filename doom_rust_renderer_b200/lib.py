@@ -246,7 +246,7 @@ class Context:
     def device_bins(self, nframes: int):
         """(colidx [nframes*W] of COLIDX_DTYPE, recs [n][2] u32 = (y0 | y1 << 16, kind | flags)) as the bin kernel wrote them."""
         ci = np.zeros(nframes * self.W, COLIDX_DTYPE)
-        recs = np.zeros((max(1, self.stats()["spans"]), 2), np.uint32)
+        recs = np.zeros((max(1, int(self._list(5, np.uint32)[-1])), 2), np.uint32)  # one slot per emitted column
         self._ck(self.L.drr_test_device_bins(self.h, _ptr(ci), _ptr(recs)))
         return ci, recs
 

@@ -78,7 +78,7 @@ def test_device_binning_equals_host_restatement(W, H, kind):
     order = np.argsort(ci_dev["first"], kind="stable")
     nz = order[ci_dev["n"][order] > 0]
     ends = ci_dev["first"][nz].astype(np.int64) + ci_dev["n"][nz]
-    assert (ends[:-1] <= ci_dev["first"][nz][1:]).all() and ends[-1] <= len(spans)
+    assert (ends[:-1] <= ci_dev["first"][nz][1:]).all() and ends[-1] <= len(recs)
     for i in np.nonzero(ci_host["n"])[0]:
         h = spans[ci_host["first"][i]:ci_host["first"][i] + ci_host["n"][i]]
         d = recs[ci_dev["first"][i]:ci_dev["first"][i] + ci_dev["n"][i]]
