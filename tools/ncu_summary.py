@@ -4,9 +4,10 @@ usage: ncu_summary.py report.ncu-rep pixels_per_launch [min_share]"""
 import csv, subprocess, sys, io
 rep, pixels = sys.argv[1], float(sys.argv[2])
 min_share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+kidx = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # which captured launch of the report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-d = dict(zip(rows[0], rows[2]))
+d = dict(zip(rows[0], rows[2 + kidx]))
 print("kernel:", d.get("Kernel Name"), "grid", d.get("Grid Size"), "block", d.get("Block Size"))
 keys = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
@@ -26,7 +27,11 @@ for k in rows[0]:
 ie = float(d["smsp__inst_executed.sum"])
 print("  warp-instructions per pixel x32 (issue slots per pixel): %.2f" % (ie * 32 / pixels))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
+allrows = list(csv.reader(io.StringIO(src)))
+starts = [i for i, r in enumerate(allrows) if r and r[0].startswith("Kernel Name")]
+lo = starts[kidx]
+hi = starts[kidx + 1] if kidx + 1 < len(starts) else len(allrows)
+rows = allrows[lo:hi]
 hdr = rows[1]
 ia, isrc, ith = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("Thread Instructions Executed")
 R = [(int(r[ia]), r[isrc].strip(), int(r[ith])) for r in rows[2:] if len(r) > ia]
