@@ -39,8 +39,8 @@ WORKLOADS = {
     "walk1280": ("e1m1", 1280, 800, 512, 7, "E1M1-class walk, 512 viewpoints, 1280x800, all phases (north_star target resolution)"),
     "walls1280": ("e1m1", 1280, 800, 256, 1, "BASELINE configs[2]: walls only, 1280x800"),
     "flats1280": ("e1m1", 1280, 800, 256, 2, "BASELINE configs[2]: flats+sky only, 1280x800"),
-    "things640": ("e1m1", 640, 400, 4096, 7, "BASELINE configs[3]: things, masked mids, lighting, 640x400"),
-    "stress1920": ("stress", 1920, 1200, 256, 7, "BASELINE configs[4] map at 1920x1200 (bounded viewpoint count)"),
+    "things640": ("e1m1", 640, 400, 1024, 7, "BASELINE configs[3]: things, masked mids, lighting, 640x400 (bounded viewpoint count)"),
+    "stress1920": ("stress", 1920, 1200, 128, 7, "BASELINE configs[4] map at 1920x1200 (bounded viewpoint count)"),
 }
 
 
@@ -230,6 +230,13 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
     setup_ms = setup_ms_tot / max(prof_steps, 1)
     peak, peak_src = measured_peak()
     achieved = alg_bytes_launch / (march_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes of one tile-kernel launch: per-frame figure from the committed ncu capture x frames of this launch
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if name in tj and args.views == 0:
+            traffic = tj[name]["dram_bytes_per_frame"] * n_views
+    except Exception:
+        pass
     res = {
         "workload": name, "desc": desc, "W": W, "H": H, "views_per_gpu": n_views, "phases": phases,
         "value": px_total / (ms_step * 1e-3) / 1e6, "frames_per_s": frames_total / (ms_step * 1e-3), "ms_per_step": ms_step,
@@ -237,7 +244,8 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         "h2d_bytes_per_step": st["device_list_bytes"], "d2h_bytes_per_step": 8 * n_views,
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": traffic,
+                     "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames)" if traffic else None,
                      "algorithmic_bytes_per_launch": alg_bytes_launch, "framebuffer_bytes_per_launch": 3 * W * H * n_views,
                      "drawlist_bytes_per_launch": st["drawlist_bytes_algorithmic"], "kernel_ms": march_ms, "setup_ms": setup_ms,
                      "kernel_share_of_step": march_ms / (march_ms + setup_ms) if march_ms + setup_ms > 0 else None},
@@ -348,7 +356,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="walk320", choices=sorted(WORKLOADS))
     ap.add_argument("--views", type=int, default=0, help="override viewpoints per GPU")
-    ap.add_argument("--secondary", default="walk1280,walls1280,flats1280", help="extra workloads reported under 'secondary' (N=1 only); '' = none")
+    ap.add_argument("--secondary", default="walk1280,walls1280,flats1280,things640,stress1920", help="extra workloads reported under 'secondary' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -155,6 +155,28 @@ def test_recording_state_machine_and_validation():
     assert ctx.stats()["frames"] == 0
 
 
+def test_sass_keeps_products_and_sums_apart():
+    """ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although both are explicitly rounded, which would
+    change results (one rounding instead of two).  drr_tile.cu adds such products with fma(p, one, c), `one` coming from
+    the kernel arguments; here the shipped SASS is checked for it: the tile kernels use the packed instructions, every
+    `one` multiply is there (an FFMA2 whose multiplier is a uniform register), and no truncating add got fused."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", drr.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels = re.split(r"\n\s*Function : ", sass)
+    tile = [k for k in kernels if "drr_tile_kernel" in k.split("\n", 1)[0]]
+    assert len(tile) >= 12  # 2 tile widths x 3 lane-group sizes x 2 store paths
+    for k in tile:
+        name = k.split("\n", 1)[0]
+        assert "FMUL2" in k and "FFMA2" in k and "FADD2" in k, name
+        # (c*f) + 2^23 must stay FMUL then FADD.RZ (the only FFMA.RZ allowed is the one inside the IEEE division subroutine)
+        assert "FFMA2.RZ" not in k and not re.search(r"FFMA\.RZ [^;]*8388608", k), name
+        assert len(re.findall(r"FADD2?\.RZ [^;]*8388608", k)) >= 4, name
+        assert len(re.findall(r"FFMA2 [^;]*UR\d+\.F32", k)) >= 6, name    # wall sum, rx, ry, factor (x2 loop copies at least)
+
+
 def test_checksum_definitions_agree():
     rng = np.random.default_rng(0)
     for n in (0, 1, 3, 4, 5, 192000, 1000 * 3):
