@@ -173,21 +173,40 @@ struct Cover {
     }
 };
 
+// Visit, in call order, the ops of the frame whose x range touches the warp's 32 columns [wx0, wx0 + 31]: 32 table
+// entries are tested at a time (one per lane), the survivors are handed to every lane through a ballot.  All 32 lanes of
+// the warp must call it together.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const DrawArgs &a, uint32_t o0, uint32_t nops, int wx0, const uint2 *s_tab, F visit) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = 0; base < nops; base += 32) {
+        const uint32_t k = base + (uint32_t)lane;
+        uint2 e = make_uint2(1u, 0u); // empty range
+        if (k < nops) e = k < (uint32_t)BIN_TAB ? s_tab[k] : op_range(a, a.ops[o0 + k]);
+        const int ex0 = (int)(short)(e.x & 0xffffu), ex1 = (int)(short)(e.x >> 16);
+        uint32_t m = __ballot_sync(0xffffffffu, ex0 <= ex1 && ex1 >= wx0 && ex0 <= wx0 + 31);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            visit(make_uint2(__shfl_sync(0xffffffffu, e.x, src), __shfl_sync(0xffffffffu, e.y, src)));
+        }
+    }
+}
+
 template <bool EMIT>
 __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, uint4 *out, Cover *cover) {
     uint32_t n = 0;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
-    for (uint32_t k = 0; k < nops; ++k) {
-        const uint2 e = k < (uint32_t)BIN_TAB ? s_tab[k] : op_range(a, a.ops[o0 + k]);
-        if (x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) continue;
+    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e) {
+        if (x >= a.W || x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) return; // (Pixels::set ignores x >= W)
         const uint32_t op = e.y;
         if (op & 0x80000000u) {
             const PlaneRec p = a.planes[op & 0x7fffffffu];
             const uint32_t tb = a.parr[p.arr_first + (uint32_t)(x - p.left)];
             const int t = max((int)(short)(tb & 0xffffu), 0);                // visplanes.rs:61 / :95
             const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
-            if (p.kind == KIND_FLAT && (int)(short)(b - t) <= 1) continue;   // :99-101 (not applied to sky)
-            if (t > b) continue;
+            if (p.kind == KIND_FLAT && (int)(short)(b - t) <= 1) return;     // :99-101 (not applied to sky)
+            if (t > b) return;
             if (EMIT) {
                 const uint32_t k = plane_record(a, p, vw, x, t, b, out + 4 * n);
                 if (k == KIND_FLAT || k == KIND_SKY) cover->add(t, b);
@@ -205,18 +224,18 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
                     const uint32_t mid = (lo + hi) >> 1;
                     if (a.cols[cols_first + mid].x < x) lo = mid + 1; else hi = mid;
                 }
-                if (lo >= gn || a.cols[cols_first + lo].x != x) continue;
+                if (lo >= gn || a.cols[cols_first + lo].x != x) return;
                 i = lo;
             }
             const ColRec c = a.cols[cols_first + i];
             const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
-            if (ya > yb) continue;
+            if (ya > yb) return;
             if (EMIT) {
                 if (wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n) == KIND_WALL) cover->add(ya, yb);
             }
             ++n;
         }
-    }
+    });
     return n;
 }
 
@@ -229,23 +248,26 @@ __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int fr
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
     for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += BIN_THREADS) s_tab[k] = op_range(a, a.ops[o0 + k]);
     __syncthreads();
-    if (x >= a.W) return;
+    if ((x & ~31) >= a.W) return; // whole warps only: the candidate walk is a warp-wide operation
+    const bool live = x < a.W;
     const View vw = a.views[f];
     // reserve one record per op whose x range contains the column (an upper bound of what survives clipping; the frame's
     // record range is sized by the host from the same bound): this pass touches shared memory only
     uint32_t cap = 0;
-    for (uint32_t k = 0; k < nops; ++k) {
-        const uint32_t r = k < (uint32_t)BIN_TAB ? s_tab[k].x : op_range(a, a.ops[o0 + k]).x;
-        cap += (x >= (int)(short)(r & 0xffffu) && x <= (int)(short)(r >> 16)) ? 1u : 0u;
-    }
+    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e) {
+        cap += (live && x >= (int)(short)(e.x & 0xffffu) && x <= (int)(short)(e.x >> 16)) ? 1u : 0u;
+    });
     uint32_t first = a.frame_rec_base[f];
     if (cap) first += atomicAdd(a.frame_cursor + f, cap);
     Cover cover;
-    const uint32_t n = cap ? walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover) : 0u;
-    ColIdx ci;
-    ci.first = first;
-    ci.n = n | (cover.covers(a.H) ? COL_COVERED : 0u);
-    a.colidx[(size_t)f * a.W + x] = ci;
+    // (a dead lane of a partly live warp, x >= W, visits nothing: it only takes part in the ballots)
+    const uint32_t n = walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
+    if (live) {
+        ColIdx ci;
+        ci.first = first;
+        ci.n = n | (cover.covers(a.H) ? COL_COVERED : 0u);
+        a.colidx[(size_t)f * a.W + x] = ci;
+    }
 }
 
 // sky ty of every screen row (visplanes.rs:68-72: depends on the row only), computed once per context
@@ -571,9 +593,10 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
 }
 
 void tile_config(int W, int H, int *tc, int *lpg) {
-    // measured (tools/sweep_tile.sh, profiles/r1_tile_geometry.md): 16-column full-height tiles with 16 lanes per span at
-    // 1280x800, 32-column tiles with 8 lanes per span at 320x200 -- short lane groups keep the warp full on short spans
-    *tc = H >= 400 ? 16 : 32;
+    // measured (tools/sweep_tile.sh, tools/sweep_env.sh; profiles/r1_ab_measurements.md): 16-column full-height tiles with 16
+    // lanes per span at 1280x800, 32-column tiles with 8 lanes per span at 320x200 and 640x400 -- short lane groups keep the
+    // warp full on short spans
+    *tc = H >= 600 ? 16 : 32;
     *lpg = H >= 600 ? 16 : 8;
     if (const char *e = getenv("DRR_TILE_COLS")) {
         const int v = atoi(e);
