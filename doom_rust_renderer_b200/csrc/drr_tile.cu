@@ -437,7 +437,7 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
 template <int TC, int LPG, bool FAST_STORE>
-__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, unsigned ntiles, int band_rows, int nbands, int RP) {
+__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
     __shared__ int s_next;
@@ -452,14 +452,16 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
     const uint16_t *__restrict__ texels = a.texels;
     const uint8_t *__restrict__ flats = a.flats;
 
-    // the palette is staged once per CTA; the CTA then draws tile bid (and bid + gridDim.x, ... when launched persistent)
+    // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
     for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
     if (threadIdx.x == 0) s_next = NW;
-    for (unsigned bid = blockIdx.x; bid < ntiles; bid += gridDim.x) {
-    __syncthreads(); // palette / s_next visible; the previous tile's write-out has finished reading the tile
-    const int band = (int)(bid % (unsigned)nbands);
-    const int g = (int)((bid / (unsigned)nbands) % (unsigned)gpf);
-    const int f = frame0 + (int)(bid / ((unsigned)nbands * (unsigned)gpf));
+    __syncthreads();
+    int g = (int)blockIdx.x, band = 0;
+    if (nbands > 1) {
+        g = (int)(blockIdx.x / (unsigned)nbands);
+        band = (int)blockIdx.x - g * nbands;
+    }
+    const int f = frame0 + (int)blockIdx.y;
     const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
     const View vw = a.views[f];
     const int px16 = sat_i16(vw.pos_x), py16 = sat_i16(vw.pos_y); // visplanes.rs:119-120 `player.position.x as i16`
@@ -514,7 +516,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
         cs = __shfl_sync(0xffffffffu, nx, 0);
     }
     __syncthreads(); // every span of the tile is in before the write-out
-    if (threadIdx.x == 0) s_next = NW; // nobody reads it again before the barrier at the top of the next tile
 
     // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x).  A row of the tile is TC*3 bytes = LPR 16-byte
     // vectors; a warp step covers RPI rows with LPR lanes each.  Vector j of a row holds bytes 16j .. 16j+15, i.e. pixels
@@ -570,7 +571,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
             p[2] = (uint8_t)(rgb >> 16);
         }
     }
-    } // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -627,34 +627,26 @@ static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cud
     const bool fast = (a.W % TC) == 0;
     *launches = 1;
     cudaError_t e;
-    // one CTA per tile by default; DRR_TILE_PERSISTENT=1 launches only as many CTAs as fit on the device at once, each
-    // walking tiles with that stride
-    auto grid_for = [&](auto kernel, unsigned *grid) -> cudaError_t {
-        static size_t dyn_done = (size_t)-1;
-        static int per_sm = 0, sms = 0;
-        if (dyn_done != dyn) {
-            cudaError_t ee = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (ee != cudaSuccess) return ee;
-            if ((ee = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_THREADS, dyn)) != cudaSuccess) return ee;
-            int dev = 0;
-            if ((ee = cudaGetDevice(&dev)) != cudaSuccess) return ee;
-            if ((ee = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return ee;
-            dyn_done = dyn;
-        }
-        long long cap = (long long)std::max(1, per_sm) * std::max(1, sms);
-        // measured (gpurun_out/sweep: 0.79 vs 0.71 ms at 320x200, 1.53 vs 1.17 ms at 1280x800): one CTA per tile wins, because the
-        // hardware hands tiles to SMs as they free up while a static stride waits for the unluckiest CTA; kept as an A/B knob
-        if (!getenv("DRR_TILE_PERSISTENT")) cap = blocks;
-        *grid = (unsigned)std::min<long long>(blocks, cap);
-        return cudaSuccess;
+    auto prepare = [&](auto kernel) -> cudaError_t {
+        static bool done = false;
+        if (done) return cudaSuccess;
+        done = true;
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     };
-    unsigned grid = 0;
-    if (fast) {
-        if ((e = grid_for(drr_tile_kernel<TC, LPG, true>, &grid)) != cudaSuccess) return e;
-        drr_tile_kernel<TC, LPG, true><<<grid, TILE_THREADS, dyn, st>>>(a, frame0, (unsigned)blocks, band_rows, nbands, RP);
-    } else {
-        if ((e = grid_for(drr_tile_kernel<TC, LPG, false>, &grid)) != cudaSuccess) return e;
-        drr_tile_kernel<TC, LPG, false><<<grid, TILE_THREADS, dyn, st>>>(a, frame0, (unsigned)blocks, band_rows, nbands, RP);
+    // one CTA per tile (a persistent variant with a static tile stride was measured and lost: profiles/r1_ab_measurements.md)
+    if ((long long)gpf * nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    for (int f0 = 0; f0 < nframes; f0 += 65535) { // gridDim.y limit
+        const dim3 grid((unsigned)(gpf * nbands), (unsigned)std::min(65535, nframes - f0));
+        if (fast) {
+            if ((e = prepare(drr_tile_kernel<TC, LPG, true>)) != cudaSuccess) return e;
+            drr_tile_kernel<TC, LPG, true><<<grid, TILE_THREADS, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
+        } else {
+            if ((e = prepare(drr_tile_kernel<TC, LPG, false>)) != cudaSuccess) return e;
+            drr_tile_kernel<TC, LPG, false><<<grid, TILE_THREADS, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
+        }
+        if (f0) ++*launches;
+    }
+    if (!fast) {
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         e = launch_checksum_pass(a, frame0, nframes, st, launches);
