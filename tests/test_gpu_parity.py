@@ -351,6 +351,35 @@ def test_redraw_is_idempotent_and_checksum_of_checksums():
         assert int(host.sum(dtype=np.uint64)) == int(c1.sum(dtype=np.uint64))
 
 
+def test_pipelined_submit_equals_upload_then_draw(monkeypatch):
+    """drr_submit cuts the batch into chunks of frames (copy stream + two compute streams); any chunking must give what
+    drr_upload_lists + drr_draw gives, and drawing the same lists again after another batch reuses the buffers correctly."""
+    path, gm = common.wad("e1m1")
+    W, H, n = 320, 200, 23
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::150], n)
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views) == []
+    ctx.upload_lists()
+    ctx.draw()
+    ctx.sync()
+    want = ctx.read_checksums(0, n)
+    frame7 = ctx.read_framebuffer(7)
+    assert int(want[7]) == drr.checksum_numpy(game.render(*[float(t) for t in views[7]]))
+    for chunks in ("1", "2", "5", "23", "64"):
+        monkeypatch.setenv("DRR_SUBMIT_CHUNKS", chunks)
+        ctx.submit()
+        ctx.submit()  # back to back: the second upload must wait for the first draw
+        ctx.sync()
+        assert (ctx.read_checksums(0, n) == want).all(), chunks
+        assert (ctx.read_framebuffer(7) == frame7).all(), chunks
+    monkeypatch.setenv("DRR_SUBMIT_ONE_STREAM", "1")
+    ctx.submit()
+    assert (ctx.read_checksums(0, n) == want).all()
+
+
 def test_error_paths():
     ctx = drr.Context(64, 32, 0, 1)
     with pytest.raises(drr.DrrError):

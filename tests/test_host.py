@@ -182,3 +182,20 @@ def test_checksum_definitions_agree():
     for n in (0, 1, 3, 4, 5, 192000, 1000 * 3):
         b = rng.integers(0, 256, n, dtype=np.uint8)
         assert drr.checksum_host(b) == drr.checksum_numpy(b)
+
+
+def test_png_export_roundtrip():
+    """Presentation/export: an RGB24 frame written as PNG decodes to the same bytes."""
+    from doom_rust_renderer_b200 import png
+    path, gm = common.wad("tiny")
+    game = orc.Game(path, "E1M1", 96, 64)
+    x, y, a = game.player_start()
+    img = game.render(x, y, a)
+    data = png.encode_png(img)
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    assert (png.decode_png(data) == img).all()
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (7, 5, 3), dtype=np.uint8)
+    assert (png.decode_png(png.encode_png(noise)) == noise).all()
+    with pytest.raises(ValueError):
+        png.encode_png(np.zeros((4, 4), np.uint8))
