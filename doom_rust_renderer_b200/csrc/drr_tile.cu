@@ -436,14 +436,14 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // TC  = screen columns per tile (16: 48-byte row segments, 3 lanes x 10 rows per write-out step; 32: 96 bytes, 6 lanes x 5 rows)
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
-template <int TC, int LPG, bool FAST_STORE>
-__global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
+template <int TC, int LPG, int NT, int NSPLIT, bool FAST_STORE>
+__global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
     __shared__ int s_next;
     constexpr int G = 32 / LPG;          // columns per warp step
     constexpr int NSETS = TC / G;
-    constexpr int NW = TILE_THREADS / 32;
+    constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gpf = (a.W + TC - 1) / TC;
     const int grp = lane / LPG, li = lane % LPG;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
     const uint8_t *__restrict__ flats = a.flats;
 
     // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
-    for (int i = threadIdx.x; i < 257; i += TILE_THREADS) s_pal[i] = a.palette[min(i, 255)];
+    for (int i = threadIdx.x; i < 257; i += NT) s_pal[i] = a.palette[min(i, 255)];
     if (threadIdx.x == 0) s_next = NW;
     __syncthreads();
     int g = (int)blockIdx.x, band = 0;
@@ -469,7 +469,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
     // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
     // list in draw order ("last writer wins, transparent texels do not write"): the kinds that always write
     // simply overwrite, the HOLES kinds skip their None texels
-    for (int cs = warp; cs < NSETS;) {
+    // (NSPLIT > 1: a work item is a column set x one of NSPLIT row ranges of the band, so that more warps than column sets
+    // have work; spans are clipped to the item's rows, which keeps the draw order where it matters: on the same pixel)
+    const int prow = (b1 - b0 + NSPLIT) / NSPLIT;
+    for (int item = warp; item < NSETS * NSPLIT;) {
+        const int cs = NSPLIT > 1 ? item % NSETS : item, part = NSPLIT > 1 ? item / NSETS : 0;
+        const int pb0 = b0 + part * prow, pb1 = min(b1, pb0 + prow - 1);
         // the G columns of a set are NSETS apart: their lane groups then store to disjoint bank ranges when they sit on the same rows
         const int c = grp * NSETS + cs, x = g * TC + c;
         ColIdx ci;
@@ -481,12 +486,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
         // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
         if (!(ci.n & COL_COVERED))
-            for (int r = li; r <= b1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
+            for (int r = pb0 - b0 + li; r <= pb1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
         for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
             __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
             if (j < n) {
                 const uint4 ra = P[4 * j];
-                const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
+                const int ya = max((int)(ra.x & 0xffff), pb0), yb = min((int)(ra.x >> 16), pb1);
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
                     if (kind == KIND_FLAT) {
@@ -513,7 +518,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
         }
         int nx = 0;
         if (lane == 0) nx = atomicAdd(&s_next, 1);
-        cs = __shfl_sync(0xffffffffu, nx, 0);
+        item = __shfl_sync(0xffffffffu, nx, 0);
     }
     __syncthreads(); // every span of the tile is in before the write-out
 
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TC == 32 ? TILE_MIN_BLOCKS_SHORT
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long *>(a.crc + slot), (unsigned long long)acc);
     } else {
-        for (int i = threadIdx.x; i < TC * nrows; i += TILE_THREADS) { // generic widths: bytewise; the checksum is a separate pass
+        for (int i = threadIdx.x; i < TC * nrows; i += NT) { // generic widths: bytewise; the checksum is a separate pass
             const int c = i % TC, r = i / TC, x = g * TC + c;
             if (x >= a.W) continue;
             const uint32_t rgb = s_tile[c * RP + r];
@@ -608,7 +613,7 @@ void tile_config(int W, int H, int *tc, int *lpg) {
     }
 }
 
-template <int TC, int LPG>
+template <int TC, int LPG, int NT, int NSPLIT>
 static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
     const int gpf = (a.W + TC - 1) / TC;
     // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
@@ -638,11 +643,11 @@ static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cud
     for (int f0 = 0; f0 < nframes; f0 += 65535) { // gridDim.y limit
         const dim3 grid((unsigned)(gpf * nbands), (unsigned)std::min(65535, nframes - f0));
         if (fast) {
-            if ((e = prepare(drr_tile_kernel<TC, LPG, true>)) != cudaSuccess) return e;
-            drr_tile_kernel<TC, LPG, true><<<grid, TILE_THREADS, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
+            if ((e = prepare(drr_tile_kernel<TC, LPG, NT, NSPLIT, true>)) != cudaSuccess) return e;
+            drr_tile_kernel<TC, LPG, NT, NSPLIT, true><<<grid, NT, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
         } else {
-            if ((e = prepare(drr_tile_kernel<TC, LPG, false>)) != cudaSuccess) return e;
-            drr_tile_kernel<TC, LPG, false><<<grid, TILE_THREADS, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
+            if ((e = prepare(drr_tile_kernel<TC, LPG, NT, NSPLIT, false>)) != cudaSuccess) return e;
+            drr_tile_kernel<TC, LPG, NT, NSPLIT, false><<<grid, NT, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
         }
         if (f0) ++*launches;
     }
@@ -659,13 +664,21 @@ cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t
     int tc, lpg;
     tile_config(a.W, a.H, &tc, &lpg);
     if (tc == 16) {
-        if (lpg == 32) return launch_tile_t<16, 32>(a, frame0, nframes, st, launches);
-        if (lpg == 16) return launch_tile_t<16, 16>(a, frame0, nframes, st, launches);
-        return launch_tile_t<16, 8>(a, frame0, nframes, st, launches);
+        // A/B knob DRR_TILE_SPLIT=2: 12 warps (40 registers) share a tile and each column set is cut into two row ranges, so
+        // that 48 instead of 32 warps are resident per SM -- measured slower (1.30 vs 1.16 ms at 1280x800), kept for the record
+        const char *e = getenv("DRR_TILE_SPLIT");
+        if (e && atoi(e) == 2) {
+            if (lpg == 32) return launch_tile_t<16, 32, 384, 2>(a, frame0, nframes, st, launches);
+            if (lpg == 16) return launch_tile_t<16, 16, 384, 2>(a, frame0, nframes, st, launches);
+            return launch_tile_t<16, 8, 384, 2>(a, frame0, nframes, st, launches);
+        }
+        if (lpg == 32) return launch_tile_t<16, 32, 256, 1>(a, frame0, nframes, st, launches);
+        if (lpg == 16) return launch_tile_t<16, 16, 256, 1>(a, frame0, nframes, st, launches);
+        return launch_tile_t<16, 8, 256, 1>(a, frame0, nframes, st, launches);
     }
-    if (lpg == 32) return launch_tile_t<32, 32>(a, frame0, nframes, st, launches);
-    if (lpg == 16) return launch_tile_t<32, 16>(a, frame0, nframes, st, launches);
-    return launch_tile_t<32, 8>(a, frame0, nframes, st, launches);
+    if (lpg == 32) return launch_tile_t<32, 32, 256, 1>(a, frame0, nframes, st, launches);
+    if (lpg == 16) return launch_tile_t<32, 16, 256, 1>(a, frame0, nframes, st, launches);
+    return launch_tile_t<32, 8, 256, 1>(a, frame0, nframes, st, launches);
 }
 
 } // namespace drr
