@@ -310,12 +310,12 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     r.opaque = 1;
     for (size_t i = 0; i < (size_t)w * h; i++)
         if (texels[i] < -1 || texels[i] > 255) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
-    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * w, 4096);
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * w, (uint16_t)TEXEL_NONE);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const int16_t t = texels[(size_t)y * w + x];
             if (t < 0) r.opaque = 0;
-            ctx->texel_pool[r.base + (size_t)x * pitch + y] = (uint16_t)(t < 0 ? 4096 : t * 16);
+            ctx->texel_pool[r.base + (size_t)x * pitch + y] = (uint16_t)(t < 0 ? TEXEL_NONE : (uint32_t)t * PAL_ENTRY);
         }
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
     ctx->bitmaps.push_back(r);
@@ -967,7 +967,7 @@ int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major 
     for (int y = 0; y < r.h; y++)
         for (int x = 0; x < r.w; x++) {
             const uint16_t t = ctx->texel_pool[r.base + (size_t)x * pitch + y];
-            out[(size_t)y * r.w + x] = t == 4096 ? (int16_t)-1 : (int16_t)(t / 16);
+            out[(size_t)y * r.w + x] = t == TEXEL_NONE ? (int16_t)-1 : (int16_t)(t / PAL_ENTRY);
         }
     return DRR_OK;
 }

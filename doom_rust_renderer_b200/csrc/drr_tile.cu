@@ -302,7 +302,18 @@ __device__ __forceinline__ uint32_t lit_rgb_unit_p(float4 p, float factor) {
     return __byte_perm(__byte_perm(__float_as_uint(rg.x), __float_as_uint(rg.y), 0x0040), __float_as_uint(b), 0x5410);
 }
 
-static constexpr uint32_t TEXEL_HOLE = 4096u; // texel pool values are palette byte offsets (index * 16); 256 * 16 = None
+static constexpr uint32_t TEXEL_HOLE = TEXEL_NONE; // texel pool values are palette byte offsets (index * PAL_ENTRY); entry 256 = None
+
+// palette entry at shared address `addr` as (r, g, b) floats
+__device__ __forceinline__ float4 pal_fetch(uint32_t addr) {
+#ifdef DRR_PAL8
+    uint32_t rg, b;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rg), "=r"(b) : "r"(addr));
+    return make_float4(__uint_as_float(rg << 16), __uint_as_float(rg & 0xffff0000u), __uint_as_float(b), 0.0f);
+#else
+    return lds_f4(addr);
+#endif
+}
 
 // bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows
 template <bool POW2>
@@ -336,7 +347,7 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
             wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
-            const uint32_t rgb0 = lit_rgb_unit_p(lds_f4(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(lds_f4(pal_addr + t1), factor);
+            const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(pal_addr + t1), factor);
             if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, rgb0);
             if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, rgb1);
         }
@@ -344,8 +355,8 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
             wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
-            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(lds_f4(pal_addr + t0), factor));
-            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(lds_f4(pal_addr + t1), factor));
+            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(pal_fetch(pal_addr + t0), factor));
+            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(pal_fetch(pal_addr + t1), factor));
         }
     }
 }
@@ -359,7 +370,7 @@ __device__ __forceinline__ uint32_t flat_pixel_slow(float vy, float gwz, float w
     const uint32_t tx = (uint32_t)(sat_i16(rx) + px16); // i16 wrap does not reach the low 6 bits
     const uint32_t ty = (uint32_t)(sat_i16(ry) + py16);
     const uint32_t texel = flat[((ty << 6) & 0xfc0u) | (tx & 63u)];
-    return lit_rgb_any(lds_f4(pal_addr + texel * 16u), light_factor(lf, sat_i16(wx)));
+    return lit_rgb_any(pal_fetch(pal_addr + texel * PAL_ENTRY), light_factor(lf, sat_i16(wx)));
 }
 
 template <int LPG, bool UNIT>
@@ -394,7 +405,7 @@ __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, i
             // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
             fac.x = fmaxf(fac.x, 0.0f);
             fac.y = fmaxf(fac.y, 0.0f);
-            const float4 p0 = lds_f4(pal_addr + t0 * 16u), p1 = lds_f4(pal_addr + t1 * 16u);
+            const float4 p0 = pal_fetch(pal_addr + t0 * PAL_ENTRY), p1 = pal_fetch(pal_addr + t1 * PAL_ENTRY);
             uint32_t rgb0, rgb1;
             if (UNIT || (fac.x <= 1.0f && fac.y <= 1.0f)) {
                 rgb0 = lit_rgb_unit_p(p0, fac.x);
@@ -423,7 +434,11 @@ __device__ __forceinline__ void tile_sky_span(const uint4 ra, int ya, int yb, in
     for (int y = ya + li; y <= yb; y += LPG, addr += 4u * LPG) {
         const uint32_t texel = texels[ra.z + sky_rows[y]]; // column-major sky: base + tx*128 + ty
         if (HOLES && texel == TEXEL_HOLE) continue;
+#ifdef DRR_PAL8
+        sts_u32(addr, lds_u32(pal_addr + 257u * 8u + (texel >> 1))); // packed RGB table behind the 8-byte entries; no lighting (visplanes.rs:74-77)
+#else
         sts_u32(addr, lds_u32(pal_addr + texel + 12u)); // no lighting (visplanes.rs:74-77)
+#endif
     }
 }
 
@@ -439,7 +454,11 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 template <int TC, int LPG, int NT, int NSPLIT, bool FAST_STORE>
 __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
+#ifdef DRR_PAL8
+    __shared__ __align__(16) uint32_t s_pal[257 * 2 + 257]; // 257 x (bf16 r | bf16 g << 16, f32 b), then 257 packed 0x00BBGGRR
+#else
     __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
+#endif
     __shared__ int s_next;
     constexpr int G = 32 / LPG;          // columns per warp step
     constexpr int NSETS = TC / G;
@@ -453,7 +472,16 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     const uint8_t *__restrict__ flats = a.flats;
 
     // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
+#ifdef DRR_PAL8
+    for (int i = threadIdx.x; i < 257; i += NT) {
+        const float4 p = a.palette[min(i, 255)];
+        s_pal[2 * i] = (__float_as_uint(p.x) >> 16) | (__float_as_uint(p.y) & 0xffff0000u); // 0..255 as f32 has 16 zero low bits
+        s_pal[2 * i + 1] = __float_as_uint(p.z);
+        s_pal[257 * 2 + i] = __float_as_uint(p.w);
+    }
+#else
     for (int i = threadIdx.x; i < 257; i += NT) s_pal[i] = a.palette[min(i, 255)];
+#endif
     if (threadIdx.x == 0) s_next = NW;
     __syncthreads();
     int g = (int)blockIdx.x, band = 0;
