@@ -515,10 +515,13 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
         if (!(ci.n & COL_COVERED))
             for (int r = pb0 - b0 + li; r <= pb1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
+        uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
+        if (n > 0) ra_next = P[0];
         for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
             __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
             if (j < n) {
-                const uint4 ra = P[4 * j];
+                const uint4 ra = ra_next;
+                if (j + 1 < n) ra_next = P[4 * (j + 1)]; // the next span's first words are fetched while this one is drawn
                 const int ya = max((int)(ra.x & 0xffff), pb0), yb = min((int)(ra.x >> 16), pb1);
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
