@@ -39,6 +39,8 @@ WORKLOADS = {
     "walk1280": ("e1m1", 1280, 800, 512, 7, "E1M1-class walk, 512 viewpoints, 1280x800, all phases (north_star target resolution)"),
     "walls1280": ("e1m1", 1280, 800, 256, 1, "BASELINE configs[2]: walls only, 1280x800"),
     "flats1280": ("e1m1", 1280, 800, 256, 2, "BASELINE configs[2]: flats+sky only, 1280x800"),
+    "empty1280": ("e1m1", 1280, 800, 256, 0, "no ops at all, 1280x800: clears + write-out only (fixed cost of a tile)"),
+    "empty320": ("e1m1", 320, 200, 4096, 0, "no ops at all, 320x200: clears + write-out only (fixed cost of a tile)"),
     "things640": ("e1m1", 640, 400, 1024, 7, "BASELINE configs[3]: things, masked mids, lighting, 640x400 (bounded viewpoint count)"),
     "stress1920": ("stress", 1920, 1200, 128, 7, "BASELINE configs[4] map at 1920x1200 (bounded viewpoint count)"),
 }
