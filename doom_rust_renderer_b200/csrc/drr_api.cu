@@ -94,6 +94,8 @@ struct drr_ctx {
     DevBuf<uint8_t> d_flats;
     DevBuf<BitmapRec> d_bitmaps;
     DevBuf<float4> d_pal;
+    uint32_t pal_image[257 * 3 + 1] = {}; // the palette exactly as the tile kernel's shared memory holds it
+    DevBuf<uint32_t> d_pal_image;
 
     // recorded lists (pinned staging, exactly what the host emitted, all frames concatenated) and their device copies
     PinnedVec<View> views;
@@ -290,6 +292,17 @@ int drr_upload_palette(drr_ctx *ctx, const uint8_t rgb[768]) {
         memcpy(&w, &packed, 4);
         ctx->pal[i] = make_float4((float)r, (float)g, (float)b, w); // `color.r as f32` (bitmap_render.rs:204)
     }
+    for (int i = 0; i < 257; i++) { // entry 256 backs the None texel (its colour is never stored)
+        const float4 p = ctx->pal[std::min(i, 255)];
+        uint32_t r, g, b, w;
+        memcpy(&r, &p.x, 4);
+        memcpy(&g, &p.y, 4);
+        memcpy(&b, &p.z, 4);
+        memcpy(&w, &p.w, 4);
+        ctx->pal_image[2 * i] = (r >> 16) | (g & 0xffff0000u); // 0..255 as f32 has 16 zero low mantissa bits: bf16 is exact
+        ctx->pal_image[2 * i + 1] = b;
+        ctx->pal_image[257 * 2 + i] = w;
+    }
     ctx->have_pal = true;
     ctx->assets_dirty = true;
     return DRR_OK;
@@ -351,6 +364,8 @@ static int upload_assets(drr_ctx *ctx) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, ctx->d_pal.reserve(256));
     CU(ctx, cudaMemcpy(ctx->d_pal.p, ctx->pal, sizeof(ctx->pal), cudaMemcpyHostToDevice));
+    CU(ctx, ctx->d_pal_image.reserve(257 * 3 + 1));
+    CU(ctx, cudaMemcpy(ctx->d_pal_image.p, ctx->pal_image, sizeof(ctx->pal_image), cudaMemcpyHostToDevice));
     CU(ctx, ctx->d_texels.reserve(std::max<size_t>(ctx->texel_pool.size(), 1)));
     if (!ctx->texel_pool.empty())
         CU(ctx, cudaMemcpy(ctx->d_texels.p, ctx->texel_pool.data(), ctx->texel_pool.size() * 2, cudaMemcpyHostToDevice));
@@ -625,6 +640,8 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.Wf = (float)(uint32_t)ctx->W;
     a.Hf = (float)(uint32_t)ctx->H;
     a.one = 1.0f;
+    a.dbg = 0;
+    if (const char *e = getenv("DRR_DBG")) a.dbg = atoi(e); // timing experiments only: results are wrong with any bit set
     a.views = ctx->d_views.p;
     a.ops = ctx->d_ops.p;
     a.frame_op_base = ctx->d_frame_op_base.p;
@@ -641,6 +658,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.flats = ctx->d_flats.p;
     a.bitmaps = ctx->d_bitmaps.p;
     a.palette = ctx->d_pal.p;
+    a.pal_image = ctx->d_pal_image.p;
     a.sky_rows = ctx->d_sky_rows;
     a.sky_base = ctx->sky_slot >= 0 ? ctx->bitmaps[ctx->sky_slot].base : 0;
     a.frames = ctx->d_frames;

@@ -32,6 +32,7 @@ struct DrawArgs {
     int W, H, nframes;
     // src/renderer/constants.rs:7-17 derived from W, H with the reference's own expressions (drr_ctx_create)
     float CFX, CFY, GCFX, ASPECT, Wf, Hf;
+    int dbg;   // timing experiments only (DRR_DBG): 1 skip clearing, 2 skip framebuffer stores, 4 skip checksum, 8 skip write-out, 16 skip drawing
     float one; // always 1.0f, but opaque to ptxas: see add2_nofuse() in drr_tile.cu
     // draw lists as emitted (all frames of the batch concatenated, draw order)
     const View *views;               // [nframes]
@@ -52,6 +53,8 @@ struct DrawArgs {
     const uint8_t *flats;            // 4096 bytes per flat slot
     const BitmapRec *bitmaps;
     const float4 *palette;           // 256 x (r, g, b as f32, packed 0x00BBGGRR bits)
+    const uint32_t *pal_image;       // the palette exactly as the tile kernel's shared memory holds it: 257 x (bf16 r | bf16 g << 16,
+                                     // f32 b), then 257 packed 0x00BBGGRR words (staging is a straight copy)
     const uint8_t *sky_rows;         // sky texture row of every screen row
     uint32_t sky_base;               // texel index of the 256x128 sky bitmap
     uint8_t *frames;                 // framebuffers, frame_stride bytes apart, RGB24 row-major

@@ -452,7 +452,7 @@ __device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph
 // LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
 // RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
 template <int TC, int LPG, int NT, int NSPLIT, bool FAST_STORE>
-__global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
+__global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(const __grid_constant__ DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
     extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
 #ifdef DRR_PAL8
     __shared__ __align__(16) uint32_t s_pal[257 * 2 + 257]; // 257 x (bf16 r | bf16 g << 16, f32 b), then 257 packed 0x00BBGGRR
@@ -472,18 +472,6 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     const uint8_t *__restrict__ flats = a.flats;
 
     // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
-#ifdef DRR_PAL8
-    for (int i = threadIdx.x; i < 257; i += NT) {
-        const float4 p = a.palette[min(i, 255)];
-        s_pal[2 * i] = (__float_as_uint(p.x) >> 16) | (__float_as_uint(p.y) & 0xffff0000u); // 0..255 as f32 has 16 zero low bits
-        s_pal[2 * i + 1] = __float_as_uint(p.z);
-        s_pal[257 * 2 + i] = __float_as_uint(p.w);
-    }
-#else
-    for (int i = threadIdx.x; i < 257; i += NT) s_pal[i] = a.palette[min(i, 255)];
-#endif
-    if (threadIdx.x == 0) s_next = NW;
-    __syncthreads();
     int g = (int)blockIdx.x, band = 0;
     if (nbands > 1) {
         g = (int)(blockIdx.x / (unsigned)nbands);
@@ -491,7 +479,24 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     }
     const int f = frame0 + (int)blockIdx.y;
     const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
+    // everything the CTA needs from global memory is requested before the first barrier, so that the L2 round trips overlap
     const View vw = a.views[f];
+    const uint32_t slot = a.frame_slot[f];
+    ColIdx ci_first;
+    ci_first.first = 0; ci_first.n = 0;
+    if (warp < NSETS * NSPLIT) {
+        const int x = g * TC + grp * NSETS + (NSPLIT > 1 ? warp % NSETS : warp);
+        if (x < a.W) ci_first = a.colidx[(size_t)f * a.W + x];
+    }
+#ifdef DRR_PAL8
+    // (passing this image as a by-value kernel parameter and copying it from the constant bank was measured: the divergent
+    // LDCs made the empty-CTA time 3x longer)
+    for (int i = threadIdx.x; i < 257 * 3; i += NT) s_pal[i] = a.pal_image[i];
+#else
+    for (int i = threadIdx.x; i < 257; i += NT) s_pal[i] = a.palette[min(i, 255)];
+#endif
+    if (threadIdx.x == 0) s_next = NW;
+    __syncthreads();
     const int px16 = sat_i16(vw.pos_x), py16 = sat_i16(vw.pos_y); // visplanes.rs:119-120 `player.position.x as i16`
 
     // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
@@ -505,15 +510,17 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
         const int pb0 = b0 + part * prow, pb1 = min(b1, pb0 + prow - 1);
         // the G columns of a set are NSETS apart: their lane groups then store to disjoint bank ranges when they sit on the same rows
         const int c = grp * NSETS + cs, x = g * TC + c;
-        ColIdx ci;
-        ci.first = 0; ci.n = 0;
-        if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
-        const int n = (int)(ci.n & ~COL_COVERED);
+        ColIdx ci = ci_first; // the warp's first item was requested in the prologue
+        if (item != warp) {
+            ci.first = 0; ci.n = 0;
+            if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
+        }
+        const int n = (a.dbg & 16) ? 0 : (int)(ci.n & ~COL_COVERED);
         const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
         const uint32_t col_addr = tile_addr + 4u * (uint32_t)(c * RP);
         // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
-        if (!(ci.n & COL_COVERED))
+        if (!(ci.n & COL_COVERED) && !(a.dbg & 1))
             for (int r = pb0 - b0 + li; r <= pb1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
         uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
         if (n > 0) ra_next = P[0];
@@ -556,7 +563,6 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x).  A row of the tile is TC*3 bytes = LPR 16-byte
     // vectors; a warp step covers RPI rows with LPR lanes each.  Vector j of a row holds bytes 16j .. 16j+15, i.e. pixels
     // (16j)/3 .. (16j+15)/3 of the tile row, starting at channel j % 3 of the first one.
-    const uint32_t slot = a.frame_slot[f];
     const size_t pitch = (size_t)a.W * 3;
     uint8_t *base = a.frames + (size_t)slot * a.frame_stride + (size_t)g * (TC * 3);
     const int nrows = b1 - b0 + 1;
@@ -564,7 +570,7 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
         constexpr int LPR = TC * 3 / 16, RPI = 32 / LPR;
         const int rl = lane / LPR, j = lane % LPR, ph = j % 3;
         uint64_t acc = 0;
-        if (lane < LPR * RPI) {
+        if (lane < LPR * RPI && !(a.dbg & 8)) {
             const int cb = (16 * j) / 3;
             // word m of the vector starts at byte 16j + 4m of the row: pixel q(m), channel (ph + m) % 3 -> selector; the pixel
             // pairs are (0,1) (1,2)|(2,3) (2,3)|(3,4) (4,5) relative to cb, depending on the phase
@@ -587,8 +593,8 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
                 v.y = __byte_perm(ph == 2 ? p2 : p1, ph == 2 ? p3 : p2, s1);
                 v.z = __byte_perm(ph == 0 ? p2 : p3, ph == 0 ? p3 : p4, s2);
                 v.w = __byte_perm(p4, p5, s3);
-                *reinterpret_cast<uint4 *>(wp) = v;
-                acc += (uint64_t)v.x * k0 + (uint64_t)v.y * (k0 + C) + (uint64_t)v.z * (k0 + 2u * C) + (uint64_t)v.w * (k0 + 3u * C);
+                if (!(a.dbg & 2)) *reinterpret_cast<uint4 *>(wp) = v;
+                if (!(a.dbg & 4)) acc += (uint64_t)v.x * k0 + (uint64_t)v.y * (k0 + C) + (uint64_t)v.z * (k0 + 2u * C) + (uint64_t)v.w * (k0 + 3u * C);
                 ta += 4u * (NW * RPI);
                 wp += wstep;
                 k0 += kstep;
