@@ -315,6 +315,14 @@ __device__ __forceinline__ float4 pal_fetch(uint32_t addr) {
 #endif
 }
 
+// read-only global load of one texel (the pointer's address space is spelled out: its provenance is hidden on purpose, see
+// tile_wall_span, and a generic LD would otherwise be emitted)
+__device__ __forceinline__ uint32_t ldg_u16(const uint16_t *p) {
+    uint16_t v;
+    asm("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+
 // bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows
 template <bool POW2>
 __device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, const uint4 rc, float hF, float2 yt, float one,
@@ -330,15 +338,18 @@ __device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, con
         u0 = __umulhi(u0, rb.z) * rb.w + u0;
         u1 = __umulhi(u1, rb.z) * rb.w + u1;
     }
-    t0 = texels[u0]; // `texels` already points at the span's texture column
-    t1 = texels[u1];
+    t0 = ldg_u16(texels + u0); // `texels` already points at the span's texture column
+    t1 = ldg_u16(texels + u1);
 }
 
 template <int LPG, bool HOLES, bool POW2>
 __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
                                                uint32_t col_addr, const uint16_t *__restrict__ texels, uint32_t pal_addr, float one) {
     const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
+    // the span's texture column as ONE 64-bit base, opaque to the compiler: otherwise it re-associates texels + (ra.z + u) and
+    // pays a 33-bit add with carry per texel instead of a single IMAD.WIDE.U32 (u * 2 + base)
     const uint16_t *__restrict__ col = texels + ra.z;
+    asm("" : "+l"(col));
     int y = ya + li;
     uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + LPG), __uint_as_float(rc.x)));
