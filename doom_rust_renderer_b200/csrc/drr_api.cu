@@ -92,6 +92,7 @@ struct drr_ctx {
     int sky_slot = -1;
     DevBuf<uint16_t> d_texels;
     DevBuf<uint8_t> d_flats;
+    cudaTextureObject_t tex_texels = 0, tex_flats = 0; // linear textures over d_texels / d_flats
     DevBuf<BitmapRec> d_bitmaps;
     DevBuf<float4> d_pal;
     uint32_t pal_image[257 * 3 + 1] = {}; // the palette exactly as the tile kernel's shared memory holds it
@@ -262,6 +263,8 @@ void drr_ctx_destroy(drr_ctx *ctx) {
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_sky_rows) cudaFree(ctx->d_sky_rows);
+    if (ctx->tex_texels) cudaDestroyTextureObject(ctx->tex_texels);
+    if (ctx->tex_flats) cudaDestroyTextureObject(ctx->tex_flats);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -374,6 +377,22 @@ static int upload_assets(drr_ctx *ctx) {
     CU(ctx, ctx->d_bitmaps.reserve(std::max<size_t>(ctx->bitmaps.size(), 1)));
     if (!ctx->bitmaps.empty())
         CU(ctx, cudaMemcpy(ctx->d_bitmaps.p, ctx->bitmaps.data(), ctx->bitmaps.size() * sizeof(BitmapRec), cudaMemcpyHostToDevice));
+    // (re)create the linear textures over the pools
+    if (ctx->tex_texels) cudaDestroyTextureObject(ctx->tex_texels);
+    if (ctx->tex_flats) cudaDestroyTextureObject(ctx->tex_flats);
+    ctx->tex_texels = ctx->tex_flats = 0;
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = ctx->d_texels.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<unsigned short>();
+    rd.res.linear.sizeInBytes = std::max<size_t>(ctx->texel_pool.size(), 1) * 2;
+    CU(ctx, cudaCreateTextureObject(&ctx->tex_texels, &rd, &td, nullptr));
+    rd.res.linear.devPtr = ctx->d_flats.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<unsigned char>();
+    rd.res.linear.sizeInBytes = std::max<size_t>(ctx->flat_pool.size(), 1);
+    CU(ctx, cudaCreateTextureObject(&ctx->tex_flats, &rd, &td, nullptr));
     ctx->assets_dirty = false;
     return DRR_OK;
 }
@@ -656,6 +675,8 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.tparams = ctx->d_tparams.p;
     a.texels = ctx->d_texels.p;
     a.flats = ctx->d_flats.p;
+    a.tex_texels = ctx->tex_texels;
+    a.tex_flats = ctx->tex_flats;
     a.bitmaps = ctx->d_bitmaps.p;
     a.palette = ctx->d_pal.p;
     a.pal_image = ctx->d_pal_image.p;

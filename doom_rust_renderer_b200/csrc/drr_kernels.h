@@ -52,6 +52,8 @@ struct DrawArgs {
     const uint16_t *texels;          // bitmap pool: column-major, pow2 column pitch, palette byte offset (index*16), 4096 = None
     const uint8_t *flats;            // 4096 bytes per flat slot
     const BitmapRec *bitmaps;
+    cudaTextureObject_t tex_texels;  // the texel pool as a 1D linear texture of u16 (tile kernel fetches texels through the TEX pipe,
+    cudaTextureObject_t tex_flats;   // which runs beside the LSU/L1 data pipe the kernel is bound by); same for the flat pool (u8)
     const float4 *palette;           // 256 x (r, g, b as f32, packed 0x00BBGGRR bits)
     const uint32_t *pal_image;       // the palette exactly as the tile kernel's shared memory holds it: 257 x (bf16 r | bf16 g << 16,
                                      // f32 b), then 257 packed 0x00BBGGRR words (staging is a straight copy)

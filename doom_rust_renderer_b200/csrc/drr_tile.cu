@@ -325,7 +325,7 @@ __device__ __forceinline__ uint32_t ldg_u16(const uint16_t *p) {
 
 // bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows
 template <bool POW2>
-__device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, const uint4 rc, float hF, float2 yt, float one,
+__device__ __forceinline__ void wall_texels2(const DrawArgs &a, const uint4 ra, const uint4 rb, const uint4 rc, float hF, float2 yt, float one,
                                              const uint16_t *__restrict__ texels, uint32_t &t0, uint32_t &t1) {
     const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));   // :256
     // :257 with uy0 == 0.0: (1.0 - ay) * 0.0 is +-0.0 for finite ay and h + (+-0.0) == h, so the middle term drops out
@@ -338,12 +338,17 @@ __device__ __forceinline__ void wall_texels2(const uint4 ra, const uint4 rb, con
         u0 = __umulhi(u0, rb.z) * rb.w + u0;
         u1 = __umulhi(u1, rb.z) * rb.w + u1;
     }
+#ifdef DRR_TEXFETCH
+    t0 = tex1Dfetch<unsigned short>(a.tex_texels, (int)(ra.z + u0)); // TEX pipe: beside the LSU/L1 data pipe the kernel is bound by
+    t1 = tex1Dfetch<unsigned short>(a.tex_texels, (int)(ra.z + u1));
+#else
     t0 = ldg_u16(texels + u0); // `texels` already points at the span's texture column
     t1 = ldg_u16(texels + u1);
+#endif
 }
 
 template <int LPG, bool HOLES, bool POW2>
-__device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
+__device__ __forceinline__ void tile_wall_span(const DrawArgs &a, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
                                                uint32_t col_addr, const uint16_t *__restrict__ texels, uint32_t pal_addr, float one) {
     const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
     // the span's texture column as ONE 64-bit base, opaque to the compiler: otherwise it re-associates texels + (ra.z + u) and
@@ -357,7 +362,7 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
 #pragma unroll 2
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
-            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
+            wall_texels2<POW2>(a, ra, rb, rc, hF, yt, one, col, t0, t1);
             const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(pal_addr + t1), factor);
             if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, rgb0);
             if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, rgb1);
@@ -365,7 +370,7 @@ __device__ __forceinline__ void tile_wall_span(const uint4 ra, const uint4 rb, c
     } else {
         for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
             uint32_t t0, t1;
-            wall_texels2<POW2>(ra, rb, rc, hF, yt, one, col, t0, t1);
+            wall_texels2<POW2>(a, ra, rb, rc, hF, yt, one, col, t0, t1);
             if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(pal_fetch(pal_addr + t0), factor));
             if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(pal_fetch(pal_addr + t1), factor));
         }
@@ -387,7 +392,7 @@ __device__ __forceinline__ uint32_t flat_pixel_slow(float vy, float gwz, float w
 template <int LPG, bool UNIT>
 __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, int ya, int yb, int b0, int li, uint32_t col_addr, float CFY,
                                                float cos_a, float sin_a, int px16, int py16, const uint8_t *__restrict__ flats,
-                                               uint32_t pal_addr, float one) {
+                                               uint32_t pal_addr, float one, cudaTextureObject_t tex_flats) {
     const float wzvx = __uint_as_float(rc.x), gwz = __uint_as_float(rc.y), lf = __uint_as_float(rc.z);
     const uint8_t *__restrict__ flat = flats + ra.z;
     int y = ya + li;
@@ -408,8 +413,13 @@ __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, i
             const float2 ry = add2_nofuse(__fmul2_rn(wy, f2(cos_a)), __fmul2_rn(wx, f2(sin_a)), one);
             const uint32_t tx0 = (uint32_t)(sat_i16(rx.x) + px16), ty0 = (uint32_t)(sat_i16(ry.x) + py16);
             const uint32_t tx1 = (uint32_t)(sat_i16(rx.y) + px16), ty1 = (uint32_t)(sat_i16(ry.y) + py16);
+#ifdef DRR_TEXFETCH
+            const uint32_t t0 = tex1Dfetch<unsigned char>(tex_flats, (int)(ra.z + (((ty0 << 6) & 0xfc0u) | (tx0 & 63u))));
+            const uint32_t t1 = tex1Dfetch<unsigned char>(tex_flats, (int)(ra.z + (((ty1 << 6) & 0xfc0u) | (tx1 & 63u))));
+#else
             const uint32_t t0 = flat[((ty0 << 6) & 0xfc0u) | (tx0 & 63u)];
             const uint32_t t1 = flat[((ty1 << 6) & 0xfc0u) | (tx1 & 63u)];
+#endif
             // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
             const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
             float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), one);
@@ -546,17 +556,17 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
                         if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV))
-                            tile_flat_span<LPG, true>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
+                            tile_flat_span<LPG, true>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one, a.tex_flats);
                         else
-                            tile_flat_span<LPG, false>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one);
+                            tile_flat_span<LPG, false>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one, a.tex_flats);
                     } else if (kind == KIND_WALL) {
                         const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
-                        if (ra.y & TS_POW2) tile_wall_span<LPG, false, true>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                        else tile_wall_span<LPG, false, false>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        if (ra.y & TS_POW2) tile_wall_span<LPG, false, true>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        else tile_wall_span<LPG, false, false>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
                     } else if (kind == KIND_WALL_HOLES) {
                         const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
-                        if (ra.y & TS_POW2) tile_wall_span<LPG, true, true>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                        else tile_wall_span<LPG, true, false>(ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        if (ra.y & TS_POW2) tile_wall_span<LPG, true, true>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
+                        else tile_wall_span<LPG, true, false>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
                     } else if (kind == KIND_SKY) {
                         tile_sky_span<LPG, false>(ra, ya, yb, b0, li, col_addr, a.sky_rows, texels, pal_addr);
                     } else if (kind == KIND_SKY_HOLES) {
