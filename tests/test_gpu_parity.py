@@ -380,6 +380,51 @@ def test_pipelined_submit_equals_upload_then_draw(monkeypatch):
     assert (ctx.read_checksums(0, n) == want).all()
 
 
+def test_full_size_batch_properties(monkeypatch):
+    """BASELINE configs[1] at its full size (4096 viewpoints, 320x200), through properties that do not need 4096 oracle frames:
+    the batch rendered whole == rendered as two halves in reversed slot order with another chunking (a frame's result depends
+    on nothing but its own lists); a seeded sample of frames equals the oracle byte for byte; drawing twice changes nothing."""
+    path, gm = common.wad("e1m1")
+    W, H, n = 320, 200, 4096
+    game = orc.Game(path, "E1M1", W, H)
+    views = np.array(synth_wad.walk_viewpoints(gm, n), np.float32)
+    scene = drr.Scene(path, "E1M1", W, H)
+    ctx = drr.Context(W, H, 0, n)
+    scene.upload_assets(ctx)
+    skipped = set(scene.emit_views(ctx, views))  # viewpoints the reference itself would panic on keep an empty slot
+    assert len(skipped) < n // 50
+    ctx.submit()
+    ctx.sync()
+    whole = ctx.read_checksums(0, n)
+    ctx.draw()
+    ctx.sync()
+    assert (ctx.read_checksums(0, n) == whole).all()
+    rng = np.random.default_rng(0xD00D1993)
+    for k in rng.choice(n, 24, replace=False):
+        if int(k) in skipped:
+            continue
+        ref = game.render(float(views[k, 0]), float(views[k, 1]), float(views[k, 2]))
+        _compare(ctx, int(k), ref, "full batch view %d" % k)
+        assert int(whole[k]) == drr.checksum_numpy(ref)
+    # two halves, slots reversed, one chunk per 64 frames
+    monkeypatch.setenv("DRR_SUBMIT_CHUNKS", "7")
+    half = n // 2
+    ctx2 = drr.Context(W, H, 0, half)
+    scene.upload_assets(ctx2)
+    for lo in (0, half):
+        ctx2.reset()
+        for i in range(half):
+            k = lo + i
+            if k in skipped:
+                continue
+            scene.emit_view(ctx2, half - 1 - i, float(views[k, 0]), float(views[k, 1]), float(views[k, 2]))
+        ctx2.submit()
+        ctx2.sync()
+        got = ctx2.read_checksums(0, half)[::-1]
+        keep = np.array([lo + i not in skipped for i in range(half)])
+        assert (got[keep] == whole[lo:lo + half][keep]).all()
+
+
 def test_error_paths():
     ctx = drr.Context(64, 32, 0, 1)
     with pytest.raises(drr.DrrError):
