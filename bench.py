@@ -122,18 +122,19 @@ def viewpoints(gm, kind: str, n_total: int) -> np.ndarray:
 
 
 def record_batch(drr, ctx, scene, views, phases):
-    """Run the host front-end for every viewpoint.  A viewpoint on which the reference would panic (a seg passing
-    exactly through the eye) is nudged by 1/8 map unit until it renders; returns the viewpoints actually used."""
+    """Run the host front-end for every viewpoint (worker threads, one recorder each).  A viewpoint on which the reference
+    would panic (a seg passing exactly through the eye) is nudged by 1/8 map unit until it renders; returns the viewpoints
+    actually used."""
     used = np.array(views, np.float32)
-    for k in range(len(used)):
+    for k in scene.emit_views(ctx, used, 0.0, phases):
         for attempt in range(16):
+            used[k, 0] += np.float32(0.125)
             try:
                 scene.emit_view(ctx, k, float(used[k, 0]), float(used[k, 1]), float(used[k, 2]), 0.0, phases)
                 break
             except drr.DrrError as e:
                 if e.code != -7:
                     raise
-                used[k, 0] += np.float32(0.125)
         else:
             raise RuntimeError("viewpoint %d cannot be rendered" % k)
     return used

@@ -75,7 +75,44 @@ struct DevBuf {
 
 } // namespace
 
-struct drr_ctx {
+// Draw lists exactly as the host emitted them, all frames concatenated.  A context records into its own (pinned staging,
+// so that the H2D copies are asynchronous); a drr_recorder records into a private one (plain memory) that is later appended
+// to a context -- that is how worker threads run the front-end in parallel.
+struct Lists {
+    PinnedVec<View> views;
+    PinnedVec<uint32_t> ops;            // per frame, call order: bit 31 = visplane, low bits = index into planes / segs
+    PinnedVec<uint32_t> frame_op_base;  // frames + 1
+    PinnedVec<uint32_t> frame_rec_base; // frames + 1: records (columns that survive clipping) before each frame
+    PinnedVec<uint32_t> frame_slot;
+    PinnedVec<SegRec> segs;
+    PinnedVec<ColRec> cols;
+    PinnedVec<PlaneRec> planes;
+    PinnedVec<uint32_t> parr;           // (top, bottom) i16 pairs
+    std::vector<uint32_t> frame_seg_base, frame_col_base, frame_plane_base, frame_parr_base; // frames + 1 each (chunked upload)
+    uint64_t rec_count = 0; // columns that survive clipping, all frames recorded so far (statistics)
+    uint64_t rec_cap = 0;   // screen columns inside the x ranges of all ops recorded so far: what the bin kernel may reserve (>= rec_count)
+    // frame being recorded
+    bool in_frame = false;
+    size_t ops_n0 = 0, segs_n0 = 0, cols_n0 = 0, planes_n0 = 0, parr_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
+    uint64_t rec0 = 0, cap0 = 0;
+    drr_stats stats0{};
+    int cur_slot = -1;
+
+    drr_stats stats{};
+    void set_pinned(bool on) {
+        views.pinned = ops.pinned = frame_op_base.pinned = frame_rec_base.pinned = frame_slot.pinned = on;
+        segs.pinned = cols.pinned = planes.pinned = parr.pinned = on;
+    }
+    void clear_lists() {
+        views.clear(); ops.clear(); frame_op_base.clear(); frame_rec_base.clear(); frame_slot.clear();
+        segs.clear(); cols.clear(); planes.clear(); parr.clear();
+        frame_seg_base.clear(); frame_col_base.clear(); frame_plane_base.clear(); frame_parr_base.clear();
+        rec_count = rec_cap = 0;
+        in_frame = false;
+    }
+};
+
+struct drr_ctx : Lists {
     int W = 0, H = 0, device = 0, max_views = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -98,17 +135,7 @@ struct drr_ctx {
     uint32_t pal_image[257 * 3 + 1] = {}; // the palette exactly as the tile kernel's shared memory holds it
     DevBuf<uint32_t> d_pal_image;
 
-    // recorded lists (pinned staging, exactly what the host emitted, all frames concatenated) and their device copies
-    PinnedVec<View> views;
-    PinnedVec<uint32_t> ops;            // per frame, call order: bit 31 = visplane, low bits = index into planes / segs
-    PinnedVec<uint32_t> frame_op_base;  // frames + 1
-    PinnedVec<uint32_t> frame_rec_base; // frames + 1: records (columns that survive clipping) before each frame
-    PinnedVec<uint32_t> frame_slot;
-    PinnedVec<SegRec> segs;
-    PinnedVec<ColRec> cols;
-    PinnedVec<PlaneRec> planes;
-    PinnedVec<uint32_t> parr;           // (top, bottom) i16 pairs
-    std::vector<uint32_t> frame_seg_base, frame_col_base, frame_plane_base, frame_parr_base; // frames + 1 each (chunked upload)
+    // device copies of the recorded lists (the lists themselves: struct Lists above)
     DevBuf<View> d_views;
     DevBuf<uint32_t> d_ops, d_frame_op_base, d_frame_rec_base, d_frame_slot, d_parr, d_frame_cursor;
     DevBuf<SegRec> d_segs;
@@ -118,21 +145,12 @@ struct drr_ctx {
     DevBuf<uint4> d_tparams; // 4 x uint4 per record
     uint8_t *d_sky_rows = nullptr;
     size_t uploaded_frames = 0;
-    uint64_t rec_count = 0; // columns that survive clipping, all frames recorded so far (statistics)
-    uint64_t rec_cap = 0;   // screen columns inside the x ranges of all ops recorded so far: what the bin kernel may reserve (>= rec_count)
     std::vector<int> slot_to_frame; // view slot -> recorded frame (or -1)
 
     uint8_t *d_frames = nullptr;
     uint64_t frame_stride = 0;
     uint64_t *d_crc = nullptr;
     PinnedVec<uint64_t> h_crc;
-
-    // frame being recorded
-    bool in_frame = false;
-    size_t ops_n0 = 0, segs_n0 = 0, cols_n0 = 0, planes_n0 = 0, parr_n0 = 0; // list sizes at drr_frame_begin (for drr_frame_abort)
-    uint64_t rec0 = 0, cap0 = 0;
-    drr_stats stats0{};
-    int cur_slot = -1;
 
     // host-side reference binning (test infrastructure: drr_test_list which = 3, 4), computed on demand
     std::vector<Span> t_spans;
@@ -147,7 +165,6 @@ struct drr_ctx {
     std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
     int prof_steps = 0;
     bool host_only = false; // CPU-test recording context: records and bins, can never draw
-    drr_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -400,91 +417,69 @@ static int upload_assets(drr_ctx *ctx) {
 // ---- recording ---------------------------------------------------------------------------------------------------
 // Recording is appending: the lists go to the device exactly as emitted (SURVEY 8d's algorithmic bytes plus indices);
 // turning per-op lists into per-column lists ("column binning") is the bin kernel's job (drr_tile.cu).
-static bool push_frame_bases(drr_ctx *ctx) {
-    ctx->frame_seg_base.push_back((uint32_t)ctx->segs.n);
-    ctx->frame_col_base.push_back((uint32_t)ctx->cols.n);
-    ctx->frame_plane_base.push_back((uint32_t)ctx->planes.n);
-    ctx->frame_parr_base.push_back((uint32_t)ctx->parr.n);
-    return ctx->frame_op_base.push((uint32_t)ctx->ops.n) && ctx->frame_rec_base.push((uint32_t)ctx->rec_cap);
+// The same code records into a context's own lists (drr_frame_begin ...) and into a recorder's (drr_recorder_frame_begin
+// ...): `L` is where the lists go, `ctx` supplies the asset tables and the screen size, `err` receives the message.
+struct drr_recorder {
+    Lists lists; // plain memory (set_pinned(false))
+    drr_ctx *ctx = nullptr;
+    std::string err;
+};
+
+static int rfail(std::string &err, int code, const char *msg) {
+    err = msg;
+    return code;
 }
 
-int drr_reset(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
-    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
-    ctx->views.clear();
-    ctx->ops.clear();
-    ctx->frame_op_base.clear();
-    ctx->frame_rec_base.clear();
-    ctx->frame_slot.clear();
-    ctx->segs.clear();
-    ctx->cols.clear();
-    ctx->planes.clear();
-    ctx->parr.clear();
-    ctx->frame_seg_base.clear();
-    ctx->frame_col_base.clear();
-    ctx->frame_plane_base.clear();
-    ctx->frame_parr_base.clear();
-    ctx->t_spans.clear();
-    ctx->t_colidx.clear();
-    ctx->rec_count = ctx->rec_cap = 0;
-    ctx->uploaded_frames = 0;
-    std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
-    const uint64_t launches = ctx->stats.kernel_launches;
-    ctx->stats = drr_stats{};
-    ctx->stats.kernel_launches = launches;
-    return DRR_OK;
+static bool push_frame_bases(Lists &L) {
+    L.frame_seg_base.push_back((uint32_t)L.segs.n);
+    L.frame_col_base.push_back((uint32_t)L.cols.n);
+    L.frame_plane_base.push_back((uint32_t)L.planes.n);
+    L.frame_parr_base.push_back((uint32_t)L.parr.n);
+    return L.frame_op_base.push((uint32_t)L.ops.n) && L.frame_rec_base.push((uint32_t)L.rec_cap);
 }
 
-int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
-    CTX_CHECK(ctx);
-    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_begin: previous frame not ended");
-    if (!view || view_idx < 0 || view_idx >= ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: bad view index");
-    if (ctx->slot_to_frame[view_idx] >= 0) return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
-    if (ctx->frame_op_base.n == 0 && !push_frame_bases(ctx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+static int rec_frame_begin(Lists &L, const drr_ctx *ctx, std::string &err, int view_idx, const drr_view *view) {
+    if (L.in_frame) return rfail(err, DRR_E_STATE, "frame_begin: previous frame not ended");
+    if (!view || view_idx < 0 || view_idx >= ctx->max_views) return rfail(err, DRR_E_INVALID, "frame_begin: bad view index");
+    if (L.frame_op_base.n == 0 && !push_frame_bases(L)) return rfail(err, DRR_E_NOMEM, "alloc");
     View v{view->pos_x, view->pos_y, view->floor_height, view->angle, view->cos_angle, view->sin_angle};
-    if (!ctx->views.push(v) || !ctx->frame_slot.push((uint32_t)view_idx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    ctx->slot_to_frame[view_idx] = (int)ctx->views.n - 1;
-    ctx->ops_n0 = ctx->ops.n;
-    ctx->segs_n0 = ctx->segs.n;
-    ctx->cols_n0 = ctx->cols.n;
-    ctx->planes_n0 = ctx->planes.n;
-    ctx->parr_n0 = ctx->parr.n;
-    ctx->rec0 = ctx->rec_count;
-    ctx->cap0 = ctx->rec_cap;
-    ctx->stats0 = ctx->stats;
-    ctx->cur_slot = view_idx;
-    ctx->in_frame = true;
-    ctx->t_spans.clear();
-    ctx->t_colidx.clear();
+    if (!L.views.push(v) || !L.frame_slot.push((uint32_t)view_idx)) return rfail(err, DRR_E_NOMEM, "alloc");
+    L.ops_n0 = L.ops.n;
+    L.segs_n0 = L.segs.n;
+    L.cols_n0 = L.cols.n;
+    L.planes_n0 = L.planes.n;
+    L.parr_n0 = L.parr.n;
+    L.rec0 = L.rec_count;
+    L.cap0 = L.rec_cap;
+    L.stats0 = L.stats;
+    L.cur_slot = view_idx;
+    L.in_frame = true;
     return DRR_OK;
 }
 
-int drr_frame_abort(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
-    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_abort outside a frame");
-    ctx->in_frame = false;
-    ctx->views.n--;
-    ctx->frame_slot.n--;
-    ctx->ops.n = ctx->ops_n0;
-    ctx->segs.n = ctx->segs_n0;
-    ctx->cols.n = ctx->cols_n0;
-    ctx->planes.n = ctx->planes_n0;
-    ctx->parr.n = ctx->parr_n0;
-    ctx->rec_count = ctx->rec0;
-    ctx->rec_cap = ctx->cap0;
-    ctx->slot_to_frame[ctx->cur_slot] = -1;
-    const uint64_t launches = ctx->stats.kernel_launches;
-    ctx->stats = ctx->stats0;
-    ctx->stats.kernel_launches = launches;
+static int rec_frame_abort(Lists &L, std::string &err) {
+    if (!L.in_frame) return rfail(err, DRR_E_STATE, "frame_abort outside a frame");
+    L.in_frame = false;
+    L.views.n--;
+    L.frame_slot.n--;
+    L.ops.n = L.ops_n0;
+    L.segs.n = L.segs_n0;
+    L.cols.n = L.cols_n0;
+    L.planes.n = L.planes_n0;
+    L.parr.n = L.parr_n0;
+    L.rec_count = L.rec0;
+    L.rec_cap = L.cap0;
+    const uint64_t launches = L.stats.kernel_launches;
+    L.stats = L.stats0;
+    L.stats.kernel_launches = launches;
     return DRR_OK;
 }
 
-int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, int n) {
-    CTX_CHECK(ctx);
-    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_emit_columns outside a frame");
-    if (!hdr || n < 0 || (n > 0 && !cols)) return fail(ctx, DRR_E_INVALID, "drr_emit_columns: null");
+static int rec_emit_columns(Lists &L, const drr_ctx *ctx, std::string &err, const drr_seg_hdr *hdr, const drr_col *cols, int n) {
+    if (!L.in_frame) return rfail(err, DRR_E_STATE, "emit_columns outside a frame");
+    if (!hdr || n < 0 || (n > 0 && !cols)) return rfail(err, DRR_E_INVALID, "emit_columns: null");
     auto it = ctx->bitmap_slot.find(hdr->bitmap_id);
-    if (it == ctx->bitmap_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_emit_columns: unknown bitmap id");
+    if (it == ctx->bitmap_slot.end()) return rfail(err, DRR_E_ASSET, "emit_columns: unknown bitmap id");
     SegRec r;
     r.bitmap_slot = (uint32_t)it->second;
     r.light_level = hdr->light_level;
@@ -502,50 +497,49 @@ int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, 
     r.offset_y = hdr->offset_y;
     r.pad = 0;
     static_assert(sizeof(drr_col) == sizeof(ColRec), "drr_col layout");
-    if (!ctx->cols.reserve(ctx->cols.n + (size_t)n)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    if (!L.cols.reserve(L.cols.n + (size_t)n)) return rfail(err, DRR_E_NOMEM, "alloc");
     const int H = ctx->H, W = ctx->W;
     // the bin kernel finds a seg's record for screen column x by index, which needs x strictly increasing within one
     // SegRec: the reference emits x = start_x .. end_x in order; anything else is split into increasing runs
     for (int i = 0; i < n;) {
         int j = i + 1;
         while (j < n && cols[j].x > cols[j - 1].x) ++j;
-        r.cols_first = (uint32_t)ctx->cols.n;
+        r.cols_first = (uint32_t)L.cols.n;
         r.n = (uint32_t)(j - i);
         r.x0 = cols[i].x;
         r.x1 = cols[j - 1].x;
-        memcpy(ctx->cols.p + ctx->cols.n, cols + i, sizeof(ColRec) * (size_t)(j - i));
-        ctx->cols.n += (size_t)(j - i);
+        memcpy(L.cols.p + L.cols.n, cols + i, sizeof(ColRec) * (size_t)(j - i));
+        L.cols.n += (size_t)(j - i);
         for (int k = i; k < j; k++) {
             const drr_col &c = cols[k];
             // Pixels::set ignores x >= W and y > H (pixels.rs:23); negative values become huge usize and are ignored too
             if (c.x < 0 || c.x >= W) continue;
-            if (std::max<int>(c.clipped_top_y, 0) <= std::min<int>(c.clipped_bottom_y, H - 1)) ctx->rec_count++;
+            if (std::max<int>(c.clipped_top_y, 0) <= std::min<int>(c.clipped_bottom_y, H - 1)) L.rec_count++;
         }
         // the bin kernel reserves one record slot per screen column inside the run's x range (its records may be sparser)
-        ctx->rec_cap += (uint64_t)std::max(0, std::min<int>(r.x1, W - 1) - std::max<int>(r.x0, 0) + 1);
-        if (!ctx->ops.push((uint32_t)ctx->segs.n) || !ctx->segs.push(r)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+        L.rec_cap += (uint64_t)std::max(0, std::min<int>(r.x1, W - 1) - std::max<int>(r.x0, 0) + 1);
+        if (!L.ops.push((uint32_t)L.segs.n) || !L.segs.push(r)) return rfail(err, DRR_E_NOMEM, "alloc");
         i = j;
     }
-    ctx->stats.seg_headers++;
-    ctx->stats.column_records += (uint64_t)n;
+    L.stats.seg_headers++;
+    L.stats.column_records += (uint64_t)n;
     return DRR_OK;
 }
 
-int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom) {
-    CTX_CHECK(ctx);
-    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_emit_visplane outside a frame");
-    if (!hdr || !top || !bottom) return fail(ctx, DRR_E_INVALID, "drr_emit_visplane: null");
+static int rec_emit_visplane(Lists &L, const drr_ctx *ctx, std::string &err, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom) {
+    if (!L.in_frame) return rfail(err, DRR_E_STATE, "emit_visplane outside a frame");
+    if (!hdr || !top || !bottom) return rfail(err, DRR_E_INVALID, "emit_visplane: null");
     const int W = ctx->W, H = ctx->H;
     // the reference indexes [i16; SCREEN_WIDTH] arrays with x (visplanes.rs:61,95): out-of-range x panics there
-    if (hdr->left < 0 || hdr->right >= W) return fail(ctx, DRR_E_INVALID, "drr_emit_visplane: left/right outside the screen");
+    if (hdr->left < 0 || hdr->right >= W) return rfail(err, DRR_E_INVALID, "emit_visplane: left/right outside the screen");
     PlaneRec p;
     if (hdr->flat_id == DRR_FLAT_SKY) {
-        if (ctx->sky_slot < 0) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: sky not set");
+        if (ctx->sky_slot < 0) return rfail(err, DRR_E_ASSET, "emit_visplane: sky not set");
         p.flat_slot = -1;
         p.kind = (int16_t)(ctx->bitmaps[ctx->sky_slot].opaque ? KIND_SKY : KIND_SKY_HOLES);
     } else {
         auto it = ctx->flat_slot.find(hdr->flat_id);
-        if (it == ctx->flat_slot.end()) return fail(ctx, DRR_E_ASSET, "drr_emit_visplane: unknown flat id");
+        if (it == ctx->flat_slot.end()) return rfail(err, DRR_E_ASSET, "emit_visplane: unknown flat id");
         p.flat_slot = (int16_t)it->second;
         p.kind = (int16_t)KIND_FLAT;
     }
@@ -553,33 +547,192 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
     p.light_level = hdr->light_level;
     p.left = hdr->left;
     p.right = hdr->right;
-    p.arr_first = (uint32_t)ctx->parr.n;
+    p.arr_first = (uint32_t)L.parr.n;
     const int ncols = hdr->right >= hdr->left ? hdr->right - hdr->left + 1 : 0;
-    if (!ctx->parr.reserve(ctx->parr.n + (size_t)ncols)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    if (!L.parr.reserve(L.parr.n + (size_t)ncols)) return rfail(err, DRR_E_NOMEM, "alloc");
     for (int i = 0; i < ncols; i++) {
-        ctx->parr.p[ctx->parr.n++] = (uint32_t)(uint16_t)top[i] | ((uint32_t)(uint16_t)bottom[i] << 16); // unclamped, as stored (quirk Q3)
+        L.parr.p[L.parr.n++] = (uint32_t)(uint16_t)top[i] | ((uint32_t)(uint16_t)bottom[i] << 16); // unclamped, as stored (quirk Q3)
         const int t = std::max<int>(top[i], 0);            // visplanes.rs:61 / :95
         const int b = std::min<int>(bottom[i], H - 1);     // :62 / :96
         if (p.kind == (int16_t)KIND_FLAT && (int16_t)(b - t) <= 1) continue; // :99-101 (not applied to sky)
-        if (t <= b) ctx->rec_count++;
+        if (t <= b) L.rec_count++;
     }
-    ctx->rec_cap += (uint64_t)ncols;
-    if (ncols > 0 && (!ctx->ops.push(0x80000000u | (uint32_t)ctx->planes.n) || !ctx->planes.push(p))) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    ctx->stats.visplanes++;
-    ctx->stats.visplane_columns += (uint64_t)ncols;
+    L.rec_cap += (uint64_t)ncols;
+    if (ncols > 0 && (!L.ops.push(0x80000000u | (uint32_t)L.planes.n) || !L.planes.push(p))) return rfail(err, DRR_E_NOMEM, "alloc");
+    L.stats.visplanes++;
+    L.stats.visplane_columns += (uint64_t)ncols;
     return DRR_OK;
+}
+
+static int rec_frame_end(Lists &L, std::string &err) {
+    if (!L.in_frame) return rfail(err, DRR_E_STATE, "frame_end outside a frame");
+    if (L.rec_cap > 0xffffffffull || L.cols.n > 0xffffffffull || L.parr.n > 0xffffffffull) {
+        rec_frame_abort(L, err);
+        return rfail(err, DRR_E_INVALID, "batch too large: more than 2^32 column records");
+    }
+    L.in_frame = false;
+    if (!push_frame_bases(L)) return rfail(err, DRR_E_NOMEM, "alloc");
+    L.stats.frames++;
+    return DRR_OK;
+}
+
+int drr_reset(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
+    ctx->clear_lists();
+    ctx->t_spans.clear();
+    ctx->t_colidx.clear();
+    ctx->uploaded_frames = 0;
+    std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
+    const uint64_t launches = ctx->stats.kernel_launches;
+    ctx->stats = drr_stats{};
+    ctx->stats.kernel_launches = launches;
+    return DRR_OK;
+}
+
+int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
+    CTX_CHECK(ctx);
+    if (view_idx >= 0 && view_idx < ctx->max_views && ctx->slot_to_frame[view_idx] >= 0 && !ctx->in_frame)
+        return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
+    const int rc = rec_frame_begin(*ctx, ctx, ctx->err, view_idx, view);
+    if (rc) return rc;
+    ctx->slot_to_frame[view_idx] = (int)ctx->views.n - 1;
+    ctx->t_spans.clear();
+    ctx->t_colidx.clear();
+    return DRR_OK;
+}
+
+int drr_frame_abort(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    const int rc = rec_frame_abort(*ctx, ctx->err);
+    if (rc == DRR_OK) ctx->slot_to_frame[ctx->cur_slot] = -1;
+    return rc;
+}
+
+int drr_emit_columns(drr_ctx *ctx, const drr_seg_hdr *hdr, const drr_col *cols, int n) {
+    CTX_CHECK(ctx);
+    return rec_emit_columns(*ctx, ctx, ctx->err, hdr, cols, n);
+}
+
+int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom) {
+    CTX_CHECK(ctx);
+    return rec_emit_visplane(*ctx, ctx, ctx->err, hdr, top, bottom);
 }
 
 int drr_frame_end(drr_ctx *ctx) {
     CTX_CHECK(ctx);
-    if (!ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_frame_end outside a frame");
-    if (ctx->rec_cap > 0xffffffffull || ctx->cols.n > 0xffffffffull || ctx->parr.n > 0xffffffffull) {
-        drr_frame_abort(ctx);
+    const int slot = ctx->cur_slot;
+    const int rc = rec_frame_end(*ctx, ctx->err);
+    if (rc != DRR_OK && !ctx->in_frame && slot >= 0 && slot < ctx->max_views && ctx->slot_to_frame[slot] == (int)ctx->views.n)
+        ctx->slot_to_frame[slot] = -1; // the frame was dropped (batch too large)
+    return rc;
+}
+
+// ---- recorders: the same recording, off-context (one per worker thread), appended to the context afterwards ------------
+int drr_recorder_create(drr_ctx *ctx, drr_recorder **out) {
+    if (!ctx || !out) return DRR_E_INVALID;
+    drr_recorder *r = new drr_recorder();
+    r->ctx = ctx;
+    r->lists.set_pinned(false);
+    *out = r;
+    return DRR_OK;
+}
+void drr_recorder_destroy(drr_recorder *rec) { delete rec; }
+const char *drr_recorder_last_error(const drr_recorder *rec) { return rec ? rec->err.c_str() : ""; }
+int drr_recorder_frame_begin(drr_recorder *rec, int view_idx, const drr_view *view) {
+    if (!rec) return DRR_E_INVALID;
+    return rec_frame_begin(rec->lists, rec->ctx, rec->err, view_idx, view);
+}
+int drr_recorder_emit_columns(drr_recorder *rec, const drr_seg_hdr *hdr, const drr_col *cols, int n) {
+    if (!rec) return DRR_E_INVALID;
+    return rec_emit_columns(rec->lists, rec->ctx, rec->err, hdr, cols, n);
+}
+int drr_recorder_emit_visplane(drr_recorder *rec, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom) {
+    if (!rec) return DRR_E_INVALID;
+    return rec_emit_visplane(rec->lists, rec->ctx, rec->err, hdr, top, bottom);
+}
+int drr_recorder_frame_end(drr_recorder *rec) {
+    if (!rec) return DRR_E_INVALID;
+    return rec_frame_end(rec->lists, rec->err);
+}
+int drr_recorder_frame_abort(drr_recorder *rec) {
+    if (!rec) return DRR_E_INVALID;
+    return rec_frame_abort(rec->lists, rec->err);
+}
+
+// Move every frame of `rec` to the end of the context's lists (indices re-based), then clear the recorder.
+int drr_append(drr_ctx *ctx, drr_recorder *rec) {
+    CTX_CHECK(ctx);
+    if (!rec || rec->ctx != ctx) return fail(ctx, DRR_E_INVALID, "drr_append: recorder of another context");
+    Lists &R = rec->lists;
+    if (ctx->in_frame || R.in_frame) return fail(ctx, DRR_E_STATE, "drr_append inside a frame");
+    const size_t nf = R.views.n;
+    if (nf == 0) return DRR_OK;
+    for (size_t i = 0; i < nf; i++) { // every view index must be free in the context and unique in the recorder
+        const uint32_t slot = R.frame_slot.p[i];
+        if (ctx->slot_to_frame[slot] >= 0) {
+            for (size_t k = 0; k < i; k++) ctx->slot_to_frame[R.frame_slot.p[k]] = -1;
+            return fail(ctx, DRR_E_INVALID, "drr_append: view index already recorded since drr_reset");
+        }
+        ctx->slot_to_frame[slot] = (int)(ctx->views.n + i);
+    }
+    auto undo = [&]() {
+        for (size_t i = 0; i < nf; i++) ctx->slot_to_frame[R.frame_slot.p[i]] = -1;
+        return fail(ctx, DRR_E_NOMEM, "pinned alloc");
+    };
+    if (ctx->rec_cap + R.rec_cap > 0xffffffffull || ctx->cols.n + R.cols.n > 0xffffffffull || ctx->parr.n + R.parr.n > 0xffffffffull) {
+        for (size_t i = 0; i < nf; i++) ctx->slot_to_frame[R.frame_slot.p[i]] = -1;
         return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 column records");
     }
-    ctx->in_frame = false;
-    if (!push_frame_bases(ctx)) return fail(ctx, DRR_E_NOMEM, "pinned alloc");
-    ctx->stats.frames++;
+    if (ctx->frame_op_base.n == 0 && !push_frame_bases(*ctx)) return undo();
+    const uint32_t op_off = (uint32_t)ctx->ops.n, seg_off = (uint32_t)ctx->segs.n, col_off = (uint32_t)ctx->cols.n;
+    const uint32_t plane_off = (uint32_t)ctx->planes.n, parr_off = (uint32_t)ctx->parr.n, cap_off = (uint32_t)ctx->rec_cap;
+    if (!ctx->views.reserve(ctx->views.n + nf) || !ctx->frame_slot.reserve(ctx->frame_slot.n + nf) || !ctx->ops.reserve(ctx->ops.n + R.ops.n) ||
+        !ctx->segs.reserve(ctx->segs.n + R.segs.n) || !ctx->cols.reserve(ctx->cols.n + R.cols.n) || !ctx->planes.reserve(ctx->planes.n + R.planes.n) ||
+        !ctx->parr.reserve(ctx->parr.n + R.parr.n) || !ctx->frame_op_base.reserve(ctx->frame_op_base.n + nf) ||
+        !ctx->frame_rec_base.reserve(ctx->frame_rec_base.n + nf))
+        return undo();
+    memcpy(ctx->views.p + ctx->views.n, R.views.p, nf * sizeof(View));
+    ctx->views.n += nf;
+    memcpy(ctx->frame_slot.p + ctx->frame_slot.n, R.frame_slot.p, nf * 4);
+    ctx->frame_slot.n += nf;
+    for (size_t i = 0; i < R.ops.n; i++) {
+        const uint32_t op = R.ops.p[i];
+        ctx->ops.p[ctx->ops.n++] = (op & 0x80000000u) ? (0x80000000u | ((op & 0x7fffffffu) + plane_off)) : op + seg_off;
+    }
+    for (size_t i = 0; i < R.segs.n; i++) {
+        SegRec g = R.segs.p[i];
+        g.cols_first += col_off;
+        ctx->segs.p[ctx->segs.n++] = g;
+    }
+    memcpy(ctx->cols.p + ctx->cols.n, R.cols.p, R.cols.n * sizeof(ColRec));
+    ctx->cols.n += R.cols.n;
+    for (size_t i = 0; i < R.planes.n; i++) {
+        PlaneRec q = R.planes.p[i];
+        q.arr_first += parr_off;
+        ctx->planes.p[ctx->planes.n++] = q;
+    }
+    memcpy(ctx->parr.p + ctx->parr.n, R.parr.p, R.parr.n * 4);
+    ctx->parr.n += R.parr.n;
+    for (size_t i = 1; i <= nf; i++) { // the recorder's bases start at 0
+        ctx->frame_op_base.p[ctx->frame_op_base.n++] = R.frame_op_base.p[i] + op_off;
+        ctx->frame_rec_base.p[ctx->frame_rec_base.n++] = R.frame_rec_base.p[i] + cap_off;
+        ctx->frame_seg_base.push_back(R.frame_seg_base[i] + seg_off);
+        ctx->frame_col_base.push_back(R.frame_col_base[i] + col_off);
+        ctx->frame_plane_base.push_back(R.frame_plane_base[i] + plane_off);
+        ctx->frame_parr_base.push_back(R.frame_parr_base[i] + parr_off);
+    }
+    ctx->rec_count += R.rec_count;
+    ctx->rec_cap += R.rec_cap;
+    ctx->stats.frames += R.stats.frames;
+    ctx->stats.seg_headers += R.stats.seg_headers;
+    ctx->stats.column_records += R.stats.column_records;
+    ctx->stats.visplanes += R.stats.visplanes;
+    ctx->stats.visplane_columns += R.stats.visplane_columns;
+    ctx->t_spans.clear();
+    ctx->t_colidx.clear();
+    R.clear_lists();
+    R.stats = drr_stats{};
     return DRR_OK;
 }
 
@@ -911,8 +1064,8 @@ int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx 
     c->CFX = (float)(uint32_t)width / 2.0f;
     c->CFY = (float)(uint32_t)height / 2.0f;
     c->slot_to_frame.assign(max_views, -1);
-    c->views.pinned = c->segs.pinned = c->planes.pinned = c->cols.pinned = c->parr.pinned = c->ops.pinned = false;
-    c->frame_op_base.pinned = c->frame_rec_base.pinned = c->frame_slot.pinned = c->h_crc.pinned = false;
+    c->set_pinned(false);
+    c->h_crc.pinned = false;
     *out = c;
     return DRR_OK;
 }

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/drr.h"
@@ -640,13 +641,21 @@ struct drr_scene {
     // per-frame front-end
     // ================================================================================================================
     drr_ctx *ctx = nullptr;
+    drr_recorder *rec = nullptr; // when set, the frame is recorded off-context (worker threads of drr_scene_emit_views)
     V2 ppos;
     float pfloor, pangle, timestamp;
     int phases;
 
     void chk(int rc) {
-        if (rc != DRR_OK) panic(std::string("libdrr: ") + drr_error_name(rc) + ": " + drr_last_error(ctx));
+        if (rc != DRR_OK) panic(std::string("libdrr: ") + drr_error_name(rc) + ": " + (rec ? drr_recorder_last_error(rec) : drr_last_error(ctx)));
     }
+    int sink_frame_begin(int idx, const drr_view *v) { return rec ? drr_recorder_frame_begin(rec, idx, v) : drr_frame_begin(ctx, idx, v); }
+    int sink_columns(const drr_seg_hdr *h, const drr_col *c, int n) { return rec ? drr_recorder_emit_columns(rec, h, c, n) : drr_emit_columns(ctx, h, c, n); }
+    int sink_visplane(const drr_visplane_hdr *h, const int16_t *t, const int16_t *b) {
+        return rec ? drr_recorder_emit_visplane(rec, h, t, b) : drr_emit_visplane(ctx, h, t, b);
+    }
+    int sink_frame_end() { return rec ? drr_recorder_frame_end(rec) : drr_frame_end(ctx); }
+    int sink_frame_abort() { return rec ? drr_recorder_frame_abort(rec) : drr_frame_abort(ctx); }
     void emit(const Render &r, const drr_col *cols, int phase) {
         if (r.bitmap < 0 || r.ncol == 0) return;
         drr_seg_hdr h;
@@ -664,7 +673,7 @@ struct drr_scene {
         h.top_height = r.top_h;
         h.offset_x = r.off_x;
         h.offset_y = r.off_y;
-        chk(drr_emit_columns(ctx, &h, cols, (int)r.ncol));
+        chk(sink_columns(&h, cols, (int)r.ncol));
     }
 
     int pick_flat(const FlatRef &fr, bool *sky) const { // flats.rs:103-111
@@ -986,23 +995,23 @@ struct drr_scene {
         bottom_clip.resize(W);
 
         drr_view v{x, y, pfloor, angle, cosf(angle), sinf(angle)};
-        chk(drr_frame_begin(ctx, view_idx, &v));
+        chk(sink_frame_begin(view_idx, &v));
         try {
             walk((int)nodes.size() - 1);         // A: mod.rs:119-120
             if (phases & DRR_PHASES_PLANES) {    // B: mod.rs:106-116, in creation order
                 for (const PlaneH &p : planes) {
                     drr_visplane_hdr h{(int16_t)(p.sky ? DRR_FLAT_SKY : p.flat), p.height, p.light, p.left, p.right, 0};
-                    chk(drr_emit_visplane(ctx, &h, plane_rows.data() + p.rows + p.left, plane_rows.data() + p.rows + W + p.left));
+                    chk(sink_visplane(&h, plane_rows.data() + p.rows + p.left, plane_rows.data() + p.rows + W + p.left));
                 }
             }
             std::reverse(renders.begin(), renders.end()); // mod.rs:124
             map_objects();                                  // C
             for (Render &r : renders) render_deferred(r, colpool.data()); // D: segs.rs:593-597
         } catch (...) {
-            drr_frame_abort(ctx); // the reference would have panicked: nothing is recorded for this view
+            sink_frame_abort(); // the reference would have panicked: nothing is recorded for this view
             throw;
         }
-        chk(drr_frame_end(ctx));
+        chk(sink_frame_end());
     }
 };
 
@@ -1069,6 +1078,63 @@ int drr_scene_emit_view(drr_scene *s, drr_ctx *ctx, int view_idx, float x, float
         return DRR_E_NOMEM;
     }
     return DRR_OK;
+}
+
+// Renderer::new(..).render() for n viewpoints at once: the front-end runs on `nthreads` worker threads (each with its own
+// copy of the scene's scratch state and its own recorder), the recorded frames are then appended to the context in view
+// order.  status[i] (may be NULL) receives DRR_OK or DRR_E_PANIC (the reference would have panicked on that viewpoint:
+// nothing is recorded for it).  Returns the first hard error, DRR_OK otherwise.
+int drr_scene_emit_views(drr_scene *s, drr_ctx *ctx, int first_view_idx, const float *xya, int n, float timestamp, int phases, int nthreads,
+                         int *status) {
+    if (!s || !ctx || n < 0 || (n > 0 && !xya)) return DRR_E_INVALID;
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    nthreads = std::max(1, std::min(nthreads, std::max(1, n / 8)));
+    std::vector<drr_recorder *> recs(nthreads, nullptr);
+    std::vector<int> hard(nthreads, DRR_OK);
+    std::vector<std::string> msgs(nthreads);
+    for (int t = 0; t < nthreads; t++)
+        if (drr_recorder_create(ctx, &recs[t]) != DRR_OK) {
+            for (auto r : recs) drr_recorder_destroy(r);
+            return DRR_E_NOMEM;
+        }
+    auto work = [&](int t) {
+        try {
+            drr_scene local(*s); // the scratch state is per thread; maps and assets are only read
+            local.rec = recs[t];
+            const int lo = (int)((long long)n * t / nthreads), hi = (int)((long long)n * (t + 1) / nthreads);
+            for (int i = lo; i < hi; i++) {
+                int rc = DRR_OK;
+                try {
+                    local.emit_view(ctx, first_view_idx + i, xya[3 * i], xya[3 * i + 1], xya[3 * i + 2], timestamp, phases);
+                } catch (const Panic &p) {
+                    rc = DRR_E_PANIC;
+                    if (p.msg.compare(0, 7, "libdrr:") == 0) { // not a reference panic: the library refused something
+                        hard[t] = DRR_E_INVALID;
+                        msgs[t] = p.msg;
+                    }
+                }
+                if (status) status[i] = rc;
+            }
+        } catch (const std::exception &e) {
+            hard[t] = DRR_E_NOMEM;
+            msgs[t] = e.what();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    int rc = DRR_OK;
+    for (int t = 0; t < nthreads && rc == DRR_OK; t++) {
+        if (hard[t] != DRR_OK) {
+            rc = hard[t];
+            s->err = msgs[t];
+        } else if ((rc = drr_append(ctx, recs[t])) != DRR_OK) {
+            s->err = std::string("drr_append: ") + drr_last_error(ctx);
+        }
+    }
+    for (auto r : recs) drr_recorder_destroy(r);
+    return rc;
 }
 
 } // extern "C"

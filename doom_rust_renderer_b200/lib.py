@@ -80,6 +80,11 @@ def _lib() -> C.CDLL:
             "drr_scene_load": (i, [C.c_char_p, C.c_char_p, i, i, C.POINTER(vp)]), "drr_scene_free": (None, [vp]),
             "drr_scene_last_error": (C.c_char_p, [vp]), "drr_scene_upload_assets": (i, [vp, vp]),
             "drr_scene_player_start": (i, [vp, vp]), "drr_scene_emit_view": (i, [vp, vp, i, f, f, f, f, i]),
+            "drr_scene_emit_views": (i, [vp, vp, i, vp, i, f, i, i, vp]),
+            "drr_recorder_create": (i, [vp, C.POINTER(vp)]), "drr_recorder_destroy": (None, [vp]), "drr_recorder_last_error": (C.c_char_p, [vp]),
+            "drr_recorder_frame_begin": (i, [vp, i, C.POINTER(DrrView)]), "drr_recorder_emit_columns": (i, [vp, C.POINTER(DrrSegHdr), vp, i]),
+            "drr_recorder_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_recorder_frame_end": (i, [vp]),
+            "drr_recorder_frame_abort": (i, [vp]), "drr_append": (i, [vp, vp]),
             "drr_test_ctx_create_host_only": (i, [i, i, i, C.POINTER(vp)]),
             "drr_test_list": (vp, [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "drr_test_bitmap_info": (i, [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
@@ -104,7 +109,9 @@ EXPORTED_SYMBOLS = [
     "drr_read_framebuffer", "drr_read_checksums", "drr_checksum_host", "drr_get_stats", "drr_time_draw",
     "drr_profile_begin", "drr_profile_end",
     "drr_scene_load", "drr_scene_free", "drr_scene_last_error", "drr_scene_upload_assets", "drr_scene_player_start",
-    "drr_scene_emit_view",
+    "drr_scene_emit_view", "drr_scene_emit_views",
+    "drr_recorder_create", "drr_recorder_destroy", "drr_recorder_last_error", "drr_recorder_frame_begin", "drr_recorder_emit_columns",
+    "drr_recorder_emit_visplane", "drr_recorder_frame_end", "drr_recorder_frame_abort", "drr_append",
 ]
 
 
@@ -328,14 +335,13 @@ class Scene:
     def emit_view(self, ctx: Context, view_idx: int, x: float, y: float, angle: float, timestamp: float = 0.0, phases: int = PHASES_ALL):
         self._ck(self.L.drr_scene_emit_view(self.h, ctx.h, view_idx, x, y, angle, timestamp, phases))
 
-    def emit_views(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = PHASES_ALL, first_slot: int = 0):
-        """views: float32 [n][3] = (x, y, angle).  Returns the list of view indices the reference would have panicked on
-        (nothing is recorded for those; their framebuffer slots keep their previous contents)."""
-        bad = []
-        for k, (x, y, a) in enumerate(np.asarray(views, np.float32)):
-            rc = self.L.drr_scene_emit_view(self.h, ctx.h, first_slot + k, float(x), float(y), float(a), timestamp, phases)
-            if rc == -7:  # DRR_E_PANIC
-                bad.append(first_slot + k)
-            elif rc != 0:
-                self._ck(rc)
-        return bad
+    def emit_views(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = PHASES_ALL, first_slot: int = 0,
+                   threads: int = 0):
+        """views: float32 [n][3] = (x, y, angle).  The front-end runs on `threads` worker threads (0 = one per host core), each
+        recording into its own recorder; frames end up in the context in view order.  Returns the list of view indices the
+        reference would have panicked on (nothing is recorded for those; their framebuffer slots keep their previous
+        contents)."""
+        v = np.ascontiguousarray(np.asarray(views, np.float32).reshape(-1, 3))
+        status = np.zeros(len(v), np.int32)
+        self._ck(self.L.drr_scene_emit_views(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, threads, _ptr(status)))
+        return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]  # DRR_E_PANIC

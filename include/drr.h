@@ -111,6 +111,22 @@ int drr_emit_visplane(drr_ctx *ctx, const drr_visplane_hdr *hdr, const int16_t *
 int drr_frame_end(drr_ctx *ctx);
 int drr_frame_abort(drr_ctx *ctx); /* discard the frame being recorded (the view index becomes free again) */
 
+/* ---- recorders: the same recording off-context ------------------------------------------------------------------ */
+/* A recorder records frames exactly like drr_frame_begin .. drr_frame_end but into private memory, so several threads can
+ * run the front-end at once (one recorder per thread; the context's asset tables are only read while recording, so assets
+ * must be uploaded before).  drr_append, called from the context's own thread, moves the recorder's frames to the end of
+ * the context's lists and empties the recorder; view indices must still be unique per drr_reset. */
+typedef struct drr_recorder drr_recorder;
+int drr_recorder_create(drr_ctx *ctx, drr_recorder **out);
+void drr_recorder_destroy(drr_recorder *rec);
+const char *drr_recorder_last_error(const drr_recorder *rec);
+int drr_recorder_frame_begin(drr_recorder *rec, int view_idx, const drr_view *view);
+int drr_recorder_emit_columns(drr_recorder *rec, const drr_seg_hdr *hdr, const drr_col *cols, int n);
+int drr_recorder_emit_visplane(drr_recorder *rec, const drr_visplane_hdr *hdr, const int16_t *top, const int16_t *bottom);
+int drr_recorder_frame_end(drr_recorder *rec);
+int drr_recorder_frame_abort(drr_recorder *rec);
+int drr_append(drr_ctx *ctx, drr_recorder *rec);
+
 /* ---- execution ---------------------------------------------------------------------------------------------- */
 int drr_upload_lists(drr_ctx *ctx); /* async H2D of everything recorded since drr_reset (from pinned staging) */
 int drr_draw(drr_ctx *ctx);         /* async: render every uploaded frame into its framebuffer (+ per-frame checksum) */
@@ -159,6 +175,11 @@ int drr_scene_player_start(drr_scene *scene, float out_xya[3]); /* Player1Start,
 /* One Renderer::new(..., player, timestamp).render() for the player at (x, y, angle): frame_begin, emits, frame_end.
  * `phases` gates which leaf call sites emit (config 3's walls-only / flats-only split). */
 int drr_scene_emit_view(drr_scene *scene, drr_ctx *ctx, int view_idx, float x, float y, float angle, float timestamp, int phases);
+/* The same for n viewpoints (xya = n x (x, y, angle)) with view indices first_view_idx .. first_view_idx+n-1, the front-end
+ * running on `nthreads` worker threads (0 = one per host core) through recorders.  status[i] (may be NULL) = DRR_OK or
+ * DRR_E_PANIC (nothing recorded for that viewpoint). */
+int drr_scene_emit_views(drr_scene *scene, drr_ctx *ctx, int first_view_idx, const float *xya, int n, float timestamp, int phases,
+                         int nthreads, int *status);
 
 #ifdef __cplusplus
 }

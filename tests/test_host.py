@@ -184,6 +184,51 @@ def test_checksum_definitions_agree():
         assert drr.checksum_host(b) == drr.checksum_numpy(b)
 
 
+def test_threaded_front_end_records_the_same_lists():
+    """drr_scene_emit_views (worker threads, one recorder each, appended in view order) records byte for byte what calling
+    drr_scene_emit_view view by view records; a recorder refuses what a context refuses; appending twice the same view fails."""
+    path, gm = common.wad("e1m1")
+    W, H, n = 160, 100, 70
+    views = np.array(synth_wad.walk_viewpoints(gm, 512)[::7][:n], np.float32)
+    scene = drr.Scene(path, "E1M1", W, H)
+    ctx_seq = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(ctx_seq)
+    skipped_seq = []
+    for k, v in enumerate(views):
+        try:
+            scene.emit_view(ctx_seq, k, float(v[0]), float(v[1]), float(v[2]))
+        except drr.DrrError as e:
+            assert e.code == -7
+            skipped_seq.append(k)
+    for threads in (1, 3, 8):
+        ctx_mt = drr.Context(W, H, 0, n, _host_only=True)
+        scene.upload_assets(ctx_mt)
+        assert scene.emit_views(ctx_mt, views, threads=threads) == skipped_seq
+        for which, dt in ((0, drr.VIEW_DTYPE), (1, drr.SEG_DTYPE), (2, drr.PLANE_DTYPE), (5, np.uint32), (6, np.uint32), (7, drr.COL_DTYPE),
+                          (8, np.uint32), (9, np.uint32), (10, np.uint32)):
+            assert ctx_mt._list(which, dt).tobytes() == ctx_seq._list(which, dt).tobytes(), (threads, which)
+        assert ctx_mt.stats() == ctx_seq.stats()
+        with pytest.raises(drr.DrrError):  # every view index is taken now
+            scene.emit_views(ctx_mt, views[:9], threads=2)
+        assert ctx_mt.stats() == ctx_seq.stats()  # and the failed append left nothing behind
+    # the raw recorder API: same validation as the context's
+    L = drr._lib()
+    rec = ctypes.c_void_p()
+    assert L.drr_recorder_create(ctx_seq.h, ctypes.byref(rec)) == 0
+    v = drr.DrrView(0, 0, 0, 0, 1, 0)
+    assert L.drr_recorder_emit_columns(rec, ctypes.byref(drr.DrrSegHdr()), None, 0) == -2     # outside a frame
+    assert L.drr_recorder_frame_begin(rec, n, ctypes.byref(v)) == -1                            # view index out of range
+    assert L.drr_recorder_frame_begin(rec, 0, ctypes.byref(v)) == 0
+    assert L.drr_recorder_frame_begin(rec, 1, ctypes.byref(v)) == -2                            # frame not ended
+    hdr = drr.DrrSegHdr(10 ** 6, 0, 0, 1, 1, 2, -1, 0, 0, 10, -8, 8, 0, 0)
+    assert L.drr_recorder_emit_columns(rec, ctypes.byref(hdr), None, 0) == -5                   # unknown bitmap
+    assert b"unknown bitmap" in L.drr_recorder_last_error(rec)
+    assert L.drr_append(ctx_seq.h, rec) == -2                                                   # recorder still inside a frame
+    assert L.drr_recorder_frame_end(rec) == 0
+    assert L.drr_append(ctx_seq.h, rec) == (-1 if 0 not in skipped_seq else 0)                  # view 0 is already recorded
+    L.drr_recorder_destroy(rec)
+
+
 def test_png_export_roundtrip():
     """Presentation/export: an RGB24 frame written as PNG decodes to the same bytes."""
     from doom_rust_renderer_b200 import png
