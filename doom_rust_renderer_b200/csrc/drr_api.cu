@@ -1,7 +1,7 @@
 // drr_api.cu -- the C ABI of include/drr.h: context, asset upload, draw-list recording, upload and launches.
 //
 // Data layout in HBM (all frames of a batch concatenated, see drr_device.cuh):
-//   as emitted:  views[frame] 24 B | ops[] 4 B (call order) | segs[] 64 B | cols[] 10 B | planes[] 16 B | (top, bottom) pairs 4 B
+//   as emitted:  views[frame] 24 B | ops[] 4 B (call order) | segs[] 80 B | cols[] 10 B | planes[] 16 B | (top, bottom) pairs 4 B
 //   device scratch: colidx[frame][x] 8 B and one decoded 64-byte record per (op, column), both written by the bin kernel
 //   framebuffers: max_views x (W*H*3 B, RGB24 row-major == Pixels.pixels, src/renderer/pixels.rs:5-14)
 //   assets: u16 texel pool (column-major, pow2 column pitch, palette byte offsets, 4096 = None), u8 flat pool (4096 B per
@@ -495,7 +495,11 @@ static int rec_emit_columns(Lists &L, const drr_ctx *ctx, std::string &err, cons
     r.top_height = hdr->top_height;
     r.offset_x = hdr->offset_x;
     r.offset_y = hdr->offset_y;
-    r.pad = 0;
+    r.tex_base = ctx->bitmaps[it->second].base;
+    r.tex_w = ctx->bitmaps[it->second].w;
+    r.tex_h = ctx->bitmaps[it->second].h;
+    r.tex_opaque = ctx->bitmaps[it->second].opaque;
+    r.pad[0] = r.pad[1] = 0;
     static_assert(sizeof(drr_col) == sizeof(ColRec), "drr_col layout");
     if (!L.cols.reserve(L.cols.n + (size_t)n)) return rfail(err, DRR_E_NOMEM, "alloc");
     const int H = ctx->H, W = ctx->W;

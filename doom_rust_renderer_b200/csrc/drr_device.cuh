@@ -32,7 +32,7 @@ struct Span {
 };
 static_assert(sizeof(Span) == 16, "Span layout");
 
-// Device copy of drr_seg_hdr (bitmap id resolved to a slot) plus where its column records are. 64 bytes.
+// Device copy of drr_seg_hdr (bitmap id resolved to a slot) plus where its column records are. 80 bytes.
 struct SegRec {
     uint32_t bitmap_slot;
     int16_t light_level;
@@ -45,9 +45,13 @@ struct SegRec {
     uint32_t cols_first; // index of the first ColRec; the records' x is strictly increasing (drr_emit_columns splits otherwise)
     uint32_t n;          // number of ColRec
     int16_t x0, x1;      // x of the first / last record
-    uint32_t pad;
+    // the bitmap's record (BitmapRec of bitmap_slot), copied in at emit time so that the bin kernel needs no dependent load
+    uint32_t tex_base;
+    int16_t tex_w, tex_h;
+    uint32_t tex_opaque;
+    uint32_t pad[2];
 };
-static_assert(sizeof(SegRec) == 64, "SegRec layout");
+static_assert(sizeof(SegRec) == 80, "SegRec layout");
 
 // == drr_col (BitmapColumn, bitmap_render.rs:19-25). 10 bytes, 2-byte aligned.
 struct ColRec {

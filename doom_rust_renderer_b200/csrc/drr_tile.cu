@@ -39,14 +39,13 @@ enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10,
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
 __device__ __forceinline__ uint32_t wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
-    const BitmapRec bm = a.bitmaps[g.bitmap_slot];
-    const uint32_t h = (uint32_t)bm.h;
-    uint32_t kind = bm.opaque ? KIND_WALL : KIND_WALL_HOLES;
+    const uint32_t h = (uint32_t)g.tex_h;
+    uint32_t kind = g.tex_opaque ? KIND_WALL : KIND_WALL_HOLES;
     uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
-    const WallColumn wc = wall_column(g, bm.w, x);
+    const WallColumn wc = wall_column(g, g.tex_w, x);
     if (wc.tx < 0) kind = KIND_NONE; // reference: negative index -> panic
     const uint32_t lp = ilog2_ceil(h); // column-major texel pool: one texture column = 1 << lp consecutive texels
-    ra.z = bm.base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
+    ra.z = g.tex_base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
     uint32_t flags = 0;
     if ((h & (h - 1u)) == 0u) {
         // floormod(wrap16(tyr + off_y), 2^k) == (tyr + off_y) & (2^k - 1): the i16 wrap only touches bits >= 16
@@ -127,6 +126,7 @@ __device__ __forceinline__ uint32_t plane_record(const DrawArgs &a, const PlaneR
 // loaded on a hit.  Ops beyond the table's capacity are read from global memory.
 static constexpr int BIN_THREADS = 128;
 static constexpr int BIN_TAB = 512;
+static constexpr int BIN_REC = 96; // ops whose whole record (80-byte SegRec / 16-byte PlaneRec) is staged in shared memory too
 
 __device__ __forceinline__ uint2 op_range(const DrawArgs &a, uint32_t op) { // (x0 | x1 << 16, op); an empty op gets x0 > x1
     if (op & 0x80000000u) {
@@ -188,20 +188,20 @@ __device__ __forceinline__ void for_each_candidate(const DrawArgs &a, uint32_t o
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
-            visit(make_uint2(__shfl_sync(0xffffffffu, e.x, src), __shfl_sync(0xffffffffu, e.y, src)));
+            visit(make_uint2(__shfl_sync(0xffffffffu, e.x, src), __shfl_sync(0xffffffffu, e.y, src)), base + (uint32_t)src);
         }
     }
 }
 
 template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, uint4 *out, Cover *cover) {
+__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, uint4 *out, Cover *cover) {
     uint32_t n = 0;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
-    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e) {
+    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t k) {
         if (x >= a.W || x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) return; // (Pixels::set ignores x >= W)
         const uint32_t op = e.y;
         if (op & 0x80000000u) {
-            const PlaneRec p = a.planes[op & 0x7fffffffu];
+            const PlaneRec p = k < (uint32_t)BIN_REC ? *reinterpret_cast<const PlaneRec *>(s_rec + 5 * k) : a.planes[op & 0x7fffffffu];
             const uint32_t tb = a.parr[p.arr_first + (uint32_t)(x - p.left)];
             const int t = max((int)(short)(tb & 0xffffu), 0);                // visplanes.rs:61 / :95
             const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             }
             ++n;
         } else {
-            const SegRec *gp = a.segs + op;
+            const SegRec *gp = k < (uint32_t)BIN_REC ? reinterpret_cast<const SegRec *>(s_rec + 5 * k) : a.segs + op;
             const uint32_t gn = gp->n, cols_first = gp->cols_first;
             const int gx0 = gp->x0, gx1 = gp->x1;
             // the records' x is strictly increasing: usually x0, x0+1, ... (direct index), otherwise binary search
@@ -243,10 +243,19 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
 // many records of the frame's range with one atomic, then writes the records in draw order ("column binning").
 __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
     __shared__ uint2 s_tab[BIN_TAB];
+    __shared__ uint4 s_rec[BIN_REC * 5]; // the first BIN_REC ops' records: the walk then depends on one global load (the column record) only
     const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
     const int x = (int)(blockIdx.x % (unsigned)bpf) * BIN_THREADS + (int)threadIdx.x;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
     for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += BIN_THREADS) s_tab[k] = op_range(a, a.ops[o0 + k]);
+    for (uint32_t i = threadIdx.x; i < min(nops, (uint32_t)BIN_REC) * 5; i += BIN_THREADS) {
+        const uint32_t k = i / 5, part = i % 5, op = a.ops[o0 + k];
+        if (op & 0x80000000u) {
+            if (part == 0) s_rec[5 * k] = *reinterpret_cast<const uint4 *>(a.planes + (op & 0x7fffffffu));
+        } else {
+            s_rec[i] = reinterpret_cast<const uint4 *>(a.segs + op)[part];
+        }
+    }
     __syncthreads();
     if ((x & ~31) >= a.W) return; // whole warps only: the candidate walk is a warp-wide operation
     const bool live = x < a.W;
@@ -254,14 +263,14 @@ __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int fr
     // reserve one record per op whose x range contains the column (an upper bound of what survives clipping; the frame's
     // record range is sized by the host from the same bound): this pass touches shared memory only
     uint32_t cap = 0;
-    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e) {
+    for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t) {
         cap += (live && x >= (int)(short)(e.x & 0xffffu) && x <= (int)(short)(e.x >> 16)) ? 1u : 0u;
     });
     uint32_t first = a.frame_rec_base[f];
     if (cap) first += atomicAdd(a.frame_cursor + f, cap);
     Cover cover;
     // (a dead lane of a partly live warp, x >= W, visits nothing: it only takes part in the ballots)
-    const uint32_t n = walk_column<true>(a, f, x, vw, s_tab, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
+    const uint32_t n = walk_column<true>(a, f, x, vw, s_tab, s_rec, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
     if (live) {
         ColIdx ci;
         ci.first = first;

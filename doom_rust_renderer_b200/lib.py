@@ -289,7 +289,7 @@ VIEW_DTYPE = np.dtype([("pos_x", "<f4"), ("pos_y", "<f4"), ("floor_height", "<f4
 SEG_DTYPE = np.dtype([("bitmap_slot", "<u4"), ("light_level", "<i2"), ("phase", "<i2"), ("lsx", "<f4"), ("lsy", "<f4"), ("lex", "<f4"),
                       ("ley", "<f4"), ("start_offset", "<f4"), ("start_x", "<i4"), ("end_x", "<i4"), ("bottom_height", "<f4"),
                       ("top_height", "<f4"), ("offset_x", "<i2"), ("offset_y", "<i2"), ("cols_first", "<u4"), ("n", "<u4"),
-                      ("x0", "<i2"), ("x1", "<i2"), ("pad", "<u4")])
+                      ("x0", "<i2"), ("x1", "<i2"), ("tex_base", "<u4"), ("tex_w", "<i2"), ("tex_h", "<i2"), ("tex_opaque", "<u4"), ("pad", "<u4", (2,))])
 PLANE_DTYPE = np.dtype([("flat_slot", "<i2"), ("height", "<i2"), ("light_level", "<i2"), ("left", "<i2"), ("right", "<i2"), ("kind", "<i2"),
                         ("arr_first", "<u4")])
 SPAN_DTYPE = np.dtype([("y0", "<u2"), ("y1", "<u2"), ("x", "<u2"), ("kind", "u1"), ("pad", "u1"), ("op", "<u4"), ("top_y", "<i2"), ("bottom_y", "<i2")])

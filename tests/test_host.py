@@ -105,6 +105,8 @@ def test_front_end_emits_the_oracles_leaf_calls():
         segs_a, segs_b = ctx_a._list(1, drr.SEG_DTYPE), ctx_b._list(1, drr.SEG_DTYPE)
         for ga, gb in zip(segs_a, segs_b):
             for f in drr.SEG_DTYPE.names[1:]:
+                if f == "tex_base":  # position in the context's texel pool: depends on the upload order
+                    continue
                 assert ga[f].tobytes() == gb[f].tobytes(), f
             assert (assets_a.bitmap(int(ga["bitmap_slot"])) == assets_b.bitmap(int(gb["bitmap_slot"]))).all()
         assert ctx_a._list(7, drr.COL_DTYPE).tobytes() == ctx_b._list(7, drr.COL_DTYPE).tobytes()  # every drr_col, in order
