@@ -124,7 +124,7 @@ __device__ __forceinline__ uint32_t plane_record(const DrawArgs &a, const PlaneR
 // is ignored, rows are clipped to the screen by the callers) and draw_visplane's (visplanes.rs:95-101).  Returns the count.
 // s_tab holds, per op of the frame, (x0 | x1 << 16, op word): the x test runs on shared memory, the op's record is only
 // loaded on a hit.  Ops beyond the table's capacity are read from global memory.
-static constexpr int BIN_THREADS = 128;
+static constexpr int BIN_THREADS = 384; // upper bound of the CTA size; the launcher picks ceil(W / ceil(W / 192)) rounded up to a warp (the size hardly matters: tools/sweep_env.sh DRR_BIN_THREADS)
 static constexpr int BIN_TAB = 512;
 static constexpr int BIN_REC = 96; // ops whose whole record (80-byte SegRec / 16-byte PlaneRec) is staged in shared memory too
 
@@ -242,13 +242,14 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
 // drr_bin_kernel: one thread per (frame, screen column).  Counts what the frame's ops draw in the column, reserves that
 // many records of the frame's range with one atomic, then writes the records in draw order ("column binning").
 __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
+    const int nthreads = (int)blockDim.x;
     __shared__ uint2 s_tab[BIN_TAB];
     __shared__ uint4 s_rec[BIN_REC * 5]; // the first BIN_REC ops' records: the walk then depends on one global load (the column record) only
     const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
-    const int x = (int)(blockIdx.x % (unsigned)bpf) * BIN_THREADS + (int)threadIdx.x;
+    const int x = (int)(blockIdx.x % (unsigned)bpf) * nthreads + (int)threadIdx.x;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
-    for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += BIN_THREADS) s_tab[k] = op_range(a, a.ops[o0 + k]);
-    for (uint32_t i = threadIdx.x; i < min(nops, (uint32_t)BIN_REC) * 5; i += BIN_THREADS) {
+    for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += nthreads) s_tab[k] = op_range(a, a.ops[o0 + k]);
+    for (uint32_t i = threadIdx.x; i < min(nops, (uint32_t)BIN_REC) * 5; i += nthreads) {
         const uint32_t k = i / 5, part = i % 5, op = a.ops[o0 + k];
         if (op & 0x80000000u) {
             if (part == 0) s_rec[5 * k] = *reinterpret_cast<const uint4 *>(a.planes + (op & 0x7fffffffu));
@@ -652,10 +653,13 @@ cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t 
     if (nframes <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(a.frame_cursor + frame0, 0, sizeof(uint32_t) * (size_t)nframes, st);
     if (e != cudaSuccess) return e;
-    const int bpf = (a.W + BIN_THREADS - 1) / BIN_THREADS;
+    int maxt = 192;
+    if (const char *e = getenv("DRR_BIN_THREADS")) maxt = std::max(32, std::min(BIN_THREADS, atoi(e) / 32 * 32));
+    const int bpf = (a.W + maxt - 1) / maxt;                        // CTAs per frame
+    const int threads = ((a.W + bpf - 1) / bpf + 31) / 32 * 32;     // columns per CTA, whole warps
     const long long blocks = (long long)nframes * bpf;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    drr_bin_kernel<<<(unsigned)blocks, BIN_THREADS, 0, st>>>(a, frame0, bpf);
+    drr_bin_kernel<<<(unsigned)blocks, threads, 0, st>>>(a, frame0, bpf);
     return cudaGetLastError();
 }
 
