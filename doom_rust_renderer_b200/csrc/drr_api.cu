@@ -753,8 +753,12 @@ static int reserve_device_lists(drr_ctx *ctx) {
     CU(ctx, ctx->d_cols.reserve(std::max<size_t>(ctx->cols.n, 1) * 5));
     CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
     CU(ctx, ctx->d_parr.reserve(std::max<size_t>(ctx->parr.n, 1)));
-    CU(ctx, ctx->d_colidx.reserve(nf * (size_t)ctx->W));
-    CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->rec_cap, 1) * 4));
+    int nbands, band_rows;
+    tile_bands(ctx->H, &nbands, &band_rows);
+    const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1; // one span list per (column, row band)
+    if (ctx->rec_cap * nlists > 0xffffffffull) return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 record slots");
+    CU(ctx, ctx->d_colidx.reserve(nf * (size_t)ctx->W * nlists));
+    CU(ctx, ctx->d_tparams.reserve(std::max<size_t>(ctx->rec_cap, 1) * 4 * nlists));
     return DRR_OK;
 }
 
@@ -809,6 +813,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.W = ctx->W;
     a.H = ctx->H;
     a.nframes = (int)nframes;
+    tile_bands(ctx->H, &a.nbands, &a.band_rows);
     a.CFX = ctx->CFX;
     a.CFY = ctx->CFY;
     a.GCFX = ctx->GCFX;
@@ -1141,6 +1146,11 @@ int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out)
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
+    {
+        int nbands, band_rows;
+        tile_bands(ctx->H, &nbands, &band_rows);
+        if (nbands != 1) return fail(ctx, DRR_E_INVALID, "drr_test_device_bins: only for screens drawn as one row band");
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
     if (ctx->rec_cap)

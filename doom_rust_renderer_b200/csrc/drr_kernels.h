@@ -30,6 +30,7 @@ static constexpr uint32_t TEXEL_NONE = 256 * PAL_ENTRY;
 
 struct DrawArgs {
     int W, H, nframes;
+    int nbands, band_rows;           // rows of a tile: the whole column (nbands == 1) or equal row bands (tile_bands())
     // src/renderer/constants.rs:7-17 derived from W, H with the reference's own expressions (drr_ctx_create)
     float CFX, CFY, GCFX, ASPECT, Wf, Hf;
     int dbg;   // timing experiments only (DRR_DBG): 1 skip clearing, 2 skip framebuffer stores, 4 skip checksum, 8 skip write-out, 16 skip drawing
@@ -46,7 +47,7 @@ struct DrawArgs {
     const uint32_t *parr;            // (top, bottom) i16 pairs of the visplane columns
     // device scratch written by the bin kernel, read by the tile kernel
     uint32_t *frame_cursor;          // [nframes] records handed out so far (zeroed before the bin kernel)
-    ColIdx *colidx;                  // [nframes * W]
+    ColIdx *colidx;                  // [nframes * nlists * W], nlists = nbands when nbands <= MAX_LIST_BANDS, else 1
     void *tparams;                   // one 64-byte decoded record per (op, column) that survives clipping, see drr_tile.cu
     // assets
     const uint16_t *texels;          // bitmap pool: column-major, pow2 column pitch, palette byte offset (index*16), 4096 = None
@@ -70,6 +71,8 @@ cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t
 cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
 cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
 void tile_config(int W, int H, int *tc, int *lpg);
+void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (1 band up to 820 rows)
+static constexpr int MAX_LIST_BANDS = 8;             // up to this many bands the bin kernel writes one span list per (column, band)
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);
 

@@ -38,7 +38,11 @@ static constexpr uint32_t COL_COVERED = 0x80000000u; // ColIdx.n flag: the colum
 enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11 };
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
-__device__ __forceinline__ uint32_t wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y, uint4 *out) {
+struct Rec { // a decoded record in registers
+    uint4 a, b, c, d;
+    uint32_t kind;
+};
+__device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y) {
     const uint32_t h = (uint32_t)g.tex_h;
     uint32_t kind = g.tex_opaque ? KIND_WALL : KIND_WALL_HOLES;
     uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
@@ -73,15 +77,11 @@ __device__ __forceinline__ uint32_t wall_record(const DrawArgs &a, const SegRec 
     rd.y = __float_as_uint(wc.factor);
     if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
     ra.y = kind | flags;
-    out[0] = ra;
-    out[1] = rb;
-    out[2] = rc;
-    out[3] = rd;
-    return kind;
+    return Rec{ra, rb, rc, rd, kind};
 }
 
 // Decoded record of a visplane column: the per-plane and per-column constants of draw_visplane / draw_sky
-__device__ __forceinline__ uint32_t plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb, uint4 *out) {
+__device__ __forceinline__ Rec plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb) {
     uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rc = make_uint4(0u, 0u, 0u, 0u);
     if (p.kind == KIND_FLAT) {
         // visplanes.rs:112  wz = visplane.height as f32 - player.floor_height - PLAYER_EYE_HEIGHT
@@ -112,11 +112,7 @@ __device__ __forceinline__ uint32_t plane_record(const DrawArgs &a, const PlaneR
         ra.z = a.sky_base + ((uint32_t)tx << 7);
         ra.y = kind;
     }
-    out[0] = ra;
-    out[1] = make_uint4(0u, 0u, 0u, 0u);
-    out[2] = rc;
-    out[3] = make_uint4(0u, 0u, 0u, 0u);
-    return ra.y & 0xffu;
+    return Rec{ra, make_uint4(0u, 0u, 0u, 0u), rc, make_uint4(0u, 0u, 0u, 0u), ra.y & 0xffu};
 }
 
 // Walk the ops of frame f in call order and visit what each of them draws in screen column x.  EMIT = false only counts;
@@ -158,9 +154,9 @@ struct Cover {
             overflow = true;
         }
     }
-    __device__ __forceinline__ bool covers(int H) const { // sweep: extend the covered prefix [0, cur) until it stops growing
+    __device__ __forceinline__ bool covers(int lo, int H) const { // rows [lo, H): sweep, extend the covered prefix [lo, cur) until it stops growing
         if (overflow) return false;
-        int cur = 0;
+        int cur = lo;
         for (int pass = 0; pass < COVER_MAX && cur < H; ++pass) {
             int reach = cur;
 #pragma unroll
@@ -193,9 +189,29 @@ __device__ __forceinline__ void for_each_candidate(const DrawArgs &a, uint32_t o
     }
 }
 
-template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, uint4 *out, Cover *cover) {
-    uint32_t n = 0;
+// Where the spans of one screen column go: one list per row band (`cap` slots each, band b's list starts at first + b*cap).
+struct ColOut {
+    uint4 *recs;      // the frame's record slots
+    uint32_t first, cap;
+    int nlists, band_rows;
+    uint32_t n[MAX_LIST_BANDS];
+    __device__ __forceinline__ void put(const Rec &r, int ya, int yb) {
+        const int b0 = nlists > 1 ? ya / band_rows : 0, b1 = nlists > 1 ? yb / band_rows : 0;
+        for (int b = b0; b <= b1; ++b) { // a span that crosses a band boundary is listed in every band it touches
+            uint32_t k = 0;
+#pragma unroll
+            for (int i = 0; i < MAX_LIST_BANDS; ++i)
+                if (i == b) k = n[i]++;
+            uint4 *out = recs + ((size_t)first + (size_t)b * cap + k) * 4;
+            out[0] = r.a;
+            out[1] = r.b;
+            out[2] = r.c;
+            out[3] = r.d;
+        }
+    }
+};
+
+__device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, ColOut &out, Cover *cover) {
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
     for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t k) {
         if (x >= a.W || x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) return; // (Pixels::set ignores x >= W)
@@ -207,11 +223,9 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             const int b = min((int)(short)(tb >> 16), a.H - 1);              // :62 / :96
             if (p.kind == KIND_FLAT && (int)(short)(b - t) <= 1) return;     // :99-101 (not applied to sky)
             if (t > b) return;
-            if (EMIT) {
-                const uint32_t k = plane_record(a, p, vw, x, t, b, out + 4 * n);
-                if (k == KIND_FLAT || k == KIND_SKY) cover->add(t, b);
-            }
-            ++n;
+            const Rec r = plane_record(a, p, vw, x, t, b);
+            if (r.kind == KIND_FLAT || r.kind == KIND_SKY) cover->add(t, b);
+            out.put(r, t, b);
         } else {
             const SegRec *gp = k < (uint32_t)BIN_REC ? reinterpret_cast<const SegRec *>(s_rec + 5 * k) : a.segs + op;
             const uint32_t gn = gp->n, cols_first = gp->cols_first;
@@ -230,13 +244,11 @@ __device__ __forceinline__ uint32_t walk_column(const DrawArgs &a, int f, int x,
             const ColRec c = a.cols[cols_first + i];
             const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
             if (ya > yb) return;
-            if (EMIT) {
-                if (wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y, out + 4 * n) == KIND_WALL) cover->add(ya, yb);
-            }
-            ++n;
+            const Rec r = wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y);
+            if (r.kind == KIND_WALL) cover->add(ya, yb);
+            out.put(r, ya, yb);
         }
     });
-    return n;
 }
 
 // drr_bin_kernel: one thread per (frame, screen column).  Counts what the frame's ops draw in the column, reserves that
@@ -267,16 +279,32 @@ __global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int fr
     for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t) {
         cap += (live && x >= (int)(short)(e.x & 0xffffu) && x <= (int)(short)(e.x >> 16)) ? 1u : 0u;
     });
-    uint32_t first = a.frame_rec_base[f];
-    if (cap) first += atomicAdd(a.frame_cursor + f, cap);
+    // one list of `cap` slots per row band (a single list when the column is not cut into bands, or into too many)
+    const int nlists = a.nbands <= MAX_LIST_BANDS ? a.nbands : 1;
+    ColOut out;
+    out.recs = reinterpret_cast<uint4 *>(a.tparams);
+    out.first = a.frame_rec_base[f] * (uint32_t)nlists;
+    out.cap = cap;
+    out.nlists = nlists;
+    out.band_rows = a.band_rows;
+#pragma unroll
+    for (int i = 0; i < MAX_LIST_BANDS; ++i) out.n[i] = 0;
+    if (cap) out.first += atomicAdd(a.frame_cursor + f, cap * (uint32_t)nlists);
     Cover cover;
     // (a dead lane of a partly live warp, x >= W, visits nothing: it only takes part in the ballots)
-    const uint32_t n = walk_column<true>(a, f, x, vw, s_tab, s_rec, reinterpret_cast<uint4 *>(a.tparams) + (size_t)first * 4, &cover);
+    walk_column(a, f, x, vw, s_tab, s_rec, out, &cover);
     if (live) {
-        ColIdx ci;
-        ci.first = first;
-        ci.n = n | (cover.covers(a.H) ? COL_COVERED : 0u);
-        a.colidx[(size_t)f * a.W + x] = ci;
+        for (int b = 0; b < nlists; ++b) {
+            uint32_t nb = 0;
+#pragma unroll
+            for (int i = 0; i < MAX_LIST_BANDS; ++i)
+                if (i == b) nb = out.n[i];
+            const int lo = nlists > 1 ? b * a.band_rows : 0, hi = nlists > 1 ? min(a.H, lo + a.band_rows) : a.H;
+            ColIdx ci;
+            ci.first = out.first + (uint32_t)b * cap;
+            ci.n = nb | (cover.covers(lo, hi) ? COL_COVERED : 0u);
+            a.colidx[((size_t)f * nlists + b) * a.W + x] = ci;
+        }
     }
 }
 
@@ -510,6 +538,7 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     }
     const int f = frame0 + (int)blockIdx.y;
     const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
+    const int nlists = nbands <= MAX_LIST_BANDS ? nbands : 1, lband = nbands <= MAX_LIST_BANDS ? band : 0; // the bin kernel's list of this band
     // everything the CTA needs from global memory is requested before the first barrier, so that the L2 round trips overlap
     const View vw = a.views[f];
     const uint32_t slot = a.frame_slot[f];
@@ -517,7 +546,7 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     ci_first.first = 0; ci_first.n = 0;
     if (warp < NSETS * NSPLIT) {
         const int x = g * TC + grp * NSETS + (NSPLIT > 1 ? warp % NSETS : warp);
-        if (x < a.W) ci_first = a.colidx[(size_t)f * a.W + x];
+        if (x < a.W) ci_first = a.colidx[((size_t)f * nlists + lband) * a.W + x];
     }
 #ifdef DRR_PAL8
     // (passing this image as a by-value kernel parameter and copying it from the constant bank was measured: the divergent
@@ -544,7 +573,7 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
         ColIdx ci = ci_first; // the warp's first item was requested in the prologue
         if (item != warp) {
             ci.first = 0; ci.n = 0;
-            if (x < a.W) ci = a.colidx[(size_t)f * a.W + x];
+            if (x < a.W) ci = a.colidx[((size_t)f * nlists + lband) * a.W + x];
         }
         const int n = (a.dbg & 16) ? 0 : (int)(ci.n & ~COL_COVERED);
         const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
@@ -668,6 +697,14 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+void tile_bands(int H, int *nbands, int *band_rows) {
+    // rows per band: the whole column while the tile stays within ~52 KB (16 columns) / ~105 KB (32 columns), else equal bands
+    int max_rows = 820;
+    if (const char *e = getenv("DRR_TILE_MAX_ROWS")) max_rows = std::max(32, atoi(e));
+    *nbands = (H + max_rows - 1) / max_rows;
+    *band_rows = (H + *nbands - 1) / *nbands;
+}
+
 void tile_config(int W, int H, int *tc, int *lpg) {
     // measured (tools/sweep_tile.sh, tools/sweep_env.sh; profiles/r1_ab_measurements.md): 16-column full-height tiles with 16
     // lanes per span at 1280x800, 32-column tiles with 8 lanes per span at 320x200 and 640x400 -- short lane groups keep the
@@ -688,10 +725,7 @@ template <int TC, int LPG, int NT, int NSPLIT>
 static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
     const int gpf = (a.W + TC - 1) / TC;
     // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
-    int max_rows = 820;
-    if (const char *e = getenv("DRR_TILE_MAX_ROWS")) max_rows = std::max(32, atoi(e));
-    const int nbands = (a.H + max_rows - 1) / max_rows;
-    const int band_rows = (a.H + nbands - 1) / nbands;
+    const int nbands = a.nbands, band_rows = a.band_rows; // tile_bands(), shared with the bin kernel
     const int want = TC == 16 ? 2 : 1;
     int RP = band_rows;
     while (RP % 32 != want) ++RP;
