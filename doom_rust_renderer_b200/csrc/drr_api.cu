@@ -1140,21 +1140,27 @@ const void *drr_test_list(drr_ctx *ctx, int which, uint64_t *count, uint64_t *el
     default: return nullptr;
     }
 }
-// What the bin kernel produced for the uploaded batch: colidx_out = nframes * W (first, n) pairs, recs_out = two words per
-// record slot (y0 | y1 << 16, kind | flags), indexed by the `first` values of colidx_out; *nrec = number of slots.
+// What the bin kernel produced for the uploaded batch: colidx_out = nframes * nlists * W (first, n) pairs (one list per row
+// band, drr_test_tile_bands), recs_out = two words per record slot (y0 | y1 << 16, kind | flags), rec_cap * nlists slots,
+// indexed by the `first` values of colidx_out.
 int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
-    {
-        int nbands, band_rows;
-        tile_bands(ctx->H, &nbands, &band_rows);
-        if (nbands != 1) return fail(ctx, DRR_E_INVALID, "drr_test_device_bins: only for screens drawn as one row band");
-    }
+    int nbands, band_rows;
+    tile_bands(ctx->H, &nbands, &band_rows);
+    const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * nlists * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
     if (ctx->rec_cap)
-        CU(ctx, cudaMemcpy2D(recs_out, 8, ctx->d_tparams.p, 64, 8, (size_t)ctx->rec_cap, cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy2D(recs_out, 8, ctx->d_tparams.p, 64, 8, (size_t)ctx->rec_cap * nlists, cudaMemcpyDeviceToHost));
+    return DRR_OK;
+}
+// how the tile kernel cuts this context's columns into row bands, and how many span lists per column the bin kernel writes
+int drr_test_tile_bands(drr_ctx *ctx, int *nbands, int *band_rows, int *nlists) {
+    if (!ctx || !nbands || !band_rows || !nlists) return DRR_E_INVALID;
+    tile_bands(ctx->H, nbands, band_rows);
+    *nlists = *nbands <= MAX_LIST_BANDS ? *nbands : 1;
     return DRR_OK;
 }
 // bitmap slot -> (w, h, opaque); flat_slot/bitmap_slot resolve ids the way the device tables do

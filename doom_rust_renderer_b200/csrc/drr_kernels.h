@@ -71,7 +71,7 @@ cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t
 cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
 cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
 void tile_config(int W, int H, int *tc, int *lpg);
-void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (1 band up to 820 rows)
+void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (bands of at most 400 rows)
 static constexpr int MAX_LIST_BANDS = 8;             // up to this many bands the bin kernel writes one span list per (column, band)
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);

@@ -698,19 +698,20 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
 }
 
 void tile_bands(int H, int *nbands, int *band_rows) {
-    // rows per band: the whole column while the tile stays within ~52 KB (16 columns) / ~105 KB (32 columns), else equal bands
-    int max_rows = 820;
+    // rows per band: at most 400 (a 32-column tile is then <= 51 KB: four CTAs per SM), equal bands.  Since the bin kernel writes
+    // one span list per (column, band), wide-and-short tiles beat the 16-column full-height ones (tools/sweep_wide.sh).
+    int max_rows = 400;
     if (const char *e = getenv("DRR_TILE_MAX_ROWS")) max_rows = std::max(32, atoi(e));
     *nbands = (H + max_rows - 1) / max_rows;
     *band_rows = (H + *nbands - 1) / *nbands;
 }
 
 void tile_config(int W, int H, int *tc, int *lpg) {
-    // measured (tools/sweep_tile.sh, tools/sweep_env.sh; profiles/r1_ab_measurements.md): 16-column full-height tiles with 16
-    // lanes per span at 1280x800, 32-column tiles with 8 lanes per span at 320x200 and 640x400 -- short lane groups keep the
-    // warp full on short spans
-    *tc = H >= 600 ? 16 : 32;
-    *lpg = H >= 600 ? 16 : 8;
+    // measured (tools/sweep_tile.sh, tools/sweep_env.sh, tools/sweep_wide.sh; profiles/r1_ab_measurements.md): 32-column tiles
+    // (96-byte row segments: full 32-byte sectors) with 8 lanes per span at every resolution -- short lane groups keep the
+    // warp full on short spans; 16-column tiles and other group sizes stay selectable for A/B runs
+    *tc = 32;
+    *lpg = 8;
     if (const char *e = getenv("DRR_TILE_COLS")) {
         const int v = atoi(e);
         if (v == 16 || v == 32) *tc = v;

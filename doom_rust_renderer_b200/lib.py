@@ -91,7 +91,7 @@ def _lib() -> C.CDLL:
             "drr_test_bitmap_texels": (i, [vp, i, vp]), "drr_test_flat_texels": (i, [vp, i, vp]), "drr_test_palette": (i, [vp, vp]),
             "drr_test_sky_slot": (i, [vp]), "drr_test_tile_config": (i, [vp, C.POINTER(i), C.POINTER(i)]),
             "drr_test_bitmap_id_of_slot": (i, [vp, i]), "drr_test_flat_id_of_slot": (i, [vp, i]),
-            "drr_test_device_bins": (i, [vp, vp, vp]),
+            "drr_test_device_bins": (i, [vp, vp, vp]), "drr_test_tile_bands": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
             "drr_test_fastdiv": (i, [vp, i, C.c_longlong, C.c_longlong, f, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), vp]),
         }
         for name, (res, args) in sig.items():
@@ -250,12 +250,20 @@ class Context:
         self._ck(self.L.drr_test_tile_config(self.h, C.byref(tc), C.byref(lpg)))
         return "drr_tile_kernel<%d,%d>" % (tc.value, lpg.value)
 
+    def tile_bands(self):
+        """(nbands, band_rows, nlists): the row bands of a tile and the number of span lists per column the bin kernel writes."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.drr_test_tile_bands(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def device_bins(self, nframes: int):
-        """(colidx [nframes*W] of COLIDX_DTYPE, recs [n][2] u32 = (y0 | y1 << 16, kind | flags)) as the bin kernel wrote them."""
-        ci = np.zeros(nframes * self.W, COLIDX_DTYPE)
-        recs = np.zeros((max(1, int(self._list(5, np.uint32)[-1])), 2), np.uint32)  # one slot per emitted column
+        """(colidx [nframes][nlists][W] of COLIDX_DTYPE, recs [n][2] u32 = (y0 | y1 << 16, kind | flags)) as the bin kernel wrote
+        them: one span list per (column, row band)."""
+        nlists = self.tile_bands()[2]
+        ci = np.zeros(nframes * nlists * self.W, COLIDX_DTYPE)
+        recs = np.zeros((max(1, int(self._list(5, np.uint32)[-1]) * nlists), 2), np.uint32)  # one slot per emitted column and list
         self._ck(self.L.drr_test_device_bins(self.h, _ptr(ci), _ptr(recs)))
-        return ci, recs
+        return ci.reshape(nframes, nlists, self.W), recs
 
     def profile_begin(self, max_steps: int):
         self._ck(self.L.drr_profile_begin(self.h, max_steps))
@@ -273,7 +281,7 @@ class Context:
         self._ck(self.L.drr_test_fastdiv(self.h, mode, n0, n1, cfy, lo, stride, C.byref(bad), _ptr(first)))
         return bad.value, (float(first[0]), float(first[1]))
 
-    # ---- test-only views of the binned lists (CPU-testable host logic)
+    # ---- test-only views of the recorded lists (CPU-testable host logic)
     def _list(self, which: int, dtype) -> np.ndarray:
         n, sz = C.c_uint64(), C.c_uint64()
         p = self.L.drr_test_list(self.h, which, C.byref(n), C.byref(sz))

@@ -67,32 +67,39 @@ def test_device_binning_equals_host_restatement(W, H, kind):
     ctx.submit()
     ctx.sync()
     ci_dev, recs = ctx.device_bins(len(views))
+    nbands, band_rows, nlists = ctx.tile_bands()
     spans, ci_host = ctx._list(3, drr.SPAN_DTYPE), ctx._list(4, drr.COLIDX_DTYPE)
-    assert len(ci_dev) == len(ci_host) == len(views) * W
-    covered = (ci_dev["n"] >> 31).astype(bool)  # bin kernel's flag: the always-writing spans cover every row of the column
-    ci_dev["n"] &= 0x7FFFFFFF
-    assert (ci_dev["n"] == ci_host["n"]).all()
-    assert kind != "e1m1" or covered.mean() > 0.5
+    assert ci_dev.shape == (len(views), nlists, W) and len(ci_host) == len(views) * W
     assert int(ci_host["n"].sum()) == ctx.stats()["spans"] == len(spans)
-    # every device range lies inside its frame's record range and ranges do not overlap
-    order = np.argsort(ci_dev["first"], kind="stable")
-    nz = order[ci_dev["n"][order] > 0]
-    ends = ci_dev["first"][nz].astype(np.int64) + ci_dev["n"][nz]
-    assert (ends[:-1] <= ci_dev["first"][nz][1:]).all() and ends[-1] <= len(recs)
+    covered = (ci_dev["n"] >> 31).astype(bool)  # bin kernel's flag: the always-writing spans cover every row of the band
+    ci_dev["n"] &= 0x7FFFFFFF
+    assert kind != "e1m1" or covered.mean() > 0.5
+    # every device list lies inside the record slots and lists do not overlap
+    flat = ci_dev.reshape(-1)
+    order = np.argsort(flat["first"], kind="stable")
+    nz = order[flat["n"][order] > 0]
+    ends = flat["first"][nz].astype(np.int64) + flat["n"][nz]
+    assert (ends[:-1] <= flat["first"][nz][1:]).all() and ends[-1] <= len(recs)
     for i in np.nonzero(ci_host["n"])[0]:
-        h = spans[ci_host["first"][i]:ci_host["first"][i] + ci_host["n"][i]]
-        d = recs[ci_dev["first"][i]:ci_dev["first"][i] + ci_dev["n"][i]]
-        assert ((d[:, 0] & 0xFFFF) == h["y0"]).all() and ((d[:, 0] >> 16) == h["y1"]).all(), i
-        kind_d = d[:, 1] & 0xFF
-        assert ((kind_d == h["kind"]) | (kind_d == 7)).all(), i  # 7 = column the reference would have panicked on
-        rows = np.zeros(H, np.int32)
-        for k, sp in zip(kind_d, h):
-            if k in (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY):
-                rows[sp["y0"]:sp["y1"] + 1] += 1
-        if covered[i]:
-            assert (rows >= 1).all(), i
-        elif int(np.isin(kind_d, (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY)).sum()) <= 6:
-            assert not (rows >= 1).all(), i
+        f, x = divmod(int(i), W)
+        h_all = spans[ci_host["first"][i]:ci_host["first"][i] + ci_host["n"][i]]
+        for b in range(nlists):
+            lo, hi = (b * band_rows, min(H, (b + 1) * band_rows) - 1) if nlists > 1 else (0, H - 1)
+            h = h_all[(h_all["y1"] >= lo) & (h_all["y0"] <= hi)]  # the spans that touch the band, in draw order
+            c = ci_dev[f, b, x]
+            assert c["n"] == len(h), (f, b, x)
+            d = recs[c["first"]:c["first"] + c["n"]]
+            assert ((d[:, 0] & 0xFFFF) == h["y0"]).all() and ((d[:, 0] >> 16) == h["y1"]).all(), (f, b, x)
+            kind_d = d[:, 1] & 0xFF
+            assert ((kind_d == h["kind"]) | (kind_d == 7)).all(), (f, b, x)  # 7 = column the reference would have panicked on
+            rows = np.zeros(H, np.int32)
+            for k, sp in zip(kind_d, h):
+                if k in (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY):
+                    rows[sp["y0"]:sp["y1"] + 1] += 1
+            if covered[f, b, x]:
+                assert (rows[lo:hi + 1] >= 1).all(), (f, b, x)
+            elif int(np.isin(h_all["kind"], (drr.KIND_WALL, drr.KIND_FLAT, drr.KIND_SKY)).sum()) <= 6:  # (it tracks 6 spans per column)
+                assert not (rows[lo:hi + 1] >= 1).all(), (f, b, x)
 
 
 def test_config1_spawn_viewpoint():
