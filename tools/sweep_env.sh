@@ -6,6 +6,6 @@ for kv in "$@"; do
   python - $wl "$kv" <<'PY'
 import json, sys
 d = json.loads(open("/tmp/s.json").read().strip().splitlines()[-1])
-print("%-9s %-40s bin %.4f tile %.4f ms frac %.4f e2e %.0f" % (sys.argv[1], sys.argv[2], d["roofline"]["setup_ms"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
+print("%-9s %-40s step %.4f ms value %.0f | bin %.4f tile %.4f ms frac %.4f e2e %.0f" % (sys.argv[1], sys.argv[2], d["ms_per_step"], d["value"], d["roofline"]["setup_ms"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
 PY
 done
