@@ -397,6 +397,11 @@ def main():
                 "result": "per-frame checksums (8 B/frame); framebuffers stay resident in HBM"},
         "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "roofline": res["roofline"], "lists": res["lists"],
         "host_build_s": res["host_build_s"], "checksum_of_checksums": res["checksum_of_checksums"],
+        # SURVEY 8(d) "separately: end-to-end incl. host list build": one batch = the C++ front-end on all host cores
+        # (drr_scene_emit_views) + one drr_submit + checksums back.  The front-end is the caller's side of the boundary (the
+        # reference's own BSP walk), not the draw path; it is what a GPU-side front-end would remove.
+        "with_front_end": {"value": res["W"] * res["H"] * res["views_per_gpu"] * world / (res["host_build_s"] + res["e2e_ms_per_step"] * 1e-3) / 1e6,
+                           "unit": "Mpixel/s", "front_end_s": res["host_build_s"], "host_threads": os.cpu_count()},
     }
     if world == 1 and rank == 0:
         if not args.no_cpu_baseline:
@@ -408,7 +413,7 @@ def main():
             a2.steps = max(3, args.steps // 2)
             r2, _ = run_workload(name, a2, rank, world, local_rank, dist, torch)
             sec.append({k: r2[k] for k in ("workload", "desc", "W", "H", "views_per_gpu", "phases", "value", "frames_per_s", "ms_per_step",
-                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks")})
+                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s")})
         if sec:
             out["secondary"] = sec
     if rank == 0:
