@@ -34,7 +34,10 @@ def _compare(ctx, k, ref, what):
 
 
 # ---- whole frames through the product front-end -----------------------------------------------------------------------
-@pytest.mark.parametrize("W,H,n", [(320, 200, 48), (640, 400, 12), (1280, 800, 6), (1024, 768, 3), (1920, 1200, 2), (200, 120, 6), (324, 200, 3)])
+# (1000x900: three row bands + a width that is no multiple of the tile; 96x2000: five bands; 64x3300: nine bands, more than the
+# bin kernel keeps separate span lists for; 200x120, 324x200: bytewise store path + checksum pass)
+@pytest.mark.parametrize("W,H,n", [(320, 200, 48), (640, 400, 12), (1280, 800, 6), (1024, 768, 3), (1920, 1200, 2), (200, 120, 6), (324, 200, 3),
+                                   (1000, 900, 2), (96, 2000, 2), (64, 3300, 2)])
 def test_scene_frames_match_oracle(W, H, n):
     path, gm = common.wad("e1m1")
     game = orc.Game(path, "E1M1", W, H)
@@ -202,7 +205,7 @@ def _fuzz_assets(rng, n_bitmaps=10):
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
-@pytest.mark.parametrize("W,H", [(320, 200), (96, 64)])
+@pytest.mark.parametrize("W,H", [(320, 200), (96, 64), (64, 900)])
 def test_fuzz_columns(seed, W, H):
     """Random render_vertical_bitmap_line arguments, including degenerate ones (zero-height columns, bottom_y == top_y,
     huge offsets, NaN / inf line ends, negative light, transparent texels, overlapping columns in draw order)."""
@@ -268,7 +271,7 @@ def test_fuzz_columns(seed, W, H):
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
-@pytest.mark.parametrize("W,H", [(320, 200), (96, 64)])
+@pytest.mark.parametrize("W,H", [(320, 200), (96, 64), (64, 900)])
 def test_fuzz_visplanes(seed, W, H):
     """Random draw_visplane / draw_sky arguments: planes crossing the horizon (vy == 0 row, negative distances -> factor > 1),
     (0,0) columns (quirk Q3), 1-pixel columns (Q4), unclamped top/bottom, overlapping planes in draw order, any angle."""
