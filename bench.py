@@ -309,6 +309,14 @@ def cpu_baseline(path, used, crc_dev, W, H, phases):
             "single_thread_sample": "%d frames" % n1, "parity_checked_frames": nm, "parity_ok": bool(ok)}
 
 
+def parity_sample(path, used, crc_dev, W, H, phases, n=16):
+    """Oracle frames of a seeded sample of the batch against the device checksums (for the secondary workloads; the default
+    workload is checked frame by frame in cpu_baseline)."""
+    idx = np.sort(np.random.default_rng(0xD00D1993).choice(len(used), min(n, len(used)), replace=False))
+    _, sums = cpu_render(path, W, H, phases, used[idx], min(os.cpu_count() or 1, len(idx)))
+    return {"frames": [int(i) for i in idx], "ok": bool(all(int(crc_dev[i]) == s for i, s in zip(idx, sums)))}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the box's host cores."""
     if rank != 0:
@@ -411,9 +419,11 @@ def main():
             a2 = argparse.Namespace(**vars(args))
             a2.views = 0
             a2.steps = max(3, args.steps // 2)
-            r2, _ = run_workload(name, a2, rank, world, local_rank, dist, torch)
+            r2, info2 = run_workload(name, a2, rank, world, local_rank, dist, torch)
+            if not args.no_cpu_baseline and not name.startswith("empty"):
+                r2["parity_sample"] = parity_sample(*info2)
             sec.append({k: r2[k] for k in ("workload", "desc", "W", "H", "views_per_gpu", "phases", "value", "frames_per_s", "ms_per_step",
-                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s")})
+                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s", "parity_sample") if k in r2})
         if sec:
             out["secondary"] = sec
     if rank == 0:
