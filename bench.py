@@ -255,6 +255,34 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         "lists": {k: st[k] for k in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans", "device_list_bytes")},
         "host_build_s": host_build_s, "checksum_of_checksums": "%016x" % coc,
     }
+    # ---- viewpoints in, checksums out: the front-end on the GPU too (walls + visplanes, no map objects) ----
+    if not (phases & 4):
+        ctx.reset()
+        assert scene.emit_views_device(ctx, used, 0.0, phases) == []
+        ctx.draw()
+        crc_fe = ctx.read_checksums(0, n_views)
+        fe_ok = bool((crc_fe == crc_dev).all())
+        st_fe = ctx.stats()
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.steps):
+                ctx.reset()
+                scene.emit_views_device(ctx, used, 0.0, phases)  # 12 B per viewpoint up; count pass, offsets on the host, emit pass
+                ctx.draw()
+                crc_fe = ctx.read_checksums(0, n_views)
+            e1.record(stream)
+        e1.synchronize()
+        count_ms, emit_ms = ctx.fe_last_times()
+        barrier()
+        ms_fe = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        res["device_front_end"] = {
+            "value": px_total / (ms_fe * 1e-3) / 1e6, "unit": "Mpixel/s", "frames_per_s": frames_total / (ms_fe * 1e-3), "ms_per_step": ms_fe,
+            "count_pass_ms": count_ms, "emit_pass_ms": emit_ms, "h2d_bytes_per_step": 28 * n_views, "d2h_bytes_per_step": (40 + 8) * n_views,
+            "what": "viewpoints -> drr_frontend_kernel (count + emit) -> bin -> tile -> checksums; no draw list crosses PCIe",
+            "checksums_equal_host_front_end": fe_ok and bool((crc_fe == crc_dev).all()),
+            "lists_equal_host_front_end": all(st_fe[k] == st[k] for k in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans")),
+            "host_front_end_s": host_build_s}
     ctx.close()
     scene.close()
     return res, (path, used, crc_dev, W, H, phases)
@@ -411,6 +439,8 @@ def main():
         "with_front_end": {"value": res["W"] * res["H"] * res["views_per_gpu"] * world / (res["host_build_s"] + res["e2e_ms_per_step"] * 1e-3) / 1e6,
                            "unit": "Mpixel/s", "front_end_s": res["host_build_s"], "host_threads": os.cpu_count()},
     }
+    if "device_front_end" in res:  # the same batch with the front-end on the GPU too: viewpoints in, checksums out
+        out["with_front_end_device"] = res["device_front_end"]
     if world == 1 and rank == 0:
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(*ctxinfo)
@@ -423,7 +453,7 @@ def main():
             if not args.no_cpu_baseline and not name.startswith("empty"):
                 r2["parity_sample"] = parity_sample(*info2)
             sec.append({k: r2[k] for k in ("workload", "desc", "W", "H", "views_per_gpu", "phases", "value", "frames_per_s", "ms_per_step",
-                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s", "parity_sample") if k in r2})
+                                            "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s", "device_front_end", "parity_sample") if k in r2})
         if sec:
             out["secondary"] = sec
     if rank == 0:

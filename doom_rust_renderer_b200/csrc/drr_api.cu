@@ -16,6 +16,8 @@
 
 #include "../../include/drr.h"
 #include "drr_kernels.h"
+#include "drr_frontend.cuh"
+#include <cmath>
 
 using namespace drr;
 
@@ -112,7 +114,41 @@ struct Lists {
     }
 };
 
+// Device front-end (drr_fe_*): the flattened map (host mirror with ids resolved to slots + device copy), per-view scratch
+// and the count / offset tables of the last batch.
+struct FeState {
+    bool have_map = false;
+    int n_things = 0;
+    std::vector<fe::Node> nodes;
+    std::vector<fe::SubSector> ssectors;
+    std::vector<fe::Seg> segs;
+    std::vector<fe::Line> lines;
+    std::vector<fe::Side> sides;
+    std::vector<fe::Sector> sectors;
+    std::vector<fe::Bitmap> bitmaps; // indexed by the caller's bitmap id
+    DevBuf<fe::Node> d_nodes;
+    DevBuf<fe::SubSector> d_ssectors;
+    DevBuf<fe::Seg> d_segs;
+    DevBuf<fe::Line> d_lines;
+    DevBuf<fe::Side> d_sides;
+    DevBuf<fe::Sector> d_sectors;
+    DevBuf<fe::Bitmap> d_bitmaps;
+    DevBuf<fe::ViewIn> d_views_in;
+    DevBuf<fe::Counts> d_counts;
+    DevBuf<fe::Bases> d_bases;
+    DevBuf<uint8_t> d_hor;
+    DevBuf<int16_t> d_focl, d_cocl;
+    DevBuf<uint32_t> d_rows;
+    PinnedVec<fe::ViewIn> h_views_in;
+    PinnedVec<fe::Counts> h_counts;
+    PinnedVec<fe::Bases> h_bases;
+    float count_ms = 0.0f, emit_ms = 0.0f;
+    uint64_t device_list_bytes = 0; // size of the lists the last drr_fe_emit_views wrote on the device
+};
+
 struct drr_ctx : Lists {
+    FeState fes;
+    bool device_lists = false; // the current batch's lists were written on the device (drr_fe_emit_views): nothing to upload
     int W = 0, H = 0, device = 0, max_views = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -584,6 +620,7 @@ int drr_reset(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
     ctx->clear_lists();
+    ctx->device_lists = false;
     ctx->t_spans.clear();
     ctx->t_colidx.clear();
     ctx->uploaded_frames = 0;
@@ -596,6 +633,7 @@ int drr_reset(drr_ctx *ctx) {
 
 int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
     CTX_CHECK(ctx);
+    if (ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_frame_begin: the batch was written by drr_fe_emit_views (call drr_reset first)");
     if (view_idx >= 0 && view_idx < ctx->max_views && ctx->slot_to_frame[view_idx] >= 0 && !ctx->in_frame)
         return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
     const int rc = rec_frame_begin(*ctx, ctx, ctx->err, view_idx, view);
@@ -666,6 +704,7 @@ int drr_recorder_frame_abort(drr_recorder *rec) {
 
 // Move every frame of `rec` to the end of the context's lists (indices re-based), then clear the recorder.
 int drr_append(drr_ctx *ctx, drr_recorder *rec) {
+    if (ctx && ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_append: the batch was written by drr_fe_emit_views (call drr_reset first)");
     CTX_CHECK(ctx);
     if (!rec || rec->ctx != ctx) return fail(ctx, DRR_E_INVALID, "drr_append: recorder of another context");
     Lists &R = rec->lists;
@@ -795,6 +834,7 @@ int drr_upload_lists(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_upload_lists inside a frame");
+    if (ctx->device_lists) return DRR_OK; // drr_fe_emit_views wrote the lists on the device: nothing to upload
     int rc = upload_assets(ctx);
     if (rc) return rc;
     const size_t nf = ctx->views.n;
@@ -922,6 +962,7 @@ int drr_submit(drr_ctx *ctx) {
     CTX_CHECK(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_submit inside a frame");
+    if (ctx->device_lists) return drr_draw(ctx); // drr_fe_emit_views wrote the lists on the device: nothing to upload
     int rc = upload_assets(ctx);
     if (rc) return rc;
     const size_t nf = ctx->views.n;
@@ -1030,7 +1071,7 @@ int drr_get_stats(drr_ctx *ctx, drr_stats *out) {
     drr_stats s = ctx->stats;
     s.spans = ctx->rec_count;
     s.drawlist_bytes_algorithmic = 24 * s.frames + 48 * s.seg_headers + 10 * s.column_records + 12 * s.visplanes + 4 * s.visplane_columns;
-    s.device_list_bytes = list_bytes(ctx);
+    s.device_list_bytes = ctx->device_lists ? ctx->fes.device_list_bytes : list_bytes(ctx);
     *out = s;
     return DRR_OK;
 }
@@ -1058,6 +1099,331 @@ int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, flo
     return DRR_OK;
 }
 
+// ---- device front-end ---------------------------------------------------------------------------
+// drr_fe_upload_map flattens nothing itself: the caller (csrc/host/drr_scene.cpp, or a Rust host) hands over the map's
+// tables; ids are resolved to slots here.  drr_fe_emit_views = count pass, host offsets, emit pass (drr_frontend.cu).
+static const char *fe_detail_message(uint32_t d) {
+    switch (d) {
+    case fe::FED_CLIP_X: return "Clipped line x < -0.01";
+    case fe::FED_UNKNOWN_TEXTURE: return "Unknown texture";
+    case fe::FED_NOT_VERTICAL: return "Wall start not vertical";
+    case fe::FED_LINE_X: return "Invalid line start/end x";
+    case fe::FED_FLAT_MISSING: return "flat lump missing";
+    case fe::FED_STACK: return "BSP deeper than the front-end's walk stack";
+    case fe::FED_BITMAP_SLOT: return "a wall's bitmap was never uploaded";
+    case fe::FED_SKY_UNSET: return "sky visplane but no sky bitmap set";
+    default: return "front-end error";
+    }
+}
+
+int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
+    CTX_CHECK(ctx);
+    if (!m || m->n_nodes <= 0 || m->n_subsectors <= 0 || m->n_segs <= 0 || m->n_linedefs <= 0 || m->n_sidedefs <= 0 || m->n_sectors <= 0 ||
+        !m->nodes || !m->subsectors || !m->segs || !m->linedefs || !m->sidedefs || !m->sectors)
+        return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: empty table");
+    static_assert(sizeof(drr_fe_node) == sizeof(fe::Node) && sizeof(drr_fe_subsector) == sizeof(fe::SubSector) && sizeof(drr_fe_seg) == sizeof(fe::Seg) &&
+                      sizeof(drr_fe_linedef) == sizeof(fe::Line) && sizeof(drr_fe_sidedef) == sizeof(fe::Side) && sizeof(drr_fe_sector) == sizeof(fe::Sector),
+                  "drr_fe_* layouts");
+    FeState &S = ctx->fes;
+    S.have_map = false;
+    // every index the walk follows is checked once here, so the kernel needs no bounds tests
+    for (int i = 0; i < m->n_nodes; i++)
+        for (int32_t ch : {m->nodes[i].right, m->nodes[i].left})
+            if (ch >= m->n_nodes || (ch < 0 && ~ch >= m->n_subsectors)) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: node child out of range");
+    for (int i = 0; i < m->n_subsectors; i++)
+        if (m->subsectors[i].first_seg < 0 || m->subsectors[i].count < 0 || (int64_t)m->subsectors[i].first_seg + m->subsectors[i].count > m->n_segs)
+            return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: subsector seg range");
+    for (int i = 0; i < m->n_segs; i++)
+        if (m->segs[i].linedef < 0 || m->segs[i].linedef >= m->n_linedefs) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: seg linedef");
+    for (int i = 0; i < m->n_linedefs; i++)
+        for (int32_t sd : {m->linedefs[i].front, m->linedefs[i].back})
+            if (sd < -1 || sd >= m->n_sidedefs) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: linedef sidedef");
+    int max_id = -1;
+    for (auto &kv : ctx->bitmap_slot) max_id = std::max(max_id, kv.first);
+    for (int i = 0; i < m->n_sidedefs; i++) {
+        const drr_fe_sidedef &sd = m->sidedefs[i];
+        if (sd.sector < 0 || sd.sector >= m->n_sectors) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: sidedef sector");
+        for (int32_t t : {sd.upper, sd.lower, sd.middle}) {
+            if (t < -2 || t > (1 << 24)) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: sidedef texture id");
+            max_id = std::max(max_id, t);
+        }
+    }
+    S.bitmaps.assign((size_t)(max_id + 1), fe::Bitmap{-1, 0u, 0, 0, 0u});
+    for (auto &kv : ctx->bitmap_slot)
+        if (kv.first >= 0) {
+            const BitmapRec &r = ctx->bitmaps[kv.second];
+            S.bitmaps[kv.first] = fe::Bitmap{kv.second, r.base, r.w, r.h, r.opaque};
+        }
+    S.nodes.assign(reinterpret_cast<const fe::Node *>(m->nodes), reinterpret_cast<const fe::Node *>(m->nodes) + m->n_nodes);
+    S.ssectors.assign(reinterpret_cast<const fe::SubSector *>(m->subsectors), reinterpret_cast<const fe::SubSector *>(m->subsectors) + m->n_subsectors);
+    S.segs.assign(reinterpret_cast<const fe::Seg *>(m->segs), reinterpret_cast<const fe::Seg *>(m->segs) + m->n_segs);
+    S.lines.assign(reinterpret_cast<const fe::Line *>(m->linedefs), reinterpret_cast<const fe::Line *>(m->linedefs) + m->n_linedefs);
+    S.sides.assign(reinterpret_cast<const fe::Side *>(m->sidedefs), reinterpret_cast<const fe::Side *>(m->sidedefs) + m->n_sidedefs);
+    S.sectors.assign(reinterpret_cast<const fe::Sector *>(m->sectors), reinterpret_cast<const fe::Sector *>(m->sectors) + m->n_sectors);
+    for (fe::Sector &sec : S.sectors)
+        for (int16_t *f : {&sec.floor_flat, &sec.ceil_flat}) { // flat id -> flat slot
+            if (*f < 0) {
+                *f = -2;
+                continue;
+            }
+            auto it = ctx->flat_slot.find(*f);
+            *f = it == ctx->flat_slot.end() ? (int16_t)-2 : (int16_t)it->second;
+        }
+    S.n_things = m->n_things;
+    if (!ctx->host_only) {
+        auto up = [&](auto &dev, const auto &host) -> cudaError_t {
+            cudaError_t e = dev.reserve(std::max<size_t>(host.size(), 1));
+            if (e != cudaSuccess || host.empty()) return e;
+            return cudaMemcpyAsync(dev.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, ctx->stream);
+        };
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // a previous batch's front-end may still read the old tables
+        CU(ctx, up(S.d_nodes, S.nodes));
+        CU(ctx, up(S.d_ssectors, S.ssectors));
+        CU(ctx, up(S.d_segs, S.segs));
+        CU(ctx, up(S.d_lines, S.lines));
+        CU(ctx, up(S.d_sides, S.sides));
+        CU(ctx, up(S.d_sectors, S.sectors));
+        CU(ctx, up(S.d_bitmaps, S.bitmaps));
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors may be reassigned by the next call
+    }
+    S.have_map = true;
+    return DRR_OK;
+}
+
+static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
+    const FeState &S = ctx->fes;
+    fe::Map m;
+    m.nodes = device ? S.d_nodes.p : S.nodes.data();
+    m.ssectors = device ? S.d_ssectors.p : S.ssectors.data();
+    m.segs = device ? S.d_segs.p : S.segs.data();
+    m.lines = device ? S.d_lines.p : S.lines.data();
+    m.sides = device ? S.d_sides.p : S.sides.data();
+    m.sectors = device ? S.d_sectors.p : S.sectors.data();
+    m.bitmaps = device ? S.d_bitmaps.p : S.bitmaps.data();
+    m.nnodes = (int)S.nodes.size();
+    m.W = ctx->W;
+    m.H = ctx->H;
+    m.ASPECT = ctx->ASPECT;
+    m.GCFX = ctx->GCFX;
+    m.CFX = ctx->CFX;
+    m.CFY = ctx->CFY;
+    m.sky_kind = ctx->sky_slot < 0 ? -1 : (int)(ctx->bitmaps[ctx->sky_slot].opaque ? KIND_SKY : KIND_SKY_HOLES);
+    m.phases = phases;
+    return m;
+}
+
+// The whole batch: count pass, offsets, emit pass.  on_host == true runs the SAME per-view code on the CPU into the
+// context's host lists (test infrastructure: lets the CPU suite compare it with the host front-end list by list).
+static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status, bool on_host) {
+    FeState &S = ctx->fes;
+    if (!S.have_map) return fail(ctx, DRR_E_STATE, "drr_fe_emit_views: no map (drr_fe_upload_map)");
+    if (n < 0 || (n > 0 && !xya) || first_view_idx < 0 || (int64_t)first_view_idx + n > ctx->max_views || (phases & ~7))
+        return fail(ctx, DRR_E_INVALID, "drr_fe_emit_views: bad arguments");
+    if (ctx->in_frame || ctx->views.n != 0 || ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_fe_emit_views: frames already recorded (call drr_reset first)");
+    if ((phases & 4) && S.n_things > 0)
+        return fail(ctx, DRR_E_INVALID, "drr_fe_emit_views: DRR_PHASES_MASKED needs the map objects' ordering, which only the host front-end has");
+    if (n == 0) return DRR_OK;
+    if (!on_host && ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU path");
+    const size_t N = (size_t)n, W = (size_t)ctx->W;
+    if (!S.h_views_in.reserve(N) || !S.h_counts.reserve(N) || !S.h_bases.reserve(N)) return fail(ctx, DRR_E_NOMEM, "alloc");
+    for (size_t i = 0; i < N; i++) {
+        const float a = xya[3 * i + 2];
+        S.h_views_in.p[i] = fe::ViewIn{xya[3 * i], xya[3 * i + 1], a, cosf(a), sinf(a), cosf(-a), sinf(-a)};
+    }
+    std::vector<uint8_t> hs_hor;
+    std::vector<int16_t> hs_focl, hs_cocl;
+    std::vector<uint32_t> hs_rows;
+    FeScratch scr{};
+    fe::Out out{};
+    if (on_host) { // one viewpoint at a time: a single view's scratch
+        hs_hor.resize(W);
+        hs_focl.resize(W);
+        hs_cocl.resize(W);
+        hs_rows.resize(2 * W);
+        const fe::Map m = fe_make_map(ctx, false, phases);
+        for (size_t i = 0; i < N; i++) {
+            fe::Frame<false> fr(m);
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
+            fr.out = out;
+            fr.run(S.h_views_in.p[i], fe::Bases{0, 0, 0, 0, 0, 0, 0, 0});
+            S.h_counts.p[i] = fr.n;
+        }
+    } else {
+        int rc = upload_assets(ctx);
+        if (rc) return rc;
+        CU(ctx, S.d_views_in.reserve(N));
+        CU(ctx, S.d_counts.reserve(N));
+        CU(ctx, S.d_bases.reserve(N));
+        CU(ctx, S.d_hor.reserve(N * W));
+        CU(ctx, S.d_focl.reserve(N * W));
+        CU(ctx, S.d_cocl.reserve(N * W));
+        CU(ctx, S.d_rows.reserve(N * W * 2));
+        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p};
+        CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        CU(ctx, launch_frontend(false, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, out, ctx->stream));
+        ctx->stats.kernel_launches++;
+        CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(ctx, cudaMemcpyAsync(S.h_counts.p, S.d_counts.p, N * sizeof(fe::Counts), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // offsets: an exclusive scan over the viewpoints that got a frame
+    uint64_t ops = 0, segs = 0, cols = 0, planes = 0, parr = 0, reccap = 0, nrec = 0;
+    size_t nf = 0;
+    ctx->frame_op_base.clear();
+    ctx->frame_rec_base.clear();
+    ctx->frame_slot.clear();
+    ctx->frame_seg_base.clear();
+    ctx->frame_col_base.clear();
+    ctx->frame_plane_base.clear();
+    ctx->frame_parr_base.clear();
+    auto push_bases = [&]() {
+        ctx->frame_seg_base.push_back((uint32_t)segs);
+        ctx->frame_col_base.push_back((uint32_t)cols);
+        ctx->frame_plane_base.push_back((uint32_t)planes);
+        ctx->frame_parr_base.push_back((uint32_t)parr);
+        return ctx->frame_op_base.push((uint32_t)ops) && ctx->frame_rec_base.push((uint32_t)reccap);
+    };
+    if (!push_bases()) return fail(ctx, DRR_E_NOMEM, "alloc");
+    for (size_t i = 0; i < N; i++) {
+        const fe::Counts &c = S.h_counts.p[i];
+        fe::Bases &b = S.h_bases.p[i];
+        b = fe::Bases{(uint32_t)ops, (uint32_t)segs, (uint32_t)cols, (uint32_t)planes, (uint32_t)parr, -1, c.nsegs, c.ncols};
+        if (c.status == fe::FE_HARD) {
+            ctx->clear_lists();
+            return fail(ctx, c.detail == fe::FED_STACK ? DRR_E_INVALID : DRR_E_ASSET,
+                        std::string("drr_fe_emit_views: view ") + std::to_string(i) + ": " + fe_detail_message(c.detail));
+        }
+        if (status) status[i] = c.status == fe::FE_OK ? DRR_OK : DRR_E_PANIC;
+        if (c.status != fe::FE_OK) continue; // the reference would have panicked: no frame for this viewpoint
+        b.frame = (int32_t)nf++;
+        ops += c.nops;
+        segs += c.nsegs;
+        cols += c.ncols;
+        planes += c.nplanes;
+        parr += c.nparr;
+        reccap += c.reccap;
+        nrec += c.nrec;
+        if (!ctx->frame_slot.push((uint32_t)(first_view_idx + (int)i)) || !push_bases()) return fail(ctx, DRR_E_NOMEM, "alloc");
+        ctx->slot_to_frame[first_view_idx + (int)i] = b.frame;
+    }
+    if (reccap > 0xffffffffull || cols > 0xffffffffull || parr > 0xffffffffull || ops > 0x7fffffffull) {
+        ctx->clear_lists();
+        return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 column records");
+    }
+    ctx->rec_cap = reccap;
+    ctx->rec_count = nrec;
+    ctx->stats.frames = nf;
+    ctx->stats.seg_headers = segs;
+    ctx->stats.column_records = cols;
+    ctx->stats.visplanes = planes;
+    ctx->stats.visplane_columns = parr;
+    S.device_list_bytes = nf * sizeof(View) + ops * 4 + (nf + 1) * 8 + nf * 4 + segs * sizeof(SegRec) + cols * sizeof(ColRec) + planes * sizeof(PlaneRec) + parr * 4;
+    if (nf == 0) return DRR_OK;
+    if (on_host) {
+        if (!ctx->views.reserve(nf) || !ctx->ops.reserve(ops) || !ctx->segs.reserve(segs) || !ctx->cols.reserve(cols) || !ctx->planes.reserve(planes) ||
+            !ctx->parr.reserve(parr))
+            return fail(ctx, DRR_E_NOMEM, "alloc");
+        ctx->views.n = nf;
+        ctx->ops.n = ops;
+        ctx->segs.n = segs;
+        ctx->cols.n = cols;
+        ctx->planes.n = planes;
+        ctx->parr.n = parr;
+        out = fe::Out{ctx->views.p, ctx->ops.p, ctx->segs.p, ctx->cols.p, ctx->planes.p, ctx->parr.p};
+        const fe::Map m = fe_make_map(ctx, false, phases);
+        for (size_t i = 0; i < N; i++) {
+            if (S.h_bases.p[i].frame < 0) continue;
+            fe::Frame<true> fr(m);
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
+            fr.out = out;
+            fr.run(S.h_views_in.p[i], S.h_bases.p[i]);
+        }
+        return DRR_OK;
+    }
+    // device lists: sized from the counts, written by the emit pass
+    CU(ctx, ctx->d_views.reserve(nf));
+    CU(ctx, ctx->d_ops.reserve(std::max<uint64_t>(ops, 1)));
+    CU(ctx, ctx->d_frame_op_base.reserve(nf + 1));
+    CU(ctx, ctx->d_frame_rec_base.reserve(nf + 1));
+    CU(ctx, ctx->d_frame_slot.reserve(nf));
+    CU(ctx, ctx->d_frame_cursor.reserve(nf));
+    CU(ctx, ctx->d_segs.reserve(std::max<uint64_t>(segs, 1)));
+    CU(ctx, ctx->d_cols.reserve(std::max<uint64_t>(cols, 1) * 5));
+    CU(ctx, ctx->d_planes.reserve(std::max<uint64_t>(planes, 1)));
+    CU(ctx, ctx->d_parr.reserve(std::max<uint64_t>(parr, 1)));
+    int nbands, band_rows;
+    tile_bands(ctx->H, &nbands, &band_rows);
+    const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
+    if (reccap * nlists > 0xffffffffull) {
+        ctx->clear_lists();
+        return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 record slots");
+    }
+    CU(ctx, ctx->d_colidx.reserve(nf * W * nlists));
+    CU(ctx, ctx->d_tparams.reserve(std::max<uint64_t>(reccap, 1) * 4 * nlists));
+    CU(ctx, cudaMemcpyAsync(S.d_bases.p, S.h_bases.p, N * sizeof(fe::Bases), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_op_base.p, ctx->frame_op_base.p, (nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_rec_base.p, ctx->frame_rec_base.p, (nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+    out = fe::Out{ctx->d_views.p, ctx->d_ops.p, ctx->d_segs.p, reinterpret_cast<ColRec *>(ctx->d_cols.p), ctx->d_planes.p, ctx->d_parr.p};
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(ctx, launch_frontend(true, fe_make_map(ctx, true, phases), S.d_views_in.p, S.d_bases.p, nullptr, n, scr, out, ctx->stream));
+    ctx->stats.kernel_launches++;
+    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->device_lists = true;
+    ctx->uploaded_frames = nf;
+    return DRR_OK;
+}
+
+int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status) {
+    CTX_CHECK(ctx);
+    return fe_emit_views(ctx, first_view_idx, xya, n, phases, status, false);
+}
+
+int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only || !ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_fe_last_times: no device front-end batch");
+    CU(ctx, cudaEventSynchronize(ctx->ev[3]));
+    float a = 0, b = 0;
+    CU(ctx, cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+    CU(ctx, cudaEventElapsedTime(&b, ctx->ev[2], ctx->ev[3]));
+    if (count_ms) *count_ms = a;
+    if (emit_ms) *emit_ms = b;
+    return DRR_OK;
+}
+
+// Test infrastructure: the per-view front-end code of drr_frontend.cuh run on the CPU into the context's host lists
+// (works in a recording-only context), so that tests/ can compare it list by list with the host front-end.
+int drr_test_fe_emit_views_host(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status) {
+    CTX_CHECK(ctx);
+    return fe_emit_views(ctx, first_view_idx, xya, n, phases, status, true);
+}
+// Test infrastructure: copy the lists the device front-end wrote back into the context's host lists (drr_test_list).
+int drr_test_fe_download_lists(drr_ctx *ctx) {
+    CTX_CHECK(ctx);
+    if (ctx->host_only || !ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_test_fe_download_lists: no device front-end batch");
+    const size_t nf = ctx->uploaded_frames;
+    const size_t ops = ctx->frame_op_base.p[nf], segs = ctx->frame_seg_base[nf], cols = ctx->frame_col_base[nf], planes = ctx->frame_plane_base[nf],
+                 parr = ctx->frame_parr_base[nf];
+    if (!ctx->views.reserve(nf) || !ctx->ops.reserve(ops) || !ctx->segs.reserve(segs) || !ctx->cols.reserve(cols) || !ctx->planes.reserve(planes) ||
+        !ctx->parr.reserve(parr))
+        return fail(ctx, DRR_E_NOMEM, "alloc");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpy(ctx->views.p, ctx->d_views.p, nf * sizeof(View), cudaMemcpyDeviceToHost));
+    if (ops) CU(ctx, cudaMemcpy(ctx->ops.p, ctx->d_ops.p, ops * 4, cudaMemcpyDeviceToHost));
+    if (segs) CU(ctx, cudaMemcpy(ctx->segs.p, ctx->d_segs.p, segs * sizeof(SegRec), cudaMemcpyDeviceToHost));
+    if (cols) CU(ctx, cudaMemcpy(ctx->cols.p, ctx->d_cols.p, cols * sizeof(ColRec), cudaMemcpyDeviceToHost));
+    if (planes) CU(ctx, cudaMemcpy(ctx->planes.p, ctx->d_planes.p, planes * sizeof(PlaneRec), cudaMemcpyDeviceToHost));
+    if (parr) CU(ctx, cudaMemcpy(ctx->parr.p, ctx->d_parr.p, parr * 4, cudaMemcpyDeviceToHost));
+    ctx->views.n = nf;
+    ctx->ops.n = ops;
+    ctx->segs.n = segs;
+    ctx->cols.n = cols;
+    ctx->planes.n = planes;
+    ctx->parr.n = parr;
+    return DRR_OK;
+}
+
 // ---- CPU-testable internals (no CUDA needed) ---------------------------------------------------------------------------
 // A context that can RECORD draw lists without a GPU (plain malloc staging) so the host logic is testable in the CPU-only
 // container.  It has no framebuffers and every execution entry point fails with DRR_E_CUDA.
@@ -1075,6 +1441,7 @@ int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx 
     c->slot_to_frame.assign(max_views, -1);
     c->set_pinned(false);
     c->h_crc.pinned = false;
+    c->fes.h_views_in.pinned = c->fes.h_counts.pinned = c->fes.h_bases.pinned = false;
     *out = c;
     return DRR_OK;
 }

@@ -1,0 +1,580 @@
+// drr_frontend.cuh -- the reference's front-end for the DEVICE: BSP walk, seg transform / clip,
+// occlusion arrays and visplane building of one viewpoint, written so that it WRITES the draw lists of include/drr.h's
+// device representation (ops / SegRec / ColRec / PlaneRec / (top, bottom) pairs) instead of drawing.  One thread runs one
+// Renderer::render():
+//   Renderer::render / render_node      src/renderer/mod.rs:69-104,118-136
+//   Segs::process_seg / process_sidedef src/renderer/segs.rs:121-590
+//   clip_to_viewport, projection        src/renderer/misc.rs:13-161
+//   SidedefVisPlanes                    src/renderer/sidedef_visplanes.rs:41-84
+//   sector lookup                       src/renderer/bsp.rs:9-44
+// Phases covered: A (walls), B (visplanes) and D (deferred masked mid-textures) -- i.e. everything except map objects
+// (sprites, src/renderer/map_objects.rs), which stay on the host front-end (csrc/host/drr_scene.cpp).
+//
+// The code is plain scalar C++ shared by nvcc (device: drr_frontend_kernel in drr_frontend.cu) and the host compiler (the
+// CPU test harness drr_test_fe_emit_views_host, test infrastructure only), so that the list equality with the host
+// front-end is checked in the CPU test suite and the device run only has to reproduce the same IEEE operations: every
+// f32 expression keeps the reference's evaluation order; the translation unit is built with -fmad=false -prec-div=true
+// -prec-sqrt=true -ftz=false (no contraction, IEEE division / sqrt, denormals kept); cos/sin of the player angle are
+// evaluated by the host libm and passed in (ViewIn), like drr_view.
+//
+// Two passes per viewpoint with the same code: COUNT (EMIT = false) sizes the view's lists, the host turns the counts
+// into offsets, EMIT = true writes.  A viewpoint on which the reference would panic reports FE_PANIC in the count pass
+// and gets no frame.
+#pragma once
+#include "drr_device.cuh"
+
+#if defined(__CUDACC__)
+#define FE_HD __host__ __device__ __forceinline__
+#define FE_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define FE_HD inline
+#define FE_HD_NOINLINE
+#endif
+
+namespace drr {
+namespace fe {
+
+// ---- the map, flattened (host side: drr_fe_upload_map) ----------------------------------------------------------
+struct Node { // map/nodes.rs
+    float x, y, dx, dy;
+    int32_t right, left; // >= 0 node, < 0: ~subsector
+};
+struct SubSector {
+    int32_t first, count;
+};
+struct Seg { // map/segs.rs; vertices resolved
+    float v1x, v1y, v2x, v2y;
+    int32_t line;
+    int16_t dir, offset;
+};
+struct Line {
+    int32_t front, back; // sidedef index, -1 none
+    int32_t flags;
+};
+struct Side {
+    float xoff, yoff;
+    int32_t upper, lower, middle; // index into Map::bitmaps, -1 = "-", -2 = unknown texture name
+    int32_t sector;
+};
+struct Sector { // flats resolved for the batch's timestamp (flats.rs:103-111)
+    int16_t floor, ceil, light;
+    int16_t ceil_name_has_sky;    // segs.rs:464-469 tests the sector's texture NAME
+    int16_t floor_flat, ceil_flat; // flat SLOT of the context, -2 = lump missing (panics when shown)
+    int16_t floor_sky, ceil_sky;   // the resolved flat's name contains "SKY" (visplanes.rs:89)
+};
+struct Bitmap {
+    int32_t slot; // bitmap slot of the context, -1 = never uploaded (zero-sized)
+    uint32_t base;
+    int16_t w, h;
+    uint32_t opaque;
+};
+struct Map {
+    const Node *nodes;
+    const SubSector *ssectors;
+    const Seg *segs;
+    const Line *lines;
+    const Side *sides;
+    const Sector *sectors;
+    const Bitmap *bitmaps;
+    int nnodes;
+    int W, H;
+    float ASPECT, GCFX, CFX, CFY; // constants.rs:7-17, derived by drr_ctx_create
+    int sky_kind;                 // KIND_SKY / KIND_SKY_HOLES, -1 = sky not set
+    int phases;                   // DRR_PHASES_* (1 walls, 2 planes, 4 masked)
+};
+
+struct ViewIn { // player (game.rs:41-45) + host-evaluated cos/sin of angle and of -angle (Vertex::rotate, vertexes.rs:20-25)
+    float x, y, angle;
+    float cos_a, sin_a;   // cosf(angle), sinf(angle): shipped to the draw kernels in View
+    float cos_n, sin_n;   // cosf(-angle), sinf(-angle): the view transform of segs.rs:380-383
+};
+
+enum : uint32_t { FE_OK = 0, FE_PANIC = 1, FE_HARD = 2 };
+enum : uint32_t { // detail codes (messages: fe_detail_message() in drr_api.cu)
+    FED_NONE = 0,
+    FED_CLIP_X,          // "Clipped line x < -0.01"            segs.rs:389-391
+    FED_UNKNOWN_TEXTURE, // "Unknown texture"                   segs.rs:152-157
+    FED_NOT_VERTICAL,    // "Wall start not vertical"           segs.rs:159-167
+    FED_LINE_X,          // "Invalid line start/end x"          segs.rs:169-184
+    FED_FLAT_MISSING,    // flat lump missing                   flats.rs:92-100
+    FED_STACK,           // BSP deeper than the walk stack      (hard)
+    FED_BITMAP_SLOT,     // emitted bitmap was never uploaded   (hard: DRR_E_ASSET on the host path)
+    FED_SKY_UNSET,       // sky visplane but no sky bitmap      (hard: DRR_E_ASSET on the host path)
+};
+
+struct Counts { // per viewpoint, written by the count pass. 40 bytes
+    uint32_t nops, nsegs, ncols, nplanes, nparr, reccap;
+    uint32_t status, detail;
+    uint32_t nrec; // columns that survive clipping (what the bin kernel will actually write; statistics)
+    uint32_t pad;
+};
+struct Bases { // per viewpoint, written by the host between the passes. 32 bytes
+    uint32_t op, seg, col, plane, parr;
+    int32_t frame; // recorded frame index, -1 = no frame (panic)
+    uint32_t nsegs, ncols; // the view's totals from the count pass: deferred parts are written from the END of the view's ranges
+};
+
+// per-viewpoint scratch (global memory): W entries each
+struct Scratch {
+    uint8_t *hor_ocl;
+    int16_t *floor_ocl, *ceil_ocl;
+    uint32_t *rows[2]; // (top, bottom) pairs of the visplane being accumulated: 0 = bottom (floor), 1 = top (ceiling)
+};
+
+struct Out { // where the emit pass writes (pointers are the batch's arrays; indices are global)
+    View *views;
+    uint32_t *ops;
+    SegRec *segs;
+    ColRec *cols;
+    PlaneRec *planes;
+    uint32_t *parr;
+};
+
+// ---- Rust scalar semantics (the same helpers as csrc/host/drr_scene.cpp) ------------------------------------------
+FE_HD int16_t as_i16(float f) {
+    if (f != f) return 0;
+    if (f <= -32768.0f) return (int16_t)-32768;
+    if (f >= 32767.0f) return (int16_t)32767;
+    return (int16_t)f;
+}
+FE_HD int32_t as_i32(float f) {
+    if (f != f) return 0;
+    if (f <= -2147483648.0f) return (int32_t)0x80000000;
+    if (f >= 2147483648.0f) return 0x7fffffff;
+    return (int32_t)f;
+}
+FE_HD int16_t w16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
+
+struct V2 {
+    float x, y;
+};
+struct Seg2 {
+    V2 s, e;
+};
+FE_HD V2 sub(V2 a, V2 b) { return V2{a.x - b.x, a.y - b.y}; }
+FE_HD V2 rot(V2 v, float c, float s) { return V2{v.x * c - v.y * s, v.y * c + v.x * s}; } // vertexes.rs:20-25 with host cos/sin
+FE_HD float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+FE_HD bool left_of(V2 v, V2 ls, V2 le) { return cross(sub(v, ls), sub(le, ls)) <= 0.0f; } // vertexes.rs:32-34
+FE_HD float dist(V2 a, V2 b) {
+    const float dx = a.x - b.x, dy = a.y - b.y;
+    return sqrtf(dx * dx + dy * dy);
+}
+FE_HD bool intersect(const Seg2 &a, const Seg2 &b, V2 *out) { // geometry.rs:56-82
+    const float x1 = a.s.x, y1 = a.s.y, x2 = a.e.x, y2 = a.e.y, x3 = b.s.x, y3 = b.s.y, x4 = b.e.x, y4 = b.e.y;
+    const float quot = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4);
+    if (fabsf(quot) < 0.001f) return false;
+    const float inv = 1.0f / quot;
+    out->x = inv * ((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4));
+    out->y = inv * ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4));
+    return true;
+}
+
+struct ScreenLine {
+    int32_t sx, sy, ex, ey;
+};
+FE_HD ScreenLine project(const Map &m, const Seg2 &l, float height) { // misc.rs:130-161
+    V2 ts = {m.GCFX * l.s.y / l.s.x, m.GCFX * height / l.s.x};
+    V2 te = {m.GCFX * l.e.y / l.e.x, m.GCFX * height / l.e.x};
+    ts.x *= m.ASPECT;
+    te.x *= m.ASPECT;
+    ScreenLine r{as_i32(m.CFX - ts.x), as_i32(m.CFY - ts.y), as_i32(m.CFX - te.x), as_i32(m.CFY - te.y)};
+    r.sx = r.sx < m.W - 1 ? r.sx : m.W - 1;
+    r.ex = r.ex < m.W - 1 ? r.ex : m.W - 1;
+    return r;
+}
+
+FE_HD bool clip_fov(const Seg2 &line, Seg2 *out, float *start_offset) { // misc.rs:13-115
+    const V2 O = {0.0f, 0.0f}, LE = {1.0f, 1.0f}, RE = {1.0f, -1.0f};
+    const Seg2 L = {O, LE}, R = {O, RE};
+    const bool s_out_l = left_of(line.s, O, LE), e_out_l = left_of(line.e, O, LE);
+    const bool s_out_r = !left_of(line.s, O, RE), e_out_r = !left_of(line.e, O, RE);
+    const bool s_in = line.s.x > 0.0f && !s_out_l && !s_out_r;
+    const bool e_in = line.e.x > 0.0f && !e_out_l && !e_out_r;
+    if (s_in && e_in) {
+        *out = line;
+        *start_offset = 0.0f;
+        return true;
+    }
+    V2 li = {0.0f, 0.0f}, ri = {0.0f, 0.0f};
+    const bool lhit = intersect(line, L, &li) && li.x >= 0.0f;
+    const bool rhit = intersect(line, R, &ri) && ri.x >= 0.0f;
+    if (!s_in && !e_in && !lhit && !rhit) return false;
+    if (!s_in && !e_in && lhit != rhit) return false;
+    if ((rhit && s_out_r && e_out_r) || (lhit && s_out_l && e_out_l)) return false;
+    V2 s = line.s, e = line.e;
+    float so = 0.0f;
+    if (lhit) {
+        if (s_out_l) {
+            so = dist(li, s);
+            s = li;
+        }
+        if (e_out_l) e = li;
+    }
+    if (rhit) {
+        if (s_out_r) s = ri;
+        if (e_out_r) e = ri;
+    }
+    out->s = s;
+    out->e = e;
+    *start_offset = so;
+    return true;
+}
+
+FE_HD int sector_at(const Map &m, V2 p) { // renderer/bsp.rs:9-44
+    int n = m.nnodes - 1;
+    for (;;) {
+        const Node nd = m.nodes[n];
+        const V2 a = {nd.x, nd.y}, b = {nd.x + nd.dx, nd.y + nd.dy};
+        const int ch = left_of(p, a, b) ? nd.left : nd.right;
+        if (ch >= 0) {
+            n = ch;
+            continue;
+        }
+        const SubSector ss = m.ssectors[~ch];
+        for (int i = 0; i < ss.count; i++) {
+            const Seg sg = m.segs[ss.first + i];
+            const Line ld = m.lines[sg.line];
+            const int sd = sg.dir ? ld.back : ld.front;
+            if (sd != -1) return m.sides[sd].sector;
+        }
+        return -1;
+    }
+}
+
+// ---- one viewpoint -----------------------------------------------------------------------------------------------
+template <bool EMIT>
+struct Frame {
+    const Map &m;
+    Scratch sc;
+    Out out;
+    Bases base;   // EMIT only
+    Counts n;     // running counts == cursors relative to the bases
+    V2 ppos;
+    float cos_n, sin_n, pfloor;
+    // SidedefVisPlanes of the sidedef part being processed
+    bool open[2];
+    int16_t pl_left[2], pl_right[2];
+    int16_t pl_flat[2], pl_sky[2], pl_height[2], pl_light;
+    // Deferred two-sided middle textures are drawn after everything else, last created first (mod.rs:124, segs.rs:593-597), and
+    // the host front-end appends a part's header and columns when it is DRAWN.  To produce the same arrays, walls fill the
+    // view's seg / column ranges from the front and deferred parts from the back (the first created one ends up last).
+    uint32_t ndeferred, dcols; // deferred parts / their columns so far
+
+    FE_HD Frame(const Map &map) : m(map) {}
+
+    FE_HD void fail(uint32_t status, uint32_t detail) {
+        if (n.status == FE_OK) {
+            n.status = status;
+            n.detail = detail;
+        }
+    }
+
+    // add_bottom_point / add_top_point, sidedef_visplanes.rs:60-84.  The reference keeps [i16; W] arrays zero-initialised
+    // (visplanes.rs:36-37): columns between left and right that never got a point stay (0, 0).
+    FE_HD void point(int which, int16_t x, int16_t top_y, int16_t bottom_y) {
+        if (!open[which]) {
+            open[which] = true;
+            pl_left[which] = x;
+        } else {
+            for (int xx = pl_right[which] + 1; xx < x; xx++) sc.rows[which][xx] = 0u;
+        }
+        pl_right[which] = x;
+        sc.rows[which][x] = (uint32_t)(uint16_t)top_y | ((uint32_t)(uint16_t)bottom_y << 16);
+    }
+    // flush, sidedef_visplanes.rs:41-58: pushes the bottom visplane, then the top one.  mod.rs:106-116 later draws the
+    // visplanes in push order (phase B comes after every wall), so the ops are appended after the walk: here the plane's
+    // record and its rows are written, the op words follow in flush_plane_ops().
+    FE_HD void flush() {
+        for (int which = 0; which < 2; which++) {
+            if (!open[which]) continue;
+            open[which] = false;
+            if (!(m.phases & 2)) continue;
+            const int left = pl_left[which], right = pl_right[which];
+            const uint32_t ncols = (uint32_t)(right - left + 1);
+            if (pl_sky[which] && m.sky_kind < 0) fail(FE_HARD, FED_SKY_UNSET);
+            const uint32_t *src = sc.rows[which] + left;
+            for (uint32_t i = 0; i < ncols; i++) { // how many of the columns draw anything (drr_api.cu: rec_emit_visplane)
+                const int t = (int)(int16_t)(src[i] & 0xffffu) > 0 ? (int)(int16_t)(src[i] & 0xffffu) : 0; // visplanes.rs:61 / :95
+                const int bq = (int)(int16_t)(src[i] >> 16) < m.H - 1 ? (int)(int16_t)(src[i] >> 16) : m.H - 1; // :62 / :96
+                if (!pl_sky[which] && (int16_t)(bq - t) <= 1) continue; // :99-101 (not applied to sky)
+                if (t <= bq) n.nrec++;
+            }
+            if (EMIT) {
+                PlaneRec p;
+                p.flat_slot = pl_sky[which] ? (int16_t)-1 : pl_flat[which];
+                p.height = pl_height[which];
+                p.light_level = pl_light;
+                p.left = (int16_t)left;
+                p.right = (int16_t)right;
+                p.kind = (int16_t)(pl_sky[which] ? m.sky_kind : (int)KIND_FLAT);
+                p.arr_first = base.parr + n.nparr;
+                out.planes[base.plane + n.nplanes] = p;
+                uint32_t *dst = out.parr + p.arr_first;
+                for (uint32_t i = 0; i < ncols; i++) dst[i] = src[i];
+            }
+            n.nplanes++;
+            n.nparr += ncols;
+            n.reccap += ncols;
+        }
+    }
+
+    FE_HD void occlude(int x) { // segs.rs:113-117
+        sc.hor_ocl[x] = 1;
+        sc.floor_ocl[x] = (int16_t)(m.H / 2);
+        sc.ceil_ocl[x] = (int16_t)(m.H / 2);
+    }
+
+    // process_sidedef, segs.rs:121-350
+    FE_HD void sidedef_part(const Seg2 &cl, float start_offset, const Side &sd, int16_t seg_offset, const Sector &sec, float bottom_h,
+                            float top_h, int32_t offset_y, int tex, bool only_occ, bool lower, bool upper, bool draw_ceiling, bool two_sided_mid) {
+        const ScreenLine bottom = project(m, cl, bottom_h), top = project(m, cl, top_h);
+        if (tex == -2) return fail(FE_PANIC, FED_UNKNOWN_TEXTURE);
+        if (bottom.sx != top.sx || bottom.ex != top.ex) return fail(FE_PANIC, FED_NOT_VERTICAL);
+        if ((int16_t)bottom.sx == (int16_t)bottom.ex || (int16_t)top.sx == (int16_t)top.ex) return;
+        if (bottom.sx < 0 || bottom.sx >= m.W || bottom.ex < 0 || bottom.ex >= m.W) return fail(FE_PANIC, FED_LINE_X);
+        const float bottom_delta = ((float)bottom.sy - (float)bottom.ey) / ((float)bottom.sx - (float)bottom.ex);
+        const float top_delta = ((float)top.sy - (float)top.ey) / ((float)top.sx - (float)top.ex);
+
+        open[0] = open[1] = false;
+        pl_flat[0] = sec.floor_flat;
+        pl_flat[1] = sec.ceil_flat;
+        pl_sky[0] = sec.floor_sky;
+        pl_sky[1] = sec.ceil_sky;
+        pl_height[0] = sec.floor;
+        pl_height[1] = sec.ceil;
+        pl_light = sec.light;
+        const bool full_height = !lower && !upper && !only_occ;
+        const int16_t H16 = (int16_t)m.H, Hm1 = w16(H16 - 1);
+        // is this part's column list ever emitted?  phase A walls are drawn at once (segs.rs:231-258), two-sided middle
+        // textures are deferred (phase D, segs.rs:593-597); occlusion-only parts and "-" textures draw nothing
+        const bool wall = !two_sided_mid && !only_occ && (m.phases & 1);
+        const bool deferred = two_sided_mid && (m.phases & 4);
+        const bool keep = (wall || deferred) && tex >= 0;
+        const uint32_t col0 = n.ncols;
+        int16_t x_first = 0, x_last = 0;
+
+        for (int16_t x = (int16_t)bottom.sx; x < w16((int16_t)bottom.ex + 1); x++) {
+            if (!sc.hor_ocl[x]) {
+                const int16_t bottom_y = as_i16((float)bottom.sy + ((float)x - (float)bottom.sx) * bottom_delta);
+                const int16_t top_y = as_i16((float)top.sy + ((float)x - (float)top.sx) * top_delta);
+                const int16_t fvo = sc.floor_ocl[x], cvo = sc.ceil_ocl[x];
+                int16_t cb = fvo < bottom_y ? fvo : bottom_y, ct = cvo > top_y ? cvo : top_y;
+                cb = Hm1 < cb ? Hm1 : cb;
+                ct = ct < 0 ? (int16_t)0 : ct;
+                const bool in_area = cb >= ct;
+                if (in_area && keep) { // add_column, bitmap_render.rs:84-99
+                    if (EMIT) {
+                        ColRec c;
+                        c.x = x;
+                        c.clipped_top_y = ct;
+                        c.clipped_bottom_y = cb;
+                        c.bottom_y = bottom_y;
+                        c.top_y = top_y;
+                        out.cols[base.col + (n.ncols - dcols)] = c; // front cursor; a deferred part's block is moved to the back below
+                    }
+                    if (n.ncols == col0) x_first = x;
+                    x_last = x;
+                    n.ncols++;
+                    n.nrec++; // 0 <= x < W and max(ct, 0) <= min(cb, H - 1) hold here
+                }
+                if (!two_sided_mid && in_area && (full_height || only_occ)) {
+                    bool added = false;
+                    if (cb < fvo && cb != Hm1) {
+                        point(0, x, cb, fvo);
+                        added = true;
+                    }
+                    if (draw_ceiling && ct > cvo && ct != -1) {
+                        point(1, x, cvo, ct);
+                        added = true;
+                    }
+                    if (!added) flush();
+                } else if (!two_sided_mid && !in_area && (full_height || only_occ) && fvo > cvo) {
+                    if (bottom_y <= cvo) {
+                        point(0, x, cvo, fvo);
+                        occlude(x);
+                    }
+                    if (draw_ceiling && top_y >= fvo) {
+                        point(1, x, cvo, fvo);
+                        occlude(x);
+                    }
+                }
+                if (!two_sided_mid && in_area && only_occ) {
+                    sc.floor_ocl[x] = cb;
+                    if (draw_ceiling) sc.ceil_ocl[x] = ct;
+                }
+                if (!two_sided_mid && in_area && lower) sc.floor_ocl[x] = ct;
+                if (!two_sided_mid && in_area && upper) sc.ceil_ocl[x] = cb;
+            } else {
+                flush();
+            }
+            if (!two_sided_mid && full_height) occlude(x);
+        }
+        flush();
+        const uint32_t ncol = n.ncols - col0;
+        if (!keep || ncol == 0) return;
+        const Bitmap bm = m.bitmaps[tex];
+        if (bm.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
+        if (EMIT) {
+            SegRec r;
+            r.bitmap_slot = (uint32_t)bm.slot;
+            r.light_level = sec.light;
+            r.phase = (int16_t)(deferred ? 2 : 0); // DRR_PHASE_MASKED / DRR_PHASE_WALL
+            r.lsx = cl.s.x;
+            r.lsy = cl.s.y;
+            r.lex = cl.e.x;
+            r.ley = cl.e.y;
+            r.start_offset = start_offset;
+            r.start_x = bottom.sx;
+            r.end_x = bottom.ex;
+            r.bottom_height = bottom_h;
+            r.top_height = top_h;
+            r.offset_x = w16(as_i16(sd.xoff) + seg_offset);
+            r.offset_y = w16(as_i16(sd.yoff) + w16(offset_y));
+            uint32_t first = base.col + (col0 - dcols); // where the loop above put the columns
+            if (deferred) { // move the block to the back of the view's column range (dst >= src: copy from the last element)
+                const uint32_t dst = base.col + base.ncols - dcols - ncol;
+                for (uint32_t i = ncol; i-- > 0;) out.cols[dst + i] = out.cols[first + i];
+                first = dst;
+            }
+            r.cols_first = first;
+            r.n = ncol;
+            r.x0 = x_first;
+            r.x1 = x_last;
+            r.tex_base = bm.base;
+            r.tex_w = bm.w;
+            r.tex_h = bm.h;
+            r.tex_opaque = bm.opaque;
+            r.pad[0] = r.pad[1] = 0;
+            const uint32_t si = deferred ? base.seg + base.nsegs - 1 - ndeferred : base.seg + (n.nsegs - ndeferred);
+            out.segs[si] = r;
+            if (wall) out.ops[base.op + n.nops] = si; // deferred parts get their op after the walk
+        }
+        if (wall) {
+            n.nops++;
+        } else {
+            ndeferred++;
+            dcols += ncol;
+        }
+        n.nsegs++;
+        // record slots the bin kernel may reserve: one per screen column inside the x range (drr_api.cu: rec_emit_columns)
+        const int lo = x_first > 0 ? x_first : 0, hi = x_last < m.W - 1 ? x_last : m.W - 1;
+        n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
+    }
+
+    // process_seg, segs.rs:353-590
+    FE_HD void seg(const Seg &sg) {
+        const Line ld = m.lines[sg.line];
+        const int fi = sg.dir ? ld.back : ld.front, bi = sg.dir ? ld.front : ld.back;
+        if (fi == -1) return;
+        const Side fs = m.sides[fi];
+        const Sector fsec = m.sectors[fs.sector];
+        const float floor_h = (float)fsec.floor;
+        float ceil_h = (float)fsec.ceil;
+        bool has_pb = false, has_pt = false;
+        float pb = 0.0f, pt = 0.0f;
+        Sector bsec = fsec;
+        if (bi != -1) {
+            bsec = m.sectors[m.sides[bi].sector];
+            if (bsec.floor > fsec.floor) {
+                has_pb = true;
+                pb = (float)bsec.floor;
+            }
+            if (bsec.ceil < fsec.ceil) {
+                has_pt = true;
+                pt = (float)bsec.ceil;
+            }
+        }
+        const bool two_sided = (ld.flags & 4) != 0, top_unpeg = (ld.flags & 8) != 0, bottom_unpeg = (ld.flags & 16) != 0;
+
+        const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
+        const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
+        Seg2 cl;
+        float so;
+        if (!clip_fov(view, &cl, &so)) return;
+        if (cl.s.x < -0.01f) return fail(FE_PANIC, FED_CLIP_X);
+        const float ph = pfloor + 41.0f;
+        const ScreenLine fl = project(m, cl, floor_h - ph);
+        if (fl.sx > fl.ex) return; // back face
+
+        if (fsec.floor_flat < 0 || fsec.ceil_flat < 0) return fail(FE_PANIC, FED_FLAT_MISSING); // Flats::get, flats.rs:92-100
+        bool draw_ceiling = true;
+        if (bi != -1) { // sky hack, segs.rs:463-477
+            if (fsec.ceil_name_has_sky && bsec.ceil_name_has_sky) {
+                has_pt = false;
+                ceil_h = fminf((float)bsec.ceil, ceil_h);
+                draw_ceiling = false;
+            }
+        }
+        if (!two_sided) {
+            sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, bottom_unpeg ? as_i32(floor_h - ceil_h) : 0, fs.middle, false,
+                         false, false, draw_ceiling, false);
+        } else {
+            sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, 0, fs.middle, true, false, false, draw_ceiling, false);
+            if (n.status != FE_OK) return;
+            const float mf = has_pb ? pb : floor_h, mc = has_pt ? pt : ceil_h;
+            sidedef_part(cl, so, fs, sg.offset, fsec, mf - ph, mc - ph, 0, fs.middle, false, false, false, draw_ceiling, true);
+            if (n.status != FE_OK) return;
+            if (has_pb)
+                sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, pb - ph, bottom_unpeg ? as_i32(ceil_h - pb) : 0, fs.lower, false, true,
+                             false, draw_ceiling, false);
+            if (n.status != FE_OK) return;
+            if (has_pt)
+                sidedef_part(cl, so, fs, sg.offset, fsec, pt - ph, ceil_h - ph, top_unpeg ? 0 : as_i32(pt - ceil_h), fs.upper, false, false, true,
+                             draw_ceiling, false);
+        }
+    }
+
+    // Renderer::render, mod.rs:118-136 (without phase C, the map objects)
+    FE_HD void run(const ViewIn &v, const Bases &b) {
+        base = b;
+        n = Counts{0, 0, 0, 0, 0, 0, FE_OK, FED_NONE, 0, 0};
+        ppos = V2{v.x, v.y};
+        cos_n = v.cos_n;
+        sin_n = v.sin_n;
+        pfloor = 0.0f; // game.rs:144-150, 376-389
+        const int s = sector_at(m, ppos);
+        if (s >= 0) pfloor = (float)m.sectors[s].floor;
+        for (int x = 0; x < m.W; x++) { // segs.rs:97-99
+            sc.hor_ocl[x] = 0;
+            sc.floor_ocl[x] = (int16_t)m.H;
+            sc.ceil_ocl[x] = (int16_t)-1;
+        }
+        open[0] = open[1] = false;
+        ndeferred = 0;
+        dcols = 0;
+        if (EMIT) out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a};
+        // A: render_node, mod.rs:69-104 -- front subtree, then back subtree (explicit stack instead of the recursion)
+        int stack[64];
+        int sp = 0;
+        stack[sp++] = m.nnodes - 1;
+        while (sp > 0 && n.status == FE_OK) {
+            const int node = stack[--sp];
+            if (node < 0) {
+                const SubSector ss = m.ssectors[~node];
+                for (int i = 0; i < ss.count && n.status == FE_OK; i++) seg(m.segs[ss.first + i]);
+                continue;
+            }
+            const Node nd = m.nodes[node];
+            const V2 a = {nd.x, nd.y}, bb = {nd.x + nd.dx, nd.y + nd.dy};
+            const bool is_left = left_of(ppos, a, bb);
+            if (sp + 2 > 64) {
+                fail(FE_HARD, FED_STACK);
+                break;
+            }
+            stack[sp++] = is_left ? nd.right : nd.left; // visited second
+            stack[sp++] = is_left ? nd.left : nd.right; // visited first
+        }
+        if (n.status != FE_OK) return;
+        // B: mod.rs:106-116 -- the visplanes in push order, after every wall
+        if (EMIT)
+            for (uint32_t i = 0; i < n.nplanes; i++) out.ops[base.op + n.nops + i] = 0x80000000u | (base.plane + i);
+        n.nops += n.nplanes;
+        // D: segs.rs:593-597 -- the deferred two-sided middle textures, last created first (mod.rs:124 reverses the list)
+        if (EMIT)
+            for (uint32_t k = 0; k < ndeferred; k++) out.ops[base.op + n.nops + k] = base.seg + base.nsegs - ndeferred + k;
+        n.nops += ndeferred;
+    }
+};
+
+} // namespace fe
+} // namespace drr

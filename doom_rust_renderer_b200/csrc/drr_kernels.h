@@ -73,6 +73,24 @@ cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cud
 void tile_config(int W, int H, int *tc, int *lpg);
 void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (bands of at most 400 rows)
 static constexpr int MAX_LIST_BANDS = 8;             // up to this many bands the bin kernel writes one span list per (column, band)
+// ---- device front-end (drr_frontend.cu / drr_frontend.cuh) ----------------------------------------------------------
+namespace fe {
+struct Map;
+struct ViewIn;
+struct Counts;
+struct Bases;
+struct Out;
+} // namespace fe
+static constexpr int FE_THREADS = 32; // one warp per CTA: a batch of a few thousand viewpoints then spreads over every SM
+struct FeScratch {                    // per-viewpoint working state of the front-end, W entries per viewpoint each
+    uint8_t *hor_ocl;
+    int16_t *floor_ocl, *ceil_ocl;
+    uint32_t *rows;                   // 2 * W per viewpoint: the (top, bottom) rows of the two visplanes being accumulated
+};
+// emit == false: count pass (writes counts[0..n)); emit == true: writes the lists at the offsets in bases[0..n)
+cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
+                            const FeScratch &s, const fe::Out &out, cudaStream_t st);
+
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);
 

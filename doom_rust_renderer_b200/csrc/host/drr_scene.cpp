@@ -1137,4 +1137,64 @@ int drr_scene_emit_views(drr_scene *s, drr_ctx *ctx, int first_view_idx, const f
     return rc;
 }
 
+// The map as the flat tables of drr_fe_upload_map, flats resolved for `timestamp` (flats.rs:103-111), then the whole batch
+// on the device front-end (csrc/drr_frontend.cuh).
+int drr_scene_emit_views_device(drr_scene *s, drr_ctx *ctx, int first_view_idx, const float *xya, int n, float timestamp, int phases, int *status) {
+    if (!s || !ctx || n < 0 || (n > 0 && !xya)) return DRR_E_INVALID;
+    std::vector<drr_fe_node> nodes(s->nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) nodes[i] = drr_fe_node{s->nodes[i].x, s->nodes[i].y, s->nodes[i].dx, s->nodes[i].dy, s->nodes[i].right, s->nodes[i].left};
+    std::vector<drr_fe_subsector> ss(s->ssectors.size());
+    for (size_t i = 0; i < ss.size(); i++) ss[i] = drr_fe_subsector{s->ssectors[i].first, s->ssectors[i].second};
+    std::vector<drr_fe_seg> segs(s->segs.size());
+    for (size_t i = 0; i < segs.size(); i++) {
+        const SegH &g = s->segs[i];
+        segs[i] = drr_fe_seg{g.v1.x, g.v1.y, g.v2.x, g.v2.y, g.line, (int16_t)(g.dir ? 1 : 0), g.offset};
+    }
+    std::vector<drr_fe_linedef> lines(s->lines.size());
+    for (size_t i = 0; i < lines.size(); i++) lines[i] = drr_fe_linedef{s->lines[i].front, s->lines[i].back, (int32_t)s->lines[i].flags};
+    std::vector<drr_fe_sidedef> sides(s->sides.size());
+    for (size_t i = 0; i < sides.size(); i++) {
+        const SideH &d = s->sides[i];
+        sides[i] = drr_fe_sidedef{d.xoff, d.yoff, d.upper, d.lower, d.middle, d.sector}; // (zero-sized bitmaps were never uploaded: the library reports them)
+    }
+    std::vector<drr_fe_sector> sectors(s->sectors.size());
+    s->timestamp = timestamp;
+    for (size_t i = 0; i < sectors.size(); i++) {
+        const SectorH &c = s->sectors[i];
+        drr_fe_sector o{};
+        o.floor_height = c.floor;
+        o.ceiling_height = c.ceil;
+        o.light_level = c.light;
+        o.ceiling_name_has_sky = c.ceil_name_has_sky ? 1 : 0;
+        auto pick = [&](const FlatRef &fr, int16_t *id, int16_t *sky) { // pick_flat without the panic: -2 marks a missing lump
+            const size_t k = fr.ids.size() == 1 ? 0 : (size_t)(as_usize(timestamp * 3.0f) % fr.ids.size());
+            *id = (int16_t)(fr.ids[k] < 0 ? -2 : fr.ids[k]);
+            *sky = fr.is_sky[k] ? 1 : 0;
+        };
+        pick(c.floor_flat, &o.floor_flat, &o.floor_is_sky);
+        pick(c.ceil_flat, &o.ceiling_flat, &o.ceiling_is_sky);
+        sectors[i] = o;
+    }
+    int things = 0;
+    for (const ObjH &mo : s->objects) things += mo.is_null ? 0 : 1;
+    drr_fe_map m{};
+    m.nodes = nodes.data();
+    m.n_nodes = (int32_t)nodes.size();
+    m.subsectors = ss.data();
+    m.n_subsectors = (int32_t)ss.size();
+    m.segs = segs.data();
+    m.n_segs = (int32_t)segs.size();
+    m.linedefs = lines.data();
+    m.n_linedefs = (int32_t)lines.size();
+    m.sidedefs = sides.data();
+    m.n_sidedefs = (int32_t)sides.size();
+    m.sectors = sectors.data();
+    m.n_sectors = (int32_t)sectors.size();
+    m.n_things = things;
+    int rc = drr_fe_upload_map(ctx, &m);
+    if (rc == DRR_OK) rc = drr_fe_emit_views(ctx, first_view_idx, xya, n, phases, status);
+    if (rc != DRR_OK) s->err = std::string("device front-end: ") + drr_last_error(ctx);
+    return rc;
+}
+
 } // extern "C"

@@ -85,6 +85,10 @@ def _lib() -> C.CDLL:
             "drr_recorder_frame_begin": (i, [vp, i, C.POINTER(DrrView)]), "drr_recorder_emit_columns": (i, [vp, C.POINTER(DrrSegHdr), vp, i]),
             "drr_recorder_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_recorder_frame_end": (i, [vp]),
             "drr_recorder_frame_abort": (i, [vp]), "drr_append": (i, [vp, vp]),
+            "drr_fe_upload_map": (i, [vp, vp]), "drr_fe_emit_views": (i, [vp, i, vp, i, i, vp]),
+            "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]),
+            "drr_scene_emit_views_device": (i, [vp, vp, i, vp, i, f, i, vp]),
+            "drr_test_fe_emit_views_host": (i, [vp, i, vp, i, i, vp]), "drr_test_fe_download_lists": (i, [vp]),
             "drr_test_ctx_create_host_only": (i, [i, i, i, C.POINTER(vp)]),
             "drr_test_list": (vp, [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
             "drr_test_bitmap_info": (i, [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
@@ -112,6 +116,7 @@ EXPORTED_SYMBOLS = [
     "drr_scene_emit_view", "drr_scene_emit_views",
     "drr_recorder_create", "drr_recorder_destroy", "drr_recorder_last_error", "drr_recorder_frame_begin", "drr_recorder_emit_columns",
     "drr_recorder_emit_visplane", "drr_recorder_frame_end", "drr_recorder_frame_abort", "drr_append",
+    "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_scene_emit_views_device",
 ]
 
 
@@ -281,6 +286,27 @@ class Context:
         self._ck(self.L.drr_test_fastdiv(self.h, mode, n0, n1, cfy, lo, stride, C.byref(bad), _ptr(first)))
         return bad.value, (float(first[0]), float(first[1]))
 
+    # ---- device front-end
+    def fe_emit_views(self, views: np.ndarray, phases: int = 3, first_slot: int = 0, _on_host: bool = False):
+        """drr_fe_emit_views on the map uploaded with drr_fe_upload_map (Scene.emit_views_device does both).  `_on_host` runs
+        the same per-view code on the CPU into the host lists (test infrastructure).  Returns the view indices the reference
+        would have panicked on."""
+        v = np.ascontiguousarray(np.asarray(views, np.float32).reshape(-1, 3))
+        status = np.zeros(len(v), np.int32)
+        fn = self.L.drr_test_fe_emit_views_host if _on_host else self.L.drr_fe_emit_views
+        self._ck(fn(self.h, first_slot, _ptr(v), len(v), phases, _ptr(status)))
+        return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
+
+    def fe_last_times(self):
+        """(count_ms, emit_ms): device time of the two front-end passes of the last fe_emit_views."""
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.drr_fe_last_times(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fe_download_lists(self):
+        """Test infrastructure: copy the device-written lists back so that _list() can show them."""
+        self._ck(self.L.drr_test_fe_download_lists(self.h))
+
     # ---- test-only views of the recorded lists (CPU-testable host logic)
     def _list(self, which: int, dtype) -> np.ndarray:
         n, sz = C.c_uint64(), C.c_uint64()
@@ -353,3 +379,16 @@ class Scene:
         status = np.zeros(len(v), np.int32)
         self._ck(self.L.drr_scene_emit_views(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, threads, _ptr(status)))
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]  # DRR_E_PANIC
+
+    def emit_views_device(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = 3, first_slot: int = 0):
+        """The same batch with the front-end running ON THE GPU (drr_fe_upload_map + drr_fe_emit_views): walls, visplanes and
+        (for maps without things) masked mid-textures.  The context must be reset first; afterwards ctx.draw() renders."""
+        v = np.ascontiguousarray(np.asarray(views, np.float32).reshape(-1, 3))
+        status = np.zeros(len(v), np.int32)
+        self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, _ptr(status)))
+        return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
+
+    def upload_map_for_device_front_end(self, ctx: Context, timestamp: float = 0.0):
+        """drr_fe_upload_map only (a zero-view drr_scene_emit_views_device)."""
+        v = np.zeros((0, 3), np.float32)
+        self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, 0, _ptr(v), 0, timestamp, 3, None))

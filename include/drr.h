@@ -160,6 +160,41 @@ int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, flo
 int drr_profile_begin(drr_ctx *ctx, int max_steps);
 int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *march_ms_total);
 
+/* ---- device front-end: Renderer::render()'s BSP walk, seg clipping, occlusion arrays and --- */
+/* visplane building for a whole batch of viewpoints ON THE GPU (csrc/drr_frontend.cuh, one thread per viewpoint): the
+ * draw lists are written where drr_draw reads them and never cross PCIe.  Covers walls, visplanes and deferred masked
+ * mid-textures (src/renderer/mod.rs:69-136, segs.rs:121-597, misc.rs:13-161, sidedef_visplanes.rs); map objects
+ * (sprites, src/renderer/map_objects.rs) remain with the host front-end, so DRR_PHASES_MASKED is refused for a map
+ * that has things.  The map goes up as flat tables (what the loaders under src/map/ read, names resolved to the handles given to
+ * drr_upload_bitmap / drr_upload_flat): */
+typedef struct { float x, y, dx, dy; int32_t right, left; } drr_fe_node;            /* src/map/nodes.rs; child >= 0 node, < 0 ~subsector */
+typedef struct { int32_t first_seg, count; } drr_fe_subsector;                      /* src/map/subsectors.rs */
+typedef struct { float v1x, v1y, v2x, v2y; int32_t linedef; int16_t direction, offset; } drr_fe_seg; /* src/map/segs.rs */
+typedef struct { int32_t front, back, flags; } drr_fe_linedef;                      /* sidedef indices, -1 = none */
+typedef struct { float x_offset, y_offset; int32_t upper, lower, middle, sector; } drr_fe_sidedef;  /* bitmap ids; -1 = "-", -2 = unknown name */
+typedef struct {
+    int16_t floor_height, ceiling_height, light_level;
+    int16_t ceiling_name_has_sky;      /* the sector's ceiling texture NAME contains "SKY" (segs.rs:464-469) */
+    int16_t floor_flat, ceiling_flat;  /* flat ids for the batch's timestamp (animation resolved, flats.rs:103-111); -2 = lump missing */
+    int16_t floor_is_sky, ceiling_is_sky; /* the resolved flat's name contains "SKY" (visplanes.rs:89) */
+} drr_fe_sector;
+typedef struct {
+    const drr_fe_node *nodes;           int32_t n_nodes;
+    const drr_fe_subsector *subsectors; int32_t n_subsectors;
+    const drr_fe_seg *segs;             int32_t n_segs;
+    const drr_fe_linedef *linedefs;     int32_t n_linedefs;
+    const drr_fe_sidedef *sidedefs;     int32_t n_sidedefs;
+    const drr_fe_sector *sectors;       int32_t n_sectors;
+    int32_t n_things;                   /* non-null map objects (the device front-end does not draw them) */
+} drr_fe_map;
+int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *map); /* assets must be uploaded before (ids are resolved here) */
+/* n x Renderer::new(..., player at xya[i], ...).render() on the device, view indices first_view_idx .. +n-1.  Replaces
+ * every frame recorded since drr_reset (call drr_reset first); afterwards drr_draw() renders the batch.  status[i]
+ * (may be NULL) = DRR_OK or DRR_E_PANIC (the reference would have panicked on that viewpoint: it gets no frame). */
+int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status);
+/* Device times (ms) of the last drr_fe_emit_views: count pass and emit pass (CUDA events on the context's stream). */
+int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms);
+
 /* ---- host front-end: the reference's Renderer for a WAD map, emitting through the functions above -------------- */
 /* Mirrors Game::new's asset/map loading (src/game.rs:118-196) without SDL. */
 typedef struct drr_scene drr_scene;
@@ -180,6 +215,10 @@ int drr_scene_emit_view(drr_scene *scene, drr_ctx *ctx, int view_idx, float x, f
  * DRR_E_PANIC (nothing recorded for that viewpoint). */
 int drr_scene_emit_views(drr_scene *scene, drr_ctx *ctx, int first_view_idx, const float *xya, int n, float timestamp, int phases,
                          int nthreads, int *status);
+
+/* drr_fe_upload_map (this scene's map, flats resolved for `timestamp`) + drr_fe_emit_views. */
+int drr_scene_emit_views_device(drr_scene *scene, drr_ctx *ctx, int first_view_idx, const float *xya, int n, float timestamp, int phases,
+                                int *status);
 
 #ifdef __cplusplus
 }

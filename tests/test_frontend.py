@@ -1,0 +1,256 @@
+"""The device front-end (BSP walk, seg clipping, occlusion arrays and visplane building per viewpoint
+on the GPU, csrc/drr_frontend.cuh) against the host front-end (csrc/host/drr_scene.cpp) and against the oracle.
+
+CPU part: the per-viewpoint code is one source compiled for both sides; here it runs on the CPU (drr_test_fe_emit_views_host,
+test infrastructure) and must produce, byte for byte, the lists the host front-end records -- views, ops, seg headers, column
+records, visplane headers, (top, bottom) rows, per-frame tables and statistics -- including which viewpoints the reference
+would panic on.  GPU part (-m gpu): the kernel's lists, downloaded, equal the host front-end's bytes, and the frames drawn
+from them equal the oracle's, bit for bit.
+"""
+from __future__ import annotations
+
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import common
+from common import drr, orc, synth_wad
+
+LISTS = ((0, drr.VIEW_DTYPE), (1, drr.SEG_DTYPE), (2, drr.PLANE_DTYPE), (5, np.uint32), (6, np.uint32), (7, drr.COL_DTYPE), (8, np.uint32),
+         (9, np.uint32), (10, np.uint32))
+NAMES = {0: "views", 1: "seg headers", 2: "visplane headers", 5: "frame_rec_base", 6: "frame_slot", 7: "column records", 8: "visplane rows",
+         9: "ops", 10: "frame_op_base"}
+
+
+def _assert_same_lists(a: drr.Context, b: drr.Context, what: str):
+    for which, dt in LISTS:
+        x, y = a._list(which, dt), b._list(which, dt)
+        assert x.shape == y.shape, (what, NAMES[which], x.shape, y.shape)
+        if x.tobytes() != y.tobytes():
+            k = int(np.nonzero(x != y)[0][0])
+            raise AssertionError("%s: %s differ first at %d: %s vs %s" % (what, NAMES[which], k, x[k], y[k]))
+
+
+def _views(kind, gm, n):
+    return np.array(synth_wad.walk_viewpoints(gm, n) if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, n), np.float32)
+
+
+def _wad_without_things(kind: str) -> str:
+    """The synthetic IWAD with only the player start left in THINGS (the device front-end draws no map objects, so it accepts
+    DRR_PHASES_MASKED only for such a map)."""
+    path, _ = common.wad(kind)
+    out = os.path.join(common.CACHE, "synth_%s_nothings.wad" % kind)
+    data = open(path, "rb").read()
+    n, diro = struct.unpack("<II", data[4:12])
+    lumps = []
+    for i in range(n):
+        off, size = struct.unpack("<II", data[diro + 16 * i: diro + 16 * i + 8])
+        name = data[diro + 16 * i + 8: diro + 16 * i + 16]
+        body = data[off: off + size] if size else b""
+        if name.rstrip(b"\0") == b"THINGS":
+            body = b"".join(body[k: k + 10] for k in range(0, len(body), 10) if struct.unpack("<h", body[k + 6: k + 8])[0] == 1)
+        lumps.append((name, body))
+    blob, directory, off = bytearray(), bytearray(), 12
+    for name, body in lumps:
+        directory += struct.pack("<II", off if body else 0, len(body)) + name
+        blob += body
+        off += len(body)
+    new = b"IWAD" + struct.pack("<II", len(lumps), 12 + len(blob)) + bytes(blob) + bytes(directory)
+    if not os.path.exists(out) or open(out, "rb").read() != new:
+        with open(out + ".tmp", "wb") as f:
+            f.write(new)
+        os.replace(out + ".tmp", out)
+    return out
+
+
+# ---- CPU: the shared per-viewpoint code against the host front-end ---------------------------------------------------------
+@pytest.mark.parametrize("kind,W,H,n,phases,ts", [("e1m1", 320, 200, 300, 3, 0.0), ("e1m1", 160, 100, 96, 1, 0.0), ("e1m1", 324, 200, 96, 2, 0.4),
+                                                  ("e1m1", 1280, 800, 40, 3, 0.7), ("stress", 200, 120, 160, 3, 0.0), ("stress", 640, 400, 24, 3, 0.0)])
+def test_front_end_code_emits_the_host_front_ends_lists(kind, W, H, n, phases, ts):
+    path, gm = common.wad(kind)
+    views = _views(kind, gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, timestamp=ts, phases=phases, threads=2)
+    b = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(b)
+    scene.upload_map_for_device_front_end(b, ts)
+    assert b.fe_emit_views(views, phases=phases, _on_host=True) == skipped
+    _assert_same_lists(a, b, "%s %dx%d phases %d" % (kind, W, H, phases))
+    assert a.stats() == b.stats()
+
+
+def test_front_end_code_masked_mid_textures_and_refusal():
+    """Phase D (deferred two-sided middle textures, last created first) on a map without things; with things the masked phase
+    is refused, because the sprites' ordering lives in the host front-end only."""
+    W, H, n = 320, 200, 200
+    path, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    bare = _wad_without_things("e1m1")
+    scene = drr.Scene(bare, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, phases=7, threads=2)
+    b = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(b)
+    scene.upload_map_for_device_front_end(b)
+    assert b.fe_emit_views(views, phases=7, _on_host=True) == skipped
+    _assert_same_lists(a, b, "no things, all phases")
+    assert a.stats() == b.stats()
+    segs = a._list(1, drr.SEG_DTYPE)
+    assert (segs["phase"] == 2).any(), "the walk shows no masked mid-texture: the test would prove nothing"
+    full = drr.Scene(path, "E1M1", W, H)
+    c = drr.Context(W, H, 0, n, _host_only=True)
+    full.upload_assets(c)
+    full.upload_map_for_device_front_end(c)
+    with pytest.raises(drr.DrrError) as e:
+        c.fe_emit_views(views, phases=7, _on_host=True)
+    assert e.value.code == -1 and "host front-end" in str(e.value)
+
+
+PANIC_VIEWS = {  # found by random search (tools: a seg exactly through the eye point makes the reference panic)
+    "e1m1": [(-59.0, -320.0, 0.785398), (-1443.0, 896.0, 0.785398)],
+    "stress": [(-883.0, 0.0, 0.785398), (1652.0, 768.0, 0.785398), (-1895.0, -512.0, 0.785398)],
+}
+
+
+def _views_with_panics(kind, gm, n):
+    v = _views(kind, gm, n)
+    bad = np.array(PANIC_VIEWS[kind], np.float32)
+    at = np.linspace(3, n - 2, len(bad)).astype(int)
+    v[at] = bad
+    return v, [int(k) for k in at]
+
+
+def test_front_end_code_panics_where_the_host_front_end_panics():
+    """Viewpoints on which the reference panics (a wall exactly through the eye) get no frame on either path, and the frames
+    after them land where the host front-end puts them."""
+    W, H, n = 160, 100, 120
+    for kind in ("e1m1", "stress"):
+        path, gm = common.wad(kind)
+        views, at = _views_with_panics(kind, gm, n)
+        scene = drr.Scene(path, "E1M1", W, H)
+        a = drr.Context(W, H, 0, n, _host_only=True)
+        scene.upload_assets(a)
+        skipped = scene.emit_views(a, views, phases=3, threads=4)
+        assert skipped == at, "the known panicking viewpoints no longer panic: the test would prove nothing"
+        b = drr.Context(W, H, 0, n, _host_only=True)
+        scene.upload_assets(b)
+        scene.upload_map_for_device_front_end(b)
+        assert b.fe_emit_views(views, phases=3, _on_host=True) == skipped
+        _assert_same_lists(a, b, kind)
+        assert a.stats() == b.stats()
+
+
+def test_front_end_state_machine():
+    W, H, n = 160, 100, 8
+    path, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    ctx = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(ctx)
+    with pytest.raises(drr.DrrError) as e:  # no map yet
+        ctx.fe_emit_views(views, _on_host=True)
+    assert e.value.code == -2
+    scene.upload_map_for_device_front_end(ctx)
+    with pytest.raises(drr.DrrError) as e:  # the device path itself needs a GPU: no CPU fallback
+        ctx.fe_emit_views(views)
+    assert e.value.code == -3
+    assert ctx.fe_emit_views(views, _on_host=True) == []
+    with pytest.raises(drr.DrrError) as e:  # a batch is already recorded
+        ctx.fe_emit_views(views, _on_host=True)
+    assert e.value.code == -2
+    ctx.reset()
+    with pytest.raises(drr.DrrError):  # more views than framebuffers
+        ctx.fe_emit_views(np.concatenate([views, views]), _on_host=True)
+    assert ctx.fe_emit_views(views[:3], first_slot=5, _on_host=True) == []
+    assert list(ctx._list(6, np.uint32)) == [5, 6, 7]
+
+
+# ---- GPU: the kernel -----------------------------------------------------------------------------------------------------
+def _compare(ctx, k, ref, what):
+    got = ctx.read_framebuffer(k)
+    diff = (got != ref).any(2)
+    if diff.any():
+        ys, xs = np.nonzero(diff)
+        raise AssertionError("%s: %d pixels differ; first at x=%d y=%d got=%s want=%s" % (what, int(diff.sum()), xs[0], ys[0], got[ys[0], xs[0]], ref[ys[0], xs[0]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,W,H,n,phases,ts", [("e1m1", 320, 200, 700, 3, 0.0), ("e1m1", 1280, 800, 40, 3, 0.4), ("stress", 200, 120, 200, 3, 0.0),
+                                                  ("e1m1", 324, 200, 33, 1, 0.0), ("stress", 1920, 1200, 6, 2, 0.0)])
+def test_device_front_end_lists_equal_host_front_end(kind, W, H, n, phases, ts):
+    path, gm = common.wad(kind)
+    views = _views(kind, gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, timestamp=ts, phases=phases)
+    b = drr.Context(W, H, 0, n)
+    scene.upload_assets(b)
+    assert scene.emit_views_device(b, views, timestamp=ts, phases=phases) == skipped
+    b.fe_download_lists()
+    _assert_same_lists(a, b, "%s %dx%d phases %d" % (kind, W, H, phases))
+    assert a.stats() == {**b.stats(), "kernel_launches": 0, "device_list_bytes": a.stats()["device_list_bytes"]}
+    count_ms, emit_ms = b.fe_last_times()
+    assert count_ms > 0 and emit_ms > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,W,H,n", [("e1m1", 320, 200, 24), ("e1m1", 1280, 800, 4), ("stress", 640, 400, 6)])
+def test_device_front_end_frames_match_oracle(kind, W, H, n):
+    """viewpoints -> device front-end -> bin kernel -> tile kernel == the oracle's frames, walls + flats + sky (no list ever
+    touches the host)."""
+    path, gm = common.wad(kind)
+    game = orc.Game(path, "E1M1", W, H)
+    src = synth_wad.walk_viewpoints(gm, 4096)[:: 4096 // (n + 4)] if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, 64)
+    views = common.usable_views(game, src, n)
+    assert len(views) == n
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views_device(ctx, views, phases=3) == []
+    ctx.submit()  # nothing to upload: the same as draw()
+    ctx.sync()
+    crcs = ctx.read_checksums(0, n)
+    for k, v in enumerate(views):
+        ref = game.render(float(v[0]), float(v[1]), float(v[2]), phases=3)
+        _compare(ctx, k, ref, "%s %dx%d view %d" % (kind, W, H, k))
+        assert int(crcs[k]) == drr.checksum_numpy(ref)
+    # a second batch through the same context, other slots first
+    ctx.reset()
+    assert scene.emit_views_device(ctx, views[::-1], phases=3) == []
+    ctx.draw()
+    ctx.sync()
+    assert list(ctx.read_checksums(0, n)) == list(crcs[::-1])
+
+
+@pytest.mark.gpu
+def test_device_front_end_skips_panicking_viewpoints_and_masked_mids():
+    W, H, n = 160, 100, 1500
+    path, gm = common.wad("stress")
+    views, at = _views_with_panics("stress", gm, n)
+    bare = _wad_without_things("stress")
+    scene = drr.Scene(bare, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, phases=7)
+    assert skipped == at
+    b = drr.Context(W, H, 0, n)
+    scene.upload_assets(b)
+    assert scene.emit_views_device(b, views, phases=7) == skipped
+    b.fe_download_lists()
+    _assert_same_lists(a, b, "stress without things, all phases")
+    # and the frames: the host front-end's lists through drr_submit in a second context
+    c = drr.Context(W, H, 0, n)
+    scene.upload_assets(c)
+    assert scene.emit_views(c, views, phases=7) == skipped
+    c.submit()
+    c.sync()
+    b.draw()
+    b.sync()
+    assert b.read_checksums(0, n).tobytes() == c.read_checksums(0, n).tobytes()
+    assert len(set(b.read_checksums(0, n).tolist())) > n // 2
