@@ -241,14 +241,67 @@ FE_HD int sector_at(const Map &m, V2 p) { // renderer/bsp.rs:9-44
     }
 }
 
-// ---- one viewpoint -----------------------------------------------------------------------------------------------
+// ---- one viewpoint = one warp ---------------------------------------------------------------------------------------
+// The walk of a viewpoint is sequential from seg to seg (occlusion arrays, open visplanes), but inside a seg the screen
+// columns are independent and inside a subsector so are the segs' visibility tests.  A WARP runs a viewpoint: everything
+// that is per-view or per-seg is computed redundantly by all 32 lanes (uniform, no divergence), the column loop of
+// process_sidedef gives lane l the column x0 + l of each 32-column chunk, and the order-dependent parts (column records
+// are appended in x order; a visplane runs from its first point to the next flush) are resolved from ballots.
+// On the host (CPU test harness) the 32 lanes are emulated by loops: FE_LANES(l) { ... } runs its body once per lane.
+#if defined(__CUDA_ARCH__)
+#define FE_LANES(l) for (int l = (int)(threadIdx.x & 31u), l##_1 = 1; l##_1; l##_1 = 0)
+#define FE_SYNC() __syncwarp()
+#define FE_LEADER if ((threadIdx.x & 31u) == 0u)
+template <class T>
+struct PerLane { // a value every lane holds its own copy of
+    T v;
+    __device__ __forceinline__ T &operator[](int) { return v; }
+};
+#else
+#define FE_LANES(l) for (int l = 0; l < 32; l++)
+#define FE_SYNC() ((void)0)
+#define FE_LEADER
+template <class T>
+struct PerLane {
+    T v[32];
+    T &operator[](int l) { return v[l]; }
+};
+#endif
+template <class F>
+FE_HD uint32_t ballot(F f) { // bit l = f(l)
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xffffffffu, f((int)(threadIdx.x & 31u)));
+#else
+    uint32_t mask = 0;
+    for (int l = 0; l < 32; l++)
+        if (f(l)) mask |= 1u << l;
+    return mask;
+#endif
+}
+FE_HD int popc32(uint32_t v) {
+    int c = 0;
+    for (; v; v &= v - 1) c++;
+    return c;
+}
+FE_HD int lowest(uint32_t v) { // index of the lowest set bit, v != 0
+    int i = 0;
+    while (!((v >> i) & 1u)) i++;
+    return i;
+}
+FE_HD int highest(uint32_t v) { // index of the highest set bit, v != 0
+    int i = 31;
+    while (!((v >> i) & 1u)) i--;
+    return i;
+}
+FE_HD uint32_t below(int l) { return l >= 32 ? 0xffffffffu : (1u << l) - 1u; } // bits of the lanes < l
+
 template <bool EMIT>
 struct Frame {
     const Map &m;
     Scratch sc;
     Out out;
     Bases base;   // EMIT only
-    Counts n;     // running counts == cursors relative to the bases
+    Counts n;     // running counts == cursors relative to the bases (uniform over the warp)
     V2 ppos;
     float cos_n, sin_n, pfloor;
     // SidedefVisPlanes of the sidedef part being processed
@@ -269,21 +322,10 @@ struct Frame {
         }
     }
 
-    // add_bottom_point / add_top_point, sidedef_visplanes.rs:60-84.  The reference keeps [i16; W] arrays zero-initialised
-    // (visplanes.rs:36-37): columns between left and right that never got a point stay (0, 0).
-    FE_HD void point(int which, int16_t x, int16_t top_y, int16_t bottom_y) {
-        if (!open[which]) {
-            open[which] = true;
-            pl_left[which] = x;
-        } else {
-            for (int xx = pl_right[which] + 1; xx < x; xx++) sc.rows[which][xx] = 0u;
-        }
-        pl_right[which] = x;
-        sc.rows[which][x] = (uint32_t)(uint16_t)top_y | ((uint32_t)(uint16_t)bottom_y << 16);
-    }
     // flush, sidedef_visplanes.rs:41-58: pushes the bottom visplane, then the top one.  mod.rs:106-116 later draws the
-    // visplanes in push order (phase B comes after every wall), so the ops are appended after the walk: here the plane's
-    // record and its rows are written, the op words follow in flush_plane_ops().
+    // visplanes in push order (phase B comes after every wall), so the op words are appended after the walk; here the
+    // plane's record is written and its rows [left, right] are copied from the accumulation buffer (the reference keeps
+    // zero-initialised [i16; W] arrays, visplanes.rs:36-37: columns inside the range that never got a point are (0, 0)).
     FE_HD void flush() {
         for (int which = 0; which < 2; which++) {
             if (!open[which]) continue;
@@ -291,31 +333,45 @@ struct Frame {
             if (!(m.phases & 2)) continue;
             const int left = pl_left[which], right = pl_right[which];
             const uint32_t ncols = (uint32_t)(right - left + 1);
-            if (pl_sky[which] && m.sky_kind < 0) fail(FE_HARD, FED_SKY_UNSET);
+            const bool sky = pl_sky[which] != 0;
+            if (sky && m.sky_kind < 0) fail(FE_HARD, FED_SKY_UNSET);
+            const uint32_t arr_first = base.parr + n.nparr;
             const uint32_t *src = sc.rows[which] + left;
-            for (uint32_t i = 0; i < ncols; i++) { // how many of the columns draw anything (drr_api.cu: rec_emit_visplane)
-                const int t = (int)(int16_t)(src[i] & 0xffffu) > 0 ? (int)(int16_t)(src[i] & 0xffffu) : 0; // visplanes.rs:61 / :95
-                const int bq = (int)(int16_t)(src[i] >> 16) < m.H - 1 ? (int)(int16_t)(src[i] >> 16) : m.H - 1; // :62 / :96
-                if (!pl_sky[which] && (int16_t)(bq - t) <= 1) continue; // :99-101 (not applied to sky)
-                if (t <= bq) n.nrec++;
+            const int H = m.H;
+            for (uint32_t i0 = 0; i0 < ncols; i0 += 32) {
+                // how many of the columns draw anything (drr_api.cu: rec_emit_visplane)
+                n.nrec += (uint32_t)popc32(ballot([&](int l) {
+                    if (i0 + (uint32_t)l >= ncols) return false;
+                    const uint32_t tb = src[i0 + l];
+                    const int t = (int)(int16_t)(tb & 0xffffu) > 0 ? (int)(int16_t)(tb & 0xffffu) : 0; // visplanes.rs:61 / :95
+                    const int b = (int)(int16_t)(tb >> 16) < H - 1 ? (int)(int16_t)(tb >> 16) : H - 1;   // :62 / :96
+                    if (!sky && (int16_t)(b - t) <= 1) return false;                                     // :99-101 (not applied to sky)
+                    return t <= b;
+                }));
+                if (EMIT) {
+                    FE_LANES(l) {
+                        if (i0 + (uint32_t)l < ncols) out.parr[arr_first + i0 + l] = src[i0 + l];
+                    }
+                }
             }
             if (EMIT) {
-                PlaneRec p;
-                p.flat_slot = pl_sky[which] ? (int16_t)-1 : pl_flat[which];
-                p.height = pl_height[which];
-                p.light_level = pl_light;
-                p.left = (int16_t)left;
-                p.right = (int16_t)right;
-                p.kind = (int16_t)(pl_sky[which] ? m.sky_kind : (int)KIND_FLAT);
-                p.arr_first = base.parr + n.nparr;
-                out.planes[base.plane + n.nplanes] = p;
-                uint32_t *dst = out.parr + p.arr_first;
-                for (uint32_t i = 0; i < ncols; i++) dst[i] = src[i];
+                FE_LEADER {
+                    PlaneRec p;
+                    p.flat_slot = sky ? (int16_t)-1 : pl_flat[which];
+                    p.height = pl_height[which];
+                    p.light_level = pl_light;
+                    p.left = (int16_t)left;
+                    p.right = (int16_t)right;
+                    p.kind = (int16_t)(sky ? m.sky_kind : (int)KIND_FLAT);
+                    p.arr_first = arr_first;
+                    out.planes[base.plane + n.nplanes] = p;
+                }
             }
             n.nplanes++;
             n.nparr += ncols;
             n.reccap += ncols;
         }
+        FE_SYNC(); // the accumulation buffers may be written again
     }
 
     FE_HD void occlude(int x) { // segs.rs:113-117
@@ -350,64 +406,126 @@ struct Frame {
         const bool wall = !two_sided_mid && !only_occ && (m.phases & 1);
         const bool deferred = two_sided_mid && (m.phases & 4);
         const bool keep = (wall || deferred) && tex >= 0;
+        const bool planes_here = !two_sided_mid && (full_height || only_occ);
         const uint32_t col0 = n.ncols;
-        int16_t x_first = 0, x_last = 0;
+        int x_first = 0, x_last = 0;
+        const int xe = bottom.ex; // the reference's `for x in start.x..end.x + 1`
 
-        for (int16_t x = (int16_t)bottom.sx; x < w16((int16_t)bottom.ex + 1); x++) {
-            if (!sc.hor_ocl[x]) {
-                const int16_t bottom_y = as_i16((float)bottom.sy + ((float)x - (float)bottom.sx) * bottom_delta);
-                const int16_t top_y = as_i16((float)top.sy + ((float)x - (float)top.sx) * top_delta);
-                const int16_t fvo = sc.floor_ocl[x], cvo = sc.ceil_ocl[x];
-                int16_t cb = fvo < bottom_y ? fvo : bottom_y, ct = cvo > top_y ? cvo : top_y;
-                cb = Hm1 < cb ? Hm1 : cb;
-                ct = ct < 0 ? (int16_t)0 : ct;
-                const bool in_area = cb >= ct;
-                if (in_area && keep) { // add_column, bitmap_render.rs:84-99
-                    if (EMIT) {
-                        ColRec c;
-                        c.x = x;
-                        c.clipped_top_y = ct;
-                        c.clipped_bottom_y = cb;
-                        c.bottom_y = bottom_y;
-                        c.top_y = top_y;
-                        out.cols[base.col + (n.ncols - dcols)] = c; // front cursor; a deferred part's block is moved to the back below
+        for (int c0 = bottom.sx; c0 <= xe; c0 += 32) {
+            // ---- per column (lane l: x = c0 + l): segs.rs:186-330
+            enum : uint32_t { EV_P0 = 1, EV_P1 = 2, EV_FLUSH = 4, EV_COL = 8 };
+            PerLane<uint32_t> ev, row0, row1;
+            PerLane<ColRec> col;
+            FE_LANES(l) {
+                const int x = c0 + l;
+                uint32_t e = 0;
+                if (x <= xe) {
+                    if (!sc.hor_ocl[x]) {
+                        const int16_t bottom_y = as_i16((float)bottom.sy + ((float)(int16_t)x - (float)bottom.sx) * bottom_delta);
+                        const int16_t top_y = as_i16((float)top.sy + ((float)(int16_t)x - (float)top.sx) * top_delta);
+                        const int16_t fvo = sc.floor_ocl[x], cvo = sc.ceil_ocl[x];
+                        int16_t cb = fvo < bottom_y ? fvo : bottom_y, ct = cvo > top_y ? cvo : top_y;
+                        cb = Hm1 < cb ? Hm1 : cb;
+                        ct = ct < 0 ? (int16_t)0 : ct;
+                        const bool in_area = cb >= ct;
+                        if (in_area && keep) { // add_column, bitmap_render.rs:84-99
+                            e |= EV_COL;
+                            ColRec c;
+                            c.x = (int16_t)x;
+                            c.clipped_top_y = ct;
+                            c.clipped_bottom_y = cb;
+                            c.bottom_y = bottom_y;
+                            c.top_y = top_y;
+                            col[l] = c;
+                        }
+                        if (planes_here && in_area) {
+                            if (cb < fvo && cb != Hm1) { // add_bottom_point(x, cb, fvo)
+                                e |= EV_P0;
+                                row0[l] = (uint32_t)(uint16_t)cb | ((uint32_t)(uint16_t)fvo << 16);
+                            }
+                            if (draw_ceiling && ct > cvo && ct != -1) { // add_top_point(x, cvo, ct)
+                                e |= EV_P1;
+                                row1[l] = (uint32_t)(uint16_t)cvo | ((uint32_t)(uint16_t)ct << 16);
+                            }
+                            if (!(e & (EV_P0 | EV_P1))) e |= EV_FLUSH;
+                        } else if (planes_here && !in_area && fvo > cvo) {
+                            if (bottom_y <= cvo) {
+                                e |= EV_P0;
+                                row0[l] = (uint32_t)(uint16_t)cvo | ((uint32_t)(uint16_t)fvo << 16);
+                                occlude(x);
+                            }
+                            if (draw_ceiling && top_y >= fvo) {
+                                e |= EV_P1;
+                                row1[l] = (uint32_t)(uint16_t)cvo | ((uint32_t)(uint16_t)fvo << 16);
+                                occlude(x);
+                            }
+                        }
+                        if (!two_sided_mid && in_area && only_occ) {
+                            sc.floor_ocl[x] = cb;
+                            if (draw_ceiling) sc.ceil_ocl[x] = ct;
+                        }
+                        if (!two_sided_mid && in_area && lower) sc.floor_ocl[x] = ct;
+                        if (!two_sided_mid && in_area && upper) sc.ceil_ocl[x] = cb;
+                    } else {
+                        e |= EV_FLUSH;
                     }
-                    if (n.ncols == col0) x_first = x;
-                    x_last = x;
-                    n.ncols++;
-                    n.nrec++; // 0 <= x < W and max(ct, 0) <= min(cb, H - 1) hold here
+                    if (!two_sided_mid && full_height) occlude(x);
                 }
-                if (!two_sided_mid && in_area && (full_height || only_occ)) {
-                    bool added = false;
-                    if (cb < fvo && cb != Hm1) {
-                        point(0, x, cb, fvo);
-                        added = true;
-                    }
-                    if (draw_ceiling && ct > cvo && ct != -1) {
-                        point(1, x, cvo, ct);
-                        added = true;
-                    }
-                    if (!added) flush();
-                } else if (!two_sided_mid && !in_area && (full_height || only_occ) && fvo > cvo) {
-                    if (bottom_y <= cvo) {
-                        point(0, x, cvo, fvo);
-                        occlude(x);
-                    }
-                    if (draw_ceiling && top_y >= fvo) {
-                        point(1, x, cvo, fvo);
-                        occlude(x);
-                    }
-                }
-                if (!two_sided_mid && in_area && only_occ) {
-                    sc.floor_ocl[x] = cb;
-                    if (draw_ceiling) sc.ceil_ocl[x] = ct;
-                }
-                if (!two_sided_mid && in_area && lower) sc.floor_ocl[x] = ct;
-                if (!two_sided_mid && in_area && upper) sc.ceil_ocl[x] = cb;
-            } else {
-                flush();
+                ev[l] = e;
             }
-            if (!two_sided_mid && full_height) occlude(x);
+            const uint32_t m_p0 = ballot([&](int l) { return (ev[l] & EV_P0) != 0; }), m_p1 = ballot([&](int l) { return (ev[l] & EV_P1) != 0; });
+            const uint32_t m_fl = ballot([&](int l) { return (ev[l] & EV_FLUSH) != 0; }), m_col = ballot([&](int l) { return (ev[l] & EV_COL) != 0; });
+            // ---- column records, in x order
+            if (m_col) {
+                if (EMIT) {
+                    const uint32_t at = base.col + (n.ncols - dcols); // front cursor; a deferred part's block is moved to the back below
+                    FE_LANES(l) {
+                        if (ev[l] & EV_COL) out.cols[at + (uint32_t)popc32(m_col & below(l))] = col[l];
+                    }
+                }
+                if (n.ncols == col0) x_first = c0 + lowest(m_col);
+                x_last = c0 + highest(m_col);
+                n.ncols += (uint32_t)popc32(m_col);
+                n.nrec += (uint32_t)popc32(m_col); // 0 <= x < W and max(ct, 0) <= min(cb, H - 1) hold for every record
+            }
+            // ---- visplane rows: a lane inside an open visplane writes its point, or (0, 0) when it has none.  Visplane
+            // `which` is open at lane l when it was open at the chunk's start and no lane below l flushes, or when a lane
+            // between the last flush below l and l itself has a point.
+            if (m_p0 | m_p1 | (uint32_t)(open[0] || open[1])) {
+                FE_LANES(l) {
+                    const int x = c0 + l;
+                    if (x <= xe) {
+                        const uint32_t fb = m_fl & below(l);
+                        const int start = fb ? highest(fb) + 1 : 0;
+                        const uint32_t run = below(l + 1) & ~below(start); // lanes start .. l
+                        if (ev[l] & EV_P0) sc.rows[0][x] = row0[l];
+                        else if ((!fb && open[0]) || (m_p0 & run)) sc.rows[0][x] = 0u;
+                        if (ev[l] & EV_P1) sc.rows[1][x] = row1[l];
+                        else if ((!fb && open[1]) || (m_p1 & run)) sc.rows[1][x] = 0u;
+                    }
+                }
+                FE_SYNC(); // a flush below copies rows other lanes wrote
+            }
+            // ---- runs: points between two flushes belong to one pair of visplanes (sidedef_visplanes.rs:41-84)
+            uint32_t f = m_fl;
+            int lo = 0;
+            for (;;) {
+                const int nf = f ? lowest(f) : 32;
+                const uint32_t run = below(nf) & ~below(lo); // lanes lo .. nf - 1
+                const uint32_t pm[2] = {m_p0 & run, m_p1 & run};
+                for (int which = 0; which < 2; which++)
+                    if (pm[which]) {
+                        if (!open[which]) {
+                            open[which] = true;
+                            pl_left[which] = (int16_t)(c0 + lowest(pm[which]));
+                        }
+                        pl_right[which] = (int16_t)(c0 + highest(pm[which]));
+                    }
+                if (nf == 32) break;
+                flush();
+                f &= f - 1;
+                lo = nf + 1;
+            }
         }
         flush();
         const uint32_t ncol = n.ncols - col0;
@@ -415,39 +533,53 @@ struct Frame {
         const Bitmap bm = m.bitmaps[tex];
         if (bm.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
         if (EMIT) {
-            SegRec r;
-            r.bitmap_slot = (uint32_t)bm.slot;
-            r.light_level = sec.light;
-            r.phase = (int16_t)(deferred ? 2 : 0); // DRR_PHASE_MASKED / DRR_PHASE_WALL
-            r.lsx = cl.s.x;
-            r.lsy = cl.s.y;
-            r.lex = cl.e.x;
-            r.ley = cl.e.y;
-            r.start_offset = start_offset;
-            r.start_x = bottom.sx;
-            r.end_x = bottom.ex;
-            r.bottom_height = bottom_h;
-            r.top_height = top_h;
-            r.offset_x = w16(as_i16(sd.xoff) + seg_offset);
-            r.offset_y = w16(as_i16(sd.yoff) + w16(offset_y));
             uint32_t first = base.col + (col0 - dcols); // where the loop above put the columns
-            if (deferred) { // move the block to the back of the view's column range (dst >= src: copy from the last element)
+            if (deferred) { // move the block to the back of the view's column range; dst >= src, so go from the top chunk down
                 const uint32_t dst = base.col + base.ncols - dcols - ncol;
-                for (uint32_t i = ncol; i-- > 0;) out.cols[dst + i] = out.cols[first + i];
+                FE_SYNC();
+                for (uint32_t i0 = (ncol - 1) / 32 * 32;; i0 -= 32) {
+                    PerLane<ColRec> t;
+                    FE_LANES(l) {
+                        if (i0 + (uint32_t)l < ncol) t[l] = out.cols[first + i0 + l];
+                    }
+                    FE_SYNC();
+                    FE_LANES(l) {
+                        if (i0 + (uint32_t)l < ncol) out.cols[dst + i0 + l] = t[l];
+                    }
+                    FE_SYNC();
+                    if (i0 == 0) break;
+                }
                 first = dst;
             }
-            r.cols_first = first;
-            r.n = ncol;
-            r.x0 = x_first;
-            r.x1 = x_last;
-            r.tex_base = bm.base;
-            r.tex_w = bm.w;
-            r.tex_h = bm.h;
-            r.tex_opaque = bm.opaque;
-            r.pad[0] = r.pad[1] = 0;
-            const uint32_t si = deferred ? base.seg + base.nsegs - 1 - ndeferred : base.seg + (n.nsegs - ndeferred);
-            out.segs[si] = r;
-            if (wall) out.ops[base.op + n.nops] = si; // deferred parts get their op after the walk
+            FE_LEADER {
+                SegRec r;
+                r.bitmap_slot = (uint32_t)bm.slot;
+                r.light_level = sec.light;
+                r.phase = (int16_t)(deferred ? 2 : 0); // DRR_PHASE_MASKED / DRR_PHASE_WALL
+                r.lsx = cl.s.x;
+                r.lsy = cl.s.y;
+                r.lex = cl.e.x;
+                r.ley = cl.e.y;
+                r.start_offset = start_offset;
+                r.start_x = bottom.sx;
+                r.end_x = bottom.ex;
+                r.bottom_height = bottom_h;
+                r.top_height = top_h;
+                r.offset_x = w16(as_i16(sd.xoff) + seg_offset);
+                r.offset_y = w16(as_i16(sd.yoff) + w16(offset_y));
+                r.cols_first = first;
+                r.n = ncol;
+                r.x0 = (int16_t)x_first;
+                r.x1 = (int16_t)x_last;
+                r.tex_base = bm.base;
+                r.tex_w = bm.w;
+                r.tex_h = bm.h;
+                r.tex_opaque = bm.opaque;
+                r.pad[0] = r.pad[1] = 0;
+                const uint32_t si = deferred ? base.seg + base.nsegs - 1 - ndeferred : base.seg + (n.nsegs - ndeferred);
+                out.segs[si] = r;
+                if (wall) out.ops[base.op + n.nops] = si; // deferred parts get their op after the walk
+            }
         }
         if (wall) {
             n.nops++;
@@ -459,6 +591,23 @@ struct Frame {
         // record slots the bin kernel may reserve: one per screen column inside the x range (drr_api.cu: rec_emit_columns)
         const int lo = x_first > 0 ? x_first : 0, hi = x_last < m.W - 1 ? x_last : m.W - 1;
         n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
+    }
+
+    // The part of process_seg that touches no per-view state (segs.rs:353-460): can this seg draw or panic at all?
+    // Evaluated for up to 32 segs of a subsector at once; the survivors go through seg() in order.
+    FE_HD bool seg_may_matter(const Seg &sg) const {
+        const Line ld = m.lines[sg.line];
+        const int fi = sg.dir ? ld.back : ld.front;
+        if (fi == -1) return false;
+        const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
+        const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
+        Seg2 cl;
+        float so;
+        if (!clip_fov(view, &cl, &so)) return false;
+        if (cl.s.x < -0.01f) return true; // panics: let seg() report it
+        const float floor_h = (float)m.sectors[m.sides[fi].sector].floor;
+        const ScreenLine fl = project(m, cl, floor_h - (pfloor + 41.0f));
+        return !(fl.sx > fl.ex); // back faces draw nothing
     }
 
     // process_seg, segs.rs:353-590
@@ -534,15 +683,20 @@ struct Frame {
         pfloor = 0.0f; // game.rs:144-150, 376-389
         const int s = sector_at(m, ppos);
         if (s >= 0) pfloor = (float)m.sectors[s].floor;
-        for (int x = 0; x < m.W; x++) { // segs.rs:97-99
-            sc.hor_ocl[x] = 0;
-            sc.floor_ocl[x] = (int16_t)m.H;
-            sc.ceil_ocl[x] = (int16_t)-1;
+        FE_LANES(l) {
+            for (int x = l; x < m.W; x += 32) { // segs.rs:97-99
+                sc.hor_ocl[x] = 0;
+                sc.floor_ocl[x] = (int16_t)m.H;
+                sc.ceil_ocl[x] = (int16_t)-1;
+            }
         }
+        FE_SYNC();
         open[0] = open[1] = false;
         ndeferred = 0;
         dcols = 0;
-        if (EMIT) out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a};
+        if (EMIT) {
+            FE_LEADER { out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a}; }
+        }
         // A: render_node, mod.rs:69-104 -- front subtree, then back subtree (explicit stack instead of the recursion)
         int stack[64];
         int sp = 0;
@@ -551,7 +705,10 @@ struct Frame {
             const int node = stack[--sp];
             if (node < 0) {
                 const SubSector ss = m.ssectors[~node];
-                for (int i = 0; i < ss.count && n.status == FE_OK; i++) seg(m.segs[ss.first + i]);
+                for (int c0 = 0; c0 < ss.count && n.status == FE_OK; c0 += 32) {
+                    uint32_t live = ballot([&](int l) { return c0 + l < ss.count && seg_may_matter(m.segs[ss.first + c0 + l]); });
+                    for (; live && n.status == FE_OK; live &= live - 1) seg(m.segs[ss.first + c0 + lowest(live)]);
+                }
                 continue;
             }
             const Node nd = m.nodes[node];
@@ -566,12 +723,18 @@ struct Frame {
         }
         if (n.status != FE_OK) return;
         // B: mod.rs:106-116 -- the visplanes in push order, after every wall
-        if (EMIT)
-            for (uint32_t i = 0; i < n.nplanes; i++) out.ops[base.op + n.nops + i] = 0x80000000u | (base.plane + i);
+        if (EMIT) {
+            FE_LANES(l) {
+                for (uint32_t i = (uint32_t)l; i < n.nplanes; i += 32) out.ops[base.op + n.nops + i] = 0x80000000u | (base.plane + i);
+            }
+        }
         n.nops += n.nplanes;
         // D: segs.rs:593-597 -- the deferred two-sided middle textures, last created first (mod.rs:124 reverses the list)
-        if (EMIT)
-            for (uint32_t k = 0; k < ndeferred; k++) out.ops[base.op + n.nops + k] = base.seg + base.nsegs - ndeferred + k;
+        if (EMIT) {
+            FE_LANES(l) {
+                for (uint32_t k = (uint32_t)l; k < ndeferred; k += 32) out.ops[base.op + n.nops + k] = base.seg + base.nsegs - ndeferred + k;
+            }
+        }
         n.nops += ndeferred;
     }
 };

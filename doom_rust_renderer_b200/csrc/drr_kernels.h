@@ -81,7 +81,7 @@ struct Counts;
 struct Bases;
 struct Out;
 } // namespace fe
-static constexpr int FE_THREADS = 32; // one warp per CTA: a batch of a few thousand viewpoints then spreads over every SM
+static constexpr int FE_THREADS = 64; // one warp per viewpoint, two viewpoints per CTA: a few thousand viewpoints spread over every SM
 struct FeScratch {                    // per-viewpoint working state of the front-end, W entries per viewpoint each
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;
