@@ -25,10 +25,10 @@
 
 #if defined(__CUDACC__)
 #define FE_HD __host__ __device__ __forceinline__
-#define FE_HD_NOINLINE __host__ __device__ __noinline__
+#define FE_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define FE_HD inline
-#define FE_HD_NOINLINE
+#define FE_NOINLINE inline
 #endif
 
 namespace drr {
@@ -172,7 +172,7 @@ FE_HD bool intersect(const Seg2 &a, const Seg2 &b, V2 *out) { // geometry.rs:56-
 struct ScreenLine {
     int32_t sx, sy, ex, ey;
 };
-FE_HD ScreenLine project(const Map &m, const Seg2 &l, float height) { // misc.rs:130-161
+FE_NOINLINE ScreenLine project(const Map &m, const Seg2 &l, float height) { // misc.rs:130-161
     V2 ts = {m.GCFX * l.s.y / l.s.x, m.GCFX * height / l.s.x};
     V2 te = {m.GCFX * l.e.y / l.e.x, m.GCFX * height / l.e.x};
     ts.x *= m.ASPECT;
@@ -183,7 +183,7 @@ FE_HD ScreenLine project(const Map &m, const Seg2 &l, float height) { // misc.rs
     return r;
 }
 
-FE_HD bool clip_fov(const Seg2 &line, Seg2 *out, float *start_offset) { // misc.rs:13-115
+FE_NOINLINE bool clip_fov(const Seg2 &line, Seg2 *out, float *start_offset) { // misc.rs:13-115
     const V2 O = {0.0f, 0.0f}, LE = {1.0f, 1.0f}, RE = {1.0f, -1.0f};
     const Seg2 L = {O, LE}, R = {O, RE};
     const bool s_out_l = left_of(line.s, O, LE), e_out_l = left_of(line.e, O, LE);
@@ -220,7 +220,7 @@ FE_HD bool clip_fov(const Seg2 &line, Seg2 *out, float *start_offset) { // misc.
     return true;
 }
 
-FE_HD int sector_at(const Map &m, V2 p) { // renderer/bsp.rs:9-44
+FE_NOINLINE int sector_at(const Map &m, V2 p) { // renderer/bsp.rs:9-44
     int n = m.nnodes - 1;
     for (;;) {
         const Node nd = m.nodes[n];
@@ -279,16 +279,25 @@ FE_HD uint32_t ballot(F f) { // bit l = f(l)
 #endif
 }
 FE_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#endif
     int c = 0;
     for (; v; v &= v - 1) c++;
     return c;
 }
 FE_HD int lowest(uint32_t v) { // index of the lowest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#endif
     int i = 0;
     while (!((v >> i) & 1u)) i++;
     return i;
 }
 FE_HD int highest(uint32_t v) { // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#endif
     int i = 31;
     while (!((v >> i) & 1u)) i--;
     return i;
@@ -326,7 +335,7 @@ struct Frame {
     // visplanes in push order (phase B comes after every wall), so the op words are appended after the walk; here the
     // plane's record is written and its rows [left, right] are copied from the accumulation buffer (the reference keeps
     // zero-initialised [i16; W] arrays, visplanes.rs:36-37: columns inside the range that never got a point are (0, 0)).
-    FE_HD void flush() {
+    FE_NOINLINE void flush() {
         for (int which = 0; which < 2; which++) {
             if (!open[which]) continue;
             open[which] = false;
@@ -381,7 +390,7 @@ struct Frame {
     }
 
     // process_sidedef, segs.rs:121-350
-    FE_HD void sidedef_part(const Seg2 &cl, float start_offset, const Side &sd, int16_t seg_offset, const Sector &sec, float bottom_h,
+    FE_NOINLINE void sidedef_part(const Seg2 &cl, float start_offset, const Side &sd, int16_t seg_offset, const Sector &sec, float bottom_h,
                             float top_h, int32_t offset_y, int tex, bool only_occ, bool lower, bool upper, bool draw_ceiling, bool two_sided_mid) {
         const ScreenLine bottom = project(m, cl, bottom_h), top = project(m, cl, top_h);
         if (tex == -2) return fail(FE_PANIC, FED_UNKNOWN_TEXTURE);
@@ -595,7 +604,7 @@ struct Frame {
 
     // The part of process_seg that touches no per-view state (segs.rs:353-460): can this seg draw or panic at all?
     // Evaluated for up to 32 segs of a subsector at once; the survivors go through seg() in order.
-    FE_HD bool seg_may_matter(const Seg &sg) const {
+    FE_NOINLINE bool seg_may_matter(const Seg &sg) const {
         const Line ld = m.lines[sg.line];
         const int fi = sg.dir ? ld.back : ld.front;
         if (fi == -1) return false;
@@ -611,7 +620,7 @@ struct Frame {
     }
 
     // process_seg, segs.rs:353-590
-    FE_HD void seg(const Seg &sg) {
+    FE_NOINLINE void seg(const Seg &sg) {
         const Line ld = m.lines[sg.line];
         const int fi = sg.dir ? ld.back : ld.front, bi = sg.dir ? ld.front : ld.back;
         if (fi == -1) return;
