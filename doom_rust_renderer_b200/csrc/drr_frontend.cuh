@@ -172,15 +172,23 @@ FE_HD bool intersect(const Seg2 &a, const Seg2 &b, V2 *out) { // geometry.rs:56-
 struct ScreenLine {
     int32_t sx, sy, ex, ey;
 };
-FE_NOINLINE ScreenLine project(const Map &m, const Seg2 &l, float height) { // misc.rs:130-161
-    V2 ts = {m.GCFX * l.s.y / l.s.x, m.GCFX * height / l.s.x};
-    V2 te = {m.GCFX * l.e.y / l.e.x, m.GCFX * height / l.e.x};
-    ts.x *= m.ASPECT;
-    te.x *= m.ASPECT;
-    ScreenLine r{as_i32(m.CFX - ts.x), as_i32(m.CFY - ts.y), as_i32(m.CFX - te.x), as_i32(m.CFY - te.y)};
+// misc.rs:130-161 (perspective projection of a view-space line at one height).  The screen x of the two ends depends on
+// the line only, the screen y on the line and the height: a seg's parts share the x pair.
+struct ScreenX {
+    int32_t sx, ex;
+};
+FE_HD ScreenX project_x(const Map &m, const Seg2 &l) {
+    float tsx = m.GCFX * l.s.y / l.s.x, tex = m.GCFX * l.e.y / l.e.x;
+    tsx *= m.ASPECT;
+    tex *= m.ASPECT;
+    ScreenX r{as_i32(m.CFX - tsx), as_i32(m.CFX - tex)};
     r.sx = r.sx < m.W - 1 ? r.sx : m.W - 1;
     r.ex = r.ex < m.W - 1 ? r.ex : m.W - 1;
     return r;
+}
+FE_HD ScreenLine project(const Map &m, const Seg2 &l, ScreenX sx, float height) {
+    const float tsy = m.GCFX * height / l.s.x, tey = m.GCFX * height / l.e.x;
+    return ScreenLine{sx.sx, as_i32(m.CFY - tsy), sx.ex, as_i32(m.CFY - tey)};
 }
 
 FE_NOINLINE bool clip_fov(const Seg2 &line, Seg2 *out, float *start_offset) { // misc.rs:13-115
@@ -278,6 +286,14 @@ FE_HD uint32_t ballot(F f) { // bit l = f(l)
     return mask;
 #endif
 }
+template <class T>
+FE_HD T from_lane(PerLane<T> &v, int src) { // lane src's value, on every lane (T: 32-bit scalar)
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(0xffffffffu, v.v, src);
+#else
+    return v[src];
+#endif
+}
 FE_HD int popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
     return __popc(v);
@@ -302,7 +318,7 @@ FE_HD int highest(uint32_t v) { // index of the highest set bit, v != 0
     while (!((v >> i) & 1u)) i--;
     return i;
 }
-FE_HD uint32_t below(int l) { return l >= 32 ? 0xffffffffu : (1u << l) - 1u; } // bits of the lanes < l
+FE_HD uint32_t below(int l) { return (uint32_t)((1ull << l) - 1ull); } // bits of the lanes < l, 0 <= l <= 32
 
 template <bool EMIT>
 struct Frame {
@@ -336,6 +352,7 @@ struct Frame {
     // plane's record is written and its rows [left, right] are copied from the accumulation buffer (the reference keeps
     // zero-initialised [i16; W] arrays, visplanes.rs:36-37: columns inside the range that never got a point are (0, 0)).
     FE_NOINLINE void flush() {
+        if (!open[0] && !open[1]) return;
         for (int which = 0; which < 2; which++) {
             if (!open[which]) continue;
             open[which] = false;
@@ -390,9 +407,9 @@ struct Frame {
     }
 
     // process_sidedef, segs.rs:121-350
-    FE_NOINLINE void sidedef_part(const Seg2 &cl, float start_offset, const Side &sd, int16_t seg_offset, const Sector &sec, float bottom_h,
+    FE_NOINLINE void sidedef_part(const Seg2 &cl, ScreenX sx, float start_offset, const Side &sd, int16_t seg_offset, const Sector &sec, float bottom_h,
                             float top_h, int32_t offset_y, int tex, bool only_occ, bool lower, bool upper, bool draw_ceiling, bool two_sided_mid) {
-        const ScreenLine bottom = project(m, cl, bottom_h), top = project(m, cl, top_h);
+        const ScreenLine bottom = project(m, cl, sx, bottom_h), top = project(m, cl, sx, top_h);
         if (tex == -2) return fail(FE_PANIC, FED_UNKNOWN_TEXTURE);
         if (bottom.sx != top.sx || bottom.ex != top.ex) return fail(FE_PANIC, FED_NOT_VERTICAL);
         if ((int16_t)bottom.sx == (int16_t)bottom.ex || (int16_t)top.sx == (int16_t)top.ex) return;
@@ -475,15 +492,20 @@ struct Frame {
                         }
                         if (!two_sided_mid && in_area && lower) sc.floor_ocl[x] = ct;
                         if (!two_sided_mid && in_area && upper) sc.ceil_ocl[x] = cb;
-                    } else {
+                    } else if (planes_here) {
                         e |= EV_FLUSH;
                     }
                     if (!two_sided_mid && full_height) occlude(x);
                 }
                 ev[l] = e;
             }
-            const uint32_t m_p0 = ballot([&](int l) { return (ev[l] & EV_P0) != 0; }), m_p1 = ballot([&](int l) { return (ev[l] & EV_P1) != 0; });
-            const uint32_t m_fl = ballot([&](int l) { return (ev[l] & EV_FLUSH) != 0; }), m_col = ballot([&](int l) { return (ev[l] & EV_COL) != 0; });
+            uint32_t m_p0 = 0, m_p1 = 0, m_fl = 0, m_col = 0;
+            if (planes_here) {
+                m_p0 = ballot([&](int l) { return (ev[l] & EV_P0) != 0; });
+                m_p1 = ballot([&](int l) { return (ev[l] & EV_P1) != 0; });
+                m_fl = ballot([&](int l) { return (ev[l] & EV_FLUSH) != 0; });
+            }
+            if (keep) m_col = ballot([&](int l) { return (ev[l] & EV_COL) != 0; });
             // ---- column records, in x order
             if (m_col) {
                 if (EMIT) {
@@ -518,6 +540,7 @@ struct Frame {
             // ---- runs: points between two flushes belong to one pair of visplanes (sidedef_visplanes.rs:41-84)
             uint32_t f = m_fl;
             int lo = 0;
+            if (!(m_p0 | m_p1) && !open[0] && !open[1]) continue; // nothing open, nothing opens: the flushes are no-ops
             for (;;) {
                 const int nf = f ? lowest(f) : 32;
                 const uint32_t run = below(nf) & ~below(lo); // lanes lo .. nf - 1
@@ -602,28 +625,44 @@ struct Frame {
         n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
     }
 
-    // The part of process_seg that touches no per-view state (segs.rs:353-460): can this seg draw or panic at all?
-    // Evaluated for up to 32 segs of a subsector at once; the survivors go through seg() in order.
-    FE_NOINLINE bool seg_may_matter(const Seg &sg) const {
+    // The part of process_seg that touches no per-view state (segs.rs:353-460): the view transform, the clip against the
+    // field of view, the screen x of the ends, the back-face test.  Evaluated for up to 32 segs of a subsector at once
+    // (one per lane); the segs that survive go through seg() in order with these values.
+    struct SegPre {
+        float csx, csy, cex, cey, so; // ClippedLine
+        int32_t sx, ex;               // screen x of its ends
+        int32_t code;                 // 0 draws nothing, 1 go on, 2 panics ("Clipped line x < -0.01")
+    };
+    FE_NOINLINE SegPre seg_pre(const Seg &sg) const {
+        SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
         const Line ld = m.lines[sg.line];
         const int fi = sg.dir ? ld.back : ld.front;
-        if (fi == -1) return false;
+        if (fi == -1) return p;
         const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
         const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
         Seg2 cl;
         float so;
-        if (!clip_fov(view, &cl, &so)) return false;
-        if (cl.s.x < -0.01f) return true; // panics: let seg() report it
-        const float floor_h = (float)m.sectors[m.sides[fi].sector].floor;
-        const ScreenLine fl = project(m, cl, floor_h - (pfloor + 41.0f));
-        return !(fl.sx > fl.ex); // back faces draw nothing
+        if (!clip_fov(view, &cl, &so)) return p;
+        p.csx = cl.s.x;
+        p.csy = cl.s.y;
+        p.cex = cl.e.x;
+        p.cey = cl.e.y;
+        p.so = so;
+        if (cl.s.x < -0.01f) {
+            p.code = 2;
+            return p;
+        }
+        const ScreenX sx = project_x(m, cl);
+        p.sx = sx.sx;
+        p.ex = sx.ex;
+        p.code = sx.sx > sx.ex ? 0 : 1; // back faces draw nothing
+        return p;
     }
 
-    // process_seg, segs.rs:353-590
-    FE_NOINLINE void seg(const Seg &sg) {
+    // process_seg, segs.rs:353-590 (after seg_pre)
+    FE_NOINLINE void seg(const Seg &sg, const SegPre &pre) {
         const Line ld = m.lines[sg.line];
         const int fi = sg.dir ? ld.back : ld.front, bi = sg.dir ? ld.front : ld.back;
-        if (fi == -1) return;
         const Side fs = m.sides[fi];
         const Sector fsec = m.sectors[fs.sector];
         const float floor_h = (float)fsec.floor;
@@ -643,16 +682,11 @@ struct Frame {
             }
         }
         const bool two_sided = (ld.flags & 4) != 0, top_unpeg = (ld.flags & 8) != 0, bottom_unpeg = (ld.flags & 16) != 0;
-
-        const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
-        const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
-        Seg2 cl;
-        float so;
-        if (!clip_fov(view, &cl, &so)) return;
-        if (cl.s.x < -0.01f) return fail(FE_PANIC, FED_CLIP_X);
+        if (pre.code == 2) return fail(FE_PANIC, FED_CLIP_X);
+        const Seg2 cl = {{pre.csx, pre.csy}, {pre.cex, pre.cey}};
+        const float so = pre.so;
+        const ScreenX sx = {pre.sx, pre.ex};
         const float ph = pfloor + 41.0f;
-        const ScreenLine fl = project(m, cl, floor_h - ph);
-        if (fl.sx > fl.ex) return; // back face
 
         if (fsec.floor_flat < 0 || fsec.ceil_flat < 0) return fail(FE_PANIC, FED_FLAT_MISSING); // Flats::get, flats.rs:92-100
         bool draw_ceiling = true;
@@ -664,20 +698,20 @@ struct Frame {
             }
         }
         if (!two_sided) {
-            sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, bottom_unpeg ? as_i32(floor_h - ceil_h) : 0, fs.middle, false,
+            sidedef_part(cl, sx, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, bottom_unpeg ? as_i32(floor_h - ceil_h) : 0, fs.middle, false,
                          false, false, draw_ceiling, false);
         } else {
-            sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, 0, fs.middle, true, false, false, draw_ceiling, false);
+            sidedef_part(cl, sx, so, fs, sg.offset, fsec, floor_h - ph, ceil_h - ph, 0, fs.middle, true, false, false, draw_ceiling, false);
             if (n.status != FE_OK) return;
             const float mf = has_pb ? pb : floor_h, mc = has_pt ? pt : ceil_h;
-            sidedef_part(cl, so, fs, sg.offset, fsec, mf - ph, mc - ph, 0, fs.middle, false, false, false, draw_ceiling, true);
+            sidedef_part(cl, sx, so, fs, sg.offset, fsec, mf - ph, mc - ph, 0, fs.middle, false, false, false, draw_ceiling, true);
             if (n.status != FE_OK) return;
             if (has_pb)
-                sidedef_part(cl, so, fs, sg.offset, fsec, floor_h - ph, pb - ph, bottom_unpeg ? as_i32(ceil_h - pb) : 0, fs.lower, false, true,
+                sidedef_part(cl, sx, so, fs, sg.offset, fsec, floor_h - ph, pb - ph, bottom_unpeg ? as_i32(ceil_h - pb) : 0, fs.lower, false, true,
                              false, draw_ceiling, false);
             if (n.status != FE_OK) return;
             if (has_pt)
-                sidedef_part(cl, so, fs, sg.offset, fsec, pt - ph, ceil_h - ph, top_unpeg ? 0 : as_i32(pt - ceil_h), fs.upper, false, false, true,
+                sidedef_part(cl, sx, so, fs, sg.offset, fsec, pt - ph, ceil_h - ph, top_unpeg ? 0 : as_i32(pt - ceil_h), fs.upper, false, false, true,
                              draw_ceiling, false);
         }
     }
@@ -715,8 +749,27 @@ struct Frame {
             if (node < 0) {
                 const SubSector ss = m.ssectors[~node];
                 for (int c0 = 0; c0 < ss.count && n.status == FE_OK; c0 += 32) {
-                    uint32_t live = ballot([&](int l) { return c0 + l < ss.count && seg_may_matter(m.segs[ss.first + c0 + l]); });
-                    for (; live && n.status == FE_OK; live &= live - 1) seg(m.segs[ss.first + c0 + lowest(live)]);
+                    PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
+                    PerLane<int32_t> p_sx, p_ex, p_code;
+                    FE_LANES(l) {
+                        SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
+                        if (c0 + l < ss.count) p = seg_pre(m.segs[ss.first + c0 + l]);
+                        p_csx[l] = p.csx;
+                        p_csy[l] = p.csy;
+                        p_cex[l] = p.cex;
+                        p_cey[l] = p.cey;
+                        p_so[l] = p.so;
+                        p_sx[l] = p.sx;
+                        p_ex[l] = p.ex;
+                        p_code[l] = p.code;
+                    }
+                    uint32_t live = ballot([&](int l) { return p_code[l] != 0; });
+                    for (; live && n.status == FE_OK; live &= live - 1) {
+                        const int src = lowest(live);
+                        const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
+                                       from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_code, src)};
+                        seg(m.segs[ss.first + c0 + src], p);
+                    }
                 }
                 continue;
             }
