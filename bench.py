@@ -278,8 +278,9 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         ms_fe = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         res["device_front_end"] = {
             "value": px_total / (ms_fe * 1e-3) / 1e6, "unit": "Mpixel/s", "frames_per_s": frames_total / (ms_fe * 1e-3), "ms_per_step": ms_fe,
-            "count_pass_ms": count_ms, "emit_pass_ms": emit_ms, "h2d_bytes_per_step": 28 * n_views, "d2h_bytes_per_step": (40 + 8) * n_views,
-            "what": "viewpoints -> drr_frontend_kernel (count + emit) -> bin -> tile -> checksums; no draw list crosses PCIe",
+            "mode": "single pass: per-view slabs, then compaction" if ctx.fe_last_mode() == 1 else "two passes: count, then emit",
+            "front_end_kernel_ms": emit_ms, "compaction_or_count_ms": count_ms, "h2d_bytes_per_step": 28 * n_views, "d2h_bytes_per_step": (40 + 8) * n_views,
+            "what": "viewpoints -> drr_frontend_kernel -> drr_fe_compact_kernel -> bin -> tile -> checksums; no draw list crosses PCIe",
             "checksums_equal_host_front_end": fe_ok and bool((crc_fe == crc_dev).all()),
             "lists_equal_host_front_end": all(st_fe[k] == st[k] for k in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans")),
             "host_front_end_s": host_build_s}

@@ -18,6 +18,7 @@
 #include "drr_kernels.h"
 #include "drr_frontend.cuh"
 #include <cmath>
+#include <type_traits>
 
 using namespace drr;
 
@@ -142,6 +143,12 @@ struct FeState {
     PinnedVec<fe::ViewIn> h_views_in;
     PinnedVec<fe::Counts> h_counts;
     PinnedVec<fe::Bases> h_bases;
+    DevBuf<View> d_sl_views; // single-pass mode: the per-view slabs
+    DevBuf<uint32_t> d_sl_ops, d_sl_parr;
+    DevBuf<SegRec> d_sl_segs;
+    DevBuf<uint16_t> d_sl_cols;
+    DevBuf<PlaneRec> d_sl_planes;
+    bool single_pass = false; // how the last batch ran
     float count_ms = 0.0f, emit_ms = 0.0f;
     uint64_t device_list_bytes = 0; // size of the lists the last drr_fe_emit_views wrote on the device
 };
@@ -1212,8 +1219,20 @@ static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
     return m;
 }
 
-// The whole batch: count pass, offsets, emit pass.  on_host == true runs the SAME per-view code on the CPU into the
-// context's host lists (test infrastructure: lets the CPU suite compare it with the host front-end list by list).
+// The whole batch.  Single-pass mode (default): the emit pass writes every view's lists into fixed-size per-view slabs
+// and leaves the counts; the host turns the counts into offsets (exclusive scan over the views that got a frame) and
+// drr_fe_compact_kernel copies the slabs into the dense arrays drr_bin_kernel reads.  If a view outgrows its slab, or
+// DRR_FE_TWO_PASS is set, the batch runs in two-pass mode instead: count pass, offsets, emit pass straight into the dense
+// arrays.  Both modes produce the same bytes.  on_host == true runs the SAME per-view code on the CPU into the context's
+// host lists (test infrastructure: lets the CPU suite compare it with the host front-end list by list).
+static fe::Caps fe_slab_caps(const drr_ctx *ctx) {
+    // room per view: E1M1-class frames use ~1.3 W column records and ~2.5 W visplane columns, the 1920x1200 stress map
+    // ~7.5 W and ~12.5 W; DRR_FE_SLAB_DIV shrinks the slabs (tests: provoke the fallback)
+    uint32_t W = (uint32_t)ctx->W, div = 1;
+    if (const char *e = getenv("DRR_FE_SLAB_DIV")) div = (uint32_t)std::max(1, atoi(e));
+    return fe::Caps{std::max(8u, 2048u / div), std::max(4u, 1024u / div), std::max(32u, 16u * W / div), std::max(4u, 1024u / div), std::max(32u, 24u * W / div)};
+}
+
 static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status, bool on_host) {
     FeState &S = ctx->fes;
     if (!S.have_map) return fail(ctx, DRR_E_STATE, "drr_fe_emit_views: no map (drr_fe_upload_map)");
@@ -1230,24 +1249,27 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         const float a = xya[3 * i + 2];
         S.h_views_in.p[i] = fe::ViewIn{xya[3 * i], xya[3 * i + 1], a, cosf(a), sinf(a), cosf(-a), sinf(-a)};
     }
+    const fe::Caps nocap{0, 0, 0, 0, 0}, unlimited{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    fe::Caps slab = fe_slab_caps(ctx);
+    bool single = getenv("DRR_FE_TWO_PASS") == nullptr;
+    if ((uint64_t)N * std::max({slab.ops, slab.segs, slab.cols, slab.planes, slab.parr}) > 0xffffffffull) single = false; // slab indices are 32-bit
+    S.single_pass = false;
+    S.count_ms = S.emit_ms = 0.0f;
+
+    // host harness state: one viewpoint at a time, so a single view's scratch; slabs in plain memory
     std::vector<uint8_t> hs_hor;
     std::vector<int16_t> hs_focl, hs_cocl;
-    std::vector<uint32_t> hs_rows;
+    std::vector<uint32_t> hs_rows, hsl_ops, hsl_parr;
+    std::vector<View> hsl_views;
+    std::vector<SegRec> hsl_segs;
+    std::vector<ColRec> hsl_cols;
+    std::vector<PlaneRec> hsl_planes;
     FeScratch scr{};
-    fe::Out out{};
-    if (on_host) { // one viewpoint at a time: a single view's scratch
+    if (on_host) {
         hs_hor.resize(W);
         hs_focl.resize(W);
         hs_cocl.resize(W);
         hs_rows.resize(2 * W);
-        const fe::Map m = fe_make_map(ctx, false, phases);
-        for (size_t i = 0; i < N; i++) {
-            fe::Frame<false> fr(m);
-            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
-            fr.out = out;
-            fr.run(S.h_views_in.p[i], fe::Bases{0, 0, 0, 0, 0, 0, 0, 0});
-            S.h_counts.p[i] = fr.n;
-        }
     } else {
         int rc = upload_assets(ctx);
         if (rc) return rc;
@@ -1260,12 +1282,73 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_rows.reserve(N * W * 2));
         scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p};
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        CU(ctx, launch_frontend(false, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, out, ctx->stream));
-        ctx->stats.kernel_launches++;
-        CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-        CU(ctx, cudaMemcpyAsync(S.h_counts.p, S.d_counts.p, N * sizeof(fe::Counts), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    auto host_pass = [&](auto emit_tag, const fe::Out &out, bool slabs) { // the kernel's body, view by view
+        constexpr bool EMIT = decltype(emit_tag)::value;
+        const fe::Map m = fe_make_map(ctx, false, phases);
+        for (size_t i = 0; i < N; i++) {
+            fe::Bases b{0, 0, 0, 0, 0, 0, 0, 0};
+            fe::Caps cap = unlimited;
+            if (EMIT && slabs) {
+                const uint32_t u = (uint32_t)i;
+                b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, (int32_t)i, slab.segs, slab.cols};
+                cap = slab;
+            } else if (EMIT) {
+                b = S.h_bases.p[i];
+                if (b.frame < 0) continue;
+            }
+            fe::Frame<EMIT> fr(m);
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
+            fr.out = out;
+            fr.cap = cap;
+            fr.run(S.h_views_in.p[i], b);
+            if (!EMIT || slabs) S.h_counts.p[i] = fr.n;
+        }
+    };
+    fe::Slabs sl{};
+    sl.cap = slab;
+    for (;;) { // at most twice: single-pass, then (on a slab overflow) two-pass
+        if (single) {
+            if (on_host) {
+                hsl_views.resize(N);
+                hsl_ops.resize(N * slab.ops);
+                hsl_segs.resize(N * slab.segs);
+                hsl_cols.resize(N * slab.cols);
+                hsl_planes.resize(N * slab.planes);
+                hsl_parr.resize(N * slab.parr);
+                sl.out = fe::Out{hsl_views.data(), hsl_ops.data(), hsl_segs.data(), hsl_cols.data(), hsl_planes.data(), hsl_parr.data()};
+                host_pass(std::true_type{}, sl.out, true);
+            } else {
+                CU(ctx, S.d_sl_views.reserve(N));
+                CU(ctx, S.d_sl_ops.reserve(N * slab.ops));
+                CU(ctx, S.d_sl_segs.reserve(N * slab.segs));
+                CU(ctx, S.d_sl_cols.reserve(N * slab.cols * 5));
+                CU(ctx, S.d_sl_planes.reserve(N * slab.planes));
+                CU(ctx, S.d_sl_parr.reserve(N * slab.parr));
+                sl.out = fe::Out{S.d_sl_views.p, S.d_sl_ops.p, S.d_sl_segs.p, reinterpret_cast<ColRec *>(S.d_sl_cols.p), S.d_sl_planes.p, S.d_sl_parr.p};
+                CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+                CU(ctx, launch_frontend(true, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, sl.out, slab, ctx->stream));
+                ctx->stats.kernel_launches++;
+                CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+            }
+        } else if (on_host) {
+            host_pass(std::false_type{}, fe::Out{}, false);
+        } else {
+            CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+            CU(ctx, launch_frontend(false, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, fe::Out{}, nocap, ctx->stream));
+            ctx->stats.kernel_launches++;
+            CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        }
+        if (!on_host) {
+            CU(ctx, cudaMemcpyAsync(S.h_counts.p, S.d_counts.p, N * sizeof(fe::Counts), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            if (single) CU(ctx, cudaEventElapsedTime(&S.emit_ms, ctx->ev[2], ctx->ev[3]));
+            else CU(ctx, cudaEventElapsedTime(&S.count_ms, ctx->ev[0], ctx->ev[1]));
+        }
+        bool overflow = false;
+        for (size_t i = 0; i < N && single; i++) overflow |= S.h_counts.p[i].status == fe::FE_HARD && S.h_counts.p[i].detail == fe::FED_CAPACITY;
+        if (!overflow) break;
+        single = false; // a view outgrew its slab: size the lists exactly
     }
     // offsets: an exclusive scan over the viewpoints that got a frame
     uint64_t ops = 0, segs = 0, cols = 0, planes = 0, parr = 0, reccap = 0, nrec = 0;
@@ -1291,6 +1374,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         b = fe::Bases{(uint32_t)ops, (uint32_t)segs, (uint32_t)cols, (uint32_t)planes, (uint32_t)parr, -1, c.nsegs, c.ncols};
         if (c.status == fe::FE_HARD) {
             ctx->clear_lists();
+            std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
             return fail(ctx, c.detail == fe::FED_STACK ? DRR_E_INVALID : DRR_E_ASSET,
                         std::string("drr_fe_emit_views: view ") + std::to_string(i) + ": " + fe_detail_message(c.detail));
         }
@@ -1307,8 +1391,12 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         if (!ctx->frame_slot.push((uint32_t)(first_view_idx + (int)i)) || !push_bases()) return fail(ctx, DRR_E_NOMEM, "alloc");
         ctx->slot_to_frame[first_view_idx + (int)i] = b.frame;
     }
-    if (reccap > 0xffffffffull || cols > 0xffffffffull || parr > 0xffffffffull || ops > 0x7fffffffull) {
+    int nbands, band_rows;
+    tile_bands(ctx->H, &nbands, &band_rows);
+    const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
+    if (reccap * nlists > 0xffffffffull || cols > 0xffffffffull || parr > 0xffffffffull || ops > 0x7fffffffull) {
         ctx->clear_lists();
+        std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
         return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 column records");
     }
     ctx->rec_cap = reccap;
@@ -1319,6 +1407,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     ctx->stats.visplanes = planes;
     ctx->stats.visplane_columns = parr;
     S.device_list_bytes = nf * sizeof(View) + ops * 4 + (nf + 1) * 8 + nf * 4 + segs * sizeof(SegRec) + cols * sizeof(ColRec) + planes * sizeof(PlaneRec) + parr * 4;
+    S.single_pass = single;
     if (nf == 0) return DRR_OK;
     if (on_host) {
         if (!ctx->views.reserve(nf) || !ctx->ops.reserve(ops) || !ctx->segs.reserve(segs) || !ctx->cols.reserve(cols) || !ctx->planes.reserve(planes) ||
@@ -1330,18 +1419,16 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         ctx->cols.n = cols;
         ctx->planes.n = planes;
         ctx->parr.n = parr;
-        out = fe::Out{ctx->views.p, ctx->ops.p, ctx->segs.p, ctx->cols.p, ctx->planes.p, ctx->parr.p};
-        const fe::Map m = fe_make_map(ctx, false, phases);
-        for (size_t i = 0; i < N; i++) {
-            if (S.h_bases.p[i].frame < 0) continue;
-            fe::Frame<true> fr(m);
-            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
-            fr.out = out;
-            fr.run(S.h_views_in.p[i], S.h_bases.p[i]);
+        const fe::Out out{ctx->views.p, ctx->ops.p, ctx->segs.p, ctx->cols.p, ctx->planes.p, ctx->parr.p};
+        if (single) {
+            for (size_t i = 0; i < N; i++)
+                if (S.h_bases.p[i].frame >= 0) fe::compact_view(sl, (uint32_t)i, S.h_counts.p[i], S.h_bases.p[i], out);
+        } else {
+            host_pass(std::true_type{}, out, false);
         }
         return DRR_OK;
     }
-    // device lists: sized from the counts, written by the emit pass
+    // the dense device lists: sized from the counts
     CU(ctx, ctx->d_views.reserve(nf));
     CU(ctx, ctx->d_ops.reserve(std::max<uint64_t>(ops, 1)));
     CU(ctx, ctx->d_frame_op_base.reserve(nf + 1));
@@ -1352,24 +1439,18 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     CU(ctx, ctx->d_cols.reserve(std::max<uint64_t>(cols, 1) * 5));
     CU(ctx, ctx->d_planes.reserve(std::max<uint64_t>(planes, 1)));
     CU(ctx, ctx->d_parr.reserve(std::max<uint64_t>(parr, 1)));
-    int nbands, band_rows;
-    tile_bands(ctx->H, &nbands, &band_rows);
-    const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
-    if (reccap * nlists > 0xffffffffull) {
-        ctx->clear_lists();
-        return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 record slots");
-    }
     CU(ctx, ctx->d_colidx.reserve(nf * W * nlists));
     CU(ctx, ctx->d_tparams.reserve(std::max<uint64_t>(reccap, 1) * 4 * nlists));
     CU(ctx, cudaMemcpyAsync(S.d_bases.p, S.h_bases.p, N * sizeof(fe::Bases), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->d_frame_op_base.p, ctx->frame_op_base.p, (nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->d_frame_rec_base.p, ctx->frame_rec_base.p, (nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * 4, cudaMemcpyHostToDevice, ctx->stream));
-    out = fe::Out{ctx->d_views.p, ctx->d_ops.p, ctx->d_segs.p, reinterpret_cast<ColRec *>(ctx->d_cols.p), ctx->d_planes.p, ctx->d_parr.p};
-    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(ctx, launch_frontend(true, fe_make_map(ctx, true, phases), S.d_views_in.p, S.d_bases.p, nullptr, n, scr, out, ctx->stream));
+    const fe::Out out{ctx->d_views.p, ctx->d_ops.p, ctx->d_segs.p, reinterpret_cast<ColRec *>(ctx->d_cols.p), ctx->d_planes.p, ctx->d_parr.p};
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (single) CU(ctx, launch_fe_compact(sl, S.d_counts.p, S.d_bases.p, n, out, ctx->stream));
+    else CU(ctx, launch_frontend(true, fe_make_map(ctx, true, phases), S.d_views_in.p, S.d_bases.p, nullptr, n, scr, out, nocap, ctx->stream));
     ctx->stats.kernel_launches++;
-    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->device_lists = true;
     ctx->uploaded_frames = nf;
     return DRR_OK;
@@ -1383,14 +1464,20 @@ int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n,
 int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms) {
     CTX_CHECK(ctx);
     if (ctx->host_only || !ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_fe_last_times: no device front-end batch");
-    CU(ctx, cudaEventSynchronize(ctx->ev[3]));
-    float a = 0, b = 0;
-    CU(ctx, cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
-    CU(ctx, cudaEventElapsedTime(&b, ctx->ev[2], ctx->ev[3]));
-    if (count_ms) *count_ms = a;
-    if (emit_ms) *emit_ms = b;
+    FeState &S = ctx->fes;
+    CU(ctx, cudaEventSynchronize(ctx->ev[1]));
+    float t = 0;
+    CU(ctx, cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1])); // the batch's last kernel: compaction (single-pass) or the emit pass (two-pass)
+    if (S.single_pass) {
+        if (count_ms) *count_ms = t;          // single-pass mode has no count pass: the second figure's slot carries the compaction
+        if (emit_ms) *emit_ms = S.emit_ms;
+    } else {
+        if (count_ms) *count_ms = S.count_ms;
+        if (emit_ms) *emit_ms = t;
+    }
     return DRR_OK;
 }
+int drr_fe_last_mode(drr_ctx *ctx) { return ctx ? (ctx->fes.single_pass ? 1 : 2) : DRR_E_INVALID; }
 
 // Test infrastructure: the per-view front-end code of drr_frontend.cuh run on the CPU into the context's host lists
 // (works in a recording-only context), so that tests/ can compare it list by list with the host front-end.

@@ -13,15 +13,24 @@
 
 namespace drr {
 
+// slab.ops != 0: single-pass mode -- no count pass ran, view v writes into its own slab of every array (drr_frontend.cuh:
+// Slabs) and leaves its counts; drr_fe_compact_kernel then makes the lists dense.
 template <bool EMIT>
-__global__ void __launch_bounds__(FE_THREADS) drr_frontend_kernel(fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
-                                                                  fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out) {
+__global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel(fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
+                                                                                 fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab) {
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
     fe::Bases b = fe::Bases{0, 0, 0, 0, 0, 0, 0, 0};
+    fe::Caps cap = fe::Caps{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     if (EMIT) {
-        b = bases[v];
-        if (b.frame < 0) return; // the reference panics on this viewpoint: no frame
+        if (slab.ops) {
+            const uint32_t u = (uint32_t)v;
+            b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, v, slab.segs, slab.cols};
+            cap = slab;
+        } else {
+            b = bases[v];
+            if (b.frame < 0) return; // the reference panics on this viewpoint: no frame
+        }
     }
     fe::Frame<EMIT> fr(m);
     const size_t o = (size_t)v * (size_t)m.W;
@@ -31,19 +40,34 @@ __global__ void __launch_bounds__(FE_THREADS) drr_frontend_kernel(fe::Map m, con
     fr.sc.rows[0] = s.rows + 2 * o;
     fr.sc.rows[1] = s.rows + 2 * o + m.W;
     fr.out = out;
+    fr.cap = cap;
     fr.run(views[v], b);
-    if (!EMIT && (threadIdx.x & 31u) == 0u) counts[v] = fr.n;
+    if ((!EMIT || slab.ops) && (threadIdx.x & 31u) == 0u) counts[v] = fr.n;
+}
+
+__global__ void __launch_bounds__(128) drr_fe_compact_kernel(fe::Slabs sl, const fe::Counts *__restrict__ counts, const fe::Bases *__restrict__ bases, int n, fe::Out dst) {
+    const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
+    if (v >= n) return;
+    const fe::Bases b = bases[v];
+    if (b.frame < 0) return;
+    fe::compact_view(sl, (uint32_t)v, counts[v], b, dst);
 }
 
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
-                            const FeScratch &s, const fe::Out &out, cudaStream_t st) {
+                            const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const int vpb = FE_THREADS / 32; // viewpoints per CTA
     const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
     if (emit)
-        drr_frontend_kernel<true><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out);
+        drr_frontend_kernel<true><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out, slab);
     else
-        drr_frontend_kernel<false><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out);
+        drr_frontend_kernel<false><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out, slab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fe_compact(const fe::Slabs &sl, const fe::Counts *counts, const fe::Bases *bases, int n, const fe::Out &dst, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    drr_fe_compact_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(sl, counts, bases, n, dst);
     return cudaGetLastError();
 }
 

@@ -100,13 +100,18 @@ enum : uint32_t { // detail codes (messages: fe_detail_message() in drr_api.cu)
     FED_STACK,           // BSP deeper than the walk stack      (hard)
     FED_BITMAP_SLOT,     // emitted bitmap was never uploaded   (hard: DRR_E_ASSET on the host path)
     FED_SKY_UNSET,       // sky visplane but no sky bitmap      (hard: DRR_E_ASSET on the host path)
+    FED_CAPACITY,        // a view's lists outgrew its slab     (single-pass mode only: the batch is redone with the count pass)
 };
 
 struct Counts { // per viewpoint, written by the count pass. 40 bytes
     uint32_t nops, nsegs, ncols, nplanes, nparr, reccap;
     uint32_t status, detail;
     uint32_t nrec; // columns that survive clipping (what the bin kernel will actually write; statistics)
+    uint32_t ndeferred, dcols; // of nsegs / ncols: deferred two-sided middle textures, written from the END of the view's ranges
     uint32_t pad;
+};
+struct Caps { // how much room a view has (single-pass mode: its slab; two-pass mode: exactly what the count pass found)
+    uint32_t ops, segs, cols, planes, parr;
 };
 struct Bases { // per viewpoint, written by the host between the passes. 32 bytes
     uint32_t op, seg, col, plane, parr;
@@ -327,6 +332,7 @@ struct Frame {
     Out out;
     Bases base;   // EMIT only
     Counts n;     // running counts == cursors relative to the bases (uniform over the warp)
+    Caps cap;     // EMIT only
     V2 ppos;
     float cos_n, sin_n, pfloor;
     // SidedefVisPlanes of the sidedef part being processed
@@ -363,6 +369,10 @@ struct Frame {
             if (sky && m.sky_kind < 0) fail(FE_HARD, FED_SKY_UNSET);
             const uint32_t arr_first = base.parr + n.nparr;
             const uint32_t *src = sc.rows[which] + left;
+            if (EMIT && (n.nplanes + 1 > cap.planes || n.nparr + ncols > cap.parr)) {
+                fail(FE_HARD, FED_CAPACITY);
+                continue;
+            }
             const int H = m.H;
             for (uint32_t i0 = 0; i0 < ncols; i0 += 32) {
                 // how many of the columns draw anything (drr_api.cu: rec_emit_visplane)
@@ -507,6 +517,10 @@ struct Frame {
             }
             if (keep) m_col = ballot([&](int l) { return (ev[l] & EV_COL) != 0; });
             // ---- column records, in x order
+            if (m_col && EMIT && n.ncols + (uint32_t)popc32(m_col) > cap.cols) {
+                fail(FE_HARD, FED_CAPACITY);
+                m_col = 0;
+            }
             if (m_col) {
                 if (EMIT) {
                     const uint32_t at = base.col + (n.ncols - dcols); // front cursor; a deferred part's block is moved to the back below
@@ -564,6 +578,7 @@ struct Frame {
         if (!keep || ncol == 0) return;
         const Bitmap bm = m.bitmaps[tex];
         if (bm.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
+        if (EMIT && (n.status != FE_OK || n.nsegs + 1 > cap.segs || n.nops + 1 > cap.ops)) return fail(FE_HARD, FED_CAPACITY);
         if (EMIT) {
             uint32_t first = base.col + (col0 - dcols); // where the loop above put the columns
             if (deferred) { // move the block to the back of the view's column range; dst >= src, so go from the top chunk down
@@ -719,7 +734,7 @@ struct Frame {
     // Renderer::render, mod.rs:118-136 (without phase C, the map objects)
     FE_HD void run(const ViewIn &v, const Bases &b) {
         base = b;
-        n = Counts{0, 0, 0, 0, 0, 0, FE_OK, FED_NONE, 0, 0};
+        n = Counts{0, 0, 0, 0, 0, 0, FE_OK, FED_NONE, 0, 0, 0, 0};
         ppos = V2{v.x, v.y};
         cos_n = v.cos_n;
         sin_n = v.sin_n;
@@ -784,6 +799,7 @@ struct Frame {
             stack[sp++] = is_left ? nd.left : nd.right; // visited first
         }
         if (n.status != FE_OK) return;
+        if (EMIT && n.nops + n.nplanes + ndeferred > cap.ops) return fail(FE_HARD, FED_CAPACITY);
         // B: mod.rs:106-116 -- the visplanes in push order, after every wall
         if (EMIT) {
             FE_LANES(l) {
@@ -798,8 +814,48 @@ struct Frame {
             }
         }
         n.nops += ndeferred;
+        n.ndeferred = ndeferred;
+        n.dcols = dcols;
     }
 };
+
+// ---- single-pass mode: slabs -> dense lists ------------------------------------------------------------------------
+// The emit pass can run WITHOUT a count pass when every view writes into its own fixed-size slab of each array (view v's
+// slab of array A starts at v * cap.A; deferred parts sit at the slab's end).  compact_view then copies a view's lists to
+// their final, dense place (the offsets come from an exclusive scan of the counts the emit pass left) and rebases the
+// indices they contain, which yields exactly the arrays the two-pass mode writes.  One warp per view.
+struct Slabs {
+    Out out;  // the slab arrays (views[] is written densely by frame index only in two-pass mode: slab mode indexes it by view)
+    Caps cap; // per view
+};
+FE_HD void compact_view(const Slabs &sl, uint32_t v, const Counts &c, const Bases &b, const Out &dst) {
+    const uint32_t nwall = c.nsegs - c.ndeferred, wcols = c.ncols - c.dcols;
+    const uint32_t s0 = v * sl.cap.segs, c0 = v * sl.cap.cols, o0 = v * sl.cap.ops, p0 = v * sl.cap.planes, r0 = v * sl.cap.parr;
+    // slab index -> final index
+    auto seg_at = [&](uint32_t s) { const uint32_t rel = s - s0; return rel < nwall ? b.seg + rel : b.seg + nwall + (rel - (sl.cap.segs - c.ndeferred)); };
+    auto col_at = [&](uint32_t k) { const uint32_t rel = k - c0; return rel < wcols ? b.col + rel : b.col + wcols + (rel - (sl.cap.cols - c.dcols)); };
+    FE_LEADER { dst.views[b.frame] = sl.out.views[v]; }
+    FE_LANES(l) {
+        for (uint32_t i = (uint32_t)l; i < c.nops; i += 32) {
+            const uint32_t op = sl.out.ops[o0 + i];
+            dst.ops[b.op + i] = (op & 0x80000000u) ? (0x80000000u | (b.plane + ((op & 0x7fffffffu) - p0))) : seg_at(op);
+        }
+        for (uint32_t i = (uint32_t)l; i < c.nsegs; i += 32) {
+            const uint32_t s = i < nwall ? s0 + i : s0 + sl.cap.segs - c.ndeferred + (i - nwall);
+            SegRec r = sl.out.segs[s];
+            r.cols_first = col_at(r.cols_first);
+            dst.segs[b.seg + i] = r;
+        }
+        for (uint32_t i = (uint32_t)l; i < c.ncols; i += 32)
+            dst.cols[b.col + i] = sl.out.cols[i < wcols ? c0 + i : c0 + sl.cap.cols - c.dcols + (i - wcols)];
+        for (uint32_t i = (uint32_t)l; i < c.nplanes; i += 32) {
+            PlaneRec p = sl.out.planes[p0 + i];
+            p.arr_first = b.parr + (p.arr_first - r0);
+            dst.planes[b.plane + i] = p;
+        }
+        for (uint32_t i = (uint32_t)l; i < c.nparr; i += 32) dst.parr[b.parr + i] = sl.out.parr[r0 + i];
+    }
+}
 
 } // namespace fe
 } // namespace drr

@@ -80,16 +80,24 @@ struct ViewIn;
 struct Counts;
 struct Bases;
 struct Out;
+struct Caps;
+struct Slabs;
 } // namespace fe
+#ifndef DRR_FE_MIN_BLOCKS
+#define DRR_FE_MIN_BLOCKS 16
+#endif
+static constexpr int FE_MIN_BLOCKS = DRR_FE_MIN_BLOCKS; // resident CTAs per SM the register budget is set for (16 x 2 warps: 64 registers)
 static constexpr int FE_THREADS = 64; // one warp per viewpoint, two viewpoints per CTA: a few thousand viewpoints spread over every SM
 struct FeScratch {                    // per-viewpoint working state of the front-end, W entries per viewpoint each
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;
     uint32_t *rows;                   // 2 * W per viewpoint: the (top, bottom) rows of the two visplanes being accumulated
 };
-// emit == false: count pass (writes counts[0..n)); emit == true: writes the lists at the offsets in bases[0..n)
+// emit == false: count pass (writes counts[0..n)); emit == true: writes the lists at the offsets in bases[0..n), or -- when
+// slab.ops != 0, single-pass mode -- into per-view slabs of those capacities, leaving counts[0..n) for launch_fe_compact
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
-                            const FeScratch &s, const fe::Out &out, cudaStream_t st);
+                            const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st);
+cudaError_t launch_fe_compact(const fe::Slabs &sl, const fe::Counts *counts, const fe::Bases *bases, int n, const fe::Out &dst, cudaStream_t st);
 
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);

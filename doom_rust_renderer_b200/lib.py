@@ -86,7 +86,7 @@ def _lib() -> C.CDLL:
             "drr_recorder_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_recorder_frame_end": (i, [vp]),
             "drr_recorder_frame_abort": (i, [vp]), "drr_append": (i, [vp, vp]),
             "drr_fe_upload_map": (i, [vp, vp]), "drr_fe_emit_views": (i, [vp, i, vp, i, i, vp]),
-            "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]),
+            "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]), "drr_fe_last_mode": (i, [vp]),
             "drr_scene_emit_views_device": (i, [vp, vp, i, vp, i, f, i, vp]),
             "drr_test_fe_emit_views_host": (i, [vp, i, vp, i, i, vp]), "drr_test_fe_download_lists": (i, [vp]),
             "drr_test_ctx_create_host_only": (i, [i, i, i, C.POINTER(vp)]),
@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "drr_scene_emit_view", "drr_scene_emit_views",
     "drr_recorder_create", "drr_recorder_destroy", "drr_recorder_last_error", "drr_recorder_frame_begin", "drr_recorder_emit_columns",
     "drr_recorder_emit_visplane", "drr_recorder_frame_end", "drr_recorder_frame_abort", "drr_append",
-    "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_scene_emit_views_device",
+    "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_fe_last_mode", "drr_scene_emit_views_device",
 ]
 
 
@@ -298,10 +298,14 @@ class Context:
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
 
     def fe_last_times(self):
-        """(count_ms, emit_ms): device time of the two front-end passes of the last fe_emit_views."""
+        """(count_ms, emit_ms) of the last fe_emit_views; in single-pass mode (fe_last_mode() == 1) the first is the compaction kernel."""
         a, b = C.c_float(), C.c_float()
         self._ck(self.L.drr_fe_last_times(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def fe_last_mode(self) -> int:
+        """1 = single pass (per-view slabs + compaction), 2 = count pass + emit pass."""
+        return int(self.L.drr_fe_last_mode(self.h))
 
     def fe_download_lists(self):
         """Test infrastructure: copy the device-written lists back so that _list() can show them."""

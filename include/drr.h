@@ -192,8 +192,12 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *map); /* assets must be up
  * every frame recorded since drr_reset (call drr_reset first); afterwards drr_draw() renders the batch.  status[i]
  * (may be NULL) = DRR_OK or DRR_E_PANIC (the reference would have panicked on that viewpoint: it gets no frame). */
 int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status);
-/* Device times (ms) of the last drr_fe_emit_views: count pass and emit pass (CUDA events on the context's stream). */
+/* How the last drr_fe_emit_views ran and its device times in ms (CUDA events on the context's stream).  Mode 1 = single
+ * pass: every view writes into its own slab, then a compaction kernel makes the lists dense (emit_ms = the front-end
+ * kernel, count_ms = the compaction).  Mode 2 = two passes (a view outgrew its slab, or DRR_FE_TWO_PASS is set): count
+ * pass, then emit pass straight into the dense lists.  Both modes write the same bytes. */
 int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms);
+int drr_fe_last_mode(drr_ctx *ctx);
 
 /* ---- host front-end: the reference's Renderer for a WAD map, emitting through the functions above -------------- */
 /* Mirrors Game::new's asset/map loading (src/game.rs:118-196) without SDL. */

@@ -145,6 +145,31 @@ def test_front_end_code_panics_where_the_host_front_end_panics():
         assert a.stats() == b.stats()
 
 
+def test_front_end_single_pass_two_pass_and_slab_overflow_agree(monkeypatch):
+    """Single-pass mode (per-view slabs + compaction), two-pass mode (count pass, exact offsets, emit pass) and the fallback
+    from the first to the second when a view outgrows its slab all write the same bytes."""
+    W, H, n = 320, 200, 150
+    bare = _wad_without_things("e1m1")
+    _, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    scene = drr.Scene(bare, "E1M1", W, H)
+    ctxs = []
+    for env, mode in (({}, 1), ({"DRR_FE_TWO_PASS": "1"}, 2), ({"DRR_FE_SLAB_DIV": "64"}, 2)):
+        for k in ("DRR_FE_TWO_PASS", "DRR_FE_SLAB_DIV"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = drr.Context(W, H, 0, n, _host_only=True)
+        scene.upload_assets(c)
+        scene.upload_map_for_device_front_end(c)
+        assert c.fe_emit_views(views, phases=7, _on_host=True) == []
+        assert c.fe_last_mode() == mode, env
+        ctxs.append(c)
+    _assert_same_lists(ctxs[0], ctxs[1], "single-pass vs two-pass")
+    _assert_same_lists(ctxs[0], ctxs[2], "single-pass vs overflow fallback")
+    assert ctxs[0].stats() == ctxs[1].stats() == ctxs[2].stats()
+
+
 def test_front_end_state_machine():
     W, H, n = 160, 100, 8
     path, gm = common.wad("e1m1")
@@ -196,7 +221,27 @@ def test_device_front_end_lists_equal_host_front_end(kind, W, H, n, phases, ts):
     _assert_same_lists(a, b, "%s %dx%d phases %d" % (kind, W, H, phases))
     assert a.stats() == {**b.stats(), "kernel_launches": 0, "device_list_bytes": a.stats()["device_list_bytes"]}
     count_ms, emit_ms = b.fe_last_times()
-    assert count_ms > 0 and emit_ms > 0
+    assert count_ms > 0 and emit_ms > 0 and b.fe_last_mode() == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"DRR_FE_TWO_PASS": "1"}, {"DRR_FE_SLAB_DIV": "64"}])
+def test_device_front_end_two_pass_and_overflow_fallback(env, monkeypatch):
+    W, H, n = 320, 200, 300
+    path, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, phases=3)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b = drr.Context(W, H, 0, n)
+    scene.upload_assets(b)
+    assert scene.emit_views_device(b, views, phases=3) == skipped
+    assert b.fe_last_mode() == 2
+    b.fe_download_lists()
+    _assert_same_lists(a, b, str(env))
 
 
 @pytest.mark.gpu
