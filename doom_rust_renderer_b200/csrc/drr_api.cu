@@ -1230,7 +1230,8 @@ static fe::Caps fe_slab_caps(const drr_ctx *ctx) {
     // ~7.5 W and ~12.5 W; DRR_FE_SLAB_DIV shrinks the slabs (tests: provoke the fallback)
     uint32_t W = (uint32_t)ctx->W, div = 1;
     if (const char *e = getenv("DRR_FE_SLAB_DIV")) div = (uint32_t)std::max(1, atoi(e));
-    return fe::Caps{std::max(8u, 2048u / div), std::max(4u, 1024u / div), std::max(32u, 16u * W / div), std::max(4u, 1024u / div), std::max(32u, 24u * W / div)};
+    return fe::Caps{std::max(8u, 2048u / div), std::max(4u, 1024u / div), std::max(32u, std::max(16u * W, 6144u) / div), std::max(4u, 1024u / div),
+                    std::max(32u, std::max(24u * W, 12288u) / div)};
 }
 
 static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status, bool on_host) {
