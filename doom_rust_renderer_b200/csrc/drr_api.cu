@@ -140,6 +140,7 @@ struct FeState {
     DevBuf<uint8_t> d_hor;
     DevBuf<int16_t> d_focl, d_cocl;
     DevBuf<uint32_t> d_rows;
+    DevBuf<int32_t> d_order;
     PinnedVec<fe::ViewIn> h_views_in;
     PinnedVec<fe::Counts> h_counts;
     PinnedVec<fe::Bases> h_bases;
@@ -1208,6 +1209,7 @@ static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
     m.sectors = device ? S.d_sectors.p : S.sectors.data();
     m.bitmaps = device ? S.d_bitmaps.p : S.bitmaps.data();
     m.nnodes = (int)S.nodes.size();
+    m.nsegs = (int)S.segs.size();
     m.W = ctx->W;
     m.H = ctx->H;
     m.ASPECT = ctx->ASPECT;
@@ -1261,6 +1263,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     std::vector<uint8_t> hs_hor;
     std::vector<int16_t> hs_focl, hs_cocl;
     std::vector<uint32_t> hs_rows, hsl_ops, hsl_parr;
+    std::vector<int32_t> hs_order;
     std::vector<View> hsl_views;
     std::vector<SegRec> hsl_segs;
     std::vector<ColRec> hsl_cols;
@@ -1271,6 +1274,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         hs_focl.resize(W);
         hs_cocl.resize(W);
         hs_rows.resize(2 * W);
+        hs_order.resize(S.segs.size());
     } else {
         int rc = upload_assets(ctx);
         if (rc) return rc;
@@ -1281,7 +1285,8 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_focl.reserve(N * W));
         CU(ctx, S.d_cocl.reserve(N * W));
         CU(ctx, S.d_rows.reserve(N * W * 2));
-        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p};
+        CU(ctx, S.d_order.reserve(N * S.segs.size()));
+        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p};
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
     }
     auto host_pass = [&](auto emit_tag, const fe::Out &out, bool slabs) { // the kernel's body, view by view
@@ -1299,7 +1304,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
                 if (b.frame < 0) continue;
             }
             fe::Frame<EMIT> fr(m);
-            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}};
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data()};
             fr.out = out;
             fr.cap = cap;
             fr.run(S.h_views_in.p[i], b);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     fr.sc.ceil_ocl = s.ceil_ocl + o;
     fr.sc.rows[0] = s.rows + 2 * o;
     fr.sc.rows[1] = s.rows + 2 * o + m.W;
+    fr.sc.order = s.order + (size_t)v * (size_t)m.nsegs;
     fr.out = out;
     fr.cap = cap;
     fr.run(views[v], b);

@@ -76,7 +76,7 @@ struct Map {
     const Side *sides;
     const Sector *sectors;
     const Bitmap *bitmaps;
-    int nnodes;
+    int nnodes, nsegs;
     int W, H;
     float ASPECT, GCFX, CFX, CFY; // constants.rs:7-17, derived by drr_ctx_create
     int sky_kind;                 // KIND_SKY / KIND_SKY_HOLES, -1 = sky not set
@@ -97,7 +97,7 @@ enum : uint32_t { // detail codes (messages: fe_detail_message() in drr_api.cu)
     FED_NOT_VERTICAL,    // "Wall start not vertical"           segs.rs:159-167
     FED_LINE_X,          // "Invalid line start/end x"          segs.rs:169-184
     FED_FLAT_MISSING,    // flat lump missing                   flats.rs:92-100
-    FED_STACK,           // BSP deeper than the walk stack      (hard)
+    FED_STACK,           // BSP deeper than the walk stack, or subsectors that share segs (hard)
     FED_BITMAP_SLOT,     // emitted bitmap was never uploaded   (hard: DRR_E_ASSET on the host path)
     FED_SKY_UNSET,       // sky visplane but no sky bitmap      (hard: DRR_E_ASSET on the host path)
     FED_CAPACITY,        // a view's lists outgrew its slab     (single-pass mode only: the batch is redone with the count pass)
@@ -124,6 +124,7 @@ struct Scratch {
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;
     uint32_t *rows[2]; // (top, bottom) pairs of the visplane being accumulated: 0 = bottom (floor), 1 = top (ceiling)
+    int32_t *order;    // nsegs entries: the map's segs in this view's BSP order
 };
 
 struct Out { // where the emit pass writes (pointers are the batch's arrays; indices are global)
@@ -755,37 +756,25 @@ struct Frame {
         if (EMIT) {
             FE_LEADER { out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a}; }
         }
-        // A: render_node, mod.rs:69-104 -- front subtree, then back subtree (explicit stack instead of the recursion)
+        // A: render_node, mod.rs:69-104 -- front subtree, then back subtree (explicit stack instead of the recursion).  The
+        // walk itself only decides the ORDER in which the segs are processed (the reference does no occlusion culling in
+        // the tree), so it first lists the segs in that order; they are then taken 32 at a time: one lane per seg for the
+        // stateless part (seg_pre), the survivors in order through seg().
         int stack[64];
-        int sp = 0;
+        int sp = 0, nord = 0;
         stack[sp++] = m.nnodes - 1;
-        while (sp > 0 && n.status == FE_OK) {
+        while (sp > 0) {
             const int node = stack[--sp];
             if (node < 0) {
                 const SubSector ss = m.ssectors[~node];
-                for (int c0 = 0; c0 < ss.count && n.status == FE_OK; c0 += 32) {
-                    PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
-                    PerLane<int32_t> p_sx, p_ex, p_code;
-                    FE_LANES(l) {
-                        SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
-                        if (c0 + l < ss.count) p = seg_pre(m.segs[ss.first + c0 + l]);
-                        p_csx[l] = p.csx;
-                        p_csy[l] = p.csy;
-                        p_cex[l] = p.cex;
-                        p_cey[l] = p.cey;
-                        p_so[l] = p.so;
-                        p_sx[l] = p.sx;
-                        p_ex[l] = p.ex;
-                        p_code[l] = p.code;
-                    }
-                    uint32_t live = ballot([&](int l) { return p_code[l] != 0; });
-                    for (; live && n.status == FE_OK; live &= live - 1) {
-                        const int src = lowest(live);
-                        const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
-                                       from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_code, src)};
-                        seg(m.segs[ss.first + c0 + src], p);
-                    }
+                if (nord + ss.count > m.nsegs) { // subsectors sharing segs: not a map the loaders produce
+                    fail(FE_HARD, FED_STACK);
+                    break;
                 }
+                FE_LANES(l) {
+                    for (int i = l; i < ss.count; i += 32) sc.order[nord + i] = ss.first + i;
+                }
+                nord += ss.count;
                 continue;
             }
             const Node nd = m.nodes[node];
@@ -797,6 +786,35 @@ struct Frame {
             }
             stack[sp++] = is_left ? nd.right : nd.left; // visited second
             stack[sp++] = is_left ? nd.left : nd.right; // visited first
+        }
+        FE_SYNC();
+        for (int c0 = 0; c0 < nord && n.status == FE_OK; c0 += 32) {
+            PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
+            PerLane<int32_t> p_sx, p_ex, p_code, p_seg;
+            FE_LANES(l) {
+                SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
+                int si = 0;
+                if (c0 + l < nord) {
+                    si = sc.order[c0 + l];
+                    p = seg_pre(m.segs[si]);
+                }
+                p_seg[l] = si;
+                p_csx[l] = p.csx;
+                p_csy[l] = p.csy;
+                p_cex[l] = p.cex;
+                p_cey[l] = p.cey;
+                p_so[l] = p.so;
+                p_sx[l] = p.sx;
+                p_ex[l] = p.ex;
+                p_code[l] = p.code;
+            }
+            uint32_t live = ballot([&](int l) { return p_code[l] != 0; });
+            for (; live && n.status == FE_OK; live &= live - 1) {
+                const int src = lowest(live);
+                const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
+                               from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_code, src)};
+                seg(m.segs[from_lane(p_seg, src)], p);
+            }
         }
         if (n.status != FE_OK) return;
         if (EMIT && n.nops + n.nplanes + ndeferred > cap.ops) return fail(FE_HARD, FED_CAPACITY);
