@@ -255,8 +255,8 @@ def run_workload(name, args, rank, world, local_rank, dist, torch):
         "lists": {k: st[k] for k in ("seg_headers", "column_records", "visplanes", "visplane_columns", "spans", "device_list_bytes")},
         "host_build_s": host_build_s, "checksum_of_checksums": "%016x" % coc,
     }
-    # ---- viewpoints in, checksums out: the front-end on the GPU too (walls + visplanes, no map objects) ----
-    if not (phases & 4):
+    # ---- viewpoints in, checksums out: the front-end on the GPU too (every phase, map objects included) ----
+    if True:
         ctx.reset()
         assert scene.emit_views_device(ctx, used, 0.0, phases) == []
         ctx.draw()

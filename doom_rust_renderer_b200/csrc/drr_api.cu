@@ -119,7 +119,14 @@ struct Lists {
 // and the count / offset tables of the last batch.
 struct FeState {
     bool have_map = false;
-    int n_things = 0;
+    std::vector<fe::Thing> things;
+    DevBuf<fe::Thing> d_things;
+    DevBuf<fe::RenderRec> d_renders;
+    DevBuf<uint16_t> d_allcols;
+    DevBuf<SegRec> d_dsegs;
+    DevBuf<fe::MoRec> d_mos;
+    DevBuf<int32_t> d_mo_order;
+    DevBuf<int16_t> d_clips;
     std::vector<fe::Node> nodes;
     std::vector<fe::SubSector> ssectors;
     std::vector<fe::Seg> segs;
@@ -1120,6 +1127,9 @@ static const char *fe_detail_message(uint32_t d) {
     case fe::FED_STACK: return "BSP deeper than the front-end's walk stack";
     case fe::FED_BITMAP_SLOT: return "a wall's bitmap was never uploaded";
     case fe::FED_SKY_UNSET: return "sky visplane but no sky bitmap set";
+    case fe::FED_SCRATCH: return "the view outgrew the front-end's working arrays";
+    case fe::FED_ROTATION: return "Invalid rotation";
+    case fe::FED_MO_X: return "map object column outside the screen";
     default: return "front-end error";
     }
 }
@@ -1130,7 +1140,8 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
         !m->nodes || !m->subsectors || !m->segs || !m->linedefs || !m->sidedefs || !m->sectors)
         return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: empty table");
     static_assert(sizeof(drr_fe_node) == sizeof(fe::Node) && sizeof(drr_fe_subsector) == sizeof(fe::SubSector) && sizeof(drr_fe_seg) == sizeof(fe::Seg) &&
-                      sizeof(drr_fe_linedef) == sizeof(fe::Line) && sizeof(drr_fe_sidedef) == sizeof(fe::Side) && sizeof(drr_fe_sector) == sizeof(fe::Sector),
+                      sizeof(drr_fe_linedef) == sizeof(fe::Line) && sizeof(drr_fe_sidedef) == sizeof(fe::Side) && sizeof(drr_fe_sector) == sizeof(fe::Sector) &&
+                      sizeof(drr_fe_thing) == sizeof(fe::Thing),
                   "drr_fe_* layouts");
     FeState &S = ctx->fes;
     S.have_map = false;
@@ -1177,7 +1188,15 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
             auto it = ctx->flat_slot.find(*f);
             *f = it == ctx->flat_slot.end() ? (int16_t)-2 : (int16_t)it->second;
         }
-    S.n_things = m->n_things;
+    S.things.clear();
+    if (m->n_things < 0 || (m->n_things > 0 && !m->things)) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: things");
+    for (int i = 0; i < m->n_things; i++) {
+        const drr_fe_thing &t = m->things[i];
+        if (t.sector < -1 || t.sector >= m->n_sectors) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: thing sector");
+        for (int r = 0; r < (t.rotate ? 8 : 1); r++)
+            if (t.bitmap[r] < 0 || t.bitmap[r] >= (int)S.bitmaps.size()) return fail(ctx, DRR_E_ASSET, "drr_fe_upload_map: thing bitmap id was never uploaded");
+        S.things.push_back(*reinterpret_cast<const fe::Thing *>(&t));
+    }
     if (!ctx->host_only) {
         auto up = [&](auto &dev, const auto &host) -> cudaError_t {
             cudaError_t e = dev.reserve(std::max<size_t>(host.size(), 1));
@@ -1192,6 +1211,7 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
         CU(ctx, up(S.d_sides, S.sides));
         CU(ctx, up(S.d_sectors, S.sectors));
         CU(ctx, up(S.d_bitmaps, S.bitmaps));
+        CU(ctx, up(S.d_things, S.things));
         CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors may be reassigned by the next call
     }
     S.have_map = true;
@@ -1208,6 +1228,8 @@ static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
     m.sides = device ? S.d_sides.p : S.sides.data();
     m.sectors = device ? S.d_sectors.p : S.sectors.data();
     m.bitmaps = device ? S.d_bitmaps.p : S.bitmaps.data();
+    m.things = device ? S.d_things.p : S.things.data();
+    m.nthings = (int)S.things.size();
     m.nnodes = (int)S.nodes.size();
     m.nsegs = (int)S.segs.size();
     m.W = ctx->W;
@@ -1242,8 +1264,6 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     if (n < 0 || (n > 0 && !xya) || first_view_idx < 0 || (int64_t)first_view_idx + n > ctx->max_views || (phases & ~7))
         return fail(ctx, DRR_E_INVALID, "drr_fe_emit_views: bad arguments");
     if (ctx->in_frame || ctx->views.n != 0 || ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_fe_emit_views: frames already recorded (call drr_reset first)");
-    if ((phases & 4) && S.n_things > 0)
-        return fail(ctx, DRR_E_INVALID, "drr_fe_emit_views: DRR_PHASES_MASKED needs the map objects' ordering, which only the host front-end has");
     if (n == 0) return DRR_OK;
     if (!on_host && ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU path");
     const size_t N = (size_t)n, W = (size_t)ctx->W;
@@ -1269,6 +1289,17 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     std::vector<ColRec> hsl_cols;
     std::vector<PlaneRec> hsl_planes;
     FeScratch scr{};
+    // masked phase: room per view for the remembered parts, their columns and the sprites' (a part has at most W columns;
+    // E1M1-class frames remember ~150 parts / ~2.5 W columns, the stress map ~700 / ~12 W)
+    const bool masked = (phases & 4) != 0;
+    const uint32_t cap_renders = masked ? 2048u : 0u, cap_dsegs = masked ? 1024u + (uint32_t)S.things.size() : 0u, cap_mos = masked ? (uint32_t)S.things.size() + 1u : 0u;
+    const uint32_t cap_allcols = masked ? std::max<uint32_t>(32u * (uint32_t)W, 16384u) : 0u;
+    std::vector<fe::RenderRec> hs_renders(cap_renders);
+    std::vector<ColRec> hs_allcols(on_host ? cap_allcols : 0);
+    std::vector<SegRec> hs_dsegs(on_host ? cap_dsegs : 0);
+    std::vector<fe::MoRec> hs_mos(cap_mos);
+    std::vector<int32_t> hs_mo_order(cap_mos);
+    std::vector<int16_t> hs_clips(2 * W);
     if (on_host) {
         hs_hor.resize(W);
         hs_focl.resize(W);
@@ -1286,25 +1317,35 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_cocl.reserve(N * W));
         CU(ctx, S.d_rows.reserve(N * W * 2));
         CU(ctx, S.d_order.reserve(N * S.segs.size()));
-        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p};
+        CU(ctx, S.d_clips.reserve(N * W * 2));
+        if (masked) {
+            CU(ctx, S.d_renders.reserve(N * cap_renders));
+            CU(ctx, S.d_allcols.reserve(N * cap_allcols * 5));
+            CU(ctx, S.d_dsegs.reserve(N * cap_dsegs));
+            CU(ctx, S.d_mos.reserve(N * cap_mos));
+            CU(ctx, S.d_mo_order.reserve(N * cap_mos));
+        }
+        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
+                        S.d_clips.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
     }
     auto host_pass = [&](auto emit_tag, const fe::Out &out, bool slabs) { // the kernel's body, view by view
         constexpr bool EMIT = decltype(emit_tag)::value;
         const fe::Map m = fe_make_map(ctx, false, phases);
         for (size_t i = 0; i < N; i++) {
-            fe::Bases b{0, 0, 0, 0, 0, 0, 0, 0};
+            fe::Bases b{0, 0, 0, 0, 0, 0, {0, 0}};
             fe::Caps cap = unlimited;
             if (EMIT && slabs) {
                 const uint32_t u = (uint32_t)i;
-                b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, (int32_t)i, slab.segs, slab.cols};
+                b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, (int32_t)i, {0, 0}};
                 cap = slab;
             } else if (EMIT) {
                 b = S.h_bases.p[i];
                 if (b.frame < 0) continue;
             }
             fe::Frame<EMIT> fr(m);
-            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data()};
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data(), hs_renders.data(),
+                                hs_allcols.data(), hs_dsegs.data(), hs_mos.data(), hs_mo_order.data(), hs_clips.data(), cap_renders, cap_allcols, cap_dsegs, cap_mos};
             fr.out = out;
             fr.cap = cap;
             fr.run(S.h_views_in.p[i], b);
@@ -1377,11 +1418,11 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     for (size_t i = 0; i < N; i++) {
         const fe::Counts &c = S.h_counts.p[i];
         fe::Bases &b = S.h_bases.p[i];
-        b = fe::Bases{(uint32_t)ops, (uint32_t)segs, (uint32_t)cols, (uint32_t)planes, (uint32_t)parr, -1, c.nsegs, c.ncols};
+        b = fe::Bases{(uint32_t)ops, (uint32_t)segs, (uint32_t)cols, (uint32_t)planes, (uint32_t)parr, -1, {0, 0}};
         if (c.status == fe::FE_HARD) {
             ctx->clear_lists();
             std::fill(ctx->slot_to_frame.begin(), ctx->slot_to_frame.end(), -1);
-            return fail(ctx, c.detail == fe::FED_STACK ? DRR_E_INVALID : DRR_E_ASSET,
+            return fail(ctx, (c.detail == fe::FED_STACK || c.detail == fe::FED_SCRATCH) ? DRR_E_INVALID : DRR_E_ASSET,
                         std::string("drr_fe_emit_views: view ") + std::to_string(i) + ": " + fe_detail_message(c.detail));
         }
         if (status) status[i] = c.status == fe::FE_OK ? DRR_OK : DRR_E_PANIC;

@@ -20,12 +20,12 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
                                                                                  fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab) {
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
-    fe::Bases b = fe::Bases{0, 0, 0, 0, 0, 0, 0, 0};
+    fe::Bases b = fe::Bases{0, 0, 0, 0, 0, 0, {0, 0}};
     fe::Caps cap = fe::Caps{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     if (EMIT) {
         if (slab.ops) {
             const uint32_t u = (uint32_t)v;
-            b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, v, slab.segs, slab.cols};
+            b = fe::Bases{u * slab.ops, u * slab.segs, u * slab.cols, u * slab.planes, u * slab.parr, v, {0, 0}};
             cap = slab;
         } else {
             b = bases[v];
@@ -40,6 +40,16 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     fr.sc.rows[0] = s.rows + 2 * o;
     fr.sc.rows[1] = s.rows + 2 * o + m.W;
     fr.sc.order = s.order + (size_t)v * (size_t)m.nsegs;
+    fr.sc.renders = static_cast<fe::RenderRec *>(s.renders) + (size_t)v * s.cap_renders;
+    fr.sc.allcols = static_cast<ColRec *>(s.allcols) + (size_t)v * s.cap_allcols;
+    fr.sc.dsegs = static_cast<SegRec *>(s.dsegs) + (size_t)v * s.cap_dsegs;
+    fr.sc.mos = static_cast<fe::MoRec *>(s.mos) + (size_t)v * s.cap_mos;
+    fr.sc.mo_order = s.mo_order + (size_t)v * s.cap_mos;
+    fr.sc.clips = s.clips + 2 * o;
+    fr.sc.cap_renders = s.cap_renders;
+    fr.sc.cap_allcols = s.cap_allcols;
+    fr.sc.cap_dsegs = s.cap_dsegs;
+    fr.sc.cap_mos = s.cap_mos;
     fr.out = out;
     fr.cap = cap;
     fr.run(views[v], b);

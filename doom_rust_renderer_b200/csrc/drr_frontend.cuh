@@ -7,8 +7,10 @@
 //   clip_to_viewport, projection        src/renderer/misc.rs:13-161
 //   SidedefVisPlanes                    src/renderer/sidedef_visplanes.rs:41-84
 //   sector lookup                       src/renderer/bsp.rs:9-44
-// Phases covered: A (walls), B (visplanes) and D (deferred masked mid-textures) -- i.e. everything except map objects
-// (sprites, src/renderer/map_objects.rs), which stay on the host front-end (csrc/host/drr_scene.cpp).
+//   draw_map_objects                    src/renderer/map_objects.rs:19-241
+//   BitmapRender ordering predicates    src/renderer/bitmap_render.rs:101-188
+// All four phases: A (walls), B (visplanes), C (map objects: sprite projection, per-sprite clip arrays, depth order,
+// interleave with the masked mid-textures behind them) and D (the remaining masked mid-textures).
 //
 // The code is plain scalar C++ shared by nvcc (device: drr_frontend_kernel in drr_frontend.cu) and the host compiler (the
 // CPU test harness drr_test_fe_emit_views_host, test infrastructure only), so that the list equality with the host
@@ -68,6 +70,14 @@ struct Bitmap {
     int16_t w, h;
     uint32_t opaque;
 };
+struct Thing { // a non-null map object at tic 0 (map_objects.rs:25-50), everything view-independent resolved by the host
+    float x, y, angle;
+    int32_t sector;      // sector_at(position), -1 = outside the map (bsp.rs:9-44)
+    int32_t full_bright; // info.rs state flag
+    int32_t rotate;      // the sprite frame has 8 rotations
+    int32_t bitmap[8];   // index into Map::bitmaps per rotation (entry 0 when !rotate)
+    int16_t top_offset[8];
+};
 struct Map {
     const Node *nodes;
     const SubSector *ssectors;
@@ -76,6 +86,8 @@ struct Map {
     const Side *sides;
     const Sector *sectors;
     const Bitmap *bitmaps;
+    const Thing *things;
+    int nthings;
     int nnodes, nsegs;
     int W, H;
     float ASPECT, GCFX, CFX, CFY; // constants.rs:7-17, derived by drr_ctx_create
@@ -101,14 +113,16 @@ enum : uint32_t { // detail codes (messages: fe_detail_message() in drr_api.cu)
     FED_BITMAP_SLOT,     // emitted bitmap was never uploaded   (hard: DRR_E_ASSET on the host path)
     FED_SKY_UNSET,       // sky visplane but no sky bitmap      (hard: DRR_E_ASSET on the host path)
     FED_CAPACITY,        // a view's lists outgrew its slab     (single-pass mode only: the batch is redone with the count pass)
+    FED_SCRATCH,         // a view outgrew the front-end's working arrays (hard)
+    FED_ROTATION,        // "Invalid rotation"                  map_objects.rs:60-62
+    FED_MO_X,            // map object column outside the screen map_objects.rs:170-176
 };
 
 struct Counts { // per viewpoint, written by the count pass. 40 bytes
     uint32_t nops, nsegs, ncols, nplanes, nparr, reccap;
     uint32_t status, detail;
     uint32_t nrec; // columns that survive clipping (what the bin kernel will actually write; statistics)
-    uint32_t ndeferred, dcols; // of nsegs / ncols: deferred two-sided middle textures, written from the END of the view's ranges
-    uint32_t pad;
+    uint32_t pad[3];
 };
 struct Caps { // how much room a view has (single-pass mode: its slab; two-pass mode: exactly what the count pass found)
     uint32_t ops, segs, cols, planes, parr;
@@ -116,15 +130,37 @@ struct Caps { // how much room a view has (single-pass mode: its slab; two-pass 
 struct Bases { // per viewpoint, written by the host between the passes. 32 bytes
     uint32_t op, seg, col, plane, parr;
     int32_t frame; // recorded frame index, -1 = no frame (panic)
-    uint32_t nsegs, ncols; // the view's totals from the count pass: deferred parts are written from the END of the view's ranges
+    uint32_t pad[2];
 };
 
-// per-viewpoint scratch (global memory): W entries each
+// masked phase only: what the reference keeps per BitmapRender (bitmap_render.rs:29-45) and per visible map object
+struct RenderRec { // 32 bytes
+    float lsx, lsy, lex, ley; // BitmapRender.clipped_line.line
+    uint32_t col0, ncol;      // its columns in Scratch::allcols
+    int32_t dseg;             // its header in Scratch::dsegs (-1: nothing to draw: texture "-")
+    uint32_t flags;           // RF_*
+};
+enum : uint32_t { RF_TWOSIDED = 1, RF_EXT_BOTTOM = 2, RF_EXT_TOP = 4, RF_DRAW_CEILING = 8, RF_DRAWN = 16 };
+struct MoRec { // 16 bytes
+    float vx, vy;  // midpoint of the clipped sprite line (map_objects.rs:222-225)
+    int32_t key;   // `line.start.x as i16` (map_objects.rs:216)
+    int32_t dseg;  // its header in Scratch::dsegs (-1: no column)
+};
+
+// per-viewpoint scratch (global memory)
 struct Scratch {
-    uint8_t *hor_ocl;
+    uint8_t *hor_ocl;              // W entries each: segs.rs:97-99
     int16_t *floor_ocl, *ceil_ocl;
-    uint32_t *rows[2]; // (top, bottom) pairs of the visplane being accumulated: 0 = bottom (floor), 1 = top (ceiling)
+    uint32_t *rows[2]; // W (top, bottom) pairs of the visplane being accumulated: 0 = bottom (floor), 1 = top (ceiling)
     int32_t *order;    // nsegs entries: the map's segs in this view's BSP order
+    // masked phase only
+    RenderRec *renders; // the parts that can clip sprites or are drawn late, in creation order
+    ColRec *allcols;    // their columns, and the sprites' columns
+    SegRec *dsegs;      // headers of what is drawn late (masked mid-textures, sprites), in creation order
+    MoRec *mos;         // the visible map objects
+    int32_t *mo_order;  // their draw order
+    int16_t *clips;     // 2 * W: top_clip, bottom_clip of the sprite being clipped (map_objects.rs:104-106)
+    uint32_t cap_renders, cap_allcols, cap_dsegs, cap_mos;
 };
 
 struct Out { // where the emit pass writes (pointers are the batch's arrays; indices are global)
@@ -148,6 +184,11 @@ FE_HD int32_t as_i32(float f) {
     if (f <= -2147483648.0f) return (int32_t)0x80000000;
     if (f >= 2147483648.0f) return 0x7fffffff;
     return (int32_t)f;
+}
+FE_HD uint8_t as_u8(float f) {
+    if (f != f || f <= 0.0f) return 0;
+    if (f >= 255.0f) return 255;
+    return (uint8_t)f;
 }
 FE_HD int16_t w16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
 
@@ -340,10 +381,9 @@ struct Frame {
     bool open[2];
     int16_t pl_left[2], pl_right[2];
     int16_t pl_flat[2], pl_sky[2], pl_height[2], pl_light;
-    // Deferred two-sided middle textures are drawn after everything else, last created first (mod.rs:124, segs.rs:593-597), and
-    // the host front-end appends a part's header and columns when it is DRAWN.  To produce the same arrays, walls fill the
-    // view's seg / column ranges from the front and deferred parts from the back (the first created one ends up last).
-    uint32_t ndeferred, dcols; // deferred parts / their columns so far
+    // Masked phase: parts that can clip sprites or are drawn late are remembered (Scratch::renders / allcols / dsegs) and
+    // drawn -- appended to the output lists -- when the reference draws them (phases C and D at the end of run()).
+    uint32_t nrenders, nallcols, ndsegs, nmos;
 
     FE_HD Frame(const Map &map) : m(map) {}
 
@@ -440,11 +480,13 @@ struct Frame {
         const int16_t H16 = (int16_t)m.H, Hm1 = w16(H16 - 1);
         // is this part's column list ever emitted?  phase A walls are drawn at once (segs.rs:231-258), two-sided middle
         // textures are deferred (phase D, segs.rs:593-597); occlusion-only parts and "-" textures draw nothing
-        const bool wall = !two_sided_mid && !only_occ && (m.phases & 1);
-        const bool deferred = two_sided_mid && (m.phases & 4);
-        const bool keep = (wall || deferred) && tex >= 0;
+        const bool wall = !two_sided_mid && !only_occ && (m.phases & 1) && tex >= 0;       // drawn now: its columns go to the output
+        const bool track = (m.phases & 4) && !only_occ;                                     // remembered: clips sprites / drawn late
+        const bool deferred = two_sided_mid && (m.phases & 4) && tex >= 0;
+        const bool keep = wall || track;
         const bool planes_here = !two_sided_mid && (full_height || only_occ);
-        const uint32_t col0 = n.ncols;
+        const uint32_t col0 = n.ncols, acol0 = nallcols;
+        uint32_t ncol = 0;
         int x_first = 0, x_last = 0;
         const int xe = bottom.ex; // the reference's `for x in start.x..end.x + 1`
 
@@ -518,21 +560,33 @@ struct Frame {
             }
             if (keep) m_col = ballot([&](int l) { return (ev[l] & EV_COL) != 0; });
             // ---- column records, in x order
-            if (m_col && EMIT && n.ncols + (uint32_t)popc32(m_col) > cap.cols) {
-                fail(FE_HARD, FED_CAPACITY);
-                m_col = 0;
+            if (m_col) {
+                const uint32_t cnt = (uint32_t)popc32(m_col);
+                if (wall && EMIT && n.ncols + cnt > cap.cols) {
+                    fail(FE_HARD, FED_CAPACITY);
+                    m_col = 0;
+                } else if (track && nallcols + cnt > sc.cap_allcols) {
+                    fail(FE_HARD, FED_SCRATCH);
+                    m_col = 0;
+                }
             }
             if (m_col) {
-                if (EMIT) {
-                    const uint32_t at = base.col + (n.ncols - dcols); // front cursor; a deferred part's block is moved to the back below
-                    FE_LANES(l) {
-                        if (ev[l] & EV_COL) out.cols[at + (uint32_t)popc32(m_col & below(l))] = col[l];
+                const uint32_t cnt = (uint32_t)popc32(m_col);
+                FE_LANES(l) {
+                    if (ev[l] & EV_COL) {
+                        const uint32_t k = (uint32_t)popc32(m_col & below(l));
+                        if (wall && EMIT) out.cols[base.col + n.ncols + k] = col[l];
+                        if (track) sc.allcols[nallcols + k] = col[l];
                     }
                 }
-                if (n.ncols == col0) x_first = c0 + lowest(m_col);
+                if (ncol == 0) x_first = c0 + lowest(m_col);
                 x_last = c0 + highest(m_col);
-                n.ncols += (uint32_t)popc32(m_col);
-                n.nrec += (uint32_t)popc32(m_col); // 0 <= x < W and max(ct, 0) <= min(cb, H - 1) hold for every record
+                ncol += cnt;
+                if (wall) {
+                    n.ncols += cnt;
+                    n.nrec += cnt; // 0 <= x < W and max(ct, 0) <= min(cb, H - 1) hold for every record
+                }
+                if (track) nallcols += cnt;
             }
             // ---- visplane rows: a lane inside an open visplane writes its point, or (0, 0) when it has none.  Visplane
             // `which` is open at lane l when it was open at the chunk's start and no lane below l flushes, or when a lane
@@ -575,70 +629,349 @@ struct Frame {
             }
         }
         flush();
-        const uint32_t ncol = n.ncols - col0;
-        if (!keep || ncol == 0) return;
-        const Bitmap bm = m.bitmaps[tex];
-        if (bm.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
-        if (EMIT && (n.status != FE_OK || n.nsegs + 1 > cap.segs || n.nops + 1 > cap.ops)) return fail(FE_HARD, FED_CAPACITY);
-        if (EMIT) {
-            uint32_t first = base.col + (col0 - dcols); // where the loop above put the columns
-            if (deferred) { // move the block to the back of the view's column range; dst >= src, so go from the top chunk down
-                const uint32_t dst = base.col + base.ncols - dcols - ncol;
-                FE_SYNC();
-                for (uint32_t i0 = (ncol - 1) / 32 * 32;; i0 -= 32) {
-                    PerLane<ColRec> t;
-                    FE_LANES(l) {
-                        if (i0 + (uint32_t)l < ncol) t[l] = out.cols[first + i0 + l];
-                    }
-                    FE_SYNC();
-                    FE_LANES(l) {
-                        if (i0 + (uint32_t)l < ncol) out.cols[dst + i0 + l] = t[l];
-                    }
-                    FE_SYNC();
-                    if (i0 == 0) break;
+        if (!keep || ncol == 0 || n.status != FE_OK) return;
+        SegRec r;
+        if (wall || deferred) {
+            const Bitmap bm = m.bitmaps[tex];
+            if (bm.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
+            r.bitmap_slot = (uint32_t)bm.slot;
+            r.light_level = sec.light;
+            r.phase = (int16_t)(deferred ? 2 : 0); // DRR_PHASE_MASKED / DRR_PHASE_WALL
+            r.lsx = cl.s.x;
+            r.lsy = cl.s.y;
+            r.lex = cl.e.x;
+            r.ley = cl.e.y;
+            r.start_offset = start_offset;
+            r.start_x = bottom.sx;
+            r.end_x = bottom.ex;
+            r.bottom_height = bottom_h;
+            r.top_height = top_h;
+            r.offset_x = w16(as_i16(sd.xoff) + seg_offset);
+            r.offset_y = w16(as_i16(sd.yoff) + w16(offset_y));
+            r.cols_first = base.col + col0;
+            r.n = ncol;
+            r.x0 = (int16_t)x_first;
+            r.x1 = (int16_t)x_last;
+            r.tex_base = bm.base;
+            r.tex_w = bm.w;
+            r.tex_h = bm.h;
+            r.tex_opaque = bm.opaque;
+            r.pad[0] = r.pad[1] = 0;
+        }
+        if (wall) { // segs.rs:231-258: drawn at once
+            if (EMIT && (n.nsegs + 1 > cap.segs || n.nops + 1 > cap.ops)) return fail(FE_HARD, FED_CAPACITY);
+            if (EMIT) {
+                FE_LEADER {
+                    out.segs[base.seg + n.nsegs] = r;
+                    out.ops[base.op + n.nops] = base.seg + n.nsegs;
                 }
-                first = dst;
             }
+            n.nops++;
+            n.nsegs++;
+            // record slots the bin kernel may reserve: one per screen column inside the x range (drr_api.cu: rec_emit_columns)
+            const int lo = x_first > 0 ? x_first : 0, hi = x_last < m.W - 1 ? x_last : m.W - 1;
+            n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
+        }
+        if (track) { // Segs::bitmap_renders.push, segs.rs:332-349
+            if (nrenders + 1 > sc.cap_renders || (deferred && ndsegs + 1 > sc.cap_dsegs)) return fail(FE_HARD, FED_SCRATCH);
+            FE_LEADER {
+                RenderRec rr;
+                rr.lsx = cl.s.x;
+                rr.lsy = cl.s.y;
+                rr.lex = cl.e.x;
+                rr.ley = cl.e.y;
+                rr.col0 = acol0;
+                rr.ncol = ncol;
+                rr.dseg = deferred ? (int32_t)ndsegs : -1;
+                rr.flags = (two_sided_mid ? RF_TWOSIDED : 0u) | ((lower || (!two_sided_mid && full_height)) ? RF_EXT_BOTTOM : 0u) |
+                           ((upper || (!two_sided_mid && full_height)) ? RF_EXT_TOP : 0u) | (draw_ceiling ? RF_DRAW_CEILING : 0u);
+                sc.renders[nrenders] = rr;
+                if (deferred) {
+                    r.cols_first = acol0; // for now: where its columns wait in allcols
+                    sc.dsegs[ndsegs] = r;
+                }
+            }
+            nrenders++;
+            if (deferred) ndsegs++;
+        }
+    }
+
+    // BitmapRender::render for what is drawn late (bitmap_render.rs:101-135): header dsegs[d] and its columns move to the
+    // end of the view's output lists, exactly where the host front-end's drr_emit_columns call puts them.
+    FE_NOINLINE void draw_late(int32_t d) {
+        SegRec r = sc.dsegs[d];
+        const uint32_t ncol = r.n, src = r.cols_first;
+        if (EMIT && (n.nsegs + 1 > cap.segs || n.nops + 1 > cap.ops || n.ncols + ncol > cap.cols)) return fail(FE_HARD, FED_CAPACITY);
+        const int W = m.W, H = m.H;
+        for (uint32_t i0 = 0; i0 < ncol; i0 += 32) {
+            PerLane<ColRec> c;
+            FE_LANES(l) {
+                if (i0 + (uint32_t)l < ncol) {
+                    c[l] = sc.allcols[src + i0 + l];
+                    if (EMIT) out.cols[base.col + n.ncols + i0 + l] = c[l];
+                }
+            }
+            n.nrec += (uint32_t)popc32(ballot([&](int l) { // drr_api.cu: rec_emit_columns
+                if (i0 + (uint32_t)l >= ncol) return false;
+                const ColRec &k = c[l];
+                if (k.x < 0 || k.x >= W) return false;
+                return (k.clipped_top_y > 0 ? (int)k.clipped_top_y : 0) <= ((int)k.clipped_bottom_y < H - 1 ? (int)k.clipped_bottom_y : H - 1);
+            }));
+        }
+        if (EMIT) {
+            FE_LEADER {
+                r.cols_first = base.col + n.ncols;
+                out.segs[base.seg + n.nsegs] = r;
+                out.ops[base.op + n.nops] = base.seg + n.nsegs;
+            }
+        }
+        n.ncols += ncol;
+        n.nsegs++;
+        n.nops++;
+        const int lo = r.x0 > 0 ? r.x0 : 0, hi = r.x1 < W - 1 ? r.x1 : W - 1;
+        n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
+    }
+
+    // bitmap_render.rs:137-165: is the part `rr` behind the view-space point v?
+    FE_HD static bool behind(const RenderRec &rr, V2 v) {
+        const float mn = fminf(rr.lsx, rr.lex), mx = fmaxf(rr.lsx, rr.lex);
+        if (mn > v.x) return true;
+        return mx > v.x && !left_of(v, V2{rr.lsx, rr.lsy}, V2{rr.lex, rr.ley});
+    }
+
+    // Every part in [0, upto) that is a not yet drawn two-sided middle texture and -- when `v` is given -- lies behind v is
+    // drawn now, last created first (the reference iterates its reversed list: mod.rs:124, map_objects.rs:226-232, segs.rs:593-597).
+    FE_NOINLINE void draw_parts_behind(bool all, V2 v) {
+        for (int c0 = ((int)nrenders - 1) / 32 * 32; c0 >= 0 && n.status == FE_OK; c0 -= 32) {
+            PerLane<int32_t> dseg;
+            uint32_t hit = ballot([&](int l) {
+                dseg[l] = -1;
+                if (c0 + l >= (int)nrenders) return false;
+                const RenderRec rr = sc.renders[c0 + l];
+                if (!(rr.flags & RF_TWOSIDED) || (rr.flags & RF_DRAWN)) return false;
+                if (!all && !behind(rr, v)) return false;
+                dseg[l] = rr.dseg;
+                return true;
+            });
+            FE_LANES(l) {
+                if (hit & (1u << l)) sc.renders[c0 + l].flags |= RF_DRAWN;
+            }
+            for (; hit && n.status == FE_OK; hit &= ~(1u << highest(hit))) {
+                const int32_t d = from_lane(dseg, highest(hit));
+                if (d >= 0) draw_late(d);
+            }
+        }
+        FE_SYNC();
+    }
+
+    // The view-independent-state part of one map object (map_objects.rs:40-102): rotation, view transform, field-of-view
+    // clip, screen x.  One lane per object.
+    struct MoPre {
+        float csx, csy, cex, cey, so;
+        int32_t sx, ex, pic; // pic: rotation index into Thing::bitmap
+        int32_t code;        // 0 not visible, 1 go on, 2 "Clipped line x < -0.01", 3 "Invalid rotation"
+    };
+    FE_NOINLINE MoPre mo_pre(const Thing &t, float pangle) const {
+        const float PI_F = 3.14159265358979323846f;
+        MoPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0, 0};
+        float ang = pangle - t.angle - PI_F; // map_objects.rs:44-58
+        ang += PI_F / 16.0f;
+        ang = fmodf(ang, 2.0f * PI_F);
+        if (ang < 0.0f) ang += 2.0f * PI_F;
+        ang = fmodf(ang, 2.0f * PI_F);
+        const uint8_t rotation = as_u8(ang * 8.0f / (2.0f * PI_F));
+        if (rotation > 7) {
+            p.code = 3;
+            return p;
+        }
+        p.pic = t.rotate ? (int32_t)rotation : 0;
+        const Bitmap bm = m.bitmaps[t.bitmap[p.pic]];
+        const V2 vpv = rot(sub(V2{t.x, t.y}, ppos), cos_n, sin_n);
+        const Seg2 line = {V2{vpv.x - 0.0f, vpv.y - (float)w16(-bm.w) / 2.0f}, V2{vpv.x - 0.0f, vpv.y - (float)bm.w / 2.0f}};
+        Seg2 cl;
+        float so;
+        if (!clip_fov(line, &cl, &so)) return p;
+        if (cl.s.x < -0.01f) {
+            p.code = 2;
+            return p;
+        }
+        if (t.sector < 0) return p; // "Thing is outside map"
+        p.csx = cl.s.x;
+        p.csy = cl.s.y;
+        p.cex = cl.e.x;
+        p.cey = cl.e.y;
+        p.so = so;
+        const ScreenX sx = project_x(m, cl);
+        p.sx = sx.sx;
+        p.ex = sx.ex;
+        p.code = 1;
+        return p;
+    }
+
+    // draw_map_objects for one visible object (map_objects.rs:104-214): clip arrays from the parts in front of it, its
+    // columns, its BitmapRender.
+    FE_NOINLINE void map_object(const Thing &t, const MoPre &pre, float vx_unused) {
+        (void)vx_unused;
+        const Bitmap bm = m.bitmaps[t.bitmap[pre.pic]];
+        const Seg2 cl = {{pre.csx, pre.csy}, {pre.cex, pre.cey}};
+        const V2 vpv = rot(sub(V2{t.x, t.y}, ppos), cos_n, sin_n);
+        const Sector sec = m.sectors[t.sector];
+        const int16_t light = t.full_bright ? (int16_t)255 : sec.light;
+        const float ph = pfloor + 41.0f;
+        const int16_t z = sec.floor;
+        float bh = (float)z - ph, th = (float)z + (float)bm.h - 1.0f - ph;
+        bh += (float)t.top_offset[pre.pic] - (float)bm.h;
+        th += (float)t.top_offset[pre.pic] - (float)bm.h;
+        const ScreenX sx = {pre.sx, pre.ex};
+        const ScreenLine bottom = project(m, cl, sx, bh), top = project(m, cl, sx, th);
+        const int W = m.W;
+        const int16_t H16 = (int16_t)m.H, Hm1 = w16(H16 - 1);
+        int16_t *top_clip = sc.clips, *bottom_clip = sc.clips + W;
+        FE_LANES(l) {
+            for (int x = l; x < W; x += 32) {
+                top_clip[x] = (int16_t)-1;
+                bottom_clip[x] = H16;
+            }
+        }
+        FE_SYNC();
+        for (int c0 = 0; c0 < (int)nrenders; c0 += 32) { // min / max: the order of the parts does not matter
+            uint32_t front = ballot([&](int l) { return c0 + l < (int)nrenders && !behind(sc.renders[c0 + l], vpv); });
+            for (; front; front &= front - 1) {
+                const RenderRec rr = sc.renders[c0 + lowest(front)];
+                FE_LANES(l) {
+                    for (uint32_t i = (uint32_t)l; i < rr.ncol; i += 32) { // a part's columns have distinct x
+                        const ColRec c = sc.allcols[rr.col0 + i];
+                        if (rr.flags & RF_TWOSIDED) {
+                            if ((rr.flags & RF_DRAW_CEILING) && c.top_y > top_clip[c.x]) top_clip[c.x] = c.top_y;
+                            if (c.bottom_y < bottom_clip[c.x]) bottom_clip[c.x] = c.bottom_y;
+                        } else {
+                            if ((rr.flags & RF_EXT_BOTTOM) && c.clipped_top_y < bottom_clip[c.x]) bottom_clip[c.x] = c.clipped_top_y;
+                            if ((rr.flags & RF_EXT_TOP) && c.clipped_bottom_y > top_clip[c.x]) top_clip[c.x] = c.clipped_bottom_y;
+                        }
+                    }
+                }
+                FE_SYNC(); // the next part may touch the same columns from other lanes
+            }
+        }
+        // its columns: x in start.x .. end.x, EXCLUSIVE (map_objects.rs:166; quirk Q6), every one recorded
+        const float bd = ((float)bottom.sy - (float)bottom.ey) / ((float)bottom.sx - (float)bottom.ex);
+        const float td = ((float)top.sy - (float)top.ey) / ((float)top.sx - (float)top.ex);
+        const int xs = (int16_t)bottom.sx, xe = (int16_t)bottom.ex;
+        const uint32_t ncol = xe > xs ? (uint32_t)(xe - xs) : 0u;
+        if (ncol && (xs < 0 || xe > W)) return fail(FE_PANIC, FED_MO_X);
+        if (nallcols + ncol > sc.cap_allcols || nmos + 1 > sc.cap_mos || ndsegs + 1 > sc.cap_dsegs) return fail(FE_HARD, FED_SCRATCH);
+        FE_LANES(l) {
+            for (int x = xs + l; x < xe; x += 32) {
+                const int16_t by = as_i16((float)bottom.sy + ((float)(int16_t)x - (float)bottom.sx) * bd);
+                const int16_t ty = as_i16((float)top.sy + ((float)(int16_t)x - (float)top.sx) * td);
+                int16_t ct = ty > top_clip[x] ? ty : top_clip[x], cb = by < bottom_clip[x] ? by : bottom_clip[x];
+                ct = ct < 0 ? (int16_t)0 : ct;
+                cb = Hm1 < cb ? Hm1 : cb;
+                ColRec c;
+                c.x = (int16_t)x;
+                c.clipped_top_y = ct;
+                c.clipped_bottom_y = cb;
+                c.bottom_y = by;
+                c.top_y = ty;
+                sc.allcols[nallcols + (uint32_t)(x - xs)] = c;
+            }
+        }
+        int32_t dseg = -1;
+        if (ncol) {
+            const Bitmap pb = bm;
+            if (pb.slot < 0) return fail(FE_HARD, FED_BITMAP_SLOT);
+            dseg = (int32_t)ndsegs;
             FE_LEADER {
                 SegRec r;
-                r.bitmap_slot = (uint32_t)bm.slot;
-                r.light_level = sec.light;
-                r.phase = (int16_t)(deferred ? 2 : 0); // DRR_PHASE_MASKED / DRR_PHASE_WALL
+                r.bitmap_slot = (uint32_t)pb.slot;
+                r.light_level = light;
+                r.phase = 2;
                 r.lsx = cl.s.x;
                 r.lsy = cl.s.y;
                 r.lex = cl.e.x;
                 r.ley = cl.e.y;
-                r.start_offset = start_offset;
+                r.start_offset = pre.so;
                 r.start_x = bottom.sx;
                 r.end_x = bottom.ex;
-                r.bottom_height = bottom_h;
-                r.top_height = top_h;
-                r.offset_x = w16(as_i16(sd.xoff) + seg_offset);
-                r.offset_y = w16(as_i16(sd.yoff) + w16(offset_y));
-                r.cols_first = first;
+                r.bottom_height = bh;
+                r.top_height = th;
+                r.offset_x = 0;
+                r.offset_y = 0;
+                r.cols_first = nallcols;
                 r.n = ncol;
-                r.x0 = (int16_t)x_first;
-                r.x1 = (int16_t)x_last;
-                r.tex_base = bm.base;
-                r.tex_w = bm.w;
-                r.tex_h = bm.h;
-                r.tex_opaque = bm.opaque;
+                r.x0 = (int16_t)xs;
+                r.x1 = (int16_t)(xe - 1);
+                r.tex_base = pb.base;
+                r.tex_w = pb.w;
+                r.tex_h = pb.h;
+                r.tex_opaque = pb.opaque;
                 r.pad[0] = r.pad[1] = 0;
-                const uint32_t si = deferred ? base.seg + base.nsegs - 1 - ndeferred : base.seg + (n.nsegs - ndeferred);
-                out.segs[si] = r;
-                if (wall) out.ops[base.op + n.nops] = si; // deferred parts get their op after the walk
+                sc.dsegs[ndsegs] = r;
+            }
+            ndsegs++;
+            nallcols += ncol;
+        }
+        FE_LEADER {
+            MoRec mo;
+            mo.vx = (cl.s.x + cl.e.x) / 2.0f;
+            mo.vy = (cl.s.y + cl.e.y) / 2.0f;
+            mo.key = (int32_t)as_i16(cl.s.x);
+            mo.dseg = dseg;
+            sc.mos[nmos] = mo;
+        }
+        nmos++;
+        FE_SYNC();
+    }
+
+    // C: draw_map_objects, map_objects.rs:19-241
+    FE_NOINLINE void map_objects(float pangle) {
+        for (int c0 = 0; c0 < m.nthings && n.status == FE_OK; c0 += 32) {
+            PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
+            PerLane<int32_t> p_sx, p_ex, p_pic, p_code;
+            FE_LANES(l) {
+                MoPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0, 0};
+                if (c0 + l < m.nthings) p = mo_pre(m.things[c0 + l], pangle);
+                p_csx[l] = p.csx;
+                p_csy[l] = p.csy;
+                p_cex[l] = p.cex;
+                p_cey[l] = p.cey;
+                p_so[l] = p.so;
+                p_sx[l] = p.sx;
+                p_ex[l] = p.ex;
+                p_pic[l] = p.pic;
+                p_code[l] = p.code;
+            }
+            uint32_t live = ballot([&](int l) { return p_code[l] != 0; });
+            for (; live && n.status == FE_OK; live &= live - 1) {
+                const int src = lowest(live);
+                const MoPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
+                              from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_pic, src), from_lane(p_code, src)};
+                if (p.code == 2) return fail(FE_PANIC, FED_CLIP_X);
+                if (p.code == 3) return fail(FE_PANIC, FED_ROTATION);
+                map_object(m.things[c0 + src], p, 0.0f);
             }
         }
-        if (wall) {
-            n.nops++;
-        } else {
-            ndeferred++;
-            dcols += ncol;
+        if (n.status != FE_OK) return;
+        // stable sort on `start.x as i16`, then reverse (map_objects.rs:216-217): descending key, later objects first among
+        // equal keys.  Rank by counting.
+        FE_LANES(l) {
+            for (uint32_t i = (uint32_t)l; i < nmos; i += 32) {
+                const int32_t ki = sc.mos[i].key;
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < nmos; j++) {
+                    const int32_t kj = sc.mos[j].key;
+                    rank += (kj > ki || (kj == ki && j > i)) ? 1u : 0u;
+                }
+                sc.mo_order[rank] = (int32_t)i;
+            }
         }
-        n.nsegs++;
-        // record slots the bin kernel may reserve: one per screen column inside the x range (drr_api.cu: rec_emit_columns)
-        const int lo = x_first > 0 ? x_first : 0, hi = x_last < m.W - 1 ? x_last : m.W - 1;
-        n.reccap += (uint32_t)(hi - lo + 1 > 0 ? hi - lo + 1 : 0);
+        FE_SYNC();
+        // map_objects.rs:219-239: before each object, the masked mid-textures behind it
+        for (uint32_t k = 0; k < nmos && n.status == FE_OK; k++) {
+            const MoRec mo = sc.mos[sc.mo_order[k]];
+            draw_parts_behind(false, V2{mo.vx, mo.vy});
+            if (mo.dseg >= 0 && n.status == FE_OK) draw_late(mo.dseg);
+        }
     }
 
     // The part of process_seg that touches no per-view state (segs.rs:353-460): the view transform, the clip against the
@@ -735,7 +1068,7 @@ struct Frame {
     // Renderer::render, mod.rs:118-136 (without phase C, the map objects)
     FE_HD void run(const ViewIn &v, const Bases &b) {
         base = b;
-        n = Counts{0, 0, 0, 0, 0, 0, FE_OK, FED_NONE, 0, 0, 0, 0};
+        n = Counts{0, 0, 0, 0, 0, 0, FE_OK, FED_NONE, 0, {0, 0, 0}};
         ppos = V2{v.x, v.y};
         cos_n = v.cos_n;
         sin_n = v.sin_n;
@@ -751,8 +1084,7 @@ struct Frame {
         }
         FE_SYNC();
         open[0] = open[1] = false;
-        ndeferred = 0;
-        dcols = 0;
+        nrenders = nallcols = ndsegs = nmos = 0;
         if (EMIT) {
             FE_LEADER { out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a}; }
         }
@@ -817,7 +1149,7 @@ struct Frame {
             }
         }
         if (n.status != FE_OK) return;
-        if (EMIT && n.nops + n.nplanes + ndeferred > cap.ops) return fail(FE_HARD, FED_CAPACITY);
+        if (EMIT && n.nops + n.nplanes > cap.ops) return fail(FE_HARD, FED_CAPACITY);
         // B: mod.rs:106-116 -- the visplanes in push order, after every wall
         if (EMIT) {
             FE_LANES(l) {
@@ -825,21 +1157,17 @@ struct Frame {
             }
         }
         n.nops += n.nplanes;
-        // D: segs.rs:593-597 -- the deferred two-sided middle textures, last created first (mod.rs:124 reverses the list)
-        if (EMIT) {
-            FE_LANES(l) {
-                for (uint32_t k = (uint32_t)l; k < ndeferred; k += 32) out.ops[base.op + n.nops + k] = base.seg + base.nsegs - ndeferred + k;
-            }
+        if (m.phases & 4) {
+            FE_SYNC();
+            if (m.nthings > 0) map_objects(v.angle);       // C: mod.rs:126-133
+            if (n.status == FE_OK) draw_parts_behind(true, V2{0.0f, 0.0f}); // D: segs.rs:593-597 -- what is left, last created first
         }
-        n.nops += ndeferred;
-        n.ndeferred = ndeferred;
-        n.dcols = dcols;
     }
 };
 
 // ---- single-pass mode: slabs -> dense lists ------------------------------------------------------------------------
 // The emit pass can run WITHOUT a count pass when every view writes into its own fixed-size slab of each array (view v's
-// slab of array A starts at v * cap.A; deferred parts sit at the slab's end).  compact_view then copies a view's lists to
+// slab of array A starts at v * cap.A).  compact_view then copies a view's lists to
 // their final, dense place (the offsets come from an exclusive scan of the counts the emit pass left) and rebases the
 // indices they contain, which yields exactly the arrays the two-pass mode writes.  One warp per view.
 struct Slabs {
@@ -847,25 +1175,19 @@ struct Slabs {
     Caps cap; // per view
 };
 FE_HD void compact_view(const Slabs &sl, uint32_t v, const Counts &c, const Bases &b, const Out &dst) {
-    const uint32_t nwall = c.nsegs - c.ndeferred, wcols = c.ncols - c.dcols;
     const uint32_t s0 = v * sl.cap.segs, c0 = v * sl.cap.cols, o0 = v * sl.cap.ops, p0 = v * sl.cap.planes, r0 = v * sl.cap.parr;
-    // slab index -> final index
-    auto seg_at = [&](uint32_t s) { const uint32_t rel = s - s0; return rel < nwall ? b.seg + rel : b.seg + nwall + (rel - (sl.cap.segs - c.ndeferred)); };
-    auto col_at = [&](uint32_t k) { const uint32_t rel = k - c0; return rel < wcols ? b.col + rel : b.col + wcols + (rel - (sl.cap.cols - c.dcols)); };
     FE_LEADER { dst.views[b.frame] = sl.out.views[v]; }
     FE_LANES(l) {
         for (uint32_t i = (uint32_t)l; i < c.nops; i += 32) {
             const uint32_t op = sl.out.ops[o0 + i];
-            dst.ops[b.op + i] = (op & 0x80000000u) ? (0x80000000u | (b.plane + ((op & 0x7fffffffu) - p0))) : seg_at(op);
+            dst.ops[b.op + i] = (op & 0x80000000u) ? (0x80000000u | (b.plane + ((op & 0x7fffffffu) - p0))) : b.seg + (op - s0);
         }
         for (uint32_t i = (uint32_t)l; i < c.nsegs; i += 32) {
-            const uint32_t s = i < nwall ? s0 + i : s0 + sl.cap.segs - c.ndeferred + (i - nwall);
-            SegRec r = sl.out.segs[s];
-            r.cols_first = col_at(r.cols_first);
+            SegRec r = sl.out.segs[s0 + i];
+            r.cols_first = b.col + (r.cols_first - c0);
             dst.segs[b.seg + i] = r;
         }
-        for (uint32_t i = (uint32_t)l; i < c.ncols; i += 32)
-            dst.cols[b.col + i] = sl.out.cols[i < wcols ? c0 + i : c0 + sl.cap.cols - c.dcols + (i - wcols)];
+        for (uint32_t i = (uint32_t)l; i < c.ncols; i += 32) dst.cols[b.col + i] = sl.out.cols[c0 + i];
         for (uint32_t i = (uint32_t)l; i < c.nplanes; i += 32) {
             PlaneRec p = sl.out.planes[p0 + i];
             p.arr_first = b.parr + (p.arr_first - r0);

@@ -1175,8 +1175,35 @@ int drr_scene_emit_views_device(drr_scene *s, drr_ctx *ctx, int first_view_idx, 
         pick(c.ceil_flat, &o.ceiling_flat, &o.ceiling_is_sky);
         sectors[i] = o;
     }
-    int things = 0;
-    for (const ObjH &mo : s->objects) things += mo.is_null ? 0 : 1;
+    // map objects (map_objects.rs:25-50): sprite frame and sector do not depend on the viewpoint
+    std::vector<drr_fe_thing> things;
+    bool every_view_panics = false;
+    if (phases & DRR_PHASES_MASKED)
+        for (const ObjH &mo : s->objects) {
+            if (mo.is_null) continue;
+            auto sp = s->sprites.find(mo.sprite);
+            if (sp == s->sprites.end() || !sp->second.count(mo.frame)) { // "Unknown frame for sprite": panics before anything view-dependent
+                every_view_panics = true;
+                break;
+            }
+            const SpriteFrame &sf = sp->second[mo.frame];
+            drr_fe_thing t{};
+            t.x = mo.pos.x;
+            t.y = mo.pos.y;
+            t.angle = mo.angle;
+            t.sector = s->sector_at(mo.pos);
+            t.full_bright = mo.full_bright ? 1 : 0;
+            t.rotate = sf.rotate ? 1 : 0;
+            for (int r = 0; r < (sf.rotate ? 8 : 1); r++) {
+                t.bitmap[r] = sf.pics[r].bitmap;
+                t.top_offset[r] = sf.pics[r].top_offset;
+            }
+            things.push_back(t);
+        }
+    if (every_view_panics) {
+        for (int i = 0; status && i < n; i++) status[i] = DRR_E_PANIC;
+        return DRR_OK;
+    }
     drr_fe_map m{};
     m.nodes = nodes.data();
     m.n_nodes = (int32_t)nodes.size();
@@ -1190,7 +1217,8 @@ int drr_scene_emit_views_device(drr_scene *s, drr_ctx *ctx, int first_view_idx, 
     m.n_sidedefs = (int32_t)sides.size();
     m.sectors = sectors.data();
     m.n_sectors = (int32_t)sectors.size();
-    m.n_things = things;
+    m.things = things.data();
+    m.n_things = (int32_t)things.size();
     int rc = drr_fe_upload_map(ctx, &m);
     if (rc == DRR_OK) rc = drr_fe_emit_views(ctx, first_view_idx, xya, n, phases, status);
     if (rc != DRR_OK) s->err = std::string("device front-end: ") + drr_last_error(ctx);

@@ -384,15 +384,20 @@ class Scene:
         self._ck(self.L.drr_scene_emit_views(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, threads, _ptr(status)))
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]  # DRR_E_PANIC
 
-    def emit_views_device(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = 3, first_slot: int = 0):
-        """The same batch with the front-end running ON THE GPU (drr_fe_upload_map + drr_fe_emit_views): walls, visplanes and
-        (for maps without things) masked mid-textures.  The context must be reset first; afterwards ctx.draw() renders."""
+    def emit_views_device(self, ctx: Context, views: np.ndarray, timestamp: float = 0.0, phases: int = PHASES_ALL, first_slot: int = 0,
+                          _on_host: bool = False):
+        """The same batch with the front-end running ON THE GPU (drr_fe_upload_map + drr_fe_emit_views), every phase.  The
+        context must be reset first; afterwards ctx.draw() renders.  `_on_host` (test infrastructure) runs the same per-view
+        code on the CPU into the context's host lists."""
         v = np.ascontiguousarray(np.asarray(views, np.float32).reshape(-1, 3))
         status = np.zeros(len(v), np.int32)
+        if _on_host:
+            self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, first_slot, _ptr(v), 0, timestamp, phases, None))  # map only
+            return ctx.fe_emit_views(v, phases=phases, first_slot=first_slot, _on_host=True)
         self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, _ptr(status)))
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
 
     def upload_map_for_device_front_end(self, ctx: Context, timestamp: float = 0.0):
         """drr_fe_upload_map only (a zero-view drr_scene_emit_views_device)."""
         v = np.zeros((0, 3), np.float32)
-        self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, 0, _ptr(v), 0, timestamp, 3, None))
+        self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, 0, _ptr(v), 0, timestamp, PHASES_ALL, None))

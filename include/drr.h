@@ -161,11 +161,11 @@ int drr_profile_begin(drr_ctx *ctx, int max_steps);
 int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *march_ms_total);
 
 /* ---- device front-end: Renderer::render()'s BSP walk, seg clipping, occlusion arrays and --- */
-/* visplane building for a whole batch of viewpoints ON THE GPU (csrc/drr_frontend.cuh, one thread per viewpoint): the
- * draw lists are written where drr_draw reads them and never cross PCIe.  Covers walls, visplanes and deferred masked
- * mid-textures (src/renderer/mod.rs:69-136, segs.rs:121-597, misc.rs:13-161, sidedef_visplanes.rs); map objects
- * (sprites, src/renderer/map_objects.rs) remain with the host front-end, so DRR_PHASES_MASKED is refused for a map
- * that has things.  The map goes up as flat tables (what the loaders under src/map/ read, names resolved to the handles given to
+/* visplane building, map-object projection / clipping / ordering for a whole batch of viewpoints ON THE GPU
+ * (csrc/drr_frontend.cuh, one warp per viewpoint): the draw lists are written where drr_draw reads them and never cross
+ * PCIe.  Covers every phase: walls, visplanes, map objects, masked mid-textures (src/renderer/mod.rs:69-136,
+ * segs.rs:121-597, misc.rs:13-161, sidedef_visplanes.rs, map_objects.rs:19-241, bitmap_render.rs:101-188).
+ * The map goes up as flat tables (what the loaders under src/map/ read, names resolved to the handles given to
  * drr_upload_bitmap / drr_upload_flat): */
 typedef struct { float x, y, dx, dy; int32_t right, left; } drr_fe_node;            /* src/map/nodes.rs; child >= 0 node, < 0 ~subsector */
 typedef struct { int32_t first_seg, count; } drr_fe_subsector;                      /* src/map/subsectors.rs */
@@ -178,6 +178,14 @@ typedef struct {
     int16_t floor_flat, ceiling_flat;  /* flat ids for the batch's timestamp (animation resolved, flats.rs:103-111); -2 = lump missing */
     int16_t floor_is_sky, ceiling_is_sky; /* the resolved flat's name contains "SKY" (visplanes.rs:89) */
 } drr_fe_sector;
+typedef struct { /* a non-null map object at tic 0 (src/map_objects.rs:25-50, src/info.rs): everything view-independent resolved */
+    float x, y, angle;
+    int32_t sector;        /* the sector its position lies in (src/renderer/bsp.rs:9-44), -1 = outside the map */
+    int32_t full_bright;
+    int32_t rotate;        /* its sprite frame has 8 rotations (src/graphics/sprites.rs:26-97) */
+    int32_t bitmap[8];     /* bitmap id per rotation (entry 0 when !rotate) */
+    int16_t top_offset[8]; /* Picture.top_offset per rotation */
+} drr_fe_thing;
 typedef struct {
     const drr_fe_node *nodes;           int32_t n_nodes;
     const drr_fe_subsector *subsectors; int32_t n_subsectors;
@@ -185,7 +193,7 @@ typedef struct {
     const drr_fe_linedef *linedefs;     int32_t n_linedefs;
     const drr_fe_sidedef *sidedefs;     int32_t n_sidedefs;
     const drr_fe_sector *sectors;       int32_t n_sectors;
-    int32_t n_things;                   /* non-null map objects (the device front-end does not draw them) */
+    const drr_fe_thing *things;         int32_t n_things; /* may be NULL / 0 */
 } drr_fe_map;
 int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *map); /* assets must be uploaded before (ids are resolved here) */
 /* n x Renderer::new(..., player at xya[i], ...).render() on the device, view indices first_view_idx .. +n-1.  Replaces

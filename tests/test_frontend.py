@@ -83,32 +83,31 @@ def test_front_end_code_emits_the_host_front_ends_lists(kind, W, H, n, phases, t
     assert a.stats() == b.stats()
 
 
-def test_front_end_code_masked_mid_textures_and_refusal():
-    """Phase D (deferred two-sided middle textures, last created first) on a map without things; with things the masked phase
-    is refused, because the sprites' ordering lives in the host front-end only."""
-    W, H, n = 320, 200, 200
-    path, gm = common.wad("e1m1")
-    views = _views("e1m1", gm, n)
-    bare = _wad_without_things("e1m1")
-    scene = drr.Scene(bare, "E1M1", W, H)
+@pytest.mark.parametrize("kind,W,H,n,things", [("e1m1", 320, 200, 260, True), ("e1m1", 320, 200, 120, False), ("e1m1", 640, 400, 60, True),
+                                                ("stress", 200, 120, 120, True), ("e1m1", 1280, 800, 24, True)])
+def test_front_end_code_all_phases(kind, W, H, n, things):
+    """Phases C and D: map objects (rotation, projection, clip arrays from the parts in front, depth order, interleave with the
+    masked mid-textures behind each sprite) and the remaining masked mid-textures, last created first -- with and without
+    things in the map."""
+    path, gm = common.wad(kind)
+    views = _views(kind, gm, n)
+    scene = drr.Scene(path if things else _wad_without_things(kind), "E1M1", W, H)
     a = drr.Context(W, H, 0, n, _host_only=True)
     scene.upload_assets(a)
     skipped = scene.emit_views(a, views, phases=7, threads=2)
     b = drr.Context(W, H, 0, n, _host_only=True)
     scene.upload_assets(b)
-    scene.upload_map_for_device_front_end(b)
-    assert b.fe_emit_views(views, phases=7, _on_host=True) == skipped
-    _assert_same_lists(a, b, "no things, all phases")
+    assert scene.emit_views_device(b, views, phases=7, _on_host=True) == skipped
+    _assert_same_lists(a, b, "%s %dx%d all phases, things=%s" % (kind, W, H, things))
     assert a.stats() == b.stats()
     segs = a._list(1, drr.SEG_DTYPE)
-    assert (segs["phase"] == 2).any(), "the walk shows no masked mid-texture: the test would prove nothing"
-    full = drr.Scene(path, "E1M1", W, H)
-    c = drr.Context(W, H, 0, n, _host_only=True)
-    full.upload_assets(c)
-    full.upload_map_for_device_front_end(c)
-    with pytest.raises(drr.DrrError) as e:
-        c.fe_emit_views(views, phases=7, _on_host=True)
-    assert e.value.code == -1 and "host front-end" in str(e.value)
+    assert (segs["phase"] == 2).any(), "the batch shows nothing masked: the test would prove nothing"
+    if things:  # sprites have no texture offsets and their own bitmaps: the batch must contain some
+        bare = drr.Scene(_wad_without_things(kind), "E1M1", W, H)
+        c = drr.Context(W, H, 0, n, _host_only=True)
+        bare.upload_assets(c)
+        bare.emit_views(c, views, phases=7, threads=2)
+        assert a.stats()["seg_headers"] > c.stats()["seg_headers"]
 
 
 PANIC_VIEWS = {  # found by random search (tools: a seg exactly through the eye point makes the reference panic)
@@ -206,7 +205,8 @@ def _compare(ctx, k, ref, what):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,W,H,n,phases,ts", [("e1m1", 320, 200, 700, 3, 0.0), ("e1m1", 1280, 800, 40, 3, 0.4), ("stress", 200, 120, 200, 3, 0.0),
-                                                  ("e1m1", 324, 200, 33, 1, 0.0), ("stress", 1920, 1200, 6, 2, 0.0)])
+                                                  ("e1m1", 324, 200, 33, 1, 0.0), ("stress", 1920, 1200, 6, 2, 0.0), ("e1m1", 320, 200, 500, 7, 0.0),
+                                                  ("e1m1", 640, 400, 64, 7, 0.7), ("stress", 640, 400, 48, 7, 0.0), ("e1m1", 1280, 800, 16, 4, 0.0)])
 def test_device_front_end_lists_equal_host_front_end(kind, W, H, n, phases, ts):
     path, gm = common.wad(kind)
     views = _views(kind, gm, n)
@@ -245,10 +245,10 @@ def test_device_front_end_two_pass_and_overflow_fallback(env, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,W,H,n", [("e1m1", 320, 200, 24), ("e1m1", 1280, 800, 4), ("stress", 640, 400, 6)])
-def test_device_front_end_frames_match_oracle(kind, W, H, n):
-    """viewpoints -> device front-end -> bin kernel -> tile kernel == the oracle's frames, walls + flats + sky (no list ever
-    touches the host)."""
+@pytest.mark.parametrize("kind,W,H,n,phases", [("e1m1", 320, 200, 24, 3), ("e1m1", 1280, 800, 4, 3), ("stress", 640, 400, 6, 3), ("e1m1", 320, 200, 32, 7),
+                                               ("e1m1", 640, 400, 8, 7), ("stress", 1920, 1200, 2, 7)])
+def test_device_front_end_frames_match_oracle(kind, W, H, n, phases):
+    """viewpoints -> device front-end -> bin kernel -> tile kernel == the oracle's frames (no list ever touches the host)."""
     path, gm = common.wad(kind)
     game = orc.Game(path, "E1M1", W, H)
     src = synth_wad.walk_viewpoints(gm, 4096)[:: 4096 // (n + 4)] if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, 64)
@@ -257,29 +257,28 @@ def test_device_front_end_frames_match_oracle(kind, W, H, n):
     ctx = drr.Context(W, H, 0, n)
     scene = drr.Scene(path, "E1M1", W, H)
     scene.upload_assets(ctx)
-    assert scene.emit_views_device(ctx, views, phases=3) == []
+    assert scene.emit_views_device(ctx, views, phases=phases) == []
     ctx.submit()  # nothing to upload: the same as draw()
     ctx.sync()
     crcs = ctx.read_checksums(0, n)
     for k, v in enumerate(views):
-        ref = game.render(float(v[0]), float(v[1]), float(v[2]), phases=3)
+        ref = game.render(float(v[0]), float(v[1]), float(v[2]), phases=phases)
         _compare(ctx, k, ref, "%s %dx%d view %d" % (kind, W, H, k))
         assert int(crcs[k]) == drr.checksum_numpy(ref)
     # a second batch through the same context, other slots first
     ctx.reset()
-    assert scene.emit_views_device(ctx, views[::-1], phases=3) == []
+    assert scene.emit_views_device(ctx, views[::-1], phases=phases) == []
     ctx.draw()
     ctx.sync()
     assert list(ctx.read_checksums(0, n)) == list(crcs[::-1])
 
 
 @pytest.mark.gpu
-def test_device_front_end_skips_panicking_viewpoints_and_masked_mids():
+def test_device_front_end_skips_panicking_viewpoints_all_phases():
     W, H, n = 160, 100, 1500
     path, gm = common.wad("stress")
     views, at = _views_with_panics("stress", gm, n)
-    bare = _wad_without_things("stress")
-    scene = drr.Scene(bare, "E1M1", W, H)
+    scene = drr.Scene(path, "E1M1", W, H)
     a = drr.Context(W, H, 0, n, _host_only=True)
     scene.upload_assets(a)
     skipped = scene.emit_views(a, views, phases=7)
@@ -288,7 +287,7 @@ def test_device_front_end_skips_panicking_viewpoints_and_masked_mids():
     scene.upload_assets(b)
     assert scene.emit_views_device(b, views, phases=7) == skipped
     b.fe_download_lists()
-    _assert_same_lists(a, b, "stress without things, all phases")
+    _assert_same_lists(a, b, "stress, all phases")
     # and the frames: the host front-end's lists through drr_submit in a second context
     c = drr.Context(W, H, 0, n)
     scene.upload_assets(c)
