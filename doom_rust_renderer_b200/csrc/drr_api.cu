@@ -1292,14 +1292,34 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     // masked phase: room per view for the remembered parts, their columns and the sprites' (a part has at most W columns;
     // E1M1-class frames remember ~150 parts / ~2.5 W columns, the stress map ~700 / ~12 W)
     const bool masked = (phases & 4) != 0;
-    const uint32_t cap_renders = masked ? 2048u : 0u, cap_dsegs = masked ? 1024u + (uint32_t)S.things.size() : 0u, cap_mos = masked ? (uint32_t)S.things.size() + 1u : 0u;
-    const uint32_t cap_allcols = masked ? std::max<uint32_t>(32u * (uint32_t)W, 16384u) : 0u;
-    std::vector<fe::RenderRec> hs_renders(cap_renders);
-    std::vector<ColRec> hs_allcols(on_host ? cap_allcols : 0);
-    std::vector<SegRec> hs_dsegs(on_host ? cap_dsegs : 0);
+    auto env_u = [](const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)std::max(1, atoi(e)) : dflt; };
+    uint32_t cap_renders = masked ? env_u("DRR_FE_CAP_RENDERS", 4096u) : 0u, cap_dsegs = masked ? env_u("DRR_FE_CAP_DSEGS", 2048u) + (uint32_t)S.things.size() : 0u;
+    const uint32_t cap_mos = masked ? (uint32_t)S.things.size() + 1u : 0u;
+    uint32_t cap_allcols = masked ? std::max<uint32_t>(env_u("DRR_FE_CAP_ALLCOLS_PER_W", 48u) * (uint32_t)W, 16384u) : 0u;
+    std::vector<fe::RenderRec> hs_renders;
+    std::vector<ColRec> hs_allcols;
+    std::vector<SegRec> hs_dsegs;
     std::vector<fe::MoRec> hs_mos(cap_mos);
     std::vector<int32_t> hs_mo_order(cap_mos);
     std::vector<int16_t> hs_clips(2 * W);
+    auto masked_scratch = [&]() -> int { // (re)allocate the masked phase's working arrays for the current capacities
+        if (on_host) {
+            hs_renders.resize(cap_renders);
+            hs_allcols.resize(cap_allcols);
+            hs_dsegs.resize(cap_dsegs);
+            return DRR_OK;
+        }
+        if (masked) {
+            CU(ctx, S.d_renders.reserve(N * cap_renders));
+            CU(ctx, S.d_allcols.reserve(N * cap_allcols * 5));
+            CU(ctx, S.d_dsegs.reserve(N * cap_dsegs));
+            CU(ctx, S.d_mos.reserve(N * cap_mos));
+            CU(ctx, S.d_mo_order.reserve(N * cap_mos));
+        }
+        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
+                        S.d_clips.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
+        return DRR_OK;
+    };
     if (on_host) {
         hs_hor.resize(W);
         hs_focl.resize(W);
@@ -1318,16 +1338,11 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_rows.reserve(N * W * 2));
         CU(ctx, S.d_order.reserve(N * S.segs.size()));
         CU(ctx, S.d_clips.reserve(N * W * 2));
-        if (masked) {
-            CU(ctx, S.d_renders.reserve(N * cap_renders));
-            CU(ctx, S.d_allcols.reserve(N * cap_allcols * 5));
-            CU(ctx, S.d_dsegs.reserve(N * cap_dsegs));
-            CU(ctx, S.d_mos.reserve(N * cap_mos));
-            CU(ctx, S.d_mo_order.reserve(N * cap_mos));
-        }
-        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
-                        S.d_clips.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    {
+        const int rc = masked_scratch();
+        if (rc) return rc;
     }
     auto host_pass = [&](auto emit_tag, const fe::Out &out, bool slabs) { // the kernel's body, view by view
         constexpr bool EMIT = decltype(emit_tag)::value;
@@ -1354,7 +1369,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     };
     fe::Slabs sl{};
     sl.cap = slab;
-    for (;;) { // at most twice: single-pass, then (on a slab overflow) two-pass
+    for (int attempt = 0;; attempt++) { // again when a view outgrew its slab (then two-pass) or the masked phase's working arrays (then larger ones)
         if (single) {
             if (on_host) {
                 hsl_views.resize(N);
@@ -1392,8 +1407,19 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             if (single) CU(ctx, cudaEventElapsedTime(&S.emit_ms, ctx->ev[2], ctx->ev[3]));
             else CU(ctx, cudaEventElapsedTime(&S.count_ms, ctx->ev[0], ctx->ev[1]));
         }
-        bool overflow = false;
-        for (size_t i = 0; i < N && single; i++) overflow |= S.h_counts.p[i].status == fe::FE_HARD && S.h_counts.p[i].detail == fe::FED_CAPACITY;
+        bool overflow = false, scratch = false;
+        for (size_t i = 0; i < N; i++) {
+            overflow |= single && S.h_counts.p[i].status == fe::FE_HARD && S.h_counts.p[i].detail == fe::FED_CAPACITY;
+            scratch |= S.h_counts.p[i].status == fe::FE_HARD && S.h_counts.p[i].detail == fe::FED_SCRATCH;
+        }
+        if (scratch && attempt < 6 && (uint64_t)N * cap_allcols * 4 * sizeof(ColRec) < (1ull << 34)) {
+            cap_renders *= 4;
+            cap_allcols *= 4;
+            cap_dsegs *= 4;
+            const int rc = masked_scratch();
+            if (rc) return rc;
+            continue;
+        }
         if (!overflow) break;
         single = false; // a view outgrew its slab: size the lists exactly
     }

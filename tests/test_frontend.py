@@ -153,8 +153,9 @@ def test_front_end_single_pass_two_pass_and_slab_overflow_agree(monkeypatch):
     views = _views("e1m1", gm, n)
     scene = drr.Scene(bare, "E1M1", W, H)
     ctxs = []
-    for env, mode in (({}, 1), ({"DRR_FE_TWO_PASS": "1"}, 2), ({"DRR_FE_SLAB_DIV": "64"}, 2)):
-        for k in ("DRR_FE_TWO_PASS", "DRR_FE_SLAB_DIV"):
+    # (the last case starts with working arrays far too small for the masked phase: they are enlarged and the batch redone)
+    for env, mode in (({}, 1), ({"DRR_FE_TWO_PASS": "1"}, 2), ({"DRR_FE_SLAB_DIV": "64"}, 2), ({"DRR_FE_CAP_RENDERS": "16", "DRR_FE_CAP_DSEGS": "2"}, 1)):
+        for k in ("DRR_FE_TWO_PASS", "DRR_FE_SLAB_DIV", "DRR_FE_CAP_RENDERS", "DRR_FE_CAP_DSEGS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -166,7 +167,8 @@ def test_front_end_single_pass_two_pass_and_slab_overflow_agree(monkeypatch):
         ctxs.append(c)
     _assert_same_lists(ctxs[0], ctxs[1], "single-pass vs two-pass")
     _assert_same_lists(ctxs[0], ctxs[2], "single-pass vs overflow fallback")
-    assert ctxs[0].stats() == ctxs[1].stats() == ctxs[2].stats()
+    _assert_same_lists(ctxs[0], ctxs[3], "single-pass vs enlarged working arrays")
+    assert ctxs[0].stats() == ctxs[1].stats() == ctxs[2].stats() == ctxs[3].stats()
 
 
 def test_front_end_state_machine():
