@@ -134,11 +134,12 @@ struct Bases { // per viewpoint, written by the host between the passes. 32 byte
 };
 
 // masked phase only: what the reference keeps per BitmapRender (bitmap_render.rs:29-45) and per visible map object
-struct RenderRec { // 32 bytes
+struct RenderRec { // 36 bytes
     float lsx, lsy, lex, ley; // BitmapRender.clipped_line.line
     uint32_t col0, ncol;      // its columns in Scratch::allcols
     int32_t dseg;             // its header in Scratch::dsegs (-1: nothing to draw: texture "-")
     uint32_t flags;           // RF_*
+    int16_t x0, x1;           // x of its first / last column
 };
 enum : uint32_t { RF_TWOSIDED = 1, RF_EXT_BOTTOM = 2, RF_EXT_TOP = 4, RF_DRAW_CEILING = 8, RF_DRAWN = 16 };
 struct MoRec { // 16 bytes
@@ -683,6 +684,8 @@ struct Frame {
                 rr.col0 = acol0;
                 rr.ncol = ncol;
                 rr.dseg = deferred ? (int32_t)ndsegs : -1;
+                rr.x0 = (int16_t)x_first;
+                rr.x1 = (int16_t)x_last;
                 rr.flags = (two_sided_mid ? RF_TWOSIDED : 0u) | ((lower || (!two_sided_mid && full_height)) ? RF_EXT_BOTTOM : 0u) |
                            ((upper || (!two_sided_mid && full_height)) ? RF_EXT_TOP : 0u) | (draw_ceiling ? RF_DRAW_CEILING : 0u);
                 sc.renders[nrenders] = rr;
@@ -826,21 +829,31 @@ struct Frame {
         const ScreenLine bottom = project(m, cl, sx, bh), top = project(m, cl, sx, th);
         const int W = m.W;
         const int16_t H16 = (int16_t)m.H, Hm1 = w16(H16 - 1);
+        // The clip arrays are only ever read at the sprite's own columns [xs, xe), so only those are initialised and only the
+        // parts whose columns reach into that range are visited (the reference walks every column of every part).
+        const int xs = (int16_t)bottom.sx, xe = (int16_t)bottom.ex;
+        const uint32_t ncol = xe > xs ? (uint32_t)(xe - xs) : 0u;
+        if (ncol && (xs < 0 || xe > W)) return fail(FE_PANIC, FED_MO_X);
         int16_t *top_clip = sc.clips, *bottom_clip = sc.clips + W;
         FE_LANES(l) {
-            for (int x = l; x < W; x += 32) {
+            for (int x = xs + l; x < xe; x += 32) {
                 top_clip[x] = (int16_t)-1;
                 bottom_clip[x] = H16;
             }
         }
         FE_SYNC();
-        for (int c0 = 0; c0 < (int)nrenders; c0 += 32) { // min / max: the order of the parts does not matter
-            uint32_t front = ballot([&](int l) { return c0 + l < (int)nrenders && !behind(sc.renders[c0 + l], vpv); });
+        for (int c0 = 0; c0 < (int)nrenders && ncol; c0 += 32) { // min / max: the order of the parts does not matter
+            uint32_t front = ballot([&](int l) {
+                if (c0 + l >= (int)nrenders) return false;
+                const RenderRec rr = sc.renders[c0 + l];
+                return rr.x1 >= xs && rr.x0 < xe && !behind(rr, vpv);
+            });
             for (; front; front &= front - 1) {
                 const RenderRec rr = sc.renders[c0 + lowest(front)];
                 FE_LANES(l) {
                     for (uint32_t i = (uint32_t)l; i < rr.ncol; i += 32) { // a part's columns have distinct x
                         const ColRec c = sc.allcols[rr.col0 + i];
+                        if (c.x < xs || c.x >= xe) continue;
                         if (rr.flags & RF_TWOSIDED) {
                             if ((rr.flags & RF_DRAW_CEILING) && c.top_y > top_clip[c.x]) top_clip[c.x] = c.top_y;
                             if (c.bottom_y < bottom_clip[c.x]) bottom_clip[c.x] = c.bottom_y;
@@ -856,9 +869,6 @@ struct Frame {
         // its columns: x in start.x .. end.x, EXCLUSIVE (map_objects.rs:166; quirk Q6), every one recorded
         const float bd = ((float)bottom.sy - (float)bottom.ey) / ((float)bottom.sx - (float)bottom.ex);
         const float td = ((float)top.sy - (float)top.ey) / ((float)top.sx - (float)top.ex);
-        const int xs = (int16_t)bottom.sx, xe = (int16_t)bottom.ex;
-        const uint32_t ncol = xe > xs ? (uint32_t)(xe - xs) : 0u;
-        if (ncol && (xs < 0 || xe > W)) return fail(FE_PANIC, FED_MO_X);
         if (nallcols + ncol > sc.cap_allcols || nmos + 1 > sc.cap_mos || ndsegs + 1 > sc.cap_dsegs) return fail(FE_HARD, FED_SCRATCH);
         FE_LANES(l) {
             for (int x = xs + l; x < xe; x += 32) {
