@@ -223,7 +223,9 @@ def test_device_front_end_lists_equal_host_front_end(kind, W, H, n, phases, ts):
     _assert_same_lists(a, b, "%s %dx%d phases %d" % (kind, W, H, phases))
     assert a.stats() == {**b.stats(), "kernel_launches": 0, "device_list_bytes": a.stats()["device_list_bytes"]}
     count_ms, emit_ms = b.fe_last_times()
-    assert count_ms > 0 and emit_ms > 0 and b.fe_last_mode() == (2 if os.environ.get("DRR_FE_TWO_PASS") else 1)
+    assert count_ms > 0 and emit_ms > 0
+    # (the stress map's sprite-heavy views outgrow the per-view slabs: that batch falls back to two passes)
+    assert b.fe_last_mode() == (2 if os.environ.get("DRR_FE_TWO_PASS") or (kind == "stress" and phases & 4) else 1)
 
 
 @pytest.mark.gpu
