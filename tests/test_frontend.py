@@ -302,3 +302,71 @@ def test_device_front_end_skips_panicking_viewpoints_all_phases():
     b.sync()
     assert b.read_checksums(0, n).tobytes() == c.read_checksums(0, n).tobytes()
     assert len(set(b.read_checksums(0, n).tolist())) > n // 2
+
+
+def test_front_end_map_validation():
+    """drr_fe_upload_map checks every index the kernel will follow (so the walk needs no bounds tests) and refuses maps it cannot
+    walk; errors come back as codes, never as a crash."""
+    import ctypes as C
+    L = drr._lib()
+
+    class Node(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("dx", C.c_float), ("dy", C.c_float), ("right", C.c_int32), ("left", C.c_int32)]
+
+    class Sub(C.Structure):
+        _fields_ = [("first", C.c_int32), ("count", C.c_int32)]
+
+    class Seg(C.Structure):
+        _fields_ = [("v1x", C.c_float), ("v1y", C.c_float), ("v2x", C.c_float), ("v2y", C.c_float), ("line", C.c_int32), ("dir", C.c_int16), ("off", C.c_int16)]
+
+    class Line(C.Structure):
+        _fields_ = [("front", C.c_int32), ("back", C.c_int32), ("flags", C.c_int32)]
+
+    class Side(C.Structure):
+        _fields_ = [("xo", C.c_float), ("yo", C.c_float), ("upper", C.c_int32), ("lower", C.c_int32), ("middle", C.c_int32), ("sector", C.c_int32)]
+
+    class Sector(C.Structure):
+        _fields_ = [("f", C.c_int16), ("c", C.c_int16), ("l", C.c_int16), ("sky", C.c_int16), ("ff", C.c_int16), ("cf", C.c_int16), ("fs", C.c_int16), ("cs", C.c_int16)]
+
+    class Thing(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("angle", C.c_float), ("sector", C.c_int32), ("fb", C.c_int32), ("rotate", C.c_int32),
+                    ("bitmap", C.c_int32 * 8), ("top", C.c_int16 * 8)]
+
+    class Map(C.Structure):
+        _fields_ = [("nodes", C.POINTER(Node)), ("n_nodes", C.c_int32), ("subs", C.POINTER(Sub)), ("n_subs", C.c_int32), ("segs", C.POINTER(Seg)), ("n_segs", C.c_int32),
+                    ("lines", C.POINTER(Line)), ("n_lines", C.c_int32), ("sides", C.POINTER(Side)), ("n_sides", C.c_int32),
+                    ("sectors", C.POINTER(Sector)), ("n_sectors", C.c_int32), ("things", C.POINTER(Thing)), ("n_things", C.c_int32)]
+
+    assert (C.sizeof(Node), C.sizeof(Sub), C.sizeof(Seg), C.sizeof(Line), C.sizeof(Side), C.sizeof(Sector), C.sizeof(Thing)) == (24, 8, 24, 12, 24, 16, 72)
+    ctx = drr.Context(64, 40, 0, 4, _host_only=True)
+
+    def good():
+        m = Map()
+        m.nodes, m.n_nodes = (Node * 1)(Node(0, 0, 1, 0, -1, -2)), 1   # children: subsectors 0 and 1
+        m.subs, m.n_subs = (Sub * 2)(Sub(0, 1), Sub(1, 1)), 2
+        m.segs, m.n_segs = (Seg * 2)(Seg(64, -32, 64, 32, 0, 0, 0), Seg(64, 32, 64, -32, 0, 1, 0)), 2
+        m.lines, m.n_lines = (Line * 1)(Line(0, -1, 1)), 1
+        m.sides, m.n_sides = (Side * 1)(Side(0, 0, -1, -1, -1, 0)), 1
+        m.sectors, m.n_sectors = (Sector * 1)(Sector(0, 128, 160, 0, -2, -2, 0, 0)), 1
+        return m
+
+    m = good()
+    assert L.drr_fe_upload_map(ctx.h, C.byref(m)) == 0
+    v = np.array([[0, 0, 0]], np.float32)
+    # a well-formed two-seg map walks: either an (empty) frame or -- a facing wall in a sector whose flat lumps are missing
+    # makes the reference panic in Flats::get -- no frame; never an error
+    assert ctx.fe_emit_views(v, phases=7, _on_host=True) in ([], [0])
+    for breakit, code in ((lambda m: setattr(m.nodes[0], "left", 5), -1), (lambda m: setattr(m.subs[1], "count", 2), -1), (lambda m: setattr(m.segs[0], "line", 1), -1),
+                          (lambda m: setattr(m.lines[0], "front", 3), -1), (lambda m: setattr(m.sides[0], "sector", -1), -1), (lambda m: setattr(m, "n_segs", 0), -1),
+                          (lambda m: setattr(m, "n_things", 1), -1)):
+        m = good()
+        breakit(m)
+        assert L.drr_fe_upload_map(ctx.h, C.byref(m)) == code
+        ctx.reset()
+        with pytest.raises(drr.DrrError):  # a refused map leaves no map behind
+            ctx.fe_emit_views(v, _on_host=True)
+    m = good()
+    t = Thing(0, 0, 0, 0, 0, 0)
+    t.bitmap[0] = 7  # never uploaded
+    m.things, m.n_things = (Thing * 1)(t), 1
+    assert L.drr_fe_upload_map(ctx.h, C.byref(m)) == -5
