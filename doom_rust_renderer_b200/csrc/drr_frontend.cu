@@ -16,7 +16,7 @@ namespace drr {
 // slab.ops != 0: single-pass mode -- no count pass ran, view v writes into its own slab of every array (drr_frontend.cuh:
 // Slabs) and leaves its counts; drr_fe_compact_kernel then makes the lists dense.
 template <bool EMIT>
-__global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel(fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
+__global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel(const __grid_constant__ fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
                                                                                  fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab) {
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
