@@ -411,7 +411,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the draw path has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on the C-level stdout: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if local_rank == 0:
@@ -457,9 +462,14 @@ def main():
                                             "e2e_value", "gpu_launches", "roofline", "lists", "clocks", "host_build_s", "device_front_end", "parity_sample") if k in r2})
         if sec:
             out["secondary"] = sec
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 
