@@ -385,6 +385,11 @@ struct Frame {
     // Masked phase: parts that can clip sprites or are drawn late are remembered (Scratch::renders / allcols / dsegs) and
     // drawn -- appended to the output lists -- when the reference draws them (phases C and D at the end of run()).
     uint32_t nrenders, nallcols, ndsegs, nmos;
+    // Which screen columns are fully occluded (hor_ocl), as a bit mask spread over the lanes: word w (columns 32w .. 32w+31)
+    // lives on lane w % 32, slot w / 32.  A seg all of whose columns are occluded can only re-occlude them and flush
+    // visplanes that are not open (segs.rs:186-330): it is skipped without touching memory.
+    PerLane<uint32_t> occ[4];
+    bool occ_on; // W <= 4096
 
     FE_HD Frame(const Map &map) : m(map) {}
 
@@ -493,7 +498,7 @@ struct Frame {
 
         for (int c0 = bottom.sx; c0 <= xe; c0 += 32) {
             // ---- per column (lane l: x = c0 + l): segs.rs:186-330
-            enum : uint32_t { EV_P0 = 1, EV_P1 = 2, EV_FLUSH = 4, EV_COL = 8 };
+            enum : uint32_t { EV_P0 = 1, EV_P1 = 2, EV_FLUSH = 4, EV_COL = 8, EV_OCC = 16 };
             PerLane<uint32_t> ev, row0, row1;
             PerLane<ColRec> col;
             FE_LANES(l) {
@@ -530,12 +535,12 @@ struct Frame {
                             if (!(e & (EV_P0 | EV_P1))) e |= EV_FLUSH;
                         } else if (planes_here && !in_area && fvo > cvo) {
                             if (bottom_y <= cvo) {
-                                e |= EV_P0;
+                                e |= EV_P0 | EV_OCC;
                                 row0[l] = (uint32_t)(uint16_t)cvo | ((uint32_t)(uint16_t)fvo << 16);
                                 occlude(x);
                             }
                             if (draw_ceiling && top_y >= fvo) {
-                                e |= EV_P1;
+                                e |= EV_P1 | EV_OCC;
                                 row1[l] = (uint32_t)(uint16_t)cvo | ((uint32_t)(uint16_t)fvo << 16);
                                 occlude(x);
                             }
@@ -549,9 +554,23 @@ struct Frame {
                     } else if (planes_here) {
                         e |= EV_FLUSH;
                     }
-                    if (!two_sided_mid && full_height) occlude(x);
+                    if (!two_sided_mid && full_height) {
+                        occlude(x);
+                        e |= EV_OCC;
+                    }
                 }
                 ev[l] = e;
+            }
+            if (occ_on && !two_sided_mid) { // newly occluded columns -> the lanes that own their mask words
+                const uint32_t m_occ = ballot([&](int l) { return (ev[l] & EV_OCC) != 0; });
+                if (m_occ) {
+                    const int w0 = c0 >> 5, sh = c0 & 31;
+                    const uint32_t lo_bits = m_occ << sh, hi_bits = sh ? m_occ >> (32 - sh) : 0u;
+                    FE_LANES(l) {
+                        if ((w0 & 31) == l) occ[(w0 >> 5) & 3][l] |= lo_bits;
+                        if (((w0 + 1) & 31) == l && hi_bits) occ[((w0 + 1) >> 5) & 3][l] |= hi_bits;
+                    }
+                }
             }
             uint32_t m_p0 = 0, m_p1 = 0, m_fl = 0, m_col = 0;
             if (planes_here) {
@@ -984,13 +1003,29 @@ struct Frame {
         }
     }
 
+    FE_HD bool all_occluded(int xs, int xe) { // every column of [xs, xe] is occluded; 0 <= xs <= xe < W
+        const int nslots = (m.W + 1023) >> 10;
+        return ballot([&](int l) {
+            bool ok = true;
+            for (int s = 0; s < nslots; s++) {
+                const int lo = ((s << 5) + l) << 5, hi = lo + 31; // columns of this lane's word in slot s
+                if (xe < lo || xs > hi) continue;
+                const uint32_t from = xs > lo ? (uint32_t)(xs - lo) : 0u, to = xe < hi ? (uint32_t)(xe - lo) : 31u;
+                const uint32_t want = (to == 31u ? 0xffffffffu : (1u << (to + 1u)) - 1u) & ~((1u << from) - 1u);
+                ok = ok && (occ[s][l] & want) == want;
+            }
+            return ok;
+        }) == 0xffffffffu;
+    }
+
     // The part of process_seg that touches no per-view state (segs.rs:353-460): the view transform, the clip against the
     // field of view, the screen x of the ends, the back-face test.  Evaluated for up to 32 segs of a subsector at once
     // (one per lane); the segs that survive go through seg() in order with these values.
     struct SegPre {
         float csx, csy, cex, cey, so; // ClippedLine
         int32_t sx, ex;               // screen x of its ends
-        int32_t code;                 // 0 draws nothing, 1 go on, 2 panics ("Clipped line x < -0.01")
+        int32_t code;                 // 0 draws nothing, 1 go on, 2 panics ("Clipped line x < -0.01"), 4 go on and nothing in its
+                                      // sidedef can panic (no unknown texture, no missing flat): may be skipped when occluded
     };
     FE_NOINLINE SegPre seg_pre(const Seg &sg) const {
         SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
@@ -1015,6 +1050,11 @@ struct Frame {
         p.sx = sx.sx;
         p.ex = sx.ex;
         p.code = sx.sx > sx.ex ? 0 : 1; // back faces draw nothing
+        if (p.code == 1 && sx.sx >= 0) {
+            const Side sd = m.sides[fi];
+            const Sector sec = m.sectors[sd.sector];
+            if (sd.upper != -2 && sd.lower != -2 && sd.middle != -2 && sec.floor_flat >= 0 && sec.ceil_flat >= 0) p.code = 4;
+        }
         return p;
     }
 
@@ -1095,6 +1135,10 @@ struct Frame {
         FE_SYNC();
         open[0] = open[1] = false;
         nrenders = nallcols = ndsegs = nmos = 0;
+        occ_on = m.W <= 4096;
+        FE_LANES(l) {
+            occ[0][l] = occ[1][l] = occ[2][l] = occ[3][l] = 0u;
+        }
         if (EMIT) {
             FE_LEADER { out.views[base.frame] = View{v.x, v.y, pfloor, v.angle, v.cos_a, v.sin_a}; }
         }
@@ -1155,6 +1199,7 @@ struct Frame {
                 const int src = lowest(live);
                 const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
                                from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_code, src)};
+                if (p.code == 4 && occ_on && all_occluded(p.sx, p.ex)) continue; // nothing of it can be seen, and it cannot panic
                 seg(m.segs[from_lane(p_seg, src)], p);
             }
         }
