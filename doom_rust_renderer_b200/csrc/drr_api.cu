@@ -18,6 +18,7 @@
 #include "drr_kernels.h"
 #include "drr_frontend.cuh"
 #include <cmath>
+#include <thread>
 #include <type_traits>
 
 using namespace drr;
@@ -119,6 +120,7 @@ struct Lists {
 // and the count / offset tables of the last batch.
 struct FeState {
     bool have_map = false;
+    uint32_t map_id = 0; // changes with every drr_fe_upload_map (drr_fe_map_id)
     std::vector<fe::Thing> things;
     DevBuf<fe::Thing> d_things;
     DevBuf<fe::RenderRec> d_renders;
@@ -404,6 +406,7 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
     ctx->bitmaps.push_back(r);
     ctx->assets_dirty = true;
+    ctx->fes.have_map = false; // a front-end map holds resolved slots: upload it again after the assets
     return DRR_OK;
 }
 
@@ -415,6 +418,7 @@ int drr_upload_flat(drr_ctx *ctx, int id, const uint8_t px[4096]) {
     ctx->flat_slot[id] = (int)(ctx->flat_pool.size() / 4096);
     ctx->flat_pool.insert(ctx->flat_pool.end(), px, px + 4096);
     ctx->assets_dirty = true;
+    ctx->fes.have_map = false;
     return DRR_OK;
 }
 
@@ -426,7 +430,7 @@ int drr_set_sky(drr_ctx *ctx, int bitmap_id) {
     // draw_sky hard-codes 256x128 (visplanes.rs:49-50); a smaller texture would index out of bounds in the reference
     if (r.w != 256 || r.h != 128) return fail(ctx, DRR_E_ASSET, "drr_set_sky: sky bitmap must be 256x128");
     ctx->sky_slot = it->second;
-    return DRR_OK;
+    return DRR_OK; // (the front-end reads the sky kind at emit time: no need to drop its map)
 }
 
 static int upload_assets(drr_ctx *ctx) {
@@ -1215,8 +1219,11 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
         CU(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors may be reassigned by the next call
     }
     S.have_map = true;
+    static uint32_t next_id = 0; // (process-wide: a new context at a recycled address still gets a fresh id)
+    S.map_id = ++next_id ? next_id : ++next_id;
     return DRR_OK;
 }
+uint32_t drr_fe_map_id(drr_ctx *ctx) { return ctx && ctx->fes.have_map ? ctx->fes.map_id : 0u; }
 
 static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
     const FeState &S = ctx->fes;
@@ -1268,9 +1275,18 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     if (!on_host && ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU path");
     const size_t N = (size_t)n, W = (size_t)ctx->W;
     if (!S.h_views_in.reserve(N) || !S.h_counts.reserve(N) || !S.h_bases.reserve(N)) return fail(ctx, DRR_E_NOMEM, "alloc");
-    for (size_t i = 0; i < N; i++) {
-        const float a = xya[3 * i + 2];
-        S.h_views_in.p[i] = fe::ViewIn{xya[3 * i], xya[3 * i + 1], a, cosf(a), sinf(a), cosf(-a), sinf(-a)};
+    { // host libm per view (the reference's Vertex::rotate calls): four calls each, spread over a few threads for large batches
+        auto fill = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                const float a = xya[3 * i + 2];
+                S.h_views_in.p[i] = fe::ViewIn{xya[3 * i], xya[3 * i + 1], a, cosf(a), sinf(a), cosf(-a), sinf(-a)};
+            }
+        };
+        const size_t nt = N >= 2048 ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(fill, N * t / nt, N * (t + 1) / nt);
+        fill(0, N / nt);
+        for (auto &x : th) x.join();
     }
     const fe::Caps nocap{0, 0, 0, 0, 0}, unlimited{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     fe::Caps slab = fe_slab_caps(ctx);

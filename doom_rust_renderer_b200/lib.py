@@ -86,7 +86,7 @@ def _lib() -> C.CDLL:
             "drr_recorder_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_recorder_frame_end": (i, [vp]),
             "drr_recorder_frame_abort": (i, [vp]), "drr_append": (i, [vp, vp]),
             "drr_fe_upload_map": (i, [vp, vp]), "drr_fe_emit_views": (i, [vp, i, vp, i, i, vp]),
-            "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]), "drr_fe_last_mode": (i, [vp]),
+            "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]), "drr_fe_last_mode": (i, [vp]), "drr_fe_map_id": (C.c_uint32, [vp]),
             "drr_scene_emit_views_device": (i, [vp, vp, i, vp, i, f, i, vp]),
             "drr_test_fe_emit_views_host": (i, [vp, i, vp, i, i, vp]), "drr_test_fe_download_lists": (i, [vp]),
             "drr_test_ctx_create_host_only": (i, [i, i, i, C.POINTER(vp)]),
@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "drr_scene_emit_view", "drr_scene_emit_views",
     "drr_recorder_create", "drr_recorder_destroy", "drr_recorder_last_error", "drr_recorder_frame_begin", "drr_recorder_emit_columns",
     "drr_recorder_emit_visplane", "drr_recorder_frame_end", "drr_recorder_frame_abort", "drr_append",
-    "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_fe_last_mode", "drr_scene_emit_views_device",
+    "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_fe_last_mode", "drr_fe_map_id", "drr_scene_emit_views_device",
 ]
 
 

@@ -196,6 +196,7 @@ typedef struct {
     const drr_fe_thing *things;         int32_t n_things; /* may be NULL / 0 */
 } drr_fe_map;
 int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *map); /* assets must be uploaded before (ids are resolved here) */
+uint32_t drr_fe_map_id(drr_ctx *ctx); /* 0 = no map; otherwise a number that changes with every drr_fe_upload_map (callers cache on it) */
 /* n x Renderer::new(..., player at xya[i], ...).render() on the device, view indices first_view_idx .. +n-1.  Replaces
  * every frame recorded since drr_reset (call drr_reset first); afterwards drr_draw() renders the batch.  status[i]
  * (may be NULL) = DRR_OK or DRR_E_PANIC (the reference would have panicked on that viewpoint: it gets no frame). */
