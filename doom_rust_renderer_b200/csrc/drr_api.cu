@@ -1152,7 +1152,8 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
     // every index the walk follows is checked once here, so the kernel needs no bounds tests
     for (int i = 0; i < m->n_nodes; i++)
         for (int32_t ch : {m->nodes[i].right, m->nodes[i].left})
-            if (ch >= m->n_nodes || (ch < 0 && ~ch >= m->n_subsectors)) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: node child out of range");
+            // (a node lump stores children before their parent, the root last: anything else could be a cycle)
+            if (ch >= i || (ch < 0 && ~ch >= m->n_subsectors)) return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: node child out of range or not before its parent");
     for (int i = 0; i < m->n_subsectors; i++)
         if (m->subsectors[i].first_seg < 0 || m->subsectors[i].count < 0 || (int64_t)m->subsectors[i].first_seg + m->subsectors[i].count > m->n_segs)
             return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: subsector seg range");

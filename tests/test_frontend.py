@@ -356,7 +356,7 @@ def test_front_end_map_validation():
     # a well-formed two-seg map walks: either an (empty) frame or -- a facing wall in a sector whose flat lumps are missing
     # makes the reference panic in Flats::get -- no frame; never an error
     assert ctx.fe_emit_views(v, phases=7, _on_host=True) in ([], [0])
-    for breakit, code in ((lambda m: setattr(m.nodes[0], "left", 5), -1), (lambda m: setattr(m.subs[1], "count", 2), -1), (lambda m: setattr(m.segs[0], "line", 1), -1),
+    for breakit, code in ((lambda m: setattr(m.nodes[0], "left", 5), -1), (lambda m: setattr(m.nodes[0], "left", 0), -1), (lambda m: setattr(m.subs[1], "count", 2), -1), (lambda m: setattr(m.segs[0], "line", 1), -1),
                           (lambda m: setattr(m.lines[0], "front", 3), -1), (lambda m: setattr(m.sides[0], "sector", -1), -1), (lambda m: setattr(m, "n_segs", 0), -1),
                           (lambda m: setattr(m, "n_things", 1), -1)):
         m = good()
