@@ -109,7 +109,7 @@ enum : uint32_t { // detail codes (messages: fe_detail_message() in drr_api.cu)
     FED_NOT_VERTICAL,    // "Wall start not vertical"           segs.rs:159-167
     FED_LINE_X,          // "Invalid line start/end x"          segs.rs:169-184
     FED_FLAT_MISSING,    // flat lump missing                   flats.rs:92-100
-    FED_STACK,           // BSP deeper than the walk stack      (hard)
+    FED_STACK,           // BSP deeper than the walk stack, or subsectors that share segs (hard)
     FED_BITMAP_SLOT,     // emitted bitmap was never uploaded   (hard: DRR_E_ASSET on the host path)
     FED_SKY_UNSET,       // sky visplane but no sky bitmap      (hard: DRR_E_ASSET on the host path)
     FED_CAPACITY,        // a view's lists outgrew its slab     (single-pass mode only: the batch is redone with the count pass)
@@ -1144,16 +1144,47 @@ struct Frame {
         }
         // A: render_node, mod.rs:69-104 -- front subtree, then back subtree (explicit stack instead of the recursion).  The
         // walk itself only decides the ORDER in which the segs are processed (the reference does no occlusion culling in
-        // the tree), so the segs it meets are collected, one per lane, and handled 32 at a time: one lane per seg for the
+        // the tree), so it first lists the segs in that order; they are then taken 32 at a time: one lane per seg for the
         // stateless part (seg_pre), the survivors in order through seg().
-        PerLane<int32_t> pend;
-        int npend = 0;
-        auto process_pending = [&]() {
+        int stack[64];
+        int sp = 0, nord = 0;
+        stack[sp++] = m.nnodes - 1;
+        while (sp > 0) {
+            const int node = stack[--sp];
+            if (node < 0) {
+                const SubSector ss = m.ssectors[~node];
+                if (nord + ss.count > m.nsegs) { // subsectors sharing segs: not a map the loaders produce
+                    fail(FE_HARD, FED_STACK);
+                    break;
+                }
+                FE_LANES(l) {
+                    for (int i = l; i < ss.count; i += 32) sc.order[nord + i] = ss.first + i;
+                }
+                nord += ss.count;
+                continue;
+            }
+            const Node nd = m.nodes[node];
+            const V2 a = {nd.x, nd.y}, bb = {nd.x + nd.dx, nd.y + nd.dy};
+            const bool is_left = left_of(ppos, a, bb);
+            if (sp + 2 > 64) {
+                fail(FE_HARD, FED_STACK);
+                break;
+            }
+            stack[sp++] = is_left ? nd.right : nd.left; // visited second
+            stack[sp++] = is_left ? nd.left : nd.right; // visited first
+        }
+        FE_SYNC();
+        for (int c0 = 0; c0 < nord && n.status == FE_OK; c0 += 32) {
             PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
-            PerLane<int32_t> p_sx, p_ex, p_code;
+            PerLane<int32_t> p_sx, p_ex, p_code, p_seg;
             FE_LANES(l) {
                 SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
-                if (l < npend) p = seg_pre(m.segs[pend[l]]);
+                int si = 0;
+                if (c0 + l < nord) {
+                    si = sc.order[c0 + l];
+                    p = seg_pre(m.segs[si]);
+                }
+                p_seg[l] = si;
                 p_csx[l] = p.csx;
                 p_csy[l] = p.csy;
                 p_cex[l] = p.cex;
@@ -1169,36 +1200,9 @@ struct Frame {
                 const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
                                from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_code, src)};
                 if (p.code == 4 && occ_on && all_occluded(p.sx, p.ex)) continue; // nothing of it can be seen, and it cannot panic
-                seg(m.segs[from_lane(pend, src)], p);
+                seg(m.segs[from_lane(p_seg, src)], p);
             }
-            npend = 0;
-        };
-        int stack[64];
-        int sp = 0;
-        stack[sp++] = m.nnodes - 1;
-        while (sp > 0 && n.status == FE_OK) {
-            const int node = stack[--sp];
-            if (node < 0) {
-                const SubSector ss = m.ssectors[~node];
-                for (int i = 0; i < ss.count && n.status == FE_OK; i++) {
-                    FE_LANES(l) {
-                        if (l == npend) pend[l] = ss.first + i;
-                    }
-                    if (++npend == 32) process_pending();
-                }
-                continue;
-            }
-            const Node nd = m.nodes[node];
-            const V2 a = {nd.x, nd.y}, bb = {nd.x + nd.dx, nd.y + nd.dy};
-            const bool is_left = left_of(ppos, a, bb);
-            if (sp + 2 > 64) {
-                fail(FE_HARD, FED_STACK);
-                break;
-            }
-            stack[sp++] = is_left ? nd.right : nd.left; // visited second
-            stack[sp++] = is_left ? nd.left : nd.right; // visited first
         }
-        if (npend && n.status == FE_OK) process_pending();
         if (n.status != FE_OK) return;
         if (EMIT && n.nops + n.nplanes > cap.ops) return fail(FE_HARD, FED_CAPACITY);
         // B: mod.rs:106-116 -- the visplanes in push order, after every wall
