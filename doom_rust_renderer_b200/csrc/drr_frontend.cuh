@@ -1,7 +1,7 @@
-// drr_frontend.cuh -- the reference's front-end for the DEVICE: BSP walk, seg transform / clip,
-// occlusion arrays and visplane building of one viewpoint, written so that it WRITES the draw lists of include/drr.h's
-// device representation (ops / SegRec / ColRec / PlaneRec / (top, bottom) pairs) instead of drawing.  One thread runs one
-// Renderer::render():
+// drr_frontend.cuh -- the reference's front-end for the DEVICE: BSP walk, seg transform /
+// clip, occlusion arrays, visplane building and the map objects of one viewpoint, written so that it WRITES the draw lists
+// of include/drr.h's device representation (ops / SegRec / ColRec / PlaneRec / (top, bottom) pairs) instead of drawing.
+// One WARP runs one Renderer::render():
 //   Renderer::render / render_node      src/renderer/mod.rs:69-104,118-136
 //   Segs::process_seg / process_sidedef src/renderer/segs.rs:121-590
 //   clip_to_viewport, projection        src/renderer/misc.rs:13-161
@@ -19,9 +19,9 @@
 // -prec-sqrt=true -ftz=false (no contraction, IEEE division / sqrt, denormals kept); cos/sin of the player angle are
 // evaluated by the host libm and passed in (ViewIn), like drr_view.
 //
-// Two passes per viewpoint with the same code: COUNT (EMIT = false) sizes the view's lists, the host turns the counts
-// into offsets, EMIT = true writes.  A viewpoint on which the reference would panic reports FE_PANIC in the count pass
-// and gets no frame.
+// The same code runs in two modes: EMIT = true writes the lists (into per-view slabs in single-pass mode, at exact
+// offsets in two-pass mode), EMIT = false only counts (the first pass of two-pass mode).  A viewpoint on which the
+// reference would panic reports FE_PANIC and gets no frame.
 #pragma once
 #include "drr_device.cuh"
 
@@ -832,8 +832,7 @@ struct Frame {
 
     // draw_map_objects for one visible object (map_objects.rs:104-214): clip arrays from the parts in front of it, its
     // columns, its BitmapRender.
-    FE_NOINLINE void map_object(const Thing &t, const MoPre &pre, float vx_unused) {
-        (void)vx_unused;
+    FE_NOINLINE void map_object(const Thing &t, const MoPre &pre) {
         const Bitmap bm = m.bitmaps[t.bitmap[pre.pic]];
         const Seg2 cl = {{pre.csx, pre.csy}, {pre.cex, pre.cey}};
         const V2 vpv = rot(sub(V2{t.x, t.y}, ppos), cos_n, sin_n);
@@ -977,7 +976,7 @@ struct Frame {
                               from_lane(p_sx, src), from_lane(p_ex, src), from_lane(p_pic, src), from_lane(p_code, src)};
                 if (p.code == 2) return fail(FE_PANIC, FED_CLIP_X);
                 if (p.code == 3) return fail(FE_PANIC, FED_ROTATION);
-                map_object(m.things[c0 + src], p, 0.0f);
+                map_object(m.things[c0 + src], p);
             }
         }
         if (n.status != FE_OK) return;
