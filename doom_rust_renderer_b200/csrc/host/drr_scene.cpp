@@ -170,6 +170,7 @@ struct FlatRef { // a sector flat resolved at load time: either one flat or an a
 };
 struct SectorH {
     int16_t floor, ceil, light;
+    int16_t special = 0, light0 = 0; // sector special (light effects, thinkers.rs:14-76) and the WAD's light level (tic 0)
     FlatRef floor_flat, ceil_flat;
     bool ceil_name_has_sky; // segs.rs:464-469 tests the SECTOR's texture name, not the animated frame's
 };
@@ -199,6 +200,7 @@ struct ObjH {
     bool full_bright, is_null;
     V2 pos;
     float angle;
+    int16_t state = 0, spawn_state = 0; // StateId now / at tic 0 (info.rs STATES)
 };
 
 // ---- per-frame records ---------------------------------------------------------------------------------------------
@@ -259,7 +261,7 @@ struct drr_scene {
     // whether things are wanted)
     uint32_t fe_map_id = 0;
     const void *fe_ctx = nullptr;
-    uint64_t fe_anim = ~0ull;
+    uint64_t fe_anim = ~0ull, fe_world = ~0ull;
     bool fe_things = false;
 
     // per-frame scratch, reused
@@ -450,7 +452,8 @@ struct drr_scene {
             s.floor_flat = flat_ref(fn);
             s.ceil_flat = flat_ref(cn);
             s.ceil_name_has_sky = cn.find("SKY") != std::string::npos;
-            s.light = wad.i16(o + 20);
+            s.light = s.light0 = wad.i16(o + 20);
+            s.special = wad.i16(o + 22);
             sectors.push_back(std::move(s));
         }
         const Lump &lsd = wad.map_lump(name, 3);
@@ -524,7 +527,8 @@ struct drr_scene {
             for (auto &ti : DRR_THING_INFOS)
                 if (ti.doomednum == type) info = &ti;
             if (!info) panic("unknown thing type " + std::to_string(type));
-            objects.push_back({info->sprite, info->frame, info->full_bright != 0, info->is_null != 0, {x, y}, ang});
+            const int16_t spawn = DRR_THING_SPAWN_STATE[info - DRR_THING_INFOS];
+            objects.push_back({info->sprite, info->frame, info->full_bright != 0, info->is_null != 0, {x, y}, ang, spawn, spawn});
         }
     }
 
@@ -642,6 +646,136 @@ struct drr_scene {
             }
             return -1;
         }
+    }
+
+    // ================================================================================================================
+    // the time axis: the world `tic` game ticks after the start of the game (game.rs:456-482)
+    // ================================================================================================================
+    // Sector light effects (lights.rs) and map-object animation (map_objects.rs:63-95) are the two things that change
+    // between tics and reach the draw path (sector light levels; sprite / frame / full-bright of the things).  The
+    // reference seeds them from rand::thread_rng(); here ONE PCG32 stream per (seed) is consumed in the reference's thinker
+    // order -- construction: sector effects in sector order, then the map objects; every tic: the same list order --
+    // with gen_range(lo..hi) = lo + next % (hi - lo).  The oracle defines the same stream (oracle/drr_oracle.cpp: Thinkers).
+    uint32_t world_tic = 0;
+    uint64_t world_seed = 0;
+    uint64_t world_version = 0; // bumped by set_tic: the device front-end's map tables depend on it
+
+    void set_tic(uint32_t tic, uint64_t seed) {
+        uint64_t st = 0, inc = (0xda3e39cb94b95bdbull << 1) | 1u;
+        auto next = [&]() -> uint32_t {
+            const uint64_t old = st;
+            st = old * 6364136223846793005ull + inc;
+            const uint32_t x = (uint32_t)(((old >> 18u) ^ old) >> 27u), r = (uint32_t)(old >> 59u);
+            return (x >> r) | (x << ((32u - r) & 31u));
+        };
+        next();
+        st += seed;
+        next();
+        auto range = [&](int lo, int hi) { return (int16_t)(lo + (int)(next() % (uint32_t)(hi - lo))); };
+
+        for (SectorH &c : sectors) c.light = c.light0;
+        for (ObjH &o : objects) {
+            o.state = o.spawn_state;
+            apply_state(o);
+        }
+        struct Effect {
+            int kind; // 1 flash, 2 strobe, 8 glow, 17 fire
+            int sector;
+            int16_t lo, hi, dark, count;
+            bool up;
+        };
+        auto darkest_neighbour = [&](int sec, int16_t start) { // lights.rs:14-43
+            int16_t m = start;
+            for (const LineH &l : lines) {
+                if (l.front == -1 || l.back == -1) continue;
+                const int fs = sides[l.front].sector, bs = sides[l.back].sector;
+                if (fs == sec) m = std::min(m, sectors[bs].light);
+                if (bs == sec) m = std::min(m, sectors[fs].light);
+            }
+            return m;
+        };
+        std::vector<Effect> fx;
+        for (int i = 0; i < (int)sectors.size(); i++) { // thinkers.rs:14-76
+            const int16_t sp = sectors[i].special, lvl = sectors[i].light;
+            if (sp == 1) {
+                fx.push_back({1, i, darkest_neighbour(i, lvl), lvl, 0, range(1, 65), false}); // LightFlash::new: count in 1..=max_time(64)
+            } else if (sp == 2 || sp == 3 || sp == 4 || sp == 12 || sp == 13) { // StrobeFlash::new
+                int16_t lo = darkest_neighbour(i, lvl);
+                if (lo == lvl) lo = 0;
+                const bool sync = sp == 12 || sp == 13;
+                const int16_t dark = (sp == 3 || sp == 12) ? 35 : 15; // SLOW_DARK / FAST_DARK
+                fx.push_back({2, i, lo, lvl, dark, sync ? (int16_t)1 : range(1, 9), false});
+            } else if (sp == 8) {
+                fx.push_back({8, i, darkest_neighbour(i, lvl), lvl, 0, 0, false}); // GlowingLight::new
+            } else if (sp == 17) {
+                fx.push_back({17, i, (int16_t)(darkest_neighbour(i, lvl) + 16), lvl, 0, 4, false}); // FireFlicker::new
+            }
+        }
+        std::vector<int16_t> mo_count(objects.size());
+        for (size_t i = 0; i < objects.size(); i++) mo_count[i] = DRR_STATES[objects[i].state].tics; // MapObjectThinker::new
+
+        for (uint32_t t = 0; t < tic; t++) {
+            for (Effect &e : fx) {
+                int16_t &lvl = sectors[e.sector].light;
+                if (e.kind == 8) { // lights.rs:192-212, GLOW_SPEED = 8
+                    if (e.up) {
+                        lvl = wrap16(lvl + 8);
+                        if (lvl >= e.hi) {
+                            lvl = wrap16(lvl - 8);
+                            e.up = false;
+                        }
+                    } else {
+                        lvl = wrap16(lvl - 8);
+                        if (lvl <= e.lo) {
+                            lvl = wrap16(lvl + 8);
+                            e.up = true;
+                        }
+                    }
+                    continue;
+                }
+                e.count = wrap16(e.count - 1);
+                if (e.count > 0) continue;
+                if (e.kind == 1) { // lights.rs:81-101: min_time 7, max_time 64
+                    if (lvl == e.hi) {
+                        lvl = e.lo;
+                        e.count = range(1, 8);
+                    } else {
+                        lvl = e.hi;
+                        e.count = range(1, 65);
+                    }
+                } else if (e.kind == 2) { // lights.rs:144-164: STROBE_BRIGHT = 5
+                    if (lvl == e.hi) {
+                        lvl = e.lo;
+                        e.count = e.dark;
+                    } else {
+                        lvl = e.hi;
+                        e.count = 5;
+                    }
+                } else { // lights.rs:242-259
+                    const int16_t amount = (int16_t)(range(0, 4) * 16);
+                    lvl = wrap16(lvl - amount) < e.lo ? e.lo : wrap16(e.hi - amount);
+                    e.count = 4;
+                }
+            }
+            for (size_t i = 0; i < objects.size(); i++) { // map_objects.rs:84-95
+                if (mo_count[i] == -1) continue;
+                mo_count[i] = wrap16(mo_count[i] - 1);
+                if (mo_count[i] > 0) continue;
+                objects[i].state = DRR_STATES[objects[i].state].next;
+                apply_state(objects[i]);
+                mo_count[i] = DRR_STATES[objects[i].state].tics;
+            }
+        }
+        world_tic = tic;
+        world_seed = seed;
+        world_version++;
+    }
+    static void apply_state(ObjH &o) { // MapObject.state -> what the renderer reads (renderer/map_objects.rs:37-63)
+        const DrrState &st = DRR_STATES[o.state];
+        o.sprite = st.sprite;
+        o.frame = st.frame;
+        o.full_bright = st.full_bright != 0;
+        o.is_null = o.state == 0; // S_NULL
     }
 
     // ================================================================================================================
@@ -1073,6 +1207,35 @@ int drr_scene_player_start(drr_scene *s, float out_xya[3]) {
     return DRR_OK;
 }
 
+int drr_scene_set_tic(drr_scene *s, uint32_t tic, uint64_t seed) {
+    if (!s) return DRR_E_INVALID;
+    try {
+        s->set_tic(tic, seed);
+    } catch (const std::exception &e) {
+        s->err = e.what();
+        return DRR_E_NOMEM;
+    }
+    return DRR_OK;
+}
+int drr_scene_world_state(drr_scene *s, int16_t *sector_lights, int32_t *object_states4) {
+    if (!s) return DRR_E_INVALID;
+    for (size_t i = 0; sector_lights && i < s->sectors.size(); i++) sector_lights[i] = s->sectors[i].light;
+    for (size_t i = 0; object_states4 && i < s->objects.size(); i++) {
+        const ObjH &o = s->objects[i];
+        object_states4[4 * i] = o.sprite;
+        object_states4[4 * i + 1] = o.frame;
+        object_states4[4 * i + 2] = o.full_bright;
+        object_states4[4 * i + 3] = o.is_null;
+    }
+    return DRR_OK;
+}
+int drr_scene_counts(drr_scene *s, int *n_sectors, int *n_objects) {
+    if (!s) return DRR_E_INVALID;
+    if (n_sectors) *n_sectors = (int)s->sectors.size();
+    if (n_objects) *n_objects = (int)s->objects.size();
+    return DRR_OK;
+}
+
 int drr_scene_emit_view(drr_scene *s, drr_ctx *ctx, int view_idx, float x, float y, float angle, float timestamp, int phases) {
     if (!s || !ctx) return DRR_E_INVALID;
     try {
@@ -1150,7 +1313,7 @@ int drr_scene_emit_views_device(drr_scene *s, drr_ctx *ctx, int first_view_idx, 
     if (!s || !ctx || n < 0 || (n > 0 && !xya)) return DRR_E_INVALID;
     const uint64_t anim = as_usize(timestamp * 3.0f); // flats.rs:103-111: all that the tables take from the timestamp
     const bool want_things = (phases & DRR_PHASES_MASKED) != 0;
-    if (s->fe_ctx == ctx && s->fe_map_id != 0 && s->fe_map_id == drr_fe_map_id(ctx) && s->fe_anim == anim && s->fe_things == want_things) {
+    if (s->fe_ctx == ctx && s->fe_map_id != 0 && s->fe_map_id == drr_fe_map_id(ctx) && s->fe_anim == anim && s->fe_things == want_things && s->fe_world == s->world_version) {
         const int rc = drr_fe_emit_views(ctx, first_view_idx, xya, n, phases, status); // the context still has this map
         if (rc != DRR_OK) s->err = std::string("device front-end: ") + drr_last_error(ctx);
         return rc;
@@ -1239,6 +1402,7 @@ int drr_scene_emit_views_device(drr_scene *s, drr_ctx *ctx, int first_view_idx, 
         s->fe_ctx = ctx;
         s->fe_map_id = drr_fe_map_id(ctx);
         s->fe_anim = anim;
+        s->fe_world = s->world_version;
         s->fe_things = want_things;
         rc = drr_fe_emit_views(ctx, first_view_idx, xya, n, phases, status);
     }

@@ -88,6 +88,8 @@ def _lib() -> C.CDLL:
             "drr_fe_upload_map": (i, [vp, vp]), "drr_fe_emit_views": (i, [vp, i, vp, i, i, vp]),
             "drr_fe_last_times": (i, [vp, C.POINTER(f), C.POINTER(f)]), "drr_fe_last_mode": (i, [vp]), "drr_fe_map_id": (C.c_uint32, [vp]),
             "drr_scene_emit_views_device": (i, [vp, vp, i, vp, i, f, i, vp]),
+            "drr_scene_set_tic": (i, [vp, C.c_uint32, C.c_uint64]), "drr_scene_counts": (i, [vp, C.POINTER(i), C.POINTER(i)]),
+            "drr_scene_world_state": (i, [vp, vp, vp]),
             "drr_test_fe_emit_views_host": (i, [vp, i, vp, i, i, vp]), "drr_test_fe_download_lists": (i, [vp]),
             "drr_test_ctx_create_host_only": (i, [i, i, i, C.POINTER(vp)]),
             "drr_test_list": (vp, [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -117,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "drr_recorder_create", "drr_recorder_destroy", "drr_recorder_last_error", "drr_recorder_frame_begin", "drr_recorder_emit_columns",
     "drr_recorder_emit_visplane", "drr_recorder_frame_end", "drr_recorder_frame_abort", "drr_append",
     "drr_fe_upload_map", "drr_fe_emit_views", "drr_fe_last_times", "drr_fe_last_mode", "drr_fe_map_id", "drr_scene_emit_views_device",
+    "drr_scene_set_tic", "drr_scene_counts", "drr_scene_world_state",
 ]
 
 
@@ -396,6 +399,19 @@ class Scene:
             return ctx.fe_emit_views(v, phases=phases, first_slot=first_slot, _on_host=True)
         self._ck(self.L.drr_scene_emit_views_device(self.h, ctx.h, first_slot, _ptr(v), len(v), timestamp, phases, _ptr(status)))
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
+
+    def set_tic(self, tic: int, seed: int = 0):
+        """The world `tic` game ticks after the start (sector light effects, map-object animation; random draws from a PCG32
+        stream seeded with `seed`).  tic 0 = the WAD as loaded."""
+        self._ck(self.L.drr_scene_set_tic(self.h, tic, seed))
+
+    def world_state(self):
+        """(sector light levels [n_sectors] int16, object states [n_objects][4] int32 = sprite, frame, full_bright, is S_NULL)."""
+        ns, no = C.c_int(), C.c_int()
+        self._ck(self.L.drr_scene_counts(self.h, C.byref(ns), C.byref(no)))
+        lights, objs = np.zeros(ns.value, np.int16), np.zeros((no.value, 4), np.int32)
+        self._ck(self.L.drr_scene_world_state(self.h, _ptr(lights), _ptr(objs)))
+        return lights, objs
 
     def upload_map_for_device_front_end(self, ctx: Context, timestamp: float = 0.0):
         """drr_fe_upload_map only (a zero-view drr_scene_emit_views_device)."""

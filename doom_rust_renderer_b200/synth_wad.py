@@ -721,7 +721,7 @@ def build_wad(kind: str = "e1m1", seed: int = SEED):
     rng = PCG32(seed)
     palette = make_palette(rng)
     patch_lumps, textures, flats, sprites = make_graphics(rng)
-    if kind == "e1m1":
+    if kind in ("e1m1", "e1m1_time"):
         gm = build_e1m1_class(rng)
     elif kind == "stress":
         gm = build_stress(rng)
@@ -729,6 +729,26 @@ def build_wad(kind: str = "e1m1", seed: int = SEED):
         gm = build_stress(rng, n=6, cell=128)
     else:
         raise ValueError(kind)
+    if kind == "e1m1_time":
+        # the same map for the time axis: every third sector gets a light effect (flash, strobes, glow, synchronised
+        # strobes, fire flicker: thinkers.rs:14-76) and the animated things get the sprite frames their states cycle through
+        # (own generator stream, so that the base content stays what 'e1m1' has)
+        for k, sec in enumerate(gm.sectors):
+            if k % 3 == 1:
+                sec.special = (1, 2, 3, 8, 12, 13, 17, 4)[(k // 3) % 8]
+        rng2 = PCG32(seed + 1)
+        for num, (prefix, rotated, w, h) in sorted(THING_SPRITES.items()):
+            base, lo, to = (num * 13) % 200, w // 2, h - 4
+            frames = {"BAR1": "B", "BON1": "BCD", "POSS": "B", "TROO": "B"}.get(prefix, "")
+            for fi, fr in enumerate(frames):
+                if not rotated:
+                    sprites.append((prefix + fr + "0", encode_picture(_sprite_image(rng2, w, h, base + 17 * (fi + 1), 0), lo, to)))
+                elif prefix == "POSS":
+                    for nm, var in (("1", 1), ("2%s8" % fr, 2), ("3%s7" % fr, 3), ("4%s6" % fr, 4), ("5", 5)):
+                        sprites.append((prefix + fr + nm, encode_picture(_sprite_image(rng2, w, h, base + 17, var), lo, to)))
+                else:
+                    for r in range(1, 9):
+                        sprites.append((prefix + fr + "%d" % r, encode_picture(_sprite_image(rng2, w + (r % 3), h - (r % 2), base + 17, r), lo, to)))
     m = compile_map(gm, rng)
     stats = m.pop("_stats")
 

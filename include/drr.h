@@ -216,6 +216,16 @@ void drr_scene_free(drr_scene *scene);
 const char *drr_scene_last_error(const drr_scene *scene); /* scene may be NULL */
 int drr_scene_upload_assets(drr_scene *scene, drr_ctx *ctx); /* palette, every bitmap/flat the map can reference, sky */
 int drr_scene_player_start(drr_scene *scene, float out_xya[3]); /* Player1Start, src/game.rs:151-157 */
+/* The time axis: put the world `tic` game ticks (1/35 s, src/game.rs:32) after the start of the game -- the
+ * sector light effects (src/lights.rs, src/thinkers.rs:14-76) and the map objects' state machines (src/map_objects.rs:63-95)
+ * stepped tic by tic as Game::tick does (src/game.rs:456-482).  The reference draws its random numbers from
+ * rand::thread_rng(); here they come from one PCG32 stream seeded with `seed`, consumed in the reference's thinker order
+ * (gen_range(lo..hi) = lo + next % (hi - lo)), so a (tic, seed) pair always gives the same world.  tic 0 = the WAD as loaded.
+ * Affects every later drr_scene_emit_* call.  The animated flats follow the `timestamp` argument of those calls. */
+int drr_scene_set_tic(drr_scene *scene, uint32_t tic, uint64_t seed);
+int drr_scene_counts(drr_scene *scene, int *n_sectors, int *n_objects);
+/* sector_lights: n_sectors values; object_states4: n_objects x (sprite index, frame, full_bright, is S_NULL); either may be NULL */
+int drr_scene_world_state(drr_scene *scene, int16_t *sector_lights, int32_t *object_states4);
 #define DRR_PHASES_WALLS 1
 #define DRR_PHASES_PLANES 2
 #define DRR_PHASES_MASKED 4

@@ -485,12 +485,13 @@ struct Thing {
     float x, y, angle;
     int16_t thing_type, flags;
 };
-struct MapObject {  // map_objects.rs:11-17 (spawn-state snapshot only)
+struct MapObject {  // map_objects.rs:11-17; sprite / frame / full_bright / is_null mirror STATES[state]
     int sprite;
     uint8_t frame;
     bool full_bright, is_null;
     Vertex position;
     float angle;
+    int state = 0;  // StateId of the current state (spawn state at tic 0)
 };
 
 struct Map {
@@ -634,7 +635,193 @@ struct Map {
             for (auto &ti : DRR_THING_INFOS)
                 if (ti.doomednum == t.thing_type) info = &ti;
             if (!info) rs_panic("unknown thing type " + std::to_string(t.thing_type));
-            objects.push_back({info->sprite, info->frame, info->full_bright != 0, info->is_null != 0, {t.x, t.y}, t.angle});
+            objects.push_back({info->sprite, info->frame, info->full_bright != 0, info->is_null != 0, {t.x, t.y}, t.angle,
+                               (int)DRR_THING_SPAWN_STATE[info - DRR_THING_INFOS]});
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// The time axis: thinkers.rs, lights.rs, map_objects.rs:63-95, game.rs:456-482.
+// The reference draws its random numbers from rand::thread_rng(), so it is not reproducible from run to run; here every
+// draw comes from ONE PCG32 stream (seed given by the caller), consumed in the reference's own order: thinker construction
+// in list order (sector thinkers in sector order, then the map objects), then list order every tic.
+// gen_range(lo..hi) = lo + next_u32() % (hi - lo).
+// ---------------------------------------------------------------------------------------
+struct Pcg32 {
+    uint64_t state = 0, inc = 1;
+    explicit Pcg32(uint64_t seed) {
+        inc = (0xda3e39cb94b95bdbull << 1) | 1u;
+        next();
+        state += seed;
+        next();
+    }
+    uint32_t next() {
+        uint64_t old = state;
+        state = old * 6364136223846793005ull + inc;
+        uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+    }
+    int16_t gen_range(int lo, int hi) { return (int16_t)(lo + (int)(next() % (uint32_t)(hi - lo))); }
+};
+
+struct Thinkers {
+    enum Kind { LIGHT_FLASH, STROBE_FLASH, GLOWING_LIGHT, FIRE_FLICKER, MAP_OBJECT };
+    struct T {
+        Kind kind;
+        int target;  // sector or map object
+        int16_t min_light = 0, max_light = 0, min_time = 0, max_time = 0, dark_time = 0, bright_time = 0, count = 0;
+        bool going_up = false;
+    };
+    std::vector<T> list;
+
+    // lights.rs:14-43
+    static int16_t find_min_surrounding_light(const Map &map, int sector_id, int16_t max) {
+        int16_t light_level = max;
+        for (const Linedef &l : map.linedefs) {
+            if (l.front_sidedef != -1 && map.sidedefs[l.front_sidedef].sector == sector_id && l.back_sidedef != -1)
+                light_level = std::min(light_level, map.sectors[map.sidedefs[l.back_sidedef].sector].light_level);
+            if (l.back_sidedef != -1 && map.sidedefs[l.back_sidedef].sector == sector_id && l.front_sidedef != -1)
+                light_level = std::min(light_level, map.sectors[map.sidedefs[l.front_sidedef].sector].light_level);
+        }
+        return light_level;
+    }
+
+    void init(Map &map, Pcg32 &rng) {  // thinkers.rs:14-91
+        list.clear();
+        for (int i = 0; i < (int)map.sectors.size(); i++) {
+            const Sector &sec = map.sectors[i];
+            T t{};
+            t.target = i;
+            auto strobe = [&](int16_t dark_time, bool in_sync) {  // lights.rs:112-141
+                t.kind = STROBE_FLASH;
+                t.min_light = find_min_surrounding_light(map, i, sec.light_level);
+                t.max_light = sec.light_level;
+                if (t.min_light == t.max_light) t.min_light = 0;
+                t.count = in_sync ? (int16_t)1 : rng.gen_range(1, 9);
+                t.dark_time = dark_time;
+                t.bright_time = 5;  // STROBE_BRIGHT
+                list.push_back(t);
+            };
+            switch (sec.special_type) {
+            case 1:  // lights.rs:58-78
+                t.kind = LIGHT_FLASH;
+                t.min_light = find_min_surrounding_light(map, i, sec.light_level);
+                t.max_light = sec.light_level;
+                t.min_time = 7;
+                t.max_time = 64;
+                t.count = rng.gen_range(1, t.max_time + 1);
+                list.push_back(t);
+                break;
+            case 2: strobe(15, false); break;   // FAST_DARK
+            case 3: strobe(35, false); break;   // SLOW_DARK
+            case 4: strobe(15, false); break;
+            case 8:  // lights.rs:177-189
+                t.kind = GLOWING_LIGHT;
+                t.min_light = find_min_surrounding_light(map, i, sec.light_level);
+                t.max_light = sec.light_level;
+                t.going_up = false;
+                list.push_back(t);
+                break;
+            case 12: strobe(35, true); break;
+            case 13: strobe(15, true); break;
+            case 17:  // lights.rs:225-239
+                t.kind = FIRE_FLICKER;
+                t.min_light = (int16_t)(find_min_surrounding_light(map, i, sec.light_level) + 16);
+                t.max_light = sec.light_level;
+                t.count = 4;
+                list.push_back(t);
+                break;
+            default: break;
+            }
+        }
+        for (int i = 0; i < (int)map.objects.size(); i++) {  // map_objects.rs:69-74
+            T t{};
+            t.kind = MAP_OBJECT;
+            t.target = i;
+            t.count = DRR_STATES[map.objects[i].state].tics;
+            list.push_back(t);
+        }
+    }
+
+    static void move_to_state(MapObject &mo, T &t, int state) {  // map_objects.rs:76-82
+        mo.state = state;
+        const DrrState &st = DRR_STATES[state];
+        mo.sprite = st.sprite;
+        mo.frame = st.frame;
+        mo.full_bright = st.full_bright != 0;
+        mo.is_null = state == 0;  // renderer/map_objects.rs:37
+        t.count = st.tics;
+    }
+
+    void tick(Map &map, Pcg32 &rng) {  // game.rs:456-460: every thinker's mutate()
+        for (T &t : list) {
+            switch (t.kind) {
+            case LIGHT_FLASH: {  // lights.rs:81-101
+                Sector &sec = map.sectors[t.target];
+                t.count = (int16_t)(t.count - 1);
+                if (t.count > 0) break;
+                if (sec.light_level == t.max_light) {
+                    sec.light_level = t.min_light;
+                    t.count = rng.gen_range(1, t.min_time + 1);
+                } else {
+                    sec.light_level = t.max_light;
+                    t.count = rng.gen_range(1, t.max_time + 1);
+                }
+                break;
+            }
+            case STROBE_FLASH: {  // lights.rs:144-164
+                Sector &sec = map.sectors[t.target];
+                t.count = (int16_t)(t.count - 1);
+                if (t.count > 0) break;
+                if (sec.light_level == t.max_light) {
+                    sec.light_level = t.min_light;
+                    t.count = t.dark_time;
+                } else {
+                    sec.light_level = t.max_light;
+                    t.count = t.bright_time;
+                }
+                break;
+            }
+            case GLOWING_LIGHT: {  // lights.rs:192-212 (GLOW_SPEED 8)
+                Sector &sec = map.sectors[t.target];
+                if (t.going_up) {
+                    sec.light_level = (int16_t)(sec.light_level + 8);
+                    if (sec.light_level >= t.max_light) {
+                        sec.light_level = (int16_t)(sec.light_level - 8);
+                        t.going_up = false;
+                    }
+                } else {
+                    sec.light_level = (int16_t)(sec.light_level - 8);
+                    if (sec.light_level <= t.min_light) {
+                        sec.light_level = (int16_t)(sec.light_level + 8);
+                        t.going_up = true;
+                    }
+                }
+                break;
+            }
+            case FIRE_FLICKER: {  // lights.rs:242-259
+                Sector &sec = map.sectors[t.target];
+                t.count = (int16_t)(t.count - 1);
+                if (t.count > 0) break;
+                const int16_t amount = (int16_t)(rng.gen_range(0, 4) * 16);
+                if ((int16_t)(sec.light_level - amount) < t.min_light)
+                    sec.light_level = t.min_light;
+                else
+                    sec.light_level = (int16_t)(t.max_light - amount);
+                t.count = 4;
+                break;
+            }
+            case MAP_OBJECT: {  // map_objects.rs:84-95
+                if (t.count == -1) break;
+                t.count = (int16_t)(t.count - 1);
+                if (t.count > 0) break;
+                MapObject &mo = map.objects[t.target];
+                move_to_state(mo, t, DRR_STATES[mo.state].next);
+                break;
+            }
+            }
         }
     }
 };
@@ -1401,6 +1588,19 @@ struct Game {
         return "SKY1";
     }
 
+    std::vector<int16_t> light0;      // the WAD's sector light levels (tic 0)
+    std::vector<MapObject> objects0;  // the spawn states (tic 0)
+
+    // game.rs:462-482: `tic` game ticks from the start of the game (thinkers created by init_thinkers, game.rs:193)
+    void set_tic(uint32_t tic, uint64_t seed) {
+        for (size_t i = 0; i < map.sectors.size(); i++) map.sectors[i].light_level = light0[i];
+        map.objects = objects0;
+        Pcg32 rng(seed);
+        Thinkers th;
+        th.init(map, rng);
+        for (uint32_t k = 0; k < tic; k++) th.tick(map, rng);
+    }
+
     void init(std::shared_ptr<WadFile> w, const std::string &name, int W_, int H_) {
         wad = w;
         map_name = name;
@@ -1408,6 +1608,8 @@ struct Game {
         H = H_;
         if (W <= 0 || H <= 0 || W > 32767 || H > 32767) rs_panic("bad screen size");
         map.load(*wad, name);
+        for (auto &sec : map.sectors) light0.push_back(sec.light_level);
+        objects0 = map.objects;
         as.wad = wad.get();
         as.load_palette();
         as.init_flats();
@@ -1519,6 +1721,30 @@ int orc_render(void *gp, float x, float y, float angle, float timestamp, uint8_t
         Player p = g->make_player(x, y, angle);
         g->render(p, timestamp, out, phases, want_trace != 0);
     });
+}
+
+// The world `tic` game ticks (1/35 s, game.rs:32) after the start: sector light effects and map-object animation stepped
+// by the reference's thinkers, random draws from a PCG32 stream seeded with `seed` (see Thinkers).  tic 0 = the WAD.
+int orc_set_tic(void *gp, uint32_t tic, uint64_t seed) {
+    Game *g = (Game *)gp;
+    return guarded([&] { g->set_tic(tic, seed); });
+}
+// sector light levels / map object (sprite, frame, full_bright, is_null) quadruples of the current tic (for the tests)
+int orc_sector_lights(void *gp, int16_t *out) {
+    Game *g = (Game *)gp;
+    for (size_t i = 0; i < g->map.sectors.size(); i++) out[i] = g->map.sectors[i].light_level;
+    return (int)g->map.sectors.size();
+}
+int orc_object_states(void *gp, int32_t *out4) {
+    Game *g = (Game *)gp;
+    for (size_t i = 0; i < g->map.objects.size(); i++) {
+        const MapObject &mo = g->map.objects[i];
+        out4[4 * i] = mo.sprite;
+        out4[4 * i + 1] = mo.frame;
+        out4[4 * i + 2] = mo.full_bright;
+        out4[4 * i + 3] = mo.is_null;
+    }
+    return (int)g->map.objects.size();
 }
 
 // ---- asset export (so a test can upload the very same assets through the C ABI) ----

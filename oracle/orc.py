@@ -38,6 +38,9 @@ def lib() -> C.CDLL:
         L.orc_floor_height_at.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_sector_at.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_render.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int]
+        L.orc_set_tic.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+        L.orc_sector_lights.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_object_states.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_palette.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_bitmap_count.argtypes = [C.c_void_p]
         L.orc_bitmap_size.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -98,6 +101,18 @@ class Game:
 
     def sector_at(self, x, y) -> int:
         return int(self.L.orc_sector_at(self.h, x, y))
+
+    def set_tic(self, tic: int, seed: int = 0):
+        """The world `tic` game ticks after the start (thinkers.rs / lights.rs / map_objects.rs:63-95; PCG32 stream `seed`)."""
+        if self.L.orc_set_tic(self.h, tic, seed) != 0:
+            raise OracleError(self.L.orc_last_error().decode())
+
+    def world_state(self):
+        lights = np.zeros(1 << 16, np.int16)
+        n = self.L.orc_sector_lights(self.h, _p(lights))
+        objs = np.zeros((1 << 16, 4), np.int32)
+        m = self.L.orc_object_states(self.h, _p(objs))
+        return lights[:n].copy(), objs[:m].copy()
 
     def render(self, x, y, angle, timestamp=0.0, phases=PHASE_ALL, trace=False, out=None) -> np.ndarray:
         if out is None:
