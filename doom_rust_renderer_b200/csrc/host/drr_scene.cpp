@@ -655,7 +655,7 @@ struct drr_scene {
     // between tics and reach the draw path (sector light levels; sprite / frame / full-bright of the things).  The
     // reference seeds them from rand::thread_rng(); here ONE PCG32 stream per (seed) is consumed in the reference's thinker
     // order -- construction: sector effects in sector order, then the map objects; every tic: the same list order --
-    // with gen_range(lo..hi) = lo + next % (hi - lo).  The oracle defines the same stream (oracle/drr_oracle.cpp: Thinkers).
+    // with gen_range(lo..hi) = lo + next % (hi - lo).  (include/drr.h: drr_scene_set_tic states the same contract.)
     uint32_t world_tic = 0;
     uint64_t world_seed = 0;
     uint64_t world_version = 0; // bumped by set_tic: the device front-end's map tables depend on it
