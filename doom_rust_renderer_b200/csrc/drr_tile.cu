@@ -253,7 +253,10 @@ __device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, con
 
 // drr_bin_kernel: one thread per (frame, screen column).  Counts what the frame's ops draw in the column, reserves that
 // many records of the frame's range with one atomic, then writes the records in draw order ("column binning").
-__global__ void __launch_bounds__(BIN_THREADS) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
+#ifndef DRR_BIN_MIN_BLOCKS
+#define DRR_BIN_MIN_BLOCKS 3 // 55 registers (tools/sweep_bin_regs.sh: 64 / 55 / 40 / 32 registers -> walk320 bin 0.204 / 0.194 / 0.214 / 0.262 ms)
+#endif
+__global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kernel(DrawArgs a, int frame0, int bpf) {
     const int nthreads = (int)blockDim.x;
     __shared__ uint2 s_tab[BIN_TAB];
     __shared__ uint4 s_rec[BIN_REC * 5]; // the first BIN_REC ops' records: the walk then depends on one global load (the column record) only
