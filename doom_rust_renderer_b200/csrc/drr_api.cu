@@ -18,6 +18,7 @@
 #include "drr_kernels.h"
 #include "drr_frontend.cuh"
 #include <cmath>
+#include <chrono>
 #include <type_traits>
 
 using namespace drr;
@@ -1274,11 +1275,18 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     if (n == 0) return DRR_OK;
     if (!on_host && ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU path");
     const size_t N = (size_t)n, W = (size_t)ctx->W;
+    // DRR_FE_TRACE=1: host-side time line of the call on stderr (where the microseconds between the kernels go)
+    const bool trace = getenv("DRR_FE_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (trace) fprintf(stderr, "drr_fe_emit_views %8.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(), what);
+    };
     if (!S.h_views_in.reserve(N) || !S.h_counts.reserve(N) || !S.h_bases.reserve(N)) return fail(ctx, DRR_E_NOMEM, "alloc");
     for (size_t i = 0; i < N; i++) { // host libm per view (the reference's Vertex::rotate calls): ~4 ns per call, 4 calls per view
         const float a = xya[3 * i + 2];
         S.h_views_in.p[i] = fe::ViewIn{xya[3 * i], xya[3 * i + 1], a, cosf(a), sinf(a), cosf(-a), sinf(-a)};
     }
+    mark("per-view cos/sin done");
     const fe::Caps nocap{0, 0, 0, 0, 0}, unlimited{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     fe::Caps slab = fe_slab_caps(ctx);
     bool single = getenv("DRR_FE_TWO_PASS") == nullptr;
@@ -1409,8 +1417,10 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
         }
         if (!on_host) {
+            mark("front-end kernel launched");
             CU(ctx, cudaMemcpyAsync(S.h_counts.p, S.d_counts.p, N * sizeof(fe::Counts), cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));
+            mark("counts on the host");
             if (single) CU(ctx, cudaEventElapsedTime(&S.emit_ms, ctx->ev[2], ctx->ev[3]));
             else CU(ctx, cudaEventElapsedTime(&S.count_ms, ctx->ev[0], ctx->ev[1]));
         }
@@ -1509,6 +1519,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         return DRR_OK;
     }
     // the dense device lists: sized from the counts
+    mark("offsets computed");
     CU(ctx, ctx->d_views.reserve(nf));
     CU(ctx, ctx->d_ops.reserve(std::max<uint64_t>(ops, 1)));
     CU(ctx, ctx->d_frame_op_base.reserve(nf + 1));
@@ -1533,6 +1544,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->device_lists = true;
     ctx->uploaded_frames = nf;
+    mark("compaction / emit pass launched");
     return DRR_OK;
 }
 
