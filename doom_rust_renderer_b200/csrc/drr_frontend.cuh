@@ -1148,21 +1148,26 @@ struct Frame {
         int stack[64];
         int sp = 0, nord = 0;
         stack[sp++] = m.nnodes - 1;
+        int32_t *const order = sc.order; // (locals: the walk is the hottest uniform loop of the kernel)
+        const Node *const nodes = m.nodes;
+        const SubSector *const ssectors = m.ssectors;
+        const int nsegs = m.nsegs;
         while (sp > 0) {
             const int node = stack[--sp];
             if (node < 0) {
-                const SubSector ss = m.ssectors[~node];
-                if (nord + ss.count > m.nsegs) { // subsectors sharing segs: not a map the loaders produce
+                const SubSector ss = ssectors[~node];
+                if (nord + ss.count > nsegs) { // subsectors sharing segs: not a map the loaders produce
                     fail(FE_HARD, FED_STACK);
                     break;
                 }
                 FE_LANES(l) {
-                    for (int i = l; i < ss.count; i += 32) sc.order[nord + i] = ss.first + i;
+                    if (l < ss.count) order[nord + l] = ss.first + l;
+                    for (int i = l + 32; i < ss.count; i += 32) order[nord + i] = ss.first + i; // (rare: more than 32 segs)
                 }
                 nord += ss.count;
                 continue;
             }
-            const Node nd = m.nodes[node];
+            const Node nd = nodes[node];
             const V2 a = {nd.x, nd.y}, bb = {nd.x + nd.dx, nd.y + nd.dy};
             const bool is_left = left_of(ppos, a, bb);
             if (sp + 2 > 64) {
