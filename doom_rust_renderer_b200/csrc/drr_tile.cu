@@ -442,6 +442,9 @@ __device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, i
         // rows y and y + LPG of this lane together (visplanes.rs:109-128, twice).  The row with vy == 0 (y == H/2 for even H)
         // divides by zero: the loop leaves garbage there (no fault), it is redone below with the IEEE division.
         float2 vy = f2(__fsub_rn(CFY, (float)y), __fsub_rn(CFY, (float)(y + LPG)));
+#ifdef DRR_FLAT_UNROLL2
+#pragma unroll 2
+#endif
         for (; y <= yb; y += 2 * LPG, vy = __fadd2_rn(vy, f2((float)(-2 * LPG))), addr += 8u * LPG) {
             float2 r0;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
