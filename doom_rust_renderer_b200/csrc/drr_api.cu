@@ -159,6 +159,8 @@ struct FeState {
     DevBuf<uint16_t> d_sl_cols;
     DevBuf<PlaneRec> d_sl_planes;
     bool single_pass = false; // how the last batch ran
+    uint32_t scratch_boost = 1; // x4 whenever a batch outgrew the masked phase's working arrays
+    uint32_t slab_boost = 1;  // doubled (up to 8) whenever a batch outgrew its slabs: the next batch of the context gets more room
     float count_ms = 0.0f, emit_ms = 0.0f;
     uint64_t device_list_bytes = 0; // size of the lists the last drr_fe_emit_views wrote on the device
 };
@@ -1260,9 +1262,10 @@ static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
 static fe::Caps fe_slab_caps(const drr_ctx *ctx) {
     // room per view: E1M1-class frames use ~1.3 W column records and ~2.5 W visplane columns, the 1920x1200 stress map
     // ~7.5 W and ~12.5 W; DRR_FE_SLAB_DIV shrinks the slabs (tests: provoke the fallback)
-    uint32_t W = (uint32_t)ctx->W, div = 1;
+    uint32_t W = (uint32_t)ctx->W * ctx->fes.slab_boost, div = 1;
     if (const char *e = getenv("DRR_FE_SLAB_DIV")) div = (uint32_t)std::max(1, atoi(e));
-    return fe::Caps{std::max(8u, 2048u / div), std::max(4u, 1024u / div), std::max(32u, std::max(16u * W, 6144u) / div), std::max(4u, 1024u / div),
+    const uint32_t k = ctx->fes.slab_boost; // the record-count capacities grow with the boost as well
+    return fe::Caps{std::max(8u, 2048u * k / div), std::max(4u, 1024u * k / div), std::max(32u, std::max(16u * W, 6144u) / div), std::max(4u, 1024u * k / div),
                     std::max(32u, std::max(24u * W, 12288u) / div)};
 }
 
@@ -1308,9 +1311,10 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     // E1M1-class frames remember ~150 parts / ~2.5 W columns, the stress map ~700 / ~12 W)
     const bool masked = (phases & 4) != 0;
     auto env_u = [](const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)std::max(1, atoi(e)) : dflt; };
-    uint32_t cap_renders = masked ? env_u("DRR_FE_CAP_RENDERS", 4096u) : 0u, cap_dsegs = masked ? env_u("DRR_FE_CAP_DSEGS", 2048u) + (uint32_t)S.things.size() : 0u;
+    uint32_t cap_renders = masked ? env_u("DRR_FE_CAP_RENDERS", 4096u) * S.scratch_boost : 0u;
+    uint32_t cap_dsegs = masked ? env_u("DRR_FE_CAP_DSEGS", 2048u) * S.scratch_boost + (uint32_t)S.things.size() : 0u;
     const uint32_t cap_mos = masked ? (uint32_t)S.things.size() + 1u : 0u;
-    uint32_t cap_allcols = masked ? std::max<uint32_t>(env_u("DRR_FE_CAP_ALLCOLS_PER_W", 48u) * (uint32_t)W, 16384u) : 0u;
+    uint32_t cap_allcols = masked ? std::max<uint32_t>(env_u("DRR_FE_CAP_ALLCOLS_PER_W", 48u) * (uint32_t)W, 16384u) * S.scratch_boost : 0u;
     std::vector<fe::RenderRec> hs_renders;
     std::vector<ColRec> hs_allcols;
     std::vector<SegRec> hs_dsegs;
@@ -1433,12 +1437,14 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             cap_renders *= 4;
             cap_allcols *= 4;
             cap_dsegs *= 4;
+            if (!getenv("DRR_FE_CAP_RENDERS") && !getenv("DRR_FE_CAP_DSEGS")) S.scratch_boost = std::min(64u, S.scratch_boost * 4u); // the context's next batch starts there
             const int rc = masked_scratch();
             if (rc) return rc;
             continue;
         }
         if (!overflow) break;
-        single = false; // a view outgrew its slab: size the lists exactly
+        single = false; // a view outgrew its slab: size the lists exactly (and give the context's next batch larger slabs)
+        if (!getenv("DRR_FE_SLAB_DIV")) S.slab_boost = std::min(8u, S.slab_boost * 2u);
     }
     // offsets: an exclusive scan over the viewpoints that got a frame
     uint64_t ops = 0, segs = 0, cols = 0, planes = 0, parr = 0, reccap = 0, nrec = 0;
