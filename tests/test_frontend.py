@@ -370,3 +370,37 @@ def test_front_end_map_validation():
     t.bitmap[0] = 7  # never uploaded
     m.things, m.n_things = (Thing * 1)(t), 1
     assert L.drr_fe_upload_map(ctx.h, C.byref(m)) == -5
+
+
+@pytest.mark.gpu
+def test_device_front_end_configs1_full_size():
+    """BASELINE configs[1] at full size (4096 viewpoints of the walk, 320x200, walls + flats + sky): the device front-end's
+    frames equal the host front-end's frame for frame (checksums), a seeded sample of them equals the oracle's pixels, and a
+    second run of the batch is idempotent."""
+    W, H, n = 320, 200, 4096
+    path, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, phases=3)
+    a.submit()
+    want = a.read_checksums(0, n)
+    a.reset()
+    assert scene.emit_views_device(a, views, phases=3) == skipped
+    assert a.fe_last_mode() == 1
+    a.draw()
+    got = a.read_checksums(0, n)
+    ok = np.ones(n, bool)
+    ok[[k for k in skipped]] = False
+    assert (got[ok] == want[ok]).all()
+    assert len(set(got[ok].tolist())) > n // 2
+    game = orc.Game(path, "E1M1", W, H)
+    for k in np.random.default_rng(0xD00D1993).choice(np.nonzero(ok)[0], 12, replace=False):
+        ref = game.render(float(views[k][0]), float(views[k][1]), float(views[k][2]), phases=3)
+        assert int(got[k]) == drr.checksum_numpy(ref), k
+        _compare(a, int(k), ref, "view %d" % k)
+    a.reset()
+    assert scene.emit_views_device(a, views, phases=3) == skipped
+    a.draw()
+    assert (a.read_checksums(0, n) == got).all()
