@@ -1005,15 +1005,14 @@ struct Frame {
     FE_HD bool all_occluded(int xs, int xe) { // every column of [xs, xe] is occluded; 0 <= xs <= xe < W
         const int nslots = (m.W + 1023) >> 10;
         return ballot([&](int l) {
-            bool ok = true;
-            for (int s = 0; s < nslots; s++) {
-                const int lo = ((s << 5) + l) << 5, hi = lo + 31; // columns of this lane's word in slot s
-                if (xe < lo || xs > hi) continue;
-                const uint32_t from = xs > lo ? (uint32_t)(xs - lo) : 0u, to = xe < hi ? (uint32_t)(xe - lo) : 31u;
-                const uint32_t want = (to == 31u ? 0xffffffffu : (1u << (to + 1u)) - 1u) & ~((1u << from) - 1u);
-                ok = ok && (occ[s][l] & want) == want;
+            uint32_t miss = 0;
+            for (int s = 0; s < nslots; s++) { // branch-free per word: the columns of [xs, xe] inside this lane's word of slot s
+                const int lo = ((s << 5) + l) << 5;
+                const int from = xs - lo > 0 ? xs - lo : 0, to = xe - lo < 31 ? xe - lo : 31; // empty when from > to
+                const uint32_t upto = (uint32_t)((2ull << (to < 0 ? 0 : to)) - 1ull), want = from <= to ? upto & ~((1u << (from > 31 ? 31 : from)) - 1u) : 0u;
+                miss |= want & ~occ[s][l];
             }
-            return ok;
+            return miss == 0u;
         }) == 0xffffffffu;
     }
 
