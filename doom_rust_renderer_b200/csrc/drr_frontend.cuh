@@ -847,61 +847,78 @@ struct Frame {
         const ScreenLine bottom = project(m, cl, sx, bh), top = project(m, cl, sx, th);
         const int W = m.W;
         const int16_t H16 = (int16_t)m.H, Hm1 = w16(H16 - 1);
-        // The clip arrays are only ever read at the sprite's own columns [xs, xe), so only those are initialised and only the
-        // parts whose columns reach into that range are visited (the reference walks every column of every part).
+        // The reference builds two [i16; W] clip arrays from EVERY column of every part in front of the sprite
+        // (map_objects.rs:104-160) and then reads them at the sprite's own columns [xs, xe) only.  Here a lane owns one sprite
+        // column and keeps its two clip values in registers: it visits the parts in front whose columns reach into the
+        // sprite's range and looks its own x up in each (a part's columns are sorted by x, usually without gaps).  min / max:
+        // the order of the parts does not matter.
         const int xs = (int16_t)bottom.sx, xe = (int16_t)bottom.ex;
         const uint32_t ncol = xe > xs ? (uint32_t)(xe - xs) : 0u;
         if (ncol && (xs < 0 || xe > W)) return fail(FE_PANIC, FED_MO_X);
-        int16_t *top_clip = sc.clips, *bottom_clip = sc.clips + W;
-        FE_LANES(l) {
-            for (int x = xs + l; x < xe; x += 32) {
-                top_clip[x] = (int16_t)-1;
-                bottom_clip[x] = H16;
-            }
-        }
-        FE_SYNC();
-        for (int c0 = 0; c0 < (int)nrenders && ncol; c0 += 32) { // min / max: the order of the parts does not matter
-            uint32_t front = ballot([&](int l) {
-                if (c0 + l >= (int)nrenders) return false;
-                const RenderRec rr = sc.renders[c0 + l];
-                return rr.x1 >= xs && rr.x0 < xe && !behind(rr, vpv);
-            });
-            for (; front; front &= front - 1) {
-                const RenderRec rr = sc.renders[c0 + lowest(front)];
-                FE_LANES(l) {
-                    for (uint32_t i = (uint32_t)l; i < rr.ncol; i += 32) { // a part's columns have distinct x
-                        const ColRec c = sc.allcols[rr.col0 + i];
-                        if (c.x < xs || c.x >= xe) continue;
-                        if (rr.flags & RF_TWOSIDED) {
-                            if ((rr.flags & RF_DRAW_CEILING) && c.top_y > top_clip[c.x]) top_clip[c.x] = c.top_y;
-                            if (c.bottom_y < bottom_clip[c.x]) bottom_clip[c.x] = c.bottom_y;
-                        } else {
-                            if ((rr.flags & RF_EXT_BOTTOM) && c.clipped_top_y < bottom_clip[c.x]) bottom_clip[c.x] = c.clipped_top_y;
-                            if ((rr.flags & RF_EXT_TOP) && c.clipped_bottom_y > top_clip[c.x]) top_clip[c.x] = c.clipped_bottom_y;
-                        }
-                    }
-                }
-                FE_SYNC(); // the next part may touch the same columns from other lanes
-            }
-        }
+        if (nallcols + ncol > sc.cap_allcols || nmos + 1 > sc.cap_mos || ndsegs + 1 > sc.cap_dsegs) return fail(FE_HARD, FED_SCRATCH);
         // its columns: x in start.x .. end.x, EXCLUSIVE (map_objects.rs:166; quirk Q6), every one recorded
         const float bd = ((float)bottom.sy - (float)bottom.ey) / ((float)bottom.sx - (float)bottom.ex);
         const float td = ((float)top.sy - (float)top.ey) / ((float)top.sx - (float)top.ex);
-        if (nallcols + ncol > sc.cap_allcols || nmos + 1 > sc.cap_mos || ndsegs + 1 > sc.cap_dsegs) return fail(FE_HARD, FED_SCRATCH);
-        FE_LANES(l) {
-            for (int x = xs + l; x < xe; x += 32) {
-                const int16_t by = as_i16((float)bottom.sy + ((float)(int16_t)x - (float)bottom.sx) * bd);
-                const int16_t ty = as_i16((float)top.sy + ((float)(int16_t)x - (float)top.sx) * td);
-                int16_t ct = ty > top_clip[x] ? ty : top_clip[x], cb = by < bottom_clip[x] ? by : bottom_clip[x];
-                ct = ct < 0 ? (int16_t)0 : ct;
-                cb = Hm1 < cb ? Hm1 : cb;
-                ColRec c;
-                c.x = (int16_t)x;
-                c.clipped_top_y = ct;
-                c.clipped_bottom_y = cb;
-                c.bottom_y = by;
-                c.top_y = ty;
-                sc.allcols[nallcols + (uint32_t)(x - xs)] = c;
+        for (int x0 = xs; x0 < xe; x0 += 32) { // 32 sprite columns at a time
+            const int x1 = x0 + 32 < xe ? x0 + 32 : xe; // this chunk: [x0, x1)
+            PerLane<int32_t> top_clip, bottom_clip;
+            FE_LANES(l) {
+                top_clip[l] = -1;
+                bottom_clip[l] = H16;
+            }
+            for (int c0 = 0; c0 < (int)nrenders; c0 += 32) {
+                uint32_t front = ballot([&](int l) {
+                    if (c0 + l >= (int)nrenders) return false;
+                    const RenderRec rr = sc.renders[c0 + l];
+                    return rr.x1 >= x0 && rr.x0 < x1 && !behind(rr, vpv);
+                });
+                for (; front; front &= front - 1) {
+                    const RenderRec rr = sc.renders[c0 + lowest(front)];
+                    const bool dense = (uint32_t)(rr.x1 - rr.x0) + 1u == rr.ncol;
+                    FE_LANES(l) {
+                        const int x = x0 + l;
+                        if (x < x1 && x >= rr.x0 && x <= rr.x1) {
+                            uint32_t i = (uint32_t)(x - rr.x0);
+                            bool found = true;
+                            if (!dense) { // columns hidden behind nearer walls are missing: lower bound on x
+                                uint32_t lo = 0, hi = rr.ncol;
+                                while (lo < hi) {
+                                    const uint32_t mid = (lo + hi) >> 1;
+                                    if (sc.allcols[rr.col0 + mid].x < x) lo = mid + 1; else hi = mid;
+                                }
+                                i = lo;
+                                found = lo < rr.ncol && sc.allcols[rr.col0 + lo].x == x;
+                            }
+                            if (found) {
+                                const ColRec c = sc.allcols[rr.col0 + i];
+                                if (rr.flags & RF_TWOSIDED) { // map_objects.rs:138-158
+                                    if ((rr.flags & RF_DRAW_CEILING) && c.top_y > top_clip[l]) top_clip[l] = c.top_y;
+                                    if (c.bottom_y < bottom_clip[l]) bottom_clip[l] = c.bottom_y;
+                                } else { // :118-136
+                                    if ((rr.flags & RF_EXT_BOTTOM) && c.clipped_top_y < bottom_clip[l]) bottom_clip[l] = c.clipped_top_y;
+                                    if ((rr.flags & RF_EXT_TOP) && c.clipped_bottom_y > top_clip[l]) top_clip[l] = c.clipped_bottom_y;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            FE_LANES(l) {
+                const int x = x0 + l;
+                if (x < x1) {
+                    const int16_t by = as_i16((float)bottom.sy + ((float)(int16_t)x - (float)bottom.sx) * bd);
+                    const int16_t ty = as_i16((float)top.sy + ((float)(int16_t)x - (float)top.sx) * td);
+                    int16_t ct = ty > (int16_t)top_clip[l] ? ty : (int16_t)top_clip[l], cb = by < (int16_t)bottom_clip[l] ? by : (int16_t)bottom_clip[l];
+                    ct = ct < 0 ? (int16_t)0 : ct;
+                    cb = Hm1 < cb ? Hm1 : cb;
+                    ColRec c;
+                    c.x = (int16_t)x;
+                    c.clipped_top_y = ct;
+                    c.clipped_bottom_y = cb;
+                    c.bottom_y = by;
+                    c.top_y = ty;
+                    sc.allcols[nallcols + (uint32_t)(x - xs)] = c;
+                }
             }
         }
         int32_t dseg = -1;
