@@ -128,7 +128,7 @@ struct FeState {
     DevBuf<SegRec> d_dsegs;
     DevBuf<fe::MoRec> d_mos;
     DevBuf<int32_t> d_mo_order;
-    DevBuf<int16_t> d_clips;
+    DevBuf<int32_t> d_dseg_part;
     std::vector<fe::Node> nodes;
     std::vector<fe::SubSector> ssectors;
     std::vector<fe::Seg> segs;
@@ -1320,23 +1320,25 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     std::vector<SegRec> hs_dsegs;
     std::vector<fe::MoRec> hs_mos(cap_mos);
     std::vector<int32_t> hs_mo_order(cap_mos);
-    std::vector<int16_t> hs_clips(2 * W);
+    std::vector<int32_t> hs_dseg_part;
     auto masked_scratch = [&]() -> int { // (re)allocate the masked phase's working arrays for the current capacities
         if (on_host) {
             hs_renders.resize(cap_renders);
             hs_allcols.resize(cap_allcols);
             hs_dsegs.resize(cap_dsegs);
+            hs_dseg_part.resize(cap_dsegs);
             return DRR_OK;
         }
         if (masked) {
             CU(ctx, S.d_renders.reserve(N * cap_renders));
             CU(ctx, S.d_allcols.reserve(N * cap_allcols * 5));
             CU(ctx, S.d_dsegs.reserve(N * cap_dsegs));
+            CU(ctx, S.d_dseg_part.reserve(N * cap_dsegs));
             CU(ctx, S.d_mos.reserve(N * cap_mos));
             CU(ctx, S.d_mo_order.reserve(N * cap_mos));
         }
         scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
-                        S.d_clips.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
+                        S.d_dseg_part.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
         return DRR_OK;
     };
     if (on_host) {
@@ -1356,7 +1358,6 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_cocl.reserve(N * W));
         CU(ctx, S.d_rows.reserve(N * W * 2));
         CU(ctx, S.d_order.reserve(N * S.segs.size()));
-        CU(ctx, S.d_clips.reserve(N * W * 2));
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
     }
     {
@@ -1379,7 +1380,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             }
             fe::Frame<EMIT> fr(m);
             fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data(), hs_renders.data(),
-                                hs_allcols.data(), hs_dsegs.data(), hs_mos.data(), hs_mo_order.data(), hs_clips.data(), cap_renders, cap_allcols, cap_dsegs, cap_mos};
+                                hs_allcols.data(), hs_dsegs.data(), hs_mos.data(), hs_mo_order.data(), hs_dseg_part.data(), cap_renders, cap_allcols, cap_dsegs, cap_mos};
             fr.out = out;
             fr.cap = cap;
             fr.run(S.h_views_in.p[i], b);

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     fr.sc.dsegs = static_cast<SegRec *>(s.dsegs) + (size_t)v * s.cap_dsegs;
     fr.sc.mos = static_cast<fe::MoRec *>(s.mos) + (size_t)v * s.cap_mos;
     fr.sc.mo_order = s.mo_order + (size_t)v * s.cap_mos;
-    fr.sc.clips = s.clips + 2 * o;
+    fr.sc.dseg_part = s.dseg_part + (size_t)v * s.cap_dsegs;
     fr.sc.cap_renders = s.cap_renders;
     fr.sc.cap_allcols = s.cap_allcols;
     fr.sc.cap_dsegs = s.cap_dsegs;

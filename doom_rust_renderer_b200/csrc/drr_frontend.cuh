@@ -160,7 +160,7 @@ struct Scratch {
     SegRec *dsegs;      // headers of what is drawn late (masked mid-textures, sprites), in creation order
     MoRec *mos;         // the visible map objects
     int32_t *mo_order;  // their draw order
-    int16_t *clips;     // 2 * W: top_clip, bottom_clip of the sprite being clipped (map_objects.rs:104-106)
+    int32_t *dseg_part; // cap_dsegs: the part (index into renders) of every masked mid-texture header in dsegs
     uint32_t cap_renders, cap_allcols, cap_dsegs, cap_mos;
 };
 
@@ -385,6 +385,7 @@ struct Frame {
     // Masked phase: parts that can clip sprites or are drawn late are remembered (Scratch::renders / allcols / dsegs) and
     // drawn -- appended to the output lists -- when the reference draws them (phases C and D at the end of run()).
     uint32_t nrenders, nallcols, ndsegs, nmos;
+    uint32_t nmids; // masked mid-texture headers: dsegs[0 .. nmids), known when the walk is over
     // Which screen columns are fully occluded (hor_ocl), as a bit mask spread over the lanes: word w (columns 32w .. 32w+31)
     // lives on lane w % 32, slot w / 32.  A seg all of whose columns are occluded can only re-occlude them and flush
     // visplanes that are not open (segs.rs:186-330): it is skipped without touching memory.
@@ -711,6 +712,7 @@ struct Frame {
                 if (deferred) {
                     r.cols_first = acol0; // for now: where its columns wait in allcols
                     sc.dsegs[ndsegs] = r;
+                    sc.dseg_part[ndsegs] = (int32_t)nrenders;
                 }
             }
             nrenders++;
@@ -761,27 +763,22 @@ struct Frame {
         return mx > v.x && !left_of(v, V2{rr.lsx, rr.lsy}, V2{rr.lex, rr.ley});
     }
 
-    // Every part in [0, upto) that is a not yet drawn two-sided middle texture and -- when `v` is given -- lies behind v is
-    // drawn now, last created first (the reference iterates its reversed list: mod.rs:124, map_objects.rs:226-232, segs.rs:593-597).
+    // Every not yet drawn masked mid-texture that -- unless `all` -- lies behind the view-space point v is drawn now, last
+    // created first (the reference iterates its reversed part list: mod.rs:124, map_objects.rs:226-232, segs.rs:593-597).
+    // Only parts that HAVE something to draw are looked at: for the others (texture "-") being "drawn" changes nothing.
+    // dsegs[0 .. nmids) are the mid-textures in creation order (the sprites' headers follow them).
     FE_NOINLINE void draw_parts_behind(bool all, V2 v) {
-        for (int c0 = ((int)nrenders - 1) / 32 * 32; c0 >= 0 && n.status == FE_OK; c0 -= 32) {
-            PerLane<int32_t> dseg;
+        for (int c0 = ((int)nmids - 1) / 32 * 32; c0 >= 0 && nmids && n.status == FE_OK; c0 -= 32) {
             uint32_t hit = ballot([&](int l) {
-                dseg[l] = -1;
-                if (c0 + l >= (int)nrenders) return false;
-                const RenderRec rr = sc.renders[c0 + l];
-                if (!(rr.flags & RF_TWOSIDED) || (rr.flags & RF_DRAWN)) return false;
-                if (!all && !behind(rr, v)) return false;
-                dseg[l] = rr.dseg;
-                return true;
+                if (c0 + l >= (int)nmids) return false;
+                const RenderRec rr = sc.renders[sc.dseg_part[c0 + l]];
+                if (rr.flags & RF_DRAWN) return false;
+                return all || behind(rr, v);
             });
             FE_LANES(l) {
-                if (hit & (1u << l)) sc.renders[c0 + l].flags |= RF_DRAWN;
+                if (hit & (1u << l)) sc.renders[sc.dseg_part[c0 + l]].flags |= RF_DRAWN;
             }
-            for (; hit && n.status == FE_OK; hit &= ~(1u << highest(hit))) {
-                const int32_t d = from_lane(dseg, highest(hit));
-                if (d >= 0) draw_late(d);
-            }
+            for (; hit && n.status == FE_OK; hit &= ~(1u << highest(hit))) draw_late(c0 + highest(hit));
         }
         FE_SYNC();
     }
@@ -1149,7 +1146,7 @@ struct Frame {
         }
         FE_SYNC();
         open[0] = open[1] = false;
-        nrenders = nallcols = ndsegs = nmos = 0;
+        nrenders = nallcols = ndsegs = nmos = nmids = 0;
         occ_on = m.W <= 4096;
         FE_LANES(l) {
             occ[0][l] = occ[1][l] = occ[2][l] = occ[3][l] = 0u;
@@ -1234,6 +1231,7 @@ struct Frame {
         n.nops += n.nplanes;
         if (m.phases & 4) {
             FE_SYNC();
+            nmids = ndsegs;
             if (m.nthings > 0) map_objects(v.angle);       // C: mod.rs:126-133
             if (n.status == FE_OK) draw_parts_behind(true, V2{0.0f, 0.0f}); // D: segs.rs:593-597 -- what is left, last created first
         }

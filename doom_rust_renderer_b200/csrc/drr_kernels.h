@@ -93,10 +93,10 @@ struct FeScratch {                    // per-viewpoint working state of the fron
     int16_t *floor_ocl, *ceil_ocl;
     uint32_t *rows;                   // 2 * W per viewpoint: the (top, bottom) rows of the two visplanes being accumulated
     int32_t *order;                   // nsegs per viewpoint: the segs in the view's BSP order
-    // masked phase only (null otherwise); per viewpoint: cap_* entries each, 2 * W clips, cap_mos draw-order entries
+    // masked phase only (null otherwise); per viewpoint: cap_* entries each, cap_dsegs part indices, cap_mos draw-order entries
     void *renders, *allcols, *dsegs, *mos;
     int32_t *mo_order;
-    int16_t *clips;
+    int32_t *dseg_part;
     uint32_t cap_renders, cap_allcols, cap_dsegs, cap_mos;
 };
 // emit == false: count pass (writes counts[0..n)); emit == true: writes the lists at the offsets in bases[0..n), or -- when
