@@ -644,12 +644,13 @@ struct Frame {
                         pl_right[which] = (int16_t)(c0 + highest(pm[which]));
                     }
                 if (nf == 32) break;
-                flush();
+                if (open[0] || open[1]) flush();
                 f &= f - 1;
                 lo = nf + 1;
             }
         }
-        flush();
+        FE_SYNC(); // the occlusion arrays written above are read by other lanes in the next part (its chunks start at another x)
+        if (open[0] || open[1]) flush();
         if (!keep || ncol == 0 || n.status != FE_OK) return;
         SegRec r;
         if (wall || deferred) {
