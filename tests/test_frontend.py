@@ -84,7 +84,8 @@ def test_front_end_code_emits_the_host_front_ends_lists(kind, W, H, n, phases, t
 
 
 @pytest.mark.parametrize("kind,W,H,n,things", [("e1m1", 320, 200, 260, True), ("e1m1", 320, 200, 120, False), ("e1m1", 640, 400, 60, True),
-                                                ("stress", 200, 120, 120, True), ("e1m1", 1280, 800, 24, True)])
+                                                ("stress", 200, 120, 120, True), ("e1m1", 1280, 800, 24, True), ("e1m1", 1000, 900, 8, True),
+                                                ("e1m1", 96, 2000, 6, True), ("e1m1", 33, 64, 40, True), ("e1m1", 4097, 48, 3, True)])
 def test_front_end_code_all_phases(kind, W, H, n, things):
     """Phases C and D: map objects (rotation, projection, clip arrays from the parts in front, depth order, interleave with the
     masked mid-textures behind each sprite) and the remaining masked mid-textures, last created first -- with and without
@@ -208,7 +209,9 @@ def _compare(ctx, k, ref, what):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,W,H,n,phases,ts", [("e1m1", 320, 200, 700, 3, 0.0), ("e1m1", 1280, 800, 40, 3, 0.4), ("stress", 200, 120, 200, 3, 0.0),
                                                   ("e1m1", 324, 200, 33, 1, 0.0), ("stress", 1920, 1200, 6, 2, 0.0), ("e1m1", 320, 200, 500, 7, 0.0),
-                                                  ("e1m1", 640, 400, 64, 7, 0.7), ("stress", 640, 400, 48, 7, 0.0), ("e1m1", 1280, 800, 16, 4, 0.0)])
+                                                  ("e1m1", 640, 400, 64, 7, 0.7), ("stress", 640, 400, 48, 7, 0.0), ("e1m1", 1280, 800, 16, 4, 0.0),
+                                                  ("e1m1", 1000, 900, 6, 7, 0.0), ("e1m1", 96, 2000, 5, 7, 0.0), ("e1m1", 33, 64, 64, 7, 0.0),
+                                                  ("e1m1", 4097, 48, 3, 7, 0.0)])
 def test_device_front_end_lists_equal_host_front_end(kind, W, H, n, phases, ts):
     path, gm = common.wad(kind)
     views = _views(kind, gm, n)
