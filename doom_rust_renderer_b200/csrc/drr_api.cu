@@ -4,8 +4,8 @@
 //   as emitted:  views[frame] 24 B | ops[] 4 B (call order) | segs[] 80 B | cols[] 10 B | planes[] 16 B | (top, bottom) pairs 4 B
 //   device scratch: colidx[frame][x] 8 B and one decoded 64-byte record per (op, column), both written by the bin kernel
 //   framebuffers: max_views x (W*H*3 B, RGB24 row-major == Pixels.pixels, src/renderer/pixels.rs:5-14)
-//   assets: u16 texel pool (column-major, pow2 column pitch, palette byte offsets, 4096 = None), u8 flat pool (4096 B per
-//           flat), float4 palette
+//   assets: u16 texel pool (column-major, pow2 column pitch; values = shared address of the palette entry in a tile CTA,
+//           entry 256 = None), u8 flat pool (4096 B per flat), the palette image a tile CTA stages
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -184,11 +184,12 @@ struct drr_ctx : Lists {
     int sky_slot = -1;
     DevBuf<uint16_t> d_texels;
     DevBuf<uint8_t> d_flats;
-    cudaTextureObject_t tex_texels = 0, tex_flats = 0; // linear textures over d_texels / d_flats
     DevBuf<BitmapRec> d_bitmaps;
-    DevBuf<float4> d_pal;
-    uint32_t pal_image[257 * 3 + 1] = {}; // the palette exactly as the tile kernel's shared memory holds it
+    uint32_t pal_image[SM_PAL_BYTES / 4] = {}; // the palette exactly as the tile kernel's shared memory holds it
     DevBuf<uint32_t> d_pal_image;
+    uint32_t pal_base = 0x400; // shared window address of a tile CTA's dynamic shared memory (probed by drr_ctx_create)
+    CUtensorMap fbmap = {};    // the framebuffers as a (x bytes, row, slot) u8 tensor with a 96-byte x 8-row box (TMA write-out)
+    bool have_fbmap = false;
 
     // device copies of the recorded lists (the lists themselves: struct Lists above)
     DevBuf<View> d_views;
@@ -216,6 +217,8 @@ struct drr_ctx : Lists {
     cudaEvent_t ev_stream2 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;   // "chunk uploaded" events
     cudaEvent_t ev_lists_free = nullptr; // recorded on `stream` after the last kernel that reads the device lists
+    cudaEvent_t ev_h2d = nullptr;        // recorded after the last asynchronous copy that reads the pinned host lists
+    bool h2d_pending = false;            // such copies may still be running: the host lists must not be touched (see lists_writable)
 
     std::vector<cudaEvent_t> prof_ev; // 3 events per profiled drr_draw: before setup, between, after march
     int prof_steps = 0;
@@ -225,6 +228,17 @@ struct drr_ctx : Lists {
 
 #define CTX_CHECK(ctx) \
     if (!(ctx)) return DRR_E_INVALID
+// entry points that touch CUDA: the context's device becomes the calling thread's current device first (another context,
+// or the caller itself, may have switched it since the last call)
+#define CTX_DEV(ctx)                                                                        \
+    CTX_CHECK(ctx);                                                                         \
+    if (!(ctx)->host_only) {                                                                \
+        cudaError_t e__ = cudaSetDevice((ctx)->device);                                     \
+        if (e__ != cudaSuccess) {                                                           \
+            (ctx)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e__);          \
+            return DRR_E_CUDA;                                                              \
+        }                                                                                   \
+    }
 #define CU(ctx, call)                                                                       \
     do {                                                                                    \
         cudaError_t e__ = (call);                                                           \
@@ -237,6 +251,15 @@ struct drr_ctx : Lists {
 static int fail(drr_ctx *ctx, int code, const std::string &msg) {
     ctx->err = msg;
     return code;
+}
+
+// drr_upload_lists / drr_submit queue asynchronous copies out of the context's pinned host lists and return; before those
+// lists are cleared, grown (reallocated) or appended to, the copies must have finished reading them.
+static int lists_writable(drr_ctx *ctx) {
+    if (!ctx->h2d_pending) return DRR_OK;
+    CU(ctx, cudaEventSynchronize(ctx->ev_h2d));
+    ctx->h2d_pending = false;
+    return DRR_OK;
 }
 
 extern "C" {
@@ -301,6 +324,30 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
     c->own_stream = true;
     if ((e = cudaMalloc((void **)&c->d_frames, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMalloc(framebuffers)", e);
     if ((e = cudaMalloc((void **)&c->d_crc, sizeof(uint64_t) * (size_t)max_views)) != cudaSuccess) return bail("cudaMalloc(crc)", e);
+    if ((e = probe_shared_base(&c->pal_base)) != cudaSuccess) return bail("shared memory probe", e);
+    if (c->pal_base % 128 != 0 || c->pal_base + SM_PAL + (TEXEL_NONE_INDEX + 1) * PAL_ENTRY > 0xffffu) {
+        g_create_error = "drr_ctx_create: unexpected shared window base " + std::to_string(c->pal_base);
+        drr_ctx_destroy(c);
+        return DRR_E_CUDA;
+    }
+    if (width % TILE_COLS == 0 && height % 8 == 0) { // the TMA write-out's view of the framebuffers
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess || !fn) return bail("cuTensorMapEncodeTiled lookup", e != cudaSuccess ? e : cudaErrorUnknown);
+        const cuuint64_t dims[3] = {(cuuint64_t)width * 3, (cuuint64_t)height, (cuuint64_t)max_views};
+        const cuuint64_t strides[2] = {(cuuint64_t)width * 3, (cuuint64_t)c->frame_stride}; // bytes, of dimensions 1 and 2
+        const cuuint32_t box[3] = {TILE_COLS * 3, 8, 1}, estr[3] = {1, 1, 1};
+        const CUresult cr = ((encode_fn)fn)(&c->fbmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            g_create_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)cr);
+            drr_ctx_destroy(c);
+            return DRR_E_CUDA;
+        }
+        c->have_fbmap = true;
+    }
     if ((e = cudaMalloc((void **)&c->d_sky_rows, (size_t)height)) != cudaSuccess) return bail("cudaMalloc(sky rows)", e);
     if ((e = launch_sky_rows(c->d_sky_rows, height, c->stream)) != cudaSuccess) return bail("sky rows kernel", e);
     if ((e = cudaMemset(c->d_frames, 0, c->frame_stride * (uint64_t)max_views)) != cudaSuccess) return bail("cudaMemset", e);
@@ -309,6 +356,7 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(copy)", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_lists_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate(2)", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_stream2, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
@@ -329,20 +377,19 @@ void drr_ctx_destroy(drr_ctx *ctx) {
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->prof_ev) cudaEventDestroy(ev);
     if (ctx->ev_lists_free) cudaEventDestroy(ctx->ev_lists_free);
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2), cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_stream2) cudaEventDestroy(ctx->ev_stream2);
     if (ctx->d_frames) cudaFree(ctx->d_frames);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->d_sky_rows) cudaFree(ctx->d_sky_rows);
-    if (ctx->tex_texels) cudaDestroyTextureObject(ctx->tex_texels);
-    if (ctx->tex_flats) cudaDestroyTextureObject(ctx->tex_flats);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int drr_set_stream(drr_ctx *ctx, void *cuda_stream) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -398,12 +445,13 @@ int drr_upload_bitmap(drr_ctx *ctx, int id, int w, int h, const int16_t *texels)
     r.opaque = 1;
     for (size_t i = 0; i < (size_t)w * h; i++)
         if (texels[i] < -1 || texels[i] > 255) return fail(ctx, DRR_E_INVALID, "drr_upload_bitmap: texel outside -1..255");
-    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * w, (uint16_t)TEXEL_NONE);
+    const uint32_t pal0 = ctx->pal_base + SM_PAL; // pool values: where a tile CTA finds the palette entry in its shared memory
+    ctx->texel_pool.resize(ctx->texel_pool.size() + (size_t)pitch * w, (uint16_t)(pal0 + TEXEL_NONE_INDEX * PAL_ENTRY));
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const int16_t t = texels[(size_t)y * w + x];
             if (t < 0) r.opaque = 0;
-            ctx->texel_pool[r.base + (size_t)x * pitch + y] = (uint16_t)(t < 0 ? TEXEL_NONE : (uint32_t)t * PAL_ENTRY);
+            ctx->texel_pool[r.base + (size_t)x * pitch + y] = (uint16_t)(pal0 + (t < 0 ? TEXEL_NONE_INDEX : (uint32_t)t) * PAL_ENTRY);
         }
     ctx->bitmap_slot[id] = (int)ctx->bitmaps.size();
     ctx->bitmaps.push_back(r);
@@ -439,9 +487,7 @@ static int upload_assets(drr_ctx *ctx) {
     if (!ctx->assets_dirty) return DRR_OK;
     if (!ctx->have_pal) return fail(ctx, DRR_E_ASSET, "palette not uploaded");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, ctx->d_pal.reserve(256));
-    CU(ctx, cudaMemcpy(ctx->d_pal.p, ctx->pal, sizeof(ctx->pal), cudaMemcpyHostToDevice));
-    CU(ctx, ctx->d_pal_image.reserve(257 * 3 + 1));
+    CU(ctx, ctx->d_pal_image.reserve(SM_PAL_BYTES / 4));
     CU(ctx, cudaMemcpy(ctx->d_pal_image.p, ctx->pal_image, sizeof(ctx->pal_image), cudaMemcpyHostToDevice));
     CU(ctx, ctx->d_texels.reserve(std::max<size_t>(ctx->texel_pool.size(), 1)));
     if (!ctx->texel_pool.empty())
@@ -451,22 +497,6 @@ static int upload_assets(drr_ctx *ctx) {
     CU(ctx, ctx->d_bitmaps.reserve(std::max<size_t>(ctx->bitmaps.size(), 1)));
     if (!ctx->bitmaps.empty())
         CU(ctx, cudaMemcpy(ctx->d_bitmaps.p, ctx->bitmaps.data(), ctx->bitmaps.size() * sizeof(BitmapRec), cudaMemcpyHostToDevice));
-    // (re)create the linear textures over the pools
-    if (ctx->tex_texels) cudaDestroyTextureObject(ctx->tex_texels);
-    if (ctx->tex_flats) cudaDestroyTextureObject(ctx->tex_flats);
-    ctx->tex_texels = ctx->tex_flats = 0;
-    cudaTextureDesc td = {};
-    td.readMode = cudaReadModeElementType;
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = ctx->d_texels.p;
-    rd.res.linear.desc = cudaCreateChannelDesc<unsigned short>();
-    rd.res.linear.sizeInBytes = std::max<size_t>(ctx->texel_pool.size(), 1) * 2;
-    CU(ctx, cudaCreateTextureObject(&ctx->tex_texels, &rd, &td, nullptr));
-    rd.res.linear.devPtr = ctx->d_flats.p;
-    rd.res.linear.desc = cudaCreateChannelDesc<unsigned char>();
-    rd.res.linear.sizeInBytes = std::max<size_t>(ctx->flat_pool.size(), 1);
-    CU(ctx, cudaCreateTextureObject(&ctx->tex_flats, &rd, &td, nullptr));
     ctx->assets_dirty = false;
     return DRR_OK;
 }
@@ -638,8 +668,9 @@ static int rec_frame_end(Lists &L, std::string &err) {
 }
 
 int drr_reset(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_reset inside a frame");
+    if (int rc = lists_writable(ctx)) return rc;
     ctx->clear_lists();
     ctx->device_lists = false;
     ctx->t_spans.clear();
@@ -653,8 +684,9 @@ int drr_reset(drr_ctx *ctx) {
 }
 
 int drr_frame_begin(drr_ctx *ctx, int view_idx, const drr_view *view) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_frame_begin: the batch was written by drr_fe_emit_views (call drr_reset first)");
+    if (int rc = lists_writable(ctx)) return rc;
     if (view_idx >= 0 && view_idx < ctx->max_views && ctx->slot_to_frame[view_idx] >= 0 && !ctx->in_frame)
         return fail(ctx, DRR_E_INVALID, "drr_frame_begin: view index already recorded since drr_reset");
     const int rc = rec_frame_begin(*ctx, ctx, ctx->err, view_idx, view);
@@ -726,8 +758,9 @@ int drr_recorder_frame_abort(drr_recorder *rec) {
 // Move every frame of `rec` to the end of the context's lists (indices re-based), then clear the recorder.
 int drr_append(drr_ctx *ctx, drr_recorder *rec) {
     if (ctx && ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_append: the batch was written by drr_fe_emit_views (call drr_reset first)");
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (!rec || rec->ctx != ctx) return fail(ctx, DRR_E_INVALID, "drr_append: recorder of another context");
+    if (int rc = lists_writable(ctx)) return rc;
     Lists &R = rec->lists;
     if (ctx->in_frame || R.in_frame) return fail(ctx, DRR_E_STATE, "drr_append inside a frame");
     const size_t nf = R.views.n;
@@ -852,7 +885,7 @@ static uint64_t list_bytes(const drr_ctx *ctx) {
 }
 
 int drr_upload_lists(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_upload_lists inside a frame");
     if (ctx->device_lists) return DRR_OK; // drr_fe_emit_views wrote the lists on the device: nothing to upload
@@ -864,6 +897,8 @@ int drr_upload_lists(drr_ctx *ctx) {
     if ((rc = reserve_device_lists(ctx))) return rc;
     if ((rc = upload_tables(ctx, ctx->stream))) return rc;
     if ((rc = upload_frames(ctx, 0, nf, ctx->stream))) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev_h2d, ctx->stream));
+    ctx->h2d_pending = true;
     ctx->uploaded_frames = nf;
     return DRR_OK;
 }
@@ -898,11 +933,9 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.tparams = ctx->d_tparams.p;
     a.texels = ctx->d_texels.p;
     a.flats = ctx->d_flats.p;
-    a.tex_texels = ctx->tex_texels;
-    a.tex_flats = ctx->tex_flats;
     a.bitmaps = ctx->d_bitmaps.p;
-    a.palette = ctx->d_pal.p;
     a.pal_image = ctx->d_pal_image.p;
+    a.pal_base = ctx->pal_base;
     a.sky_rows = ctx->d_sky_rows;
     a.sky_base = ctx->sky_slot >= 0 ? ctx->bitmaps[ctx->sky_slot].base : 0;
     a.frames = ctx->d_frames;
@@ -923,7 +956,7 @@ static int draw_range(drr_ctx *ctx, const DrawArgs &a, int f0, int n, bool bin, 
     if (prof) CU(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_steps * 3 + 1], st));
     if (tile) {
         int launches = 0;
-        CU(ctx, launch_tile(a, f0, n, st, &launches));
+        CU(ctx, launch_tile(a, ctx->have_fbmap ? &ctx->fbmap : nullptr, f0, n, st, &launches));
         ctx->stats.kernel_launches += (uint64_t)launches;
     }
     if (prof) {
@@ -934,7 +967,7 @@ static int draw_range(drr_ctx *ctx, const DrawArgs &a, int f0, int n, bool bin, 
 }
 
 int drr_draw(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     DrawArgs a;
     int rc = make_args(ctx, a, ctx->uploaded_frames);
     if (rc) return rc;
@@ -945,7 +978,7 @@ int drr_draw(drr_ctx *ctx) {
 // Per-kernel device times of the drr_draw() calls made since drr_profile_begin, from CUDA events recorded on the
 // context's stream around each kernel.
 int drr_profile_begin(drr_ctx *ctx, int max_steps) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (max_steps < 0 || max_steps > 4096) return fail(ctx, DRR_E_INVALID, "drr_profile_begin: max_steps");
     while (ctx->prof_ev.size() < (size_t)max_steps * 3) {
@@ -957,7 +990,7 @@ int drr_profile_begin(drr_ctx *ctx, int max_steps) {
     return DRR_OK;
 }
 int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *march_ms_total) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     float s = 0, m = 0;
@@ -980,7 +1013,7 @@ int drr_profile_end(drr_ctx *ctx, int *steps, float *setup_ms_total, float *marc
 // drr_submit: upload and draw, pipelined.  The batch is cut into chunks of frames; chunk k+1's lists travel over PCIe
 // on the copy stream while chunk k is binned and drawn on the context's stream.
 int drr_submit(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU draw path");
     if (ctx->in_frame) return fail(ctx, DRR_E_STATE, "drr_submit inside a frame");
     if (ctx->device_lists) return drr_draw(ctx); // drr_fe_emit_views wrote the lists on the device: nothing to upload
@@ -1028,6 +1061,8 @@ int drr_submit(drr_ctx *ctx) {
         if ((rc = draw_range(ctx, a, (int)f0, (int)(f1 - f0), true, true, false, st))) return rc;
         if (trace) CU(ctx, cudaEventRecord(tev[2 + 2 * c], st));
     }
+    CU(ctx, cudaEventRecord(ctx->ev_h2d, ctx->cstream));
+    ctx->h2d_pending = true;
     if (two) { // everything is complete when the context's stream is
         CU(ctx, cudaEventRecord(ctx->ev_stream2, ctx->stream2));
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_stream2, 0));
@@ -1047,14 +1082,14 @@ int drr_submit(drr_ctx *ctx) {
 }
 
 int drr_sync(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return DRR_OK;
 }
 
 int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!out || view_idx < 0 || view_idx >= ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_read_framebuffer: bad view index");
     CU(ctx, cudaMemcpyAsync(out, ctx->d_frames + (uint64_t)view_idx * ctx->frame_stride, (size_t)ctx->W * ctx->H * 3, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1063,7 +1098,7 @@ int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out) {
 }
 
 int drr_read_checksums(drr_ctx *ctx, int first, int count, uint64_t *out) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!out || first < 0 || count < 0 || first + count > ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_read_checksums: bad range");
     if (count == 0) return DRR_OK;
@@ -1098,7 +1133,7 @@ int drr_get_stats(drr_ctx *ctx, drr_stats *out) {
 }
 
 int drr_time_draw(drr_ctx *ctx, int iters, float *total_ms, float *setup_ms, float *march_ms) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (iters <= 0) return fail(ctx, DRR_E_INVALID, "drr_time_draw: iters");
     DrawArgs a;
     int rc = make_args(ctx, a, ctx->uploaded_frames);
@@ -1141,7 +1176,7 @@ static const char *fe_detail_message(uint32_t d) {
 }
 
 int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (!m || m->n_nodes <= 0 || m->n_subsectors <= 0 || m->n_segs <= 0 || m->n_linedefs <= 0 || m->n_sidedefs <= 0 || m->n_sectors <= 0 ||
         !m->nodes || !m->subsectors || !m->segs || !m->linedefs || !m->sidedefs || !m->sectors)
         return fail(ctx, DRR_E_INVALID, "drr_fe_upload_map: empty table");
@@ -1556,12 +1591,12 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
 }
 
 int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     return fe_emit_views(ctx, first_view_idx, xya, n, phases, status, false);
 }
 
 int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only || !ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_fe_last_times: no device front-end batch");
     FeState &S = ctx->fes;
     CU(ctx, cudaEventSynchronize(ctx->ev[1]));
@@ -1586,7 +1621,7 @@ int drr_test_fe_emit_views_host(drr_ctx *ctx, int first_view_idx, const float *x
 }
 // Test infrastructure: copy the lists the device front-end wrote back into the context's host lists (drr_test_list).
 int drr_test_fe_download_lists(drr_ctx *ctx) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only || !ctx->device_lists) return fail(ctx, DRR_E_STATE, "drr_test_fe_download_lists: no device front-end batch");
     const size_t nf = ctx->uploaded_frames;
     const size_t ops = ctx->frame_op_base.p[nf], segs = ctx->frame_seg_base[nf], cols = ctx->frame_col_base[nf], planes = ctx->frame_plane_base[nf],
@@ -1697,7 +1732,7 @@ const void *drr_test_list(drr_ctx *ctx, int which, uint64_t *count, uint64_t *el
 // band, drr_test_tile_bands), recs_out = two words per record slot (y0 | y1 << 16, kind | flags), rec_cap * nlists slots,
 // indexed by the `first` values of colidx_out.
 int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out) {
-    CTX_CHECK(ctx);
+    CTX_DEV(ctx);
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
     int nbands, band_rows;
@@ -1732,7 +1767,8 @@ int drr_test_bitmap_texels(drr_ctx *ctx, int slot, int16_t *out) { // row-major 
     for (int y = 0; y < r.h; y++)
         for (int x = 0; x < r.w; x++) {
             const uint16_t t = ctx->texel_pool[r.base + (size_t)x * pitch + y];
-            out[(size_t)y * r.w + x] = t == TEXEL_NONE ? (int16_t)-1 : (int16_t)(t / PAL_ENTRY);
+            const uint32_t idx = ((uint32_t)t - (ctx->pal_base + SM_PAL)) / PAL_ENTRY;
+            out[(size_t)y * r.w + x] = idx == TEXEL_NONE_INDEX ? (int16_t)-1 : (int16_t)idx;
         }
     return DRR_OK;
 }

@@ -1,32 +1,36 @@
 // drr_kernels.h -- kernel argument block and launchers (shared by drr_tile.cu, drr_kernels.cu and drr_api.cu)
 #pragma once
 #include "drr_device.cuh"
+#include <cuda.h> // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace drr {
 
-static constexpr int TILE_THREADS = 256;
-#ifndef DRR_TILE_MIN_BLOCKS
-#define DRR_TILE_MIN_BLOCKS 4
-#endif
-static constexpr int TILE_MIN_BLOCKS = DRR_TILE_MIN_BLOCKS; // 16-column full-height tiles (tall screens): shared memory allows 4 CTAs per SM
-#ifndef DRR_TILE_MIN_BLOCKS_SHORT
-#define DRR_TILE_MIN_BLOCKS_SHORT 6
-#endif
-static constexpr int TILE_MIN_BLOCKS_SHORT = DRR_TILE_MIN_BLOCKS_SHORT; // 32-column tiles (short screens): small tiles, more CTAs hide latency (tools/sweep.sh)
+static constexpr int TILE_THREADS = 256; // 8 warps: one per group of four adjacent screen columns of the 32-column tile
+static constexpr int TILE_COLS = 32;     // 96-byte row segments of the RGB24 framebuffer: whole 32-byte sectors
+static constexpr int TILE_LPG = 8;       // lanes per span: a warp draws the four columns of its group at once
 
-// Palette entry size in shared memory: 8 bytes (r and g as bf16 -- exact for 0..255 -- in one word, b as f32): half the
-// shared-memory traffic per lookup for two more ALU instructions (measured: -4.7 % tile time at 320x200, neutral at
-// 1280x800); -DDRR_PAL16 builds the 16-byte (r, g, b as f32 + packed RGB) variant for A/B.
-// Texel pool values are byte offsets into that table.
-#ifndef DRR_PAL16
-#define DRR_PAL8 1
-#endif
-#ifdef DRR_PAL8
+// Shared memory of a tile CTA.  All of it is dynamic (the kernel declares no static shared memory), so the map starts at the
+// CTA's shared window base, which drr_ctx_create probes once (DrawArgs::pal_base): the texel pool holds ABSOLUTE shared
+// addresses of palette entries (pal_base + 8 * index), so a texel feeds the palette load without an add.
+//   [SM_PAL, +3088)  palette image: 257 x 8 bytes (r and g as bf16 -- exact for 0..255 -- in one word, b as f32; entry 256 backs
+//                    the None texel), then 257 packed 0x00BBGGRR words (sky: no lighting); staged by ONE bulk copy
+//   [SM_BAR, +8)     mbarrier of that copy
+//   [SM_TILE, ...)   the tile: band_rows x 128 bytes, see tile_offset()
 static constexpr uint32_t PAL_ENTRY = 8;
-#else
-static constexpr uint32_t PAL_ENTRY = 16;
-#endif
-static constexpr uint32_t TEXEL_NONE = 256 * PAL_ENTRY;
+static constexpr uint32_t SM_PAL = 0, SM_PAL_PACKED = 257 * PAL_ENTRY, SM_PAL_BYTES = 3088, SM_BAR = 3088, SM_TILE = 3200;
+static constexpr uint32_t TEXEL_NONE_INDEX = 256; // palette index that stands for a None texel in the pool
+
+// Byte offset of pixel (column c of the tile, row r of the band) in the tile.  Blocks of 8 rows (1 KB); inside a block the
+// four columns of a group ("quad") are interleaved per row: 16 bytes = pixels c&3 = 0..3 of one row, so that
+//   * drawing is conflict-free whatever rows the four lane groups of a warp are on: 8 lanes = 8 consecutive rows = 8
+//     different 16-byte slots, the 4 groups = the 4 words of a slot;
+//   * the write-out reads four pixels of a row with one LDS.128, and (rows ^ 4 for the upper four quads) a quarter warp
+//     reading 4 rows x 2 halves of the tile hits eight different slots;
+//   * the rows y and y + 8 of a lane are exactly 1 KB apart.
+__host__ __device__ __forceinline__ uint32_t tile_offset(int c, int r) {
+    const uint32_t q = (uint32_t)c >> 2;
+    return (((uint32_t)r >> 3) << 10) + (q << 7) + ((((uint32_t)r & 7u) ^ (q & 4u)) << 4) + (((uint32_t)c & 3u) << 2);
+}
 
 struct DrawArgs {
     int W, H, nframes;
@@ -50,14 +54,11 @@ struct DrawArgs {
     ColIdx *colidx;                  // [nframes * nlists * W], nlists = nbands when nbands <= MAX_LIST_BANDS, else 1
     void *tparams;                   // one 64-byte decoded record per (op, column) that survives clipping, see drr_tile.cu
     // assets
-    const uint16_t *texels;          // bitmap pool: column-major, pow2 column pitch, palette byte offset (index*16), 4096 = None
-    const uint8_t *flats;            // 4096 bytes per flat slot
+    const uint16_t *texels;          // bitmap pool: column-major, pow2 column pitch; values = pal_base + 8 * palette index (256 = None)
+    const uint8_t *flats;            // 4096 bytes per flat slot (palette indices)
     const BitmapRec *bitmaps;
-    cudaTextureObject_t tex_texels;  // the texel pool as a 1D linear texture of u16 (tile kernel fetches texels through the TEX pipe,
-    cudaTextureObject_t tex_flats;   // which runs beside the LSU/L1 data pipe the kernel is bound by); same for the flat pool (u8)
-    const float4 *palette;           // 256 x (r, g, b as f32, packed 0x00BBGGRR bits)
-    const uint32_t *pal_image;       // the palette exactly as the tile kernel's shared memory holds it: 257 x (bf16 r | bf16 g << 16,
-                                     // f32 b), then 257 packed 0x00BBGGRR words (staging is a straight copy)
+    const uint32_t *pal_image;       // the palette exactly as the tile kernel's shared memory holds it (SM_PAL_BYTES, 16-byte aligned)
+    uint32_t pal_base;               // shared window address of a CTA's dynamic shared memory (probed at drr_ctx_create)
     const uint8_t *sky_rows;         // sky texture row of every screen row
     uint32_t sky_base;               // texel index of the 256x128 sky bitmap
     uint8_t *frames;                 // framebuffers, frame_stride bytes apart, RGB24 row-major
@@ -67,11 +68,13 @@ struct DrawArgs {
 
 // Every launcher works on the frame range [frame0, frame0 + nframes) of the uploaded batch.
 cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t st);
-cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
+// fbmap: the framebuffers as a 3-D u8 tensor (x bytes, row, slot) with a 96-byte x 8-row box, or null when W % 32 != 0
+cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0, int nframes, cudaStream_t st, int *launches);
+cudaError_t probe_shared_base(uint32_t *base); // shared window address of a CTA's dynamic shared memory on the current device
 cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
 cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
 void tile_config(int W, int H, int *tc, int *lpg);
-void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (bands of at most 400 rows)
+void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (equal bands of at most 400 rows, a multiple of 8 when H is)
 static constexpr int MAX_LIST_BANDS = 8;             // up to this many bands the bin kernel writes one span list per (column, band)
 // ---- device front-end (drr_frontend.cu / drr_frontend.cuh) ----------------------------------------------------------
 namespace fe {

@@ -7,24 +7,27 @@
 //                           draw_visplane (src/renderer/visplanes.rs:108,112-114) or draw_sky's tx (visplanes.rs:54-66),
 //                           decoded all the way into the register values the pixel loops use (64 B per span), so that
 //                           the draw kernel spends no instructions on decoding.
-//   drr_tile_kernel       : one CTA per (frame, TC screen columns, band of rows; the band is the whole column for
-//                           H <= 800).  A span belongs to one screen column, so all of its parameters are uniform over
-//                           the lanes that work on it: a group of LPG lanes (the whole warp for tall screens, 16 or 8 lanes
-//                           for short ones, so that short spans still fill the warp) takes a span, each lane takes TWO rows
-//                           (y and y + LPG) at a time and evaluates them with Blackwell's packed FP32 instructions
-//                           (FFMA2 / FMUL2 / FADD2: two independent IEEE f32 results per issue slot).  The per-PIXEL part:
-//                           wall/sprite ty + texel + diminish_color (bitmap_render.rs:253-275, 190-208), flat inverse
-//                           projection (visplanes.rs:103-128), sky (visplanes.rs:65-77).  Pixels go to a column-major u32
-//                           tile in shared memory (consecutive lanes -> consecutive words: conflict-free); a column's
-//                           spans are drawn by ONE lane group in draw order (the kinds that always write overwrite, the
-//                           kinds with None texels skip them), and finally the tile is written out row by row as 16-byte
-//                           vectors of the row-major RGB24 framebuffer (Pixels::set, src/renderer/pixels.rs:22-30) while
-//                           the per-frame checksum is accumulated.  Column sets are handed to warps dynamically (shared
-//                           counter), so a warp that drew short columns takes more of them.
+//   drr_tile_kernel       : one CTA (8 warps) per (frame, 32 screen columns, band of at most 400 rows).  A warp owns four
+//                           adjacent columns; a span belongs to one column, so all of its parameters are uniform over the
+//                           8 lanes that work on it, each lane takes TWO rows (y and y + 8) at a time and evaluates them
+//                           with Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2: two independent IEEE f32
+//                           results per issue slot).  The per-PIXEL part: wall/sprite ty + texel + diminish_color
+//                           (bitmap_render.rs:253-275, 190-208), flat inverse projection (visplanes.rs:103-128), sky
+//                           (visplanes.rs:65-77).  Pixels go to a u32 tile in shared memory (layout: tile_offset() in
+//                           drr_kernels.h; every store of the draw loops is bank-conflict free); a column's spans are drawn
+//                           by ONE lane group in draw order (the kinds that always write overwrite, the kinds with None
+//                           texels skip them).  Write-out: a warp reads 16 rows of the tile with four LDS.128 per lane,
+//                           packs them to RGB24 (Pixels::set, src/renderer/pixels.rs:22-30) IN PLACE as a row-major 96-byte
+//                           x 8-row box per block, and hands the boxes to the TMA unit (cp.async.bulk.tensor, one
+//                           instruction per 768 bytes) while the per-frame checksum is accumulated from the packed words.
+//                           The palette image (3 KB) arrives by one cp.async.bulk on an mbarrier.
 #include "drr_device.cuh"
 #include "drr_kernels.h"
 #include "drr_math.cuh"
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace drr {
 
@@ -35,7 +38,7 @@ namespace drr {
 //               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
 static constexpr uint32_t COL_COVERED = 0x80000000u; // ColIdx.n flag: the column's always-writing spans cover every row
-enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11 };
+enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11, TS_TRUNC = 1u << 12 };
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
 struct Rec { // a decoded record in registers
@@ -76,6 +79,16 @@ __device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, i
     rd.x = den != 0 ? __float_as_uint((float)h) : 0x7fc00000u;
     rd.y = __float_as_uint(wc.factor);
     if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
+    // Is 0 <= ay * uy1 + h <= 32767 on every row of the span?  The sum is a monotonic function of y (every step of
+    // bitmap_render.rs:256-257 is), so its values on the rows ya and yb bound it; then `as i16` is a plain truncation of a
+    // non-negative number, which the pixel loop does with a round-toward-zero add of 2^23 (two rows per instruction, no
+    // conversion unit).  The two sums are evaluated exactly as the pixel loop evaluates them.
+    if (den != 0) {
+        const float r = __uint_as_float(rc.z), hF = (float)h;
+        const float sa = __fadd_rn(__fmul_rn(fast_div(__fadd_rn((float)ya, -(float)top_y), denF, r), wc.uy1), hF);
+        const float sb = __fadd_rn(__fmul_rn(fast_div(__fadd_rn((float)yb, -(float)top_y), denF, r), wc.uy1), hF);
+        if (sa >= 0.0f && sa <= 32767.0f && sb >= 0.0f && sb <= 32767.0f) flags |= TS_TRUNC;
+    }
     ra.y = kind | flags;
     return Rec{ra, rb, rc, rd, kind};
 }
@@ -318,9 +331,20 @@ __global__ void drr_sky_rows_kernel(uint8_t *rows, int H, float Hf) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// pixel loops
+// pixel loops.  A lane group (8 lanes) draws one span: lane li takes the rows ya + li, + 16, ... and, in the same
+// iteration, the row 8 below (1 KB further on in the tile); `addr` is the shared address of the lane's first row.
 // ------------------------------------------------------------------------------------------------------------------
+static constexpr uint32_t ROW8 = 1024, ROW16 = 2048; // tile distance of rows y -> y + 8, y -> y + 16 (tile_offset())
+
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // ---- Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2: two independent IEEE f32 operations per instruction, same rounding
 // as the scalar forms) ------------------------------------------------------------------------------------------------
@@ -343,17 +367,11 @@ __device__ __forceinline__ uint32_t lit_rgb_unit_p(float4 p, float factor) {
     return __byte_perm(__byte_perm(__float_as_uint(rg.x), __float_as_uint(rg.y), 0x0040), __float_as_uint(b), 0x5410);
 }
 
-static constexpr uint32_t TEXEL_HOLE = TEXEL_NONE; // texel pool values are palette byte offsets (index * PAL_ENTRY); entry 256 = None
-
-// palette entry at shared address `addr` as (r, g, b) floats
+// palette entry at shared address `addr` as (r, g, b) floats: r and g are bf16 halves of one word, b is an f32
 __device__ __forceinline__ float4 pal_fetch(uint32_t addr) {
-#ifdef DRR_PAL8
     uint32_t rg, b;
     asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rg), "=r"(b) : "r"(addr));
     return make_float4(__uint_as_float(rg << 16), __uint_as_float(rg & 0xffff0000u), __uint_as_float(b), 0.0f);
-#else
-    return lds_f4(addr);
-#endif
 }
 
 // read-only global load of one texel (the pointer's address space is spelled out: its provenance is hidden on purpose, see
@@ -363,231 +381,269 @@ __device__ __forceinline__ uint32_t ldg_u16(const uint16_t *p) {
     asm("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
+    uint32_t v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
-// bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows
-template <bool POW2>
-__device__ __forceinline__ void wall_texels2(const DrawArgs &a, const uint4 ra, const uint4 rb, const uint4 rc, float hF, float2 yt, float one,
-                                             const uint16_t *__restrict__ texels, uint32_t &t0, uint32_t &t1) {
+struct TileCtx { // what every pixel loop needs besides its span
+    uint32_t pal;      // shared address of the palette image
+    uint32_t hole;     // texel pool value of a None texel
+    float one;         // 1.0f, opaque to ptxas
+    int li;            // lane within its group
+};
+
+// bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows.  TRUNC: the bin kernel has
+// proven 0 <= sum <= 32767 on the span (TS_TRUNC), K = K1 - 0x4b000000.
+template <bool POW2, bool TRUNC>
+__device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uint32_t K, float hF, float2 yt, float one,
+                                             const uint16_t *__restrict__ col, uint32_t &t0, uint32_t &t1) {
     const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));   // :256
     // :257 with uy0 == 0.0: (1.0 - ay) * 0.0 is +-0.0 for finite ay and h + (+-0.0) == h, so the middle term drops out
     const float2 sum = add2_nofuse(__fmul2_rn(ay, f2(__uint_as_float(rc.w))), f2(hF), one);
-    uint32_t u0 = ((uint32_t)sat_i16(sum.x) + ra.w) & rb.x; // :259
-    uint32_t u1 = ((uint32_t)sat_i16(sum.y) + ra.w) & rb.x;
+    uint32_t u0, u1;
+    if (TRUNC) { // `sum as i16` of 0 <= sum <= 32767: the integer part lands in the low mantissa bits of sum + 2^23 (RZ)
+        const float2 tr = __fadd2_rz(sum, f2(8388608.0f));
+        u0 = (__float_as_uint(tr.x) + K) & rb.x; // :259 (the mask also drops the 0x4b000000 of the float)
+        u1 = (__float_as_uint(tr.y) + K) & rb.x;
+    } else {
+        u0 = ((uint32_t)sat_i16(sum.x) + K) & rb.x;
+        u1 = ((uint32_t)sat_i16(sum.y) + K) & rb.x;
+    }
     if (!POW2) { // :260-263 == floormod (identity checked in tests/: test_wrap_mod_idiom_is_floormod)
         u0 += rb.y;
         u1 += rb.y;
         u0 = __umulhi(u0, rb.z) * rb.w + u0;
         u1 = __umulhi(u1, rb.z) * rb.w + u1;
     }
-#ifdef DRR_TEXFETCH
-    t0 = tex1Dfetch<unsigned short>(a.tex_texels, (int)(ra.z + u0)); // TEX pipe: beside the LSU/L1 data pipe the kernel is bound by
-    t1 = tex1Dfetch<unsigned short>(a.tex_texels, (int)(ra.z + u1));
-#else
-    t0 = ldg_u16(texels + u0); // `texels` already points at the span's texture column
-    t1 = ldg_u16(texels + u1);
-#endif
+    t0 = ldg_u16(col + u0);
+    t1 = ldg_u16(col + u1);
 }
 
-template <int LPG, bool HOLES, bool POW2>
-__device__ __forceinline__ void tile_wall_span(const DrawArgs &a, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0, int li,
-                                               uint32_t col_addr, const uint16_t *__restrict__ texels, uint32_t pal_addr, float one) {
+// the fast wall loop: factor <= 1 and TS_TRUNC (every wall of an ordinary scene)
+template <bool HOLES, bool POW2>
+__device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb,
+                                               uint32_t addr, const uint16_t *__restrict__ texels) {
     const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
     // the span's texture column as ONE 64-bit base, opaque to the compiler: otherwise it re-associates texels + (ra.z + u) and
     // pays a 33-bit add with carry per texel instead of a single IMAD.WIDE.U32 (u * 2 + base)
     const uint16_t *__restrict__ col = texels + ra.z;
     asm("" : "+l"(col));
-    int y = ya + li;
-    uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
-    float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + LPG), __uint_as_float(rc.x)));
-    if (!(ra.y & TS_BRIGHT)) {
+    const uint32_t K = ra.w - 0x4b000000u;
+    const int yb8 = yb - TILE_LPG;
+    int y = ya + t.li;
+    float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
 #pragma unroll 2
-        for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
-            uint32_t t0, t1;
-            wall_texels2<POW2>(a, ra, rb, rc, hF, yt, one, col, t0, t1);
-            const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(pal_addr + t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(pal_addr + t1), factor);
-            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, rgb0);
-            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, rgb1);
-        }
-    } else {
-        for (; y <= yb; y += 2 * LPG, yt = __fadd2_rn(yt, f2((float)(2 * LPG))), addr += 8u * LPG) {
-            uint32_t t0, t1;
-            wall_texels2<POW2>(a, ra, rb, rc, hF, yt, one, col, t0, t1);
-            if (!HOLES || t0 != TEXEL_HOLE) sts_u32(addr, lit_rgb(pal_fetch(pal_addr + t0), factor));
-            if (y + LPG <= yb && (!HOLES || t1 != TEXEL_HOLE)) sts_u32(addr + 4u * LPG, lit_rgb(pal_fetch(pal_addr + t1), factor));
-        }
+    for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
+        uint32_t t0, t1;
+        wall_texels2<POW2, true>(rb, rc, K, hF, yt, t.one, col, t0, t1);
+        const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(t1), factor);
+        if (!HOLES || t0 != t.hole) sts_u32(addr, rgb0);
+        if (y <= yb8 && (!HOLES || t1 != t.hole)) sts_u32(addr + ROW8, rgb1);
+    }
+}
+
+// every other wall span (light level above 255, negative depth, texture rows outside 0..32767, NaN geometry): same
+// arithmetic with the saturating conversions spelled out
+__device__ __noinline__ void tile_wall_span_any(TileCtx t, uint4 ra, uint4 rb, uint4 rc, uint4 rd, int ya, int yb, uint32_t addr,
+                                                const uint16_t *__restrict__ texels) {
+    const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y);
+    const uint16_t *__restrict__ col = texels + ra.z;
+    const bool holes = (ra.y & 0xffu) == KIND_WALL_HOLES, pow2 = (ra.y & TS_POW2) != 0;
+    const int yb8 = yb - TILE_LPG;
+    int y = ya + t.li;
+    float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
+    for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
+        uint32_t t0, t1;
+        if (pow2) wall_texels2<true, false>(rb, rc, ra.w, hF, yt, t.one, col, t0, t1);
+        else wall_texels2<false, false>(rb, rc, ra.w, hF, yt, t.one, col, t0, t1);
+        if (!holes || t0 != t.hole) sts_u32(addr, lit_rgb_any(pal_fetch(t0), factor));
+        if (y <= yb8 && (!holes || t1 != t.hole)) sts_u32(addr + ROW8, lit_rgb_any(pal_fetch(t1), factor));
     }
 }
 
 // visplanes.rs:103-128 for one pixel of a flat span, every division IEEE
 __device__ __forceinline__ uint32_t flat_pixel_slow(float vy, float gwz, float wzvx, float lf, float cos_a, float sin_a, int px16, int py16,
-                                                    const uint8_t *__restrict__ flat, uint32_t pal_addr) {
+                                                    const uint8_t *__restrict__ flat, uint32_t pal) {
     const float wx = __fdiv_rn(gwz, vy), wy = __fdiv_rn(wzvx, vy);
     const float rx = __fsub_rn(__fmul_rn(wx, cos_a), __fmul_rn(wy, sin_a)); // vertexes.rs:20-25
     const float ry = __fadd_rn(__fmul_rn(wy, cos_a), __fmul_rn(wx, sin_a));
     const uint32_t tx = (uint32_t)(sat_i16(rx) + px16); // i16 wrap does not reach the low 6 bits
     const uint32_t ty = (uint32_t)(sat_i16(ry) + py16);
     const uint32_t texel = flat[((ty << 6) & 0xfc0u) | (tx & 63u)];
-    return lit_rgb_any(pal_fetch(pal_addr + texel * PAL_ENTRY), light_factor(lf, sat_i16(wx)));
+    return lit_rgb_any(pal_fetch(pal + texel * PAL_ENTRY), light_factor(lf, sat_i16(wx)));
 }
 
-template <int LPG, bool UNIT>
-__device__ __forceinline__ void tile_flat_span(const uint4 ra, const uint4 rc, int ya, int yb, int b0, int li, uint32_t col_addr, float CFY,
-                                               float cos_a, float sin_a, int px16, int py16, const uint8_t *__restrict__ flats,
-                                               uint32_t pal_addr, float one, cudaTextureObject_t tex_flats) {
+struct FlatView { // per-frame constants of the flat loops
+    float CFY, cos_a, sin_a;
+    int px16, py16;
+};
+
+// the fast flat loop: TS_FASTDIV and TS_UNIT (the span does not touch the horizon row, factor <= 1 on every row)
+__device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView &v, const uint4 ra, const uint4 rc, int ya, int yb, uint32_t addr,
+                                               const uint8_t *__restrict__ flats) {
+    const float wzvx = __uint_as_float(rc.x), gwz = __uint_as_float(rc.y), lf = __uint_as_float(rc.z);
+    const uint8_t *__restrict__ flat = flats + ra.z; // ONE 64-bit base, opaque to the compiler (see tile_wall_span)
+    asm("" : "+l"(flat));
+    const int yb8 = yb - TILE_LPG, py6 = v.py16 << 6;
+    int y = ya + t.li;
+    // rows y and y + 8 of this lane together (visplanes.rs:109-128, twice)
+    float2 vy = f2(__fsub_rn(v.CFY, (float)y), __fsub_rn(v.CFY, (float)(y + TILE_LPG)));
+    for (; y <= yb; y += 2 * TILE_LPG, vy = __fadd2_rn(vy, f2((float)(-2 * TILE_LPG))), addr += ROW16) {
+        float2 r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.y) : "f"(vy.y));
+        const float2 nvy = f2(-vy.x, -vy.y);
+        const float2 r = __ffma2_rn(r0, __ffma2_rn(nvy, r0, f2(1.0f)), r0); // refined_rcp, twice
+        const float2 wx = fast_div2(f2(gwz), nvy, r);                       // :113
+        const float2 wy = fast_div2(f2(wzvx), nvy, r);                      // :114
+        const float2 rx = add2_nofuse(__fmul2_rn(wx, f2(v.cos_a)), __fmul2_rn(wy, f2(-v.sin_a)), t.one); // wx*cos - wy*sin (vertexes.rs:20-25)
+        const float2 ry = add2_nofuse(__fmul2_rn(wy, f2(v.cos_a)), __fmul2_rn(wx, f2(v.sin_a)), t.one);
+        // :119-122  tx = (rx as i16 + px) & 63, ty = (ry as i16 + py) & 63 (the i16 wrap does not reach the low 6 bits); the flat
+        // is row-major: offset = ty * 64 + tx
+        const uint32_t o0 = ((uint32_t)(sat_i16(ry.x) * 64 + py6) & 0xfc0u) | ((uint32_t)(sat_i16(rx.x) + v.px16) & 63u);
+        const uint32_t o1 = ((uint32_t)(sat_i16(ry.y) * 64 + py6) & 0xfc0u) | ((uint32_t)(sat_i16(rx.y) + v.px16) & 63u);
+        const uint32_t t0 = ldg_u8(flat + o0), t1 = ldg_u8(flat + o1);
+        // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
+        const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
+        float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), t.one);
+        // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
+        fac.x = fmaxf(fac.x, 0.0f);
+        fac.y = fmaxf(fac.y, 0.0f);
+        const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(t.pal + t0 * PAL_ENTRY), fac.x), rgb1 = lit_rgb_unit_p(pal_fetch(t.pal + t1 * PAL_ENTRY), fac.y);
+        sts_u32(addr, rgb0);
+        if (y <= yb8) sts_u32(addr + ROW8, rgb1);
+    }
+}
+
+// every other flat span: one row per lane and iteration, the IEEE division where the hoisted reciprocal is not proven
+// (operands outside 2^-60..2^60, the horizon row vy == 0), the saturating colour path where the factor may exceed 1
+__device__ __noinline__ void tile_flat_span_any(TileCtx t, FlatView v, uint4 ra, uint4 rc, int ya, int yb, uint32_t addr, const uint8_t *__restrict__ flats) {
     const float wzvx = __uint_as_float(rc.x), gwz = __uint_as_float(rc.y), lf = __uint_as_float(rc.z);
     const uint8_t *__restrict__ flat = flats + ra.z;
-    int y = ya + li;
-    uint32_t addr = col_addr + 4u * (uint32_t)(y - b0);
-    if (ra.y & TS_FASTDIV) {
-        // rows y and y + LPG of this lane together (visplanes.rs:109-128, twice).  The row with vy == 0 (y == H/2 for even H)
-        // divides by zero: the loop leaves garbage there (no fault), it is redone below with the IEEE division.
-        float2 vy = f2(__fsub_rn(CFY, (float)y), __fsub_rn(CFY, (float)(y + LPG)));
-#ifdef DRR_FLAT_UNROLL2
-#pragma unroll 2
-#endif
-        for (; y <= yb; y += 2 * LPG, vy = __fadd2_rn(vy, f2((float)(-2 * LPG))), addr += 8u * LPG) {
-            float2 r0;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.y) : "f"(vy.y));
-            const float2 nvy = f2(-vy.x, -vy.y);
-            const float2 r = __ffma2_rn(r0, __ffma2_rn(nvy, r0, f2(1.0f)), r0); // refined_rcp, twice
-            const float2 wx = fast_div2(f2(gwz), nvy, r);                       // :113
-            const float2 wy = fast_div2(f2(wzvx), nvy, r);                      // :114
-            const float2 rx = add2_nofuse(__fmul2_rn(wx, f2(cos_a)), __fmul2_rn(wy, f2(-sin_a)), one); // wx*cos - wy*sin (vertexes.rs:20-25)
-            const float2 ry = add2_nofuse(__fmul2_rn(wy, f2(cos_a)), __fmul2_rn(wx, f2(sin_a)), one);
-            const uint32_t tx0 = (uint32_t)(sat_i16(rx.x) + px16), ty0 = (uint32_t)(sat_i16(ry.x) + py16);
-            const uint32_t tx1 = (uint32_t)(sat_i16(rx.y) + px16), ty1 = (uint32_t)(sat_i16(ry.y) + py16);
-#ifdef DRR_TEXFETCH
-            const uint32_t t0 = tex1Dfetch<unsigned char>(tex_flats, (int)(ra.z + (((ty0 << 6) & 0xfc0u) | (tx0 & 63u))));
-            const uint32_t t1 = tex1Dfetch<unsigned char>(tex_flats, (int)(ra.z + (((ty1 << 6) & 0xfc0u) | (tx1 & 63u))));
-#else
-            const uint32_t t0 = flat[((ty0 << 6) & 0xfc0u) | (tx0 & 63u)];
-            const uint32_t t1 = flat[((ty1 << 6) & 0xfc0u) | (tx1 & 63u)];
-#endif
-            // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
-            const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
-            float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), one);
-            // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
-            fac.x = fmaxf(fac.x, 0.0f);
-            fac.y = fmaxf(fac.y, 0.0f);
-            const float4 p0 = pal_fetch(pal_addr + t0 * PAL_ENTRY), p1 = pal_fetch(pal_addr + t1 * PAL_ENTRY);
-            uint32_t rgb0, rgb1;
-            if (UNIT || (fac.x <= 1.0f && fac.y <= 1.0f)) {
-                rgb0 = lit_rgb_unit_p(p0, fac.x);
-                rgb1 = lit_rgb_unit_p(p1, fac.y);
-            } else {
-                rgb0 = lit_rgb_any(p0, fac.x);
-                rgb1 = lit_rgb_any(p1, fac.y);
-            }
-            sts_u32(addr, rgb0);
-            if (y + LPG <= yb) sts_u32(addr + 4u * LPG, rgb1);
+    const bool fast = (ra.y & TS_FASTDIV) != 0;
+    int y = ya + t.li;
+    float vy = __fsub_rn(v.CFY, (float)y);
+    for (; y <= yb; y += TILE_LPG, vy = __fadd_rn(vy, (float)-TILE_LPG), addr += ROW8) {
+        uint32_t rgb;
+        if (fast && vy != 0.0f) {
+            const float r = refined_rcp(vy);
+            const float wx = fast_div(gwz, vy, r), wy = fast_div(wzvx, vy, r);
+            const float rx = __fsub_rn(__fmul_rn(wx, v.cos_a), __fmul_rn(wy, v.sin_a));
+            const float ry = __fadd_rn(__fmul_rn(wy, v.cos_a), __fmul_rn(wx, v.sin_a));
+            const uint32_t tx = (uint32_t)(sat_i16(rx) + v.px16), ty = (uint32_t)(sat_i16(ry) + v.py16);
+            const uint32_t texel = flat[((ty << 6) & 0xfc0u) | (tx & 63u)];
+            rgb = lit_rgb_any(pal_fetch(t.pal + texel * PAL_ENTRY), light_factor(lf, sat_i16(wx)));
+        } else {
+            rgb = flat_pixel_slow(vy, gwz, wzvx, lf, v.cos_a, v.sin_a, v.px16, v.py16, flat, t.pal);
         }
-        const int ym = (int)CFY; // exact integer when H is even
-        if (!UNIT && (float)ym == CFY && ym >= ya && ym <= yb && li == ((ym - ya) % LPG)) // (a UNIT span does not touch that row)
-            sts_u32(col_addr + 4u * (uint32_t)(ym - b0), flat_pixel_slow(0.0f, gwz, wzvx, lf, cos_a, sin_a, px16, py16, flat, pal_addr));
-    } else {
-        float vy = __fsub_rn(CFY, (float)y);
-        for (; y <= yb; y += LPG, vy -= (float)LPG, addr += 4u * LPG)
-            sts_u32(addr, flat_pixel_slow(vy, gwz, wzvx, lf, cos_a, sin_a, px16, py16, flat, pal_addr));
+        sts_u32(addr, rgb);
     }
 }
 
-template <int LPG, bool HOLES>
-__device__ __forceinline__ void tile_sky_span(const uint4 ra, int ya, int yb, int b0, int li, uint32_t col_addr,
-                                              const uint8_t *__restrict__ sky_rows, const uint16_t *__restrict__ texels, uint32_t pal_addr) {
-    uint32_t addr = col_addr + 4u * (uint32_t)(ya + li - b0);
-    for (int y = ya + li; y <= yb; y += LPG, addr += 4u * LPG) {
+__device__ __forceinline__ void tile_sky_span(const TileCtx &t, const uint4 ra, int ya, int yb, uint32_t addr, const uint8_t *__restrict__ sky_rows,
+                                              const uint16_t *__restrict__ texels) {
+    const bool holes = (ra.y & 0xffu) == KIND_SKY_HOLES;
+    // packed 0x00BBGGRR word of the entry whose 8-byte slot is at shared address e: pal + SM_PAL_PACKED + (e - pal) / 2
+    const uint32_t packed = t.pal - (t.pal >> 1) + SM_PAL_PACKED;
+    for (int y = ya + t.li; y <= yb; y += TILE_LPG, addr += ROW8) {
         const uint32_t texel = texels[ra.z + sky_rows[y]]; // column-major sky: base + tx*128 + ty
-        if (HOLES && texel == TEXEL_HOLE) continue;
-#ifdef DRR_PAL8
-        sts_u32(addr, lds_u32(pal_addr + 257u * 8u + (texel >> 1))); // packed RGB table behind the 8-byte entries; no lighting (visplanes.rs:74-77)
-#else
-        sts_u32(addr, lds_u32(pal_addr + texel + 12u)); // no lighting (visplanes.rs:74-77)
-#endif
+        if (holes && texel == t.hole) continue;
+        sts_u32(addr, lds_u32(packed + (texel >> 1))); // no lighting (visplanes.rs:74-77)
     }
 }
 
-// PRMT selector that assembles an output word starting at channel `ph` of pixel a: bytes a[ph..2] then b[0..]
-__device__ __forceinline__ uint32_t wsel(int ph) { return ph == 0 ? 0x4210u : ph == 1 ? 0x5421u : 0x6542u; }
+// ---- asynchronous copies (mbarrier, bulk copy, TMA store) ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared bulk copy (16-byte aligned, a multiple of 16 bytes), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared -> global: one box of the framebuffer tensor (96 bytes x 8 rows) from a dense row-major image of it in shared memory
+__device__ __forceinline__ void tma_store_box(const CUtensorMap *map, uint32_t src, int x_bytes, int row, int slot) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(x_bytes), "r"(row), "r"(slot) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
-// TC  = screen columns per tile (16: 48-byte row segments, 3 lanes x 10 rows per write-out step; 32: 96 bytes, 6 lanes x 5 rows)
-// LPG = lanes per span (32, 16 or 8); a warp works on 32 / LPG adjacent columns at once
-// RP  = tile column pitch in words: >= rows, RP % 32 == 2 (TC 16) or 1 (TC 32) so that the write-out reads are conflict-free
-template <int TC, int LPG, int NT, int NSPLIT, bool FAST_STORE>
-__global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MIN_BLOCKS) drr_tile_kernel(const __grid_constant__ DrawArgs a, int frame0, int band_rows, int nbands, int RP) {
-    extern __shared__ uint32_t s_tile[]; // [TC columns][RP] u32 pixels (0x00BBGGRR)
-#ifdef DRR_PAL8
-    __shared__ __align__(16) uint32_t s_pal[257 * 2 + 257]; // 257 x (bf16 r | bf16 g << 16, f32 b), then 257 packed 0x00BBGGRR
-#else
-    __shared__ float4 s_pal[257];        // entry 256 backs the None texel (its colour is never stored)
-#endif
-    __shared__ int s_next;
-    constexpr int G = 32 / LPG;          // columns per warp step
-    constexpr int NSETS = TC / G;
-    constexpr int NW = NT / 32;
+// MINB = resident CTAs per SM the register budget is set for (6: tiles of up to ~224 rows; 4: up to 400 rows)
+// FAST = W % 32 == 0 and every band a multiple of 8 rows: TMA write-out with the checksum fused; otherwise a bytewise
+//        write-out and a separate checksum pass
+template <int MINB, bool FAST>
+__global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __grid_constant__ DrawArgs a, const __grid_constant__ CUtensorMap fbmap, int frame0) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    // Every shared address below is derived from the PROBED base in the kernel arguments (a constant-bank operand), not from
+    // cvta(s_dyn) (which ptxas re-derives from SR_CgaCtaId wherever it runs out of registers); the two must agree, since the
+    // texel pool holds absolute shared addresses of palette entries.
+    if ((uint32_t)__cvta_generic_to_shared(s_dyn) != a.pal_base) __trap();
+    const uint32_t pal = a.pal_base + SM_PAL, bar = a.pal_base + SM_BAR, tile = a.pal_base + SM_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gpf = (a.W + TC - 1) / TC;
-    const int grp = lane / LPG, li = lane % LPG;
-    const uint32_t pal_addr = (uint32_t)__cvta_generic_to_shared(s_pal);
-    const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(s_tile);
+    const int grp = lane >> 3, li = lane & 7;
     const uint16_t *__restrict__ texels = a.texels;
     const uint8_t *__restrict__ flats = a.flats;
 
     // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
     int g = (int)blockIdx.x, band = 0;
-    if (nbands > 1) {
-        g = (int)(blockIdx.x / (unsigned)nbands);
-        band = (int)blockIdx.x - g * nbands;
+    if (a.nbands > 1) {
+        g = (int)(blockIdx.x / (unsigned)a.nbands);
+        band = (int)blockIdx.x - g * a.nbands;
     }
     const int f = frame0 + (int)blockIdx.y;
-    const int b0 = band * band_rows, b1 = min(a.H, b0 + band_rows) - 1;
-    const int nlists = nbands <= MAX_LIST_BANDS ? nbands : 1, lband = nbands <= MAX_LIST_BANDS ? band : 0; // the bin kernel's list of this band
-    // everything the CTA needs from global memory is requested before the first barrier, so that the L2 round trips overlap
+    const int b0 = band * a.band_rows, b1 = min(a.H, b0 + a.band_rows) - 1;
+    const int nlists = a.nbands <= MAX_LIST_BANDS ? a.nbands : 1, lband = a.nbands <= MAX_LIST_BANDS ? band : 0; // the bin kernel's list of this band
+    // the palette image: one bulk copy, completion on an mbarrier
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_proxy_async(); // the initialised barrier is visible to the copy engine
+        mbar_expect_tx(bar, SM_PAL_BYTES);
+        bulk_load(pal, a.pal_image, SM_PAL_BYTES, bar);
+    }
+    // everything else the CTA needs from global memory is requested before the first barrier, so that the round trips overlap
     const View vw = a.views[f];
     const uint32_t slot = a.frame_slot[f];
-    ColIdx ci_first;
-    ci_first.first = 0; ci_first.n = 0;
-    if (warp < NSETS * NSPLIT) {
-        const int x = g * TC + grp * NSETS + (NSPLIT > 1 ? warp % NSETS : warp);
-        if (x < a.W) ci_first = a.colidx[((size_t)f * nlists + lband) * a.W + x];
-    }
-#ifdef DRR_PAL8
-    // (passing this image as a by-value kernel parameter and copying it from the constant bank was measured: the divergent
-    // LDCs made the empty-CTA time 3x longer)
-    for (int i = threadIdx.x; i < 257 * 3; i += NT) s_pal[i] = a.pal_image[i];
-#else
-    for (int i = threadIdx.x; i < 257; i += NT) s_pal[i] = a.palette[min(i, 255)];
-#endif
-    if (threadIdx.x == 0) s_next = NW;
-    __syncthreads();
-    const int px16 = sat_i16(vw.pos_x), py16 = sat_i16(vw.pos_y); // visplanes.rs:119-120 `player.position.x as i16`
+    const int c = warp * 4 + grp, x = g * TILE_COLS + c; // a warp owns four adjacent columns, a lane group one of them
+    ColIdx ci;
+    ci.first = 0; ci.n = 0;
+    if (x < a.W) ci = a.colidx[((size_t)f * nlists + lband) * a.W + x];
+    __syncthreads(); // the barrier's initialisation is visible to every thread
+    mbar_wait(bar, 0);
 
-    // ---- draw: a warp takes column sets (G adjacent columns) until none is left; each lane group walks its column's span
-    // list in draw order ("last writer wins, transparent texels do not write"): the kinds that always write
-    // simply overwrite, the HOLES kinds skip their None texels
-    // (NSPLIT > 1: a work item is a column set x one of NSPLIT row ranges of the band, so that more warps than column sets
-    // have work; spans are clipped to the item's rows, which keeps the draw order where it matters: on the same pixel)
-    const int prow = (b1 - b0 + NSPLIT) / NSPLIT;
-    for (int item = warp; item < NSETS * NSPLIT;) {
-        const int cs = NSPLIT > 1 ? item % NSETS : item, part = NSPLIT > 1 ? item / NSETS : 0;
-        const int pb0 = b0 + part * prow, pb1 = min(b1, pb0 + prow - 1);
-        // the G columns of a set are NSETS apart: their lane groups then store to disjoint bank ranges when they sit on the same rows
-        const int c = grp * NSETS + cs, x = g * TC + c;
-        ColIdx ci = ci_first; // the warp's first item was requested in the prologue
-        if (item != warp) {
-            ci.first = 0; ci.n = 0;
-            if (x < a.W) ci = a.colidx[((size_t)f * nlists + lband) * a.W + x];
-        }
+    // ---- draw: each lane group walks its column's span list in draw order ("last writer wins, transparent texels do not
+    // write"): the kinds that always write simply overwrite, the kinds with None texels skip them
+    {
+        TileCtx t;
+        t.pal = pal;
+        t.hole = a.pal_base + SM_PAL + TEXEL_NONE_INDEX * PAL_ENTRY;
+        t.one = a.one;
+        t.li = li;
+        FlatView fv;
+        fv.CFY = a.CFY;
+        fv.cos_a = vw.cos_a;
+        fv.sin_a = vw.sin_a;
+        fv.px16 = sat_i16(vw.pos_x); // visplanes.rs:119-120 `player.position.x as i16`
+        fv.py16 = sat_i16(vw.pos_y);
         const int n = (a.dbg & 16) ? 0 : (int)(ci.n & ~COL_COVERED);
         const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
-        const uint32_t col_addr = tile_addr + 4u * (uint32_t)(c * RP);
+        // shared address of row r (of the band) of this lane group's column: tile_offset(c, r)
+        const uint32_t colbase = tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2), sw = (uint32_t)warp & 4u;
+        auto row_addr = [&](int r) { return colbase + (((uint32_t)r >> 3) << 10) + ((((uint32_t)r & 7u) ^ sw) << 4); };
         // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
-        if (!(ci.n & COL_COVERED) && !(a.dbg & 1))
-            for (int r = pb0 - b0 + li; r <= pb1 - b0; r += LPG) sts_u32(col_addr + 4u * (uint32_t)r, 0u);
+        if (!(ci.n & COL_COVERED) && !(a.dbg & 1)) {
+            uint32_t addr = row_addr(li);
+            for (int r = li; r <= b1 - b0; r += TILE_LPG, addr += ROW8) sts_u32(addr, 0u);
+        }
         uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
         if (n > 0) ra_next = P[0];
         for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
@@ -595,85 +651,96 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
             if (j < n) {
                 const uint4 ra = ra_next;
                 if (j + 1 < n) ra_next = P[4 * (j + 1)]; // the next span's first words are fetched while this one is drawn
-                const int ya = max((int)(ra.x & 0xffff), pb0), yb = min((int)(ra.x >> 16), pb1);
+                const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
+                    const uint32_t addr = row_addr(ya + li - b0);
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
-                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV))
-                            tile_flat_span<LPG, true>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one, a.tex_flats);
-                        else
-                            tile_flat_span<LPG, false>(ra, P[4 * j + 2], ya, yb, b0, li, col_addr, a.CFY, vw.cos_a, vw.sin_a, px16, py16, flats, pal_addr, a.one, a.tex_flats);
-                    } else if (kind == KIND_WALL) {
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, P[4 * j + 2], ya, yb, addr, flats);
+                        else tile_flat_span_any(t, fv, ra, P[4 * j + 2], ya, yb, addr, flats);
+                    } else if (kind <= KIND_WALL_HOLES) {
                         const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
-                        if (ra.y & TS_POW2) tile_wall_span<LPG, false, true>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                        else tile_wall_span<LPG, false, false>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                    } else if (kind == KIND_WALL_HOLES) {
-                        const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
-                        if (ra.y & TS_POW2) tile_wall_span<LPG, true, true>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                        else tile_wall_span<LPG, true, false>(a, ra, rb, rc, rd, ya, yb, b0, li, col_addr, texels, pal_addr, a.one);
-                    } else if (kind == KIND_SKY) {
-                        tile_sky_span<LPG, false>(ra, ya, yb, b0, li, col_addr, a.sky_rows, texels, pal_addr);
-                    } else if (kind == KIND_SKY_HOLES) {
-                        tile_sky_span<LPG, true>(ra, ya, yb, b0, li, col_addr, a.sky_rows, texels, pal_addr);
+                        if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                        else if (kind == KIND_WALL) {
+                            if (ra.y & TS_POW2) tile_wall_span<false, true>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<false, false>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                        } else {
+                            if (ra.y & TS_POW2) tile_wall_span<true, true>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<true, false>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                        }
+                    } else if (kind == KIND_SKY || kind == KIND_SKY_HOLES) {
+                        tile_sky_span(t, ra, ya, yb, addr, a.sky_rows, texels);
                     }
                 }
             }
         }
-        int nx = 0;
-        if (lane == 0) nx = atomicAdd(&s_next, 1);
-        item = __shfl_sync(0xffffffffu, nx, 0);
     }
     __syncthreads(); // every span of the tile is in before the write-out
 
-    // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x).  A row of the tile is TC*3 bytes = LPR 16-byte
-    // vectors; a warp step covers RPI rows with LPR lanes each.  Vector j of a row holds bytes 16j .. 16j+15, i.e. pixels
-    // (16j)/3 .. (16j+15)/3 of the tile row, starting at channel j % 3 of the first one.
-    const size_t pitch = (size_t)a.W * 3;
-    uint8_t *base = a.frames + (size_t)slot * a.frame_stride + (size_t)g * (TC * 3);
+    // ---- write-out: Pixels::set (pixels.rs:22-30), RGB24 at 3*(y*W + x)
     const int nrows = b1 - b0 + 1;
-    if (FAST_STORE) {
-        constexpr int LPR = TC * 3 / 16, RPI = 32 / LPR;
-        const int rl = lane / LPR, j = lane % LPR, ph = j % 3;
+    if (FAST) {
+        // A warp step = 16 rows of the tile (two blocks) = 16 x 96 bytes of the framebuffer.  Lane (rhi, h, rlo) reads the
+        // 16 pixels of half h (quads 4h .. 4h+3) of row rr = 4*rhi + rlo: four LDS.128, conflict-free (a quarter warp = 4 rows
+        // x 2 halves, see tile_offset()); packs them into 48 bytes; and, once every lane of the warp has read, stores them at
+        // rr*96 + h*48 of the SAME two blocks (conflict-free too), which then hold two dense 96-byte x 8-row boxes for the TMA.
+        const int rlo = lane & 3, h = (lane >> 2) & 1, rr = (lane >> 3) * 4 + rlo;
+        const int nblk = nrows >> 3;
+        const uint32_t pw = (uint32_t)a.W * 3u / 4u; // framebuffer row pitch in words
+        const uint32_t src_off = ((uint32_t)(rr >> 3) << 10) + ((uint32_t)h << 9) + ((((uint32_t)rr & 7u) ^ ((uint32_t)h << 2)) << 4);
+        const uint32_t dst_off = (uint32_t)rr * 96u + (uint32_t)h * 48u;
+        const uint32_t C = 0x9E3779B1u; // checksum weight of word i is (i + 1) * C mod 2^32 (drr.h)
         uint64_t acc = 0;
-        if (lane < LPR * RPI && !(a.dbg & 8)) {
-            const int cb = (16 * j) / 3;
-            // word m of the vector starts at byte 16j + 4m of the row: pixel q(m), channel (ph + m) % 3 -> selector; the pixel
-            // pairs are (0,1) (1,2)|(2,3) (2,3)|(3,4) (4,5) relative to cb, depending on the phase
-            const uint32_t s0 = wsel(ph), s1 = wsel((ph + 1) % 3), s2 = wsel((ph + 2) % 3), s3 = s0;
-            const uint32_t pw = (uint32_t)(pitch >> 2);
-            int r = warp * RPI + rl;
-            uint32_t ta = tile_addr + 4u * (uint32_t)(cb * RP + r);
-            uint32_t *wp = reinterpret_cast<uint32_t *>(base) + (size_t)(b0 + r) * pw + 4 * j;
-            // checksum weight of word i is (i + 1) * C mod 2^32 (drr.h); this lane's words are i0 .. i0+3, i0 advancing by a row step
-            const uint32_t C = 0x9E3779B1u;
-            uint32_t k0 = ((uint32_t)(b0 + r) * pw + (uint32_t)g * (TC * 3 / 4) + 4u * (uint32_t)j + 1u) * C;
-            const uint32_t kstep = (uint32_t)(NW * RPI) * pw * C;
-            const size_t wstep = (size_t)(NW * RPI) * pw;
-#pragma unroll 2
-            for (; r < nrows; r += NW * RPI) {
-                const uint32_t p0 = lds_u32(ta), p1 = lds_u32(ta + 4u * RP), p2 = lds_u32(ta + 8u * RP), p3 = lds_u32(ta + 12u * RP),
-                               p4 = lds_u32(ta + 16u * RP), p5 = lds_u32(ta + 20u * RP);
-                uint4 v;
-                v.x = __byte_perm(p0, p1, s0);
-                v.y = __byte_perm(ph == 2 ? p2 : p1, ph == 2 ? p3 : p2, s1);
-                v.z = __byte_perm(ph == 0 ? p2 : p3, ph == 0 ? p3 : p4, s2);
-                v.w = __byte_perm(p4, p5, s3);
-                if (!(a.dbg & 2)) *reinterpret_cast<uint4 *>(wp) = v;
-                if (!(a.dbg & 4)) acc += (uint64_t)v.x * k0 + (uint64_t)v.y * (k0 + C) + (uint64_t)v.z * (k0 + 2u * C) + (uint64_t)v.w * (k0 + 3u * C);
-                ta += 4u * (NW * RPI);
-                wp += wstep;
-                k0 += kstep;
+        for (int s = warp; 2 * s < nblk; s += TILE_THREADS / 32) {
+            const uint32_t region = tile + ((uint32_t)s << 11);
+            const bool act = 2 * s + (rr >> 3) < nblk && !(a.dbg & 8);
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+            if (act) {
+                q0 = lds_u128(region + src_off);
+                q1 = lds_u128(region + src_off + 128u);
+                q2 = lds_u128(region + src_off + 256u);
+                q3 = lds_u128(region + src_off + 384u);
+            }
+            // 4 pixels (0x??BBGGRR each) -> 3 words of the byte stream R G B R | G B R G | B R G B
+            uint4 v0, v1, v2;
+            v0.x = __byte_perm(q0.x, q0.y, 0x4210); v0.y = __byte_perm(q0.y, q0.z, 0x5421); v0.z = __byte_perm(q0.z, q0.w, 0x6542);
+            v0.w = __byte_perm(q1.x, q1.y, 0x4210); v1.x = __byte_perm(q1.y, q1.z, 0x5421); v1.y = __byte_perm(q1.z, q1.w, 0x6542);
+            v1.z = __byte_perm(q2.x, q2.y, 0x4210); v1.w = __byte_perm(q2.y, q2.z, 0x5421); v2.x = __byte_perm(q2.z, q2.w, 0x6542);
+            v2.y = __byte_perm(q3.x, q3.y, 0x4210); v2.z = __byte_perm(q3.y, q3.z, 0x5421); v2.w = __byte_perm(q3.z, q3.w, 0x6542);
+            __syncwarp(); // every lane has read its pixels: the two blocks may be overwritten
+            if (act) {
+                sts_u128(region + dst_off, v0);
+                sts_u128(region + dst_off + 16u, v1);
+                sts_u128(region + dst_off + 32u, v2);
+                if (!(a.dbg & 4)) {
+                    const uint32_t k0 = ((uint32_t)(b0 + 16 * s + rr) * pw + (uint32_t)g * (TILE_COLS * 3 / 4) + 12u * (uint32_t)h + 1u) * C;
+                    acc += (uint64_t)v0.x * k0 + (uint64_t)v0.y * (k0 + C) + (uint64_t)v0.z * (k0 + 2u * C) + (uint64_t)v0.w * (k0 + 3u * C);
+                    acc += (uint64_t)v1.x * (k0 + 4u * C) + (uint64_t)v1.y * (k0 + 5u * C) + (uint64_t)v1.z * (k0 + 6u * C) + (uint64_t)v1.w * (k0 + 7u * C);
+                    acc += (uint64_t)v2.x * (k0 + 8u * C) + (uint64_t)v2.y * (k0 + 9u * C) + (uint64_t)v2.z * (k0 + 10u * C) + (uint64_t)v2.w * (k0 + 11u * C);
+                }
+            }
+            fence_proxy_async(); // this lane's stores are visible to the copy engine ...
+            __syncwarp();        // ... and so are everybody else's, before lane 0 hands the boxes over
+            if (lane == 0 && !(a.dbg & 2)) {
+                tma_store_box(&fbmap, region, g * (TILE_COLS * 3), b0 + 16 * s, (int)slot);
+                if (2 * s + 1 < nblk) tma_store_box(&fbmap, region + 768u, g * (TILE_COLS * 3), b0 + 16 * s + 8, (int)slot);
+                bulk_commit();
             }
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (lane == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long *>(a.crc + slot), (unsigned long long)acc);
+        if (lane == 0) {
+            if (acc) atomicAdd(reinterpret_cast<unsigned long long *>(a.crc + slot), (unsigned long long)acc);
+            bulk_wait_read_all(); // the copy engine has read this warp's boxes: the CTA's shared memory may be handed on
+        }
     } else {
-        for (int i = threadIdx.x; i < TC * nrows; i += NT) { // generic widths: bytewise; the checksum is a separate pass
-            const int c = i % TC, r = i / TC, x = g * TC + c;
-            if (x >= a.W) continue;
-            const uint32_t rgb = s_tile[c * RP + r];
-            uint8_t *p = base + (size_t)(b0 + r) * pitch + c * 3;
+        const size_t pitch = (size_t)a.W * 3;
+        uint8_t *base = a.frames + (size_t)slot * a.frame_stride + (size_t)g * (TILE_COLS * 3);
+        for (int i = threadIdx.x; i < TILE_COLS * nrows; i += TILE_THREADS) { // generic widths: bytewise; the checksum is a separate pass
+            const int cc = i % TILE_COLS, r = i / TILE_COLS;
+            if (g * TILE_COLS + cc >= a.W) continue;
+            const uint32_t rgb = lds_u32(tile + tile_offset(cc, r));
+            uint8_t *p = base + (size_t)(b0 + r) * pitch + cc * 3;
             p[0] = (uint8_t)rgb;
             p[1] = (uint8_t)(rgb >> 8);
             p[2] = (uint8_t)(rgb >> 16);
@@ -681,15 +748,30 @@ __global__ void __launch_bounds__(NT, TC == 32 ? TILE_MIN_BLOCKS_SHORT : TILE_MI
     }
 }
 
+// shared window address of a CTA's dynamic shared memory (no static shared memory, like the tile kernel)
+__global__ void drr_shared_base_kernel(uint32_t *out) {
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(s_dyn);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------------
+cudaError_t probe_shared_base(uint32_t *base) {
+    uint32_t *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    drr_shared_base_kernel<<<1, 32, SM_TILE + 1024>>>(d);
+    e = cudaMemcpy(base, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e;
+}
+
 cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t st) {
     if (nframes <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(a.frame_cursor + frame0, 0, sizeof(uint32_t) * (size_t)nframes, st);
     if (e != cudaSuccess) return e;
-    int maxt = 192;
-    if (const char *e = getenv("DRR_BIN_THREADS")) maxt = std::max(32, std::min(BIN_THREADS, atoi(e) / 32 * 32));
+    const int maxt = 192;                                           // (the CTA size hardly matters: 128 .. 384 measured)
     const int bpf = (a.W + maxt - 1) / maxt;                        // CTAs per frame
     const int threads = ((a.W + bpf - 1) / bpf + 31) / 32 * 32;     // columns per CTA, whole warps
     const long long blocks = (long long)nframes * bpf;
@@ -704,93 +786,63 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
 }
 
 void tile_bands(int H, int *nbands, int *band_rows) {
-    // rows per band: at most 400 (a 32-column tile is then <= 51 KB: four CTAs per SM), equal bands.  Since the bin kernel writes
-    // one span list per (column, band), wide-and-short tiles beat the 16-column full-height ones (tools/sweep_wide.sh).
-    int max_rows = 400;
-    if (const char *e = getenv("DRR_TILE_MAX_ROWS")) max_rows = std::max(32, atoi(e));
+    // rows per band: at most 400 (a tile is then 51 KB: four CTAs per SM), equal bands; a multiple of 8 rows when H is, so that
+    // every band is whole 8-row blocks (the TMA write-out's box).  The bin kernel writes one span list per (column, band).
+    const int max_rows = 400;
     *nbands = (H + max_rows - 1) / max_rows;
     *band_rows = (H + *nbands - 1) / *nbands;
+    if (H % 8 == 0) *band_rows = (*band_rows + 7) / 8 * 8;
 }
 
 void tile_config(int W, int H, int *tc, int *lpg) {
-    // measured (tools/sweep_tile.sh, tools/sweep_env.sh, tools/sweep_wide.sh; profiles/r1_ab_measurements.md): 32-column tiles
-    // (96-byte row segments: full 32-byte sectors) with 8 lanes per span at every resolution -- short lane groups keep the
-    // warp full on short spans; 16-column tiles and other group sizes stay selectable for A/B runs
-    *tc = 32;
-    *lpg = 8;
-    if (const char *e = getenv("DRR_TILE_COLS")) {
-        const int v = atoi(e);
-        if (v == 16 || v == 32) *tc = v;
-    }
-    if (const char *e = getenv("DRR_TILE_LPG")) {
-        const int v = atoi(e);
-        if (v == 8 || v == 16 || v == 32) *lpg = v;
-    }
+    *tc = TILE_COLS;
+    *lpg = TILE_LPG;
 }
 
-template <int TC, int LPG, int NT, int NSPLIT>
-static cudaError_t launch_tile_t(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
-    const int gpf = (a.W + TC - 1) / TC;
-    // rows per band: the whole column while the tile stays within ~52 KB (TC 16) / ~105 KB (TC 32), else equal bands
-    const int nbands = a.nbands, band_rows = a.band_rows; // tile_bands(), shared with the bin kernel
-    const int want = TC == 16 ? 2 : 1;
-    int RP = band_rows;
-    while (RP % 32 != want) ++RP;
-    const long long blocks = (long long)nframes * gpf * nbands;
-    if (blocks == 0) return cudaSuccess;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    size_t dyn = ((size_t)TC * RP * 4 + 15) / 16 * 16;
-    if (const char *e = getenv("DRR_TILE_SMEM_PAD_KB")) dyn += (size_t)atoi(e) * 1024; // A/B: fewer CTAs per SM, more L1
-    const bool fast = (a.W % TC) == 0;
-    *launches = 1;
-    cudaError_t e;
-    auto prepare = [&](auto kernel) -> cudaError_t {
-        static bool done = false;
-        if (done) return cudaSuccess;
-        done = true;
-        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    };
-    // one CTA per tile (a persistent variant with a static tile stride was measured and lost: profiles/r1_ab_measurements.md)
-    if ((long long)gpf * nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which (device, kernel) pairs have it
+static cudaError_t allow_big_tiles(const void *kernel) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, kernel})) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) done.insert({dev, kernel});
+    return e;
+}
+
+template <int MINB, bool FAST>
+static cudaError_t launch_tile_t(const DrawArgs &a, const CUtensorMap &map, int frame0, int nframes, size_t dyn, cudaStream_t st, int *launches) {
+    const int gpf = (a.W + TILE_COLS - 1) / TILE_COLS;
+    cudaError_t e = allow_big_tiles(reinterpret_cast<const void *>(&drr_tile_kernel<MINB, FAST>));
+    if (e != cudaSuccess) return e;
     for (int f0 = 0; f0 < nframes; f0 += 65535) { // gridDim.y limit
-        const dim3 grid((unsigned)(gpf * nbands), (unsigned)std::min(65535, nframes - f0));
-        if (fast) {
-            if ((e = prepare(drr_tile_kernel<TC, LPG, NT, NSPLIT, true>)) != cudaSuccess) return e;
-            drr_tile_kernel<TC, LPG, NT, NSPLIT, true><<<grid, NT, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
-        } else {
-            if ((e = prepare(drr_tile_kernel<TC, LPG, NT, NSPLIT, false>)) != cudaSuccess) return e;
-            drr_tile_kernel<TC, LPG, NT, NSPLIT, false><<<grid, NT, dyn, st>>>(a, frame0 + f0, band_rows, nbands, RP);
-        }
-        if (f0) ++*launches;
-    }
-    if (!fast) {
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        e = launch_checksum_pass(a, frame0, nframes, st, launches);
-        if (e != cudaSuccess) return e;
+        const dim3 grid((unsigned)(gpf * a.nbands), (unsigned)std::min(65535, nframes - f0));
+        drr_tile_kernel<MINB, FAST><<<grid, TILE_THREADS, dyn, st>>>(a, map, frame0 + f0);
+        ++*launches;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches) {
-    int tc, lpg;
-    tile_config(a.W, a.H, &tc, &lpg);
-    if (tc == 16) {
-        // A/B knob DRR_TILE_SPLIT=2: 12 warps (40 registers) share a tile and each column set is cut into two row ranges, so
-        // that 48 instead of 32 warps are resident per SM -- measured slower (1.30 vs 1.16 ms at 1280x800), kept for the record
-        const char *e = getenv("DRR_TILE_SPLIT");
-        if (e && atoi(e) == 2) {
-            if (lpg == 32) return launch_tile_t<16, 32, 384, 2>(a, frame0, nframes, st, launches);
-            if (lpg == 16) return launch_tile_t<16, 16, 384, 2>(a, frame0, nframes, st, launches);
-            return launch_tile_t<16, 8, 384, 2>(a, frame0, nframes, st, launches);
-        }
-        if (lpg == 32) return launch_tile_t<16, 32, 256, 1>(a, frame0, nframes, st, launches);
-        if (lpg == 16) return launch_tile_t<16, 16, 256, 1>(a, frame0, nframes, st, launches);
-        return launch_tile_t<16, 8, 256, 1>(a, frame0, nframes, st, launches);
+cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0, int nframes, cudaStream_t st, int *launches) {
+    *launches = 0;
+    if (nframes <= 0) return cudaSuccess;
+    const int gpf = (a.W + TILE_COLS - 1) / TILE_COLS;
+    if ((long long)gpf * a.nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const size_t dyn = SM_TILE + (size_t)((a.band_rows + 7) / 8) * 1024; // whole 8-row blocks
+    const bool fast = fbmap && a.W % TILE_COLS == 0 && a.H % 8 == 0 && a.band_rows % 8 == 0;
+    const bool small = dyn <= 36 * 1024; // six CTAs per SM fit: 40 registers; else four: 56
+    cudaError_t e;
+    if (fast) {
+        e = small ? launch_tile_t<6, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);
+    } else {
+        static const CUtensorMap none = {};
+        e = small ? launch_tile_t<6, false>(a, none, frame0, nframes, dyn, st, launches) : launch_tile_t<4, false>(a, none, frame0, nframes, dyn, st, launches);
+        if (e == cudaSuccess) e = launch_checksum_pass(a, frame0, nframes, st, launches);
     }
-    if (lpg == 32) return launch_tile_t<32, 32, 256, 1>(a, frame0, nframes, st, launches);
-    if (lpg == 16) return launch_tile_t<32, 16, 256, 1>(a, frame0, nframes, st, launches);
-    return launch_tile_t<32, 8, 256, 1>(a, frame0, nframes, st, launches);
+    return e;
 }
 
 } // namespace drr

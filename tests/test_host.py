@@ -169,14 +169,17 @@ def test_sass_keeps_products_and_sums_apart():
     sass = subprocess.run(["cuobjdump", "-sass", drr.LIB_PATH], capture_output=True, text=True, check=True).stdout
     kernels = re.split(r"\n\s*Function : ", sass)
     tile = [k for k in kernels if "drr_tile_kernel" in k.split("\n", 1)[0]]
-    assert len(tile) >= 12  # 2 tile widths x 3 lane-group sizes x 2 store paths
+    assert len(tile) == 4  # 2 register budgets (4 / 6 CTAs per SM) x 2 write-out paths
     for k in tile:
         name = k.split("\n", 1)[0]
         assert "FMUL2" in k and "FFMA2" in k and "FADD2" in k, name
         # (c*f) + 2^23 must stay FMUL then FADD.RZ (the only FFMA.RZ allowed is the one inside the IEEE division subroutine)
         assert "FFMA2.RZ" not in k and not re.search(r"FFMA\.RZ [^;]*8388608", k), name
         assert len(re.findall(r"FADD2?\.RZ [^;]*8388608", k)) >= 4, name
-        assert len(re.findall(r"FFMA2 [^;]*UR\d+\.F32", k)) >= 6, name    # wall sum, rx, ry, factor (x2 loop copies at least)
+        # the `one` multiplies: wall sum, rx, ry, factor (the multiplier is a register or a uniform register, never an immediate 1)
+        assert not re.search(r"FFMA2 [^;]*, 1, ", k), name
+        assert "UBLKCP" in k and "SYNCS" in k, name                       # palette image: bulk copy on an mbarrier
+        assert ("UTMASTG" in k) == ("ELb1E" in name), name               # TMA write-out in the fast-store kernels only
 
 
 def test_checksum_definitions_agree():
