@@ -165,8 +165,38 @@ struct FeState {
     uint64_t device_list_bytes = 0; // size of the lists the last drr_fe_emit_views wrote on the device
 };
 
+// Tuning / diagnostic knobs: each has an environment variable that is read ONCE, when the context is created (never on
+// the launch path); drr_set_knob() changes one afterwards.  0 / false = the built-in default.
+struct Knobs {
+    int dbg = 0;                 // DRR_DBG: timing experiments of a -DDRR_DBG_KNOBS build only (drr_tile.cu)
+    int submit_chunks = 0;       // DRR_SUBMIT_CHUNKS: upload chunks of drr_submit (default: ~4 MB of lists each, at most 8)
+    int submit_one_stream = 0;   // DRR_SUBMIT_ONE_STREAM: all chunks on the context's stream
+    int submit_trace = 0;        // DRR_SUBMIT_TRACE: per-chunk time line on stderr
+    int fe_trace = 0;            // DRR_FE_TRACE: host-side time line of drr_fe_emit_views on stderr
+    int fe_two_pass = 0;         // DRR_FE_TWO_PASS: count pass + emit pass instead of slabs + compaction
+    int fe_slab_div = 0;         // DRR_FE_SLAB_DIV: shrink the per-view slabs (tests: provoke the fallback)
+    int fe_cap_renders = 0, fe_cap_dsegs = 0, fe_cap_allcols_per_w = 0; // DRR_FE_CAP_*: masked phase working arrays
+    struct Name { const char *env, *name; int Knobs::*field; };
+    static const Name *table(size_t *n) {
+        static const Name t[] = {{"DRR_DBG", "dbg", &Knobs::dbg}, {"DRR_SUBMIT_CHUNKS", "submit_chunks", &Knobs::submit_chunks},
+                                 {"DRR_SUBMIT_ONE_STREAM", "submit_one_stream", &Knobs::submit_one_stream}, {"DRR_SUBMIT_TRACE", "submit_trace", &Knobs::submit_trace},
+                                 {"DRR_FE_TRACE", "fe_trace", &Knobs::fe_trace}, {"DRR_FE_TWO_PASS", "fe_two_pass", &Knobs::fe_two_pass},
+                                 {"DRR_FE_SLAB_DIV", "fe_slab_div", &Knobs::fe_slab_div}, {"DRR_FE_CAP_RENDERS", "fe_cap_renders", &Knobs::fe_cap_renders},
+                                 {"DRR_FE_CAP_DSEGS", "fe_cap_dsegs", &Knobs::fe_cap_dsegs}, {"DRR_FE_CAP_ALLCOLS_PER_W", "fe_cap_allcols_per_w", &Knobs::fe_cap_allcols_per_w}};
+        *n = sizeof(t) / sizeof(t[0]);
+        return t;
+    }
+    void read_environment() {
+        size_t n;
+        const Name *t = table(&n);
+        for (size_t i = 0; i < n; i++)
+            if (const char *e = getenv(t[i].env)) this->*(t[i].field) = std::max(1, atoi(e)); // (set but "0" or empty counts as 1, as before)
+    }
+};
+
 struct drr_ctx : Lists {
     FeState fes;
+    Knobs knobs;
     bool device_lists = false; // the current batch's lists were written on the device (drr_fe_emit_views): nothing to upload
     int W = 0, H = 0, device = 0, max_views = 0;
     cudaStream_t stream = nullptr;
@@ -303,6 +333,7 @@ int drr_ctx_create(int width, int height, int device_ordinal, int max_views, drr
         return DRR_E_CUDA;
     }
     drr_ctx *c = new drr_ctx();
+    c->knobs.read_environment();
     c->W = width;
     c->H = height;
     c->device = device_ordinal;
@@ -402,6 +433,18 @@ int drr_set_stream(drr_ctx *ctx, void *cuda_stream) {
     return DRR_OK;
 }
 void *drr_get_stream(drr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int drr_set_knob(drr_ctx *ctx, const char *name, int value) {
+    CTX_CHECK(ctx);
+    size_t n;
+    const Knobs::Name *t = Knobs::table(&n);
+    for (size_t i = 0; name && i < n; i++)
+        if (!strcmp(name, t[i].name)) {
+            ctx->knobs.*(t[i].field) = value;
+            return DRR_OK;
+        }
+    return fail(ctx, DRR_E_INVALID, "drr_set_knob: unknown knob");
+}
 
 // ---- assets ------------------------------------------------------------------------------------------------------
 int drr_upload_palette(drr_ctx *ctx, const uint8_t rgb[768]) {
@@ -917,8 +960,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.Wf = (float)(uint32_t)ctx->W;
     a.Hf = (float)(uint32_t)ctx->H;
     a.one = 1.0f;
-    a.dbg = 0;
-    if (const char *e = getenv("DRR_DBG")) a.dbg = atoi(e); // timing experiments only: results are wrong with any bit set
+    a.dbg = ctx->knobs.dbg; // timing experiments of a -DDRR_DBG_KNOBS build only
     a.views = ctx->d_views.p;
     a.ops = ctx->d_ops.p;
     a.frame_op_base = ctx->d_frame_op_base.p;
@@ -1025,7 +1067,7 @@ int drr_submit(drr_ctx *ctx) {
     if ((rc = reserve_device_lists(ctx))) return rc;
     // ~4 MB of lists per chunk, at most 8 chunks (measured: tools/sweep_submit.sh; more chunks cost more in launches than they hide)
     size_t nchunks = std::min<size_t>({(size_t)8, nf, (size_t)(list_bytes(ctx) / (4u << 20)) + 1});
-    if (const char *e = getenv("DRR_SUBMIT_CHUNKS")) nchunks = std::min<size_t>(nf, (size_t)std::max(1, atoi(e)));
+    if (ctx->knobs.submit_chunks > 0) nchunks = std::min<size_t>(nf, (size_t)ctx->knobs.submit_chunks);
     while (ctx->chunk_ev.size() < nchunks) {
         cudaEvent_t e;
         CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1037,14 +1079,14 @@ int drr_submit(drr_ctx *ctx) {
     CU(ctx, cudaEventRecord(ctx->ev_lists_free, ctx->stream));
     CU(ctx, cudaStreamWaitEvent(ctx->cstream, ctx->ev_lists_free, 0));
     CU(ctx, cudaMemsetAsync(ctx->d_crc, 0, sizeof(uint64_t) * (size_t)ctx->max_views, ctx->stream));
-    const bool two = nchunks > 1 && !getenv("DRR_SUBMIT_ONE_STREAM");
+    const bool two = nchunks > 1 && !ctx->knobs.submit_one_stream;
     if (two) { // stream2's first kernel must come after the checksum memset queued on the context's stream
         CU(ctx, cudaEventRecord(ctx->ev_stream2, ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_stream2, 0));
     }
     if ((rc = upload_tables(ctx, ctx->cstream))) return rc;
     // DRR_SUBMIT_TRACE=1: print when each chunk's copy and draw finished (device time since the start of the call)
-    const bool trace = getenv("DRR_SUBMIT_TRACE") != nullptr;
+    const bool trace = ctx->knobs.submit_trace != 0;
     std::vector<cudaEvent_t> tev;
     if (trace) {
         tev.resize(1 + 2 * nchunks);
@@ -1298,7 +1340,7 @@ static fe::Caps fe_slab_caps(const drr_ctx *ctx) {
     // room per view: E1M1-class frames use ~1.3 W column records and ~2.5 W visplane columns, the 1920x1200 stress map
     // ~7.5 W and ~12.5 W; DRR_FE_SLAB_DIV shrinks the slabs (tests: provoke the fallback)
     uint32_t W = (uint32_t)ctx->W * ctx->fes.slab_boost, div = 1;
-    if (const char *e = getenv("DRR_FE_SLAB_DIV")) div = (uint32_t)std::max(1, atoi(e));
+    if (ctx->knobs.fe_slab_div > 0) div = (uint32_t)ctx->knobs.fe_slab_div;
     const uint32_t k = ctx->fes.slab_boost; // the record-count capacities grow with the boost as well
     return fe::Caps{std::max(8u, 2048u * k / div), std::max(4u, 1024u * k / div), std::max(32u, std::max(16u * W, 6144u) / div), std::max(4u, 1024u * k / div),
                     std::max(32u, std::max(24u * W, 12288u) / div)};
@@ -1314,7 +1356,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     if (!on_host && ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context: libdrr has no CPU path");
     const size_t N = (size_t)n, W = (size_t)ctx->W;
     // DRR_FE_TRACE=1: host-side time line of the call on stderr (where the microseconds between the kernels go)
-    const bool trace = getenv("DRR_FE_TRACE") != nullptr;
+    const bool trace = ctx->knobs.fe_trace != 0;
     const auto t_begin = std::chrono::steady_clock::now();
     auto mark = [&](const char *what) {
         if (trace) fprintf(stderr, "drr_fe_emit_views %8.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(), what);
@@ -1327,7 +1369,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     mark("per-view cos/sin done");
     const fe::Caps nocap{0, 0, 0, 0, 0}, unlimited{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     fe::Caps slab = fe_slab_caps(ctx);
-    bool single = getenv("DRR_FE_TWO_PASS") == nullptr;
+    bool single = !ctx->knobs.fe_two_pass;
     if ((uint64_t)N * std::max({slab.ops, slab.segs, slab.cols, slab.planes, slab.parr}) > 0xffffffffull) single = false; // slab indices are 32-bit
     S.single_pass = false;
     S.count_ms = S.emit_ms = 0.0f;
@@ -1345,11 +1387,11 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     // masked phase: room per view for the remembered parts, their columns and the sprites' (a part has at most W columns;
     // E1M1-class frames remember ~150 parts / ~2.5 W columns, the stress map ~700 / ~12 W)
     const bool masked = (phases & 4) != 0;
-    auto env_u = [](const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)std::max(1, atoi(e)) : dflt; };
-    uint32_t cap_renders = masked ? env_u("DRR_FE_CAP_RENDERS", 4096u) * S.scratch_boost : 0u;
-    uint32_t cap_dsegs = masked ? env_u("DRR_FE_CAP_DSEGS", 2048u) * S.scratch_boost + (uint32_t)S.things.size() : 0u;
+    auto knob_u = [](int v, uint32_t dflt) { return v > 0 ? (uint32_t)v : dflt; };
+    uint32_t cap_renders = masked ? knob_u(ctx->knobs.fe_cap_renders, 4096u) * S.scratch_boost : 0u;
+    uint32_t cap_dsegs = masked ? knob_u(ctx->knobs.fe_cap_dsegs, 2048u) * S.scratch_boost + (uint32_t)S.things.size() : 0u;
     const uint32_t cap_mos = masked ? (uint32_t)S.things.size() + 1u : 0u;
-    uint32_t cap_allcols = masked ? std::max<uint32_t>(env_u("DRR_FE_CAP_ALLCOLS_PER_W", 48u) * (uint32_t)W, 16384u) * S.scratch_boost : 0u;
+    uint32_t cap_allcols = masked ? std::max<uint32_t>(knob_u(ctx->knobs.fe_cap_allcols_per_w, 48u) * (uint32_t)W, 16384u) * S.scratch_boost : 0u;
     std::vector<fe::RenderRec> hs_renders;
     std::vector<ColRec> hs_allcols;
     std::vector<SegRec> hs_dsegs;
@@ -1473,14 +1515,14 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             cap_renders *= 4;
             cap_allcols *= 4;
             cap_dsegs *= 4;
-            if (!getenv("DRR_FE_CAP_RENDERS") && !getenv("DRR_FE_CAP_DSEGS")) S.scratch_boost = std::min(64u, S.scratch_boost * 4u); // the context's next batch starts there
+            if (!ctx->knobs.fe_cap_renders && !ctx->knobs.fe_cap_dsegs) S.scratch_boost = std::min(64u, S.scratch_boost * 4u); // the context's next batch starts there
             const int rc = masked_scratch();
             if (rc) return rc;
             continue;
         }
         if (!overflow) break;
         single = false; // a view outgrew its slab: size the lists exactly (and give the context's next batch larger slabs)
-        if (!getenv("DRR_FE_SLAB_DIV")) S.slab_boost = std::min(8u, S.slab_boost * 2u);
+        if (!ctx->knobs.fe_slab_div) S.slab_boost = std::min(8u, S.slab_boost * 2u);
     }
     // offsets: an exclusive scan over the viewpoints that got a frame
     uint64_t ops = 0, segs = 0, cols = 0, planes = 0, parr = 0, reccap = 0, nrec = 0;
@@ -1651,6 +1693,7 @@ int drr_test_fe_download_lists(drr_ctx *ctx) {
 int drr_test_ctx_create_host_only(int width, int height, int max_views, drr_ctx **out) {
     if (!out || width <= 0 || height <= 0 || width > 16384 || height > 16384 || max_views <= 0) return DRR_E_INVALID;
     drr_ctx *c = new drr_ctx();
+    c->knobs.read_environment();
     c->host_only = true;
     c->W = width;
     c->H = height;

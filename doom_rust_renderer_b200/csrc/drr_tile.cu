@@ -33,7 +33,8 @@ namespace drr {
 
 // Decoded span record, 64 bytes.  Word layout (a.x .. d.w):
 //   all kinds : a.x = y0 | y1 << 16     a.y = kind | flags << 8      a.z = texel index / flat byte offset of the column
-//   wall kinds: a.w = K1   b.x = mask   b.y = K2   b.z = magic   b.w = -h      (ty = ((tyr + K1) & mask) + K2, then mod h)
+//   wall kinds: a.w = K1   d.z = mask   b.y = K2   b.z = magic   b.w = -h      (ty = ((tyr + K1) & mask) + K2, then mod h;
+//                                                                              word b is only read when h is not a power of two)
 //               c.x = -top_y (f32)   c.y = -(bottom_y - top_y) (f32)   c.z = refined 1/(bottom_y - top_y)   c.w = uy1
 //               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
@@ -58,13 +59,13 @@ __device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, i
         // floormod(wrap16(tyr + off_y), 2^k) == (tyr + off_y) & (2^k - 1): the i16 wrap only touches bits >= 16
         flags |= TS_POW2;
         ra.w = (uint32_t)(int)g.offset_y;
-        rb.x = h - 1u;
+        rd.z = h - 1u;
     } else {
         // floormod(v, h) for v in i16 via u = v + M (M = multiple of h >= 32768), q = umulhi(u, magic), r = u - q*h;
         // wrap16(t + off) + M == ((t + off + 32768) & 0xffff) + (M - 32768)
         const uint32_t M = h * ((32768u + h - 1u) / h);
         ra.w = (uint32_t)((int)g.offset_y + 32768);
-        rb.x = 0xffffu;
+        rd.z = 0xffffu;
         rb.y = M - 32768u;
         rb.z = (uint32_t)(0x100000000ull / h) + 1u;
         rb.w = 0u - h;
@@ -397,7 +398,7 @@ struct TileCtx { // what every pixel loop needs besides its span
 // bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows.  TRUNC: the bin kernel has
 // proven 0 <= sum <= 32767 on the span (TS_TRUNC), K = K1 - 0x4b000000.
 template <bool POW2, bool TRUNC>
-__device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uint32_t K, float hF, float2 yt, float one,
+__device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uint32_t K, uint32_t mask, float hF, float2 yt, float one,
                                              const uint16_t *__restrict__ col, uint32_t &t0, uint32_t &t1) {
     const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));   // :256
     // :257 with uy0 == 0.0: (1.0 - ay) * 0.0 is +-0.0 for finite ay and h + (+-0.0) == h, so the middle term drops out
@@ -405,11 +406,11 @@ __device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uin
     uint32_t u0, u1;
     if (TRUNC) { // `sum as i16` of 0 <= sum <= 32767: the integer part lands in the low mantissa bits of sum + 2^23 (RZ)
         const float2 tr = __fadd2_rz(sum, f2(8388608.0f));
-        u0 = (__float_as_uint(tr.x) + K) & rb.x; // :259 (the mask also drops the 0x4b000000 of the float)
-        u1 = (__float_as_uint(tr.y) + K) & rb.x;
+        u0 = (__float_as_uint(tr.x) + K) & mask; // :259 (the mask also drops the 0x4b000000 of the float)
+        u1 = (__float_as_uint(tr.y) + K) & mask;
     } else {
-        u0 = ((uint32_t)sat_i16(sum.x) + K) & rb.x;
-        u1 = ((uint32_t)sat_i16(sum.y) + K) & rb.x;
+        u0 = ((uint32_t)sat_i16(sum.x) + K) & mask;
+        u1 = ((uint32_t)sat_i16(sum.y) + K) & mask;
     }
     if (!POW2) { // :260-263 == floormod (identity checked in tests/: test_wrap_mod_idiom_is_floormod)
         u0 += rb.y;
@@ -437,7 +438,7 @@ __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra,
 #pragma unroll 2
     for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
         uint32_t t0, t1;
-        wall_texels2<POW2, true>(rb, rc, K, hF, yt, t.one, col, t0, t1);
+        wall_texels2<POW2, true>(rb, rc, K, rd.z, hF, yt, t.one, col, t0, t1);
         const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(t1), factor);
         if (!HOLES || t0 != t.hole) sts_u32(addr, rgb0);
         if (y <= yb8 && (!HOLES || t1 != t.hole)) sts_u32(addr + ROW8, rgb1);
@@ -456,8 +457,8 @@ __device__ __noinline__ void tile_wall_span_any(TileCtx t, uint4 ra, uint4 rb, u
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
     for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
         uint32_t t0, t1;
-        if (pow2) wall_texels2<true, false>(rb, rc, ra.w, hF, yt, t.one, col, t0, t1);
-        else wall_texels2<false, false>(rb, rc, ra.w, hF, yt, t.one, col, t0, t1);
+        if (pow2) wall_texels2<true, false>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
+        else wall_texels2<false, false>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
         if (!holes || t0 != t.hole) sts_u32(addr, lit_rgb_any(pal_fetch(t0), factor));
         if (y <= yb8 && (!holes || t1 != t.hole)) sts_u32(addr + ROW8, lit_rgb_any(pal_fetch(t1), factor));
     }
@@ -577,6 +578,14 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
+// Timing experiments (results are WRONG with any bit set): a build with -DDRR_DBG_KNOBS reads DrawArgs::dbg (env DRR_DBG):
+// 1 skip clearing, 2 skip the TMA stores, 4 skip the checksum, 8 skip the write-out, 16 skip drawing.  The shipped library
+// has none of these tests.
+#ifdef DRR_DBG_KNOBS
+#define DBG(bit) ((a.dbg & (bit)) != 0)
+#else
+#define DBG(bit) false
+#endif
 // MINB = resident CTAs per SM the register budget is set for (6: tiles of up to ~224 rows; 4: up to 400 rows)
 // FAST = W % 32 == 0 and every band a multiple of 8 rows: TMA write-out with the checksum fused; otherwise a bytewise
 //        write-out and a separate checksum pass
@@ -633,41 +642,45 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         fv.sin_a = vw.sin_a;
         fv.px16 = sat_i16(vw.pos_x); // visplanes.rs:119-120 `player.position.x as i16`
         fv.py16 = sat_i16(vw.pos_y);
-        const int n = (a.dbg & 16) ? 0 : (int)(ci.n & ~COL_COVERED);
-        const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams) + (size_t)ci.first * 4;
-        // shared address of row r (of the band) of this lane group's column: tile_offset(c, r)
-        const uint32_t colbase = tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2), sw = (uint32_t)warp & 4u;
-        auto row_addr = [&](int r) { return colbase + (((uint32_t)r >> 3) << 10) + ((((uint32_t)r & 7u) ^ sw) << 4); };
+        int left = DBG(16) ? 0 : (int)(ci.n & ~COL_COVERED); // spans of the column still to draw
+        uint32_t rec = ci.first;                             // record of the next one
+        const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams);
+        // shared address of row r (of the band) of this lane group's column, tile_offset(c, r): the tile base is 128-byte
+        // aligned, so the row's slot (bits 4..6, swizzled with bit 2 of the quad = warp) goes in with an exclusive or
+        const uint32_t colx = (tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2)) ^ (((uint32_t)warp & 4u) << 4);
+        auto row_addr = [&](int r) { return (colx ^ (((uint32_t)r & 7u) << 4)) + (((uint32_t)r >> 3) << 10); };
         // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
-        if (!(ci.n & COL_COVERED) && !(a.dbg & 1)) {
+        if (!(ci.n & COL_COVERED) && !DBG(1)) {
             uint32_t addr = row_addr(li);
             for (int r = li; r <= b1 - b0; r += TILE_LPG, addr += ROW8) sts_u32(addr, 0u);
         }
         uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
-        if (n > 0) ra_next = P[0];
-        for (int j = 0; __any_sync(0xffffffffu, j < n); ++j) {
+        if (left > 0) ra_next = P[(size_t)rec * 4];
+        while (__any_sync(0xffffffffu, left > 0)) {
             __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
-            if (j < n) {
+            if (left > 0) {
                 const uint4 ra = ra_next;
-                if (j + 1 < n) ra_next = P[4 * (j + 1)]; // the next span's first words are fetched while this one is drawn
+                const uint4 *__restrict__ R = P + (size_t)rec * 4;
+                ++rec;
+                if (--left > 0) ra_next = R[4]; // the next span's first words are fetched while this one is drawn
                 const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
                     const uint32_t addr = row_addr(ya + li - b0);
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
-                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, P[4 * j + 2], ya, yb, addr, flats);
-                        else tile_flat_span_any(t, fv, ra, P[4 * j + 2], ya, yb, addr, flats);
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, R[2], ya, yb, addr, flats);
+                        else tile_flat_span_any(t, fv, ra, R[2], ya, yb, addr, flats);
                     } else if (kind <= KIND_WALL_HOLES) {
-                        const uint4 rb = P[4 * j + 1], rc = P[4 * j + 2], rd = P[4 * j + 3];
-                        if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                        const uint4 rc = R[2], rd = R[3];
+                        if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, R[1], rc, rd, ya, yb, addr, texels);
                         else if (kind == KIND_WALL) {
-                            if (ra.y & TS_POW2) tile_wall_span<false, true>(t, ra, rb, rc, rd, ya, yb, addr, texels);
-                            else tile_wall_span<false, false>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                            if (ra.y & TS_POW2) tile_wall_span<false, true>(t, ra, ra, rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<false, false>(t, ra, R[1], rc, rd, ya, yb, addr, texels);
                         } else {
-                            if (ra.y & TS_POW2) tile_wall_span<true, true>(t, ra, rb, rc, rd, ya, yb, addr, texels);
-                            else tile_wall_span<true, false>(t, ra, rb, rc, rd, ya, yb, addr, texels);
+                            if (ra.y & TS_POW2) tile_wall_span<true, true>(t, ra, ra, rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<true, false>(t, ra, R[1], rc, rd, ya, yb, addr, texels);
                         }
                     } else if (kind == KIND_SKY || kind == KIND_SKY_HOLES) {
                         tile_sky_span(t, ra, ya, yb, addr, a.sky_rows, texels);
@@ -687,45 +700,46 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         // rr*96 + h*48 of the SAME two blocks (conflict-free too), which then hold two dense 96-byte x 8-row boxes for the TMA.
         const int rlo = lane & 3, h = (lane >> 2) & 1, rr = (lane >> 3) * 4 + rlo;
         const int nblk = nrows >> 3;
-        const uint32_t pw = (uint32_t)a.W * 3u / 4u; // framebuffer row pitch in words
         const uint32_t src_off = ((uint32_t)(rr >> 3) << 10) + ((uint32_t)h << 9) + ((((uint32_t)rr & 7u) ^ ((uint32_t)h << 2)) << 4);
         const uint32_t dst_off = (uint32_t)rr * 96u + (uint32_t)h * 48u;
         const uint32_t C = 0x9E3779B1u; // checksum weight of word i is (i + 1) * C mod 2^32 (drr.h)
+        const uint32_t pw = (uint32_t)a.W * 3u / 4u; // framebuffer row pitch in words
+        // weight of this lane's first word in step s: k0 + s * kstep
+        uint32_t k0 = ((uint32_t)(b0 + 16 * warp + rr) * pw + (uint32_t)g * (TILE_COLS * 3 / 4) + 12u * (uint32_t)h + 1u) * C;
+        const uint32_t kstep = 16u * (TILE_THREADS / 32) * pw * C;
         uint64_t acc = 0;
-        for (int s = warp; 2 * s < nblk; s += TILE_THREADS / 32) {
+        if (!DBG(8))
+        for (int s = warp; 2 * s < nblk; s += TILE_THREADS / 32, k0 += kstep) {
             const uint32_t region = tile + ((uint32_t)s << 11);
-            const bool act = 2 * s + (rr >> 3) < nblk && !(a.dbg & 8);
-            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+            const bool act = 2 * s + (rr >> 3) < nblk; // (the last step of a band of 8 * odd rows has one block only)
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
             if (act) {
-                q0 = lds_u128(region + src_off);
-                q1 = lds_u128(region + src_off + 128u);
-                q2 = lds_u128(region + src_off + 256u);
-                q3 = lds_u128(region + src_off + 384u);
+                const uint4 q0 = lds_u128(region + src_off), q1 = lds_u128(region + src_off + 128u);
+                const uint4 q2 = lds_u128(region + src_off + 256u), q3 = lds_u128(region + src_off + 384u);
+                // 4 pixels (0x??BBGGRR each) -> 3 words of the byte stream R G B R | G B R G | B R G B
+                v0.x = __byte_perm(q0.x, q0.y, 0x4210); v0.y = __byte_perm(q0.y, q0.z, 0x5421); v0.z = __byte_perm(q0.z, q0.w, 0x6542);
+                v0.w = __byte_perm(q1.x, q1.y, 0x4210); v1.x = __byte_perm(q1.y, q1.z, 0x5421); v1.y = __byte_perm(q1.z, q1.w, 0x6542);
+                v1.z = __byte_perm(q2.x, q2.y, 0x4210); v1.w = __byte_perm(q2.y, q2.z, 0x5421); v2.x = __byte_perm(q2.z, q2.w, 0x6542);
+                v2.y = __byte_perm(q3.x, q3.y, 0x4210); v2.z = __byte_perm(q3.y, q3.z, 0x5421); v2.w = __byte_perm(q3.z, q3.w, 0x6542);
             }
-            // 4 pixels (0x??BBGGRR each) -> 3 words of the byte stream R G B R | G B R G | B R G B
-            uint4 v0, v1, v2;
-            v0.x = __byte_perm(q0.x, q0.y, 0x4210); v0.y = __byte_perm(q0.y, q0.z, 0x5421); v0.z = __byte_perm(q0.z, q0.w, 0x6542);
-            v0.w = __byte_perm(q1.x, q1.y, 0x4210); v1.x = __byte_perm(q1.y, q1.z, 0x5421); v1.y = __byte_perm(q1.z, q1.w, 0x6542);
-            v1.z = __byte_perm(q2.x, q2.y, 0x4210); v1.w = __byte_perm(q2.y, q2.z, 0x5421); v2.x = __byte_perm(q2.z, q2.w, 0x6542);
-            v2.y = __byte_perm(q3.x, q3.y, 0x4210); v2.z = __byte_perm(q3.y, q3.z, 0x5421); v2.w = __byte_perm(q3.z, q3.w, 0x6542);
             __syncwarp(); // every lane has read its pixels: the two blocks may be overwritten
             if (act) {
                 sts_u128(region + dst_off, v0);
                 sts_u128(region + dst_off + 16u, v1);
                 sts_u128(region + dst_off + 32u, v2);
-                if (!(a.dbg & 4)) {
-                    const uint32_t k0 = ((uint32_t)(b0 + 16 * s + rr) * pw + (uint32_t)g * (TILE_COLS * 3 / 4) + 12u * (uint32_t)h + 1u) * C;
-                    acc += (uint64_t)v0.x * k0 + (uint64_t)v0.y * (k0 + C) + (uint64_t)v0.z * (k0 + 2u * C) + (uint64_t)v0.w * (k0 + 3u * C);
-                    acc += (uint64_t)v1.x * (k0 + 4u * C) + (uint64_t)v1.y * (k0 + 5u * C) + (uint64_t)v1.z * (k0 + 6u * C) + (uint64_t)v1.w * (k0 + 7u * C);
-                    acc += (uint64_t)v2.x * (k0 + 8u * C) + (uint64_t)v2.y * (k0 + 9u * C) + (uint64_t)v2.z * (k0 + 10u * C) + (uint64_t)v2.w * (k0 + 11u * C);
-                }
             }
             fence_proxy_async(); // this lane's stores are visible to the copy engine ...
             __syncwarp();        // ... and so are everybody else's, before lane 0 hands the boxes over
-            if (lane == 0 && !(a.dbg & 2)) {
+            if (lane == 0 && !DBG(2)) {
                 tma_store_box(&fbmap, region, g * (TILE_COLS * 3), b0 + 16 * s, (int)slot);
                 if (2 * s + 1 < nblk) tma_store_box(&fbmap, region + 768u, g * (TILE_COLS * 3), b0 + 16 * s + 8, (int)slot);
                 bulk_commit();
+            }
+            if (!DBG(4)) { // (an inactive lane's words are zero)
+                uint32_t k = k0;
+                acc += (uint64_t)v0.x * k; k += C; acc += (uint64_t)v0.y * k; k += C; acc += (uint64_t)v0.z * k; k += C; acc += (uint64_t)v0.w * k; k += C;
+                acc += (uint64_t)v1.x * k; k += C; acc += (uint64_t)v1.y * k; k += C; acc += (uint64_t)v1.z * k; k += C; acc += (uint64_t)v1.w * k; k += C;
+                acc += (uint64_t)v2.x * k; k += C; acc += (uint64_t)v2.y * k; k += C; acc += (uint64_t)v2.z * k; k += C; acc += (uint64_t)v2.w * k;
             }
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);

@@ -67,7 +67,7 @@ def _lib() -> C.CDLL:
         sig = {
             "drr_ctx_create": (i, [i, i, i, i, C.POINTER(vp)]), "drr_ctx_destroy": (None, [vp]),
             "drr_last_error": (C.c_char_p, [vp]), "drr_error_name": (C.c_char_p, [i]),
-            "drr_set_stream": (i, [vp, vp]), "drr_get_stream": (vp, [vp]),
+            "drr_set_stream": (i, [vp, vp]), "drr_get_stream": (vp, [vp]), "drr_set_knob": (i, [vp, C.c_char_p, i]),
             "drr_upload_palette": (i, [vp, vp]), "drr_upload_bitmap": (i, [vp, i, i, i, vp]), "drr_upload_flat": (i, [vp, i, vp]),
             "drr_set_sky": (i, [vp, i]), "drr_reset": (i, [vp]), "drr_frame_begin": (i, [vp, i, C.POINTER(DrrView)]),
             "drr_emit_columns": (i, [vp, C.POINTER(DrrSegHdr), vp, i]),
@@ -109,7 +109,7 @@ def _lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "drr_ctx_create", "drr_ctx_destroy", "drr_last_error", "drr_error_name", "drr_set_stream", "drr_get_stream",
+    "drr_ctx_create", "drr_ctx_destroy", "drr_last_error", "drr_error_name", "drr_set_stream", "drr_get_stream", "drr_set_knob",
     "drr_upload_palette", "drr_upload_bitmap", "drr_upload_flat", "drr_set_sky", "drr_reset", "drr_frame_begin",
     "drr_emit_columns", "drr_emit_visplane", "drr_frame_end", "drr_frame_abort", "drr_upload_lists", "drr_draw", "drr_submit", "drr_sync",
     "drr_read_framebuffer", "drr_read_checksums", "drr_checksum_host", "drr_get_stats", "drr_time_draw",
@@ -218,6 +218,10 @@ class Context:
         self._ck(self.L.drr_frame_abort(self.h))
 
     # ---- execution
+    def set_knob(self, name: str, value: int):
+        """Tuning / diagnostic knob (drr.h: drr_set_knob); the DRR_* environment variables are only read at creation."""
+        self._ck(self.L.drr_set_knob(self.h, name.encode(), int(value)))
+
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.drr_set_stream(self.h, C.c_void_p(cuda_stream)))
 

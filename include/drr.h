@@ -94,6 +94,12 @@ const char *drr_error_name(int code);
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all copies and launches; NULL = own stream. */
 int drr_set_stream(drr_ctx *ctx, void *cuda_stream);
 void *drr_get_stream(drr_ctx *ctx);
+/* Tuning / diagnostic knobs (nothing the results depend on).  Each knob has an environment variable that is read ONCE, by
+ * drr_ctx_create -- never on the launch path --, and drr_set_knob changes it afterwards; value 0 = built-in default.
+ *   "submit_chunks" (DRR_SUBMIT_CHUNKS), "submit_one_stream" (DRR_SUBMIT_ONE_STREAM), "submit_trace" (DRR_SUBMIT_TRACE),
+ *   "fe_trace" (DRR_FE_TRACE), "fe_two_pass" (DRR_FE_TWO_PASS), "fe_slab_div" (DRR_FE_SLAB_DIV), "fe_cap_renders",
+ *   "fe_cap_dsegs", "fe_cap_allcols_per_w" (DRR_FE_CAP_*), "dbg" (DRR_DBG; -DDRR_DBG_KNOBS builds only). */
+int drr_set_knob(drr_ctx *ctx, const char *name, int value);
 
 /* ---- assets (uploaded once, device resident) ------------------------------------------------------------------ */
 int drr_upload_palette(drr_ctx *ctx, const uint8_t rgb[768]);                                   /* Palette::new, src/graphics/palette.rs:11-28 */

@@ -379,13 +379,13 @@ def test_pipelined_submit_equals_upload_then_draw(monkeypatch):
     frame7 = ctx.read_framebuffer(7)
     assert int(want[7]) == drr.checksum_numpy(game.render(*[float(t) for t in views[7]]))
     for chunks in ("1", "2", "5", "23", "64"):
-        monkeypatch.setenv("DRR_SUBMIT_CHUNKS", chunks)
+        ctx.set_knob("submit_chunks", int(chunks))
         ctx.submit()
         ctx.submit()  # back to back: the second upload must wait for the first draw
         ctx.sync()
         assert (ctx.read_checksums(0, n) == want).all(), chunks
         assert (ctx.read_framebuffer(7) == frame7).all(), chunks
-    monkeypatch.setenv("DRR_SUBMIT_ONE_STREAM", "1")
+    ctx.set_knob("submit_one_stream", 1)
     ctx.submit()
     assert (ctx.read_checksums(0, n) == want).all()
 
