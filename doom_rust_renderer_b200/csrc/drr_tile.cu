@@ -36,7 +36,7 @@ namespace drr {
 //   wall kinds: a.w = K1   d.z = mask   b.y = K2   b.z = magic   b.w = -h      (ty = ((tyr + K1) & mask) + K2, then mod h;
 //                                                                              word b is only read when h is not a power of two)
 //               c.x = -top_y (f32)   c.y = -(bottom_y - top_y) (f32)   c.z = refined 1/(bottom_y - top_y)   c.w = uy1
-//               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor
+//               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor   d.w = 2^23 + offset_y (f32, TS_TRUNC)
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
 static constexpr uint32_t COL_COVERED = 0x80000000u; // ColIdx.n flag: the column's always-writing spans cover every row
 enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11, TS_TRUNC = 1u << 12 };
@@ -80,15 +80,19 @@ __device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, i
     rd.x = den != 0 ? __float_as_uint((float)h) : 0x7fc00000u;
     rd.y = __float_as_uint(wc.factor);
     if (!(wc.factor <= 1.0f)) flags |= TS_BRIGHT; // light level above 255 or negative depth: channels saturate at 255
-    // Is 0 <= ay * uy1 + h <= 32767 on every row of the span?  The sum is a monotonic function of y (every step of
-    // bitmap_render.rs:256-257 is), so its values on the rows ya and yb bound it; then `as i16` is a plain truncation of a
-    // non-negative number, which the pixel loop does with a round-toward-zero add of 2^23 (two rows per instruction, no
-    // conversion unit).  The two sums are evaluated exactly as the pixel loop evaluates them.
+    // Are 0 <= sum <= 32767 and 0 <= trunc(sum) + offset_y <= 32767 on every row of the span (sum = ay * uy1 + h)?  The sum is
+    // a monotonic function of y (every step of bitmap_render.rs:256-257 is), so its values on the rows ya and yb bound it.
+    // Then `sum as i16` is a plain truncation of a non-negative number and `+ offset_y` neither wraps nor goes negative
+    // (:259-263 reduce to v mod h), and the pixel loop gets v from ONE round-toward-zero add: the integer part of
+    // sum + (2^23 + offset_y) sits in the low mantissa bits (two rows per instruction, no conversion unit).  The two sums are
+    // evaluated exactly as the pixel loop evaluates them.
     if (den != 0) {
-        const float r = __uint_as_float(rc.z), hF = (float)h;
+        const float r = __uint_as_float(rc.z), hF = (float)h, off = (float)(int)g.offset_y;
         const float sa = __fadd_rn(__fmul_rn(fast_div(__fadd_rn((float)ya, -(float)top_y), denF, r), wc.uy1), hF);
         const float sb = __fadd_rn(__fmul_rn(fast_div(__fadd_rn((float)yb, -(float)top_y), denF, r), wc.uy1), hF);
-        if (sa >= 0.0f && sa <= 32767.0f && sb >= 0.0f && sb <= 32767.0f) flags |= TS_TRUNC;
+        const float lo = fminf(sa, sb), hi = fmaxf(sa, sb); // (a NaN fails the comparisons below through sa / sb themselves)
+        if (sa >= 0.0f && sb >= 0.0f && hi <= 32767.0f && __fadd_rz(lo, off) >= 0.0f && truncf(hi) + off <= 32767.0f) flags |= TS_TRUNC;
+        rd.w = __float_as_uint(8388608.0f + off);
     }
     ra.y = kind | flags;
     return Rec{ra, rb, rc, rd, kind};
@@ -395,23 +399,15 @@ struct TileCtx { // what every pixel loop needs besides its span
     int li;            // lane within its group
 };
 
-// bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows.  TRUNC: the bin kernel has
-// proven 0 <= sum <= 32767 on the span (TS_TRUNC), K = K1 - 0x4b000000.
-template <bool POW2, bool TRUNC>
+// bitmap_render.rs:256-265 for the two rows of a lane; yt = (y - top_y) as f32 of both rows.  K = K1 (ra.w).
+template <bool POW2>
 __device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uint32_t K, uint32_t mask, float hF, float2 yt, float one,
                                              const uint16_t *__restrict__ col, uint32_t &t0, uint32_t &t1) {
     const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));   // :256
     // :257 with uy0 == 0.0: (1.0 - ay) * 0.0 is +-0.0 for finite ay and h + (+-0.0) == h, so the middle term drops out
     const float2 sum = add2_nofuse(__fmul2_rn(ay, f2(__uint_as_float(rc.w))), f2(hF), one);
-    uint32_t u0, u1;
-    if (TRUNC) { // `sum as i16` of 0 <= sum <= 32767: the integer part lands in the low mantissa bits of sum + 2^23 (RZ)
-        const float2 tr = __fadd2_rz(sum, f2(8388608.0f));
-        u0 = (__float_as_uint(tr.x) + K) & mask; // :259 (the mask also drops the 0x4b000000 of the float)
-        u1 = (__float_as_uint(tr.y) + K) & mask;
-    } else {
-        u0 = ((uint32_t)sat_i16(sum.x) + K) & mask;
-        u1 = ((uint32_t)sat_i16(sum.y) + K) & mask;
-    }
+    uint32_t u0 = ((uint32_t)sat_i16(sum.x) + K) & mask; // :259
+    uint32_t u1 = ((uint32_t)sat_i16(sum.y) + K) & mask;
     if (!POW2) { // :260-263 == floormod (identity checked in tests/: test_wrap_mod_idiom_is_floormod)
         u0 += rb.y;
         u1 += rb.y;
@@ -420,6 +416,39 @@ __device__ __forceinline__ void wall_texels2(const uint4 rb, const uint4 rc, uin
     }
     t0 = ldg_u16(col + u0);
     t1 = ldg_u16(col + u1);
+}
+// the same for a TS_TRUNC span: v = trunc(sum) + offset_y is in 0..32767 and comes out of one packed add (magic = 2^23 +
+// offset_y, round toward zero); ty = v mod h
+template <bool POW2>
+__device__ __forceinline__ void wall_texels2_trunc(const uint4 rb, const uint4 rc, float magic, uint32_t mask, float hF, float2 yt, float one,
+                                                   const uint16_t *__restrict__ col, uint32_t &t0, uint32_t &t1) {
+    const float2 ay = fast_div2(yt, f2(__uint_as_float(rc.y)), f2(__uint_as_float(rc.z)));
+    const float2 sum = add2_nofuse(__fmul2_rn(ay, f2(__uint_as_float(rc.w))), f2(hF), one);
+    const float2 tr = __fadd2_rz(sum, f2(magic));
+    uint32_t u0 = __float_as_uint(tr.x) & mask, u1 = __float_as_uint(tr.y) & mask; // (the mask, <= 0xffff, drops the float's exponent)
+    if (!POW2) { // v mod h for 0 <= v < 2^16, h < 2^15: q = (v * (floor(2^32 / h) + 1)) >> 32 is exact
+        u0 = __umulhi(u0, rb.z) * rb.w + u0;
+        u1 = __umulhi(u1, rb.z) * rb.w + u1;
+    }
+    t0 = ldg_u16(col + u0);
+    t1 = ldg_u16(col + u1);
+}
+
+// Two pixels' lit colours for 0 <= factor <= 1: (c as f32 * factor) as u8 per channel is the low byte of c*f + 2^23 rounded
+// toward zero (lit_rgb_unit).  The six channels go through three packed multiplies and adds: (g0, b0), (g1, b1), (r0, r1) --
+// g is unpacked in place next to b, which the 8-byte palette entry already holds as an f32.
+__device__ __forceinline__ void lit_rgb_unit_2(uint2 e0, uint2 e1, float f0, float f1, uint32_t &rgb0, uint32_t &rgb1) {
+    const float2 m = f2(8388608.0f);
+    const float2 gb0 = __fadd2_rz(__fmul2_rn(f2(__uint_as_float(e0.x & 0xffff0000u), __uint_as_float(e0.y)), f2(f0)), m);
+    const float2 gb1 = __fadd2_rz(__fmul2_rn(f2(__uint_as_float(e1.x & 0xffff0000u), __uint_as_float(e1.y)), f2(f1)), m);
+    const float2 rr = __fadd2_rz(__fmul2_rn(f2(__uint_as_float(e0.x << 16), __uint_as_float(e1.x << 16)), f2(f0, f1)), m);
+    rgb0 = __byte_perm(__byte_perm(__float_as_uint(rr.x), __float_as_uint(gb0.x), 0x0040), __float_as_uint(gb0.y), 0x5410);
+    rgb1 = __byte_perm(__byte_perm(__float_as_uint(rr.y), __float_as_uint(gb1.x), 0x0040), __float_as_uint(gb1.y), 0x5410);
+}
+__device__ __forceinline__ uint2 pal_fetch_raw(uint32_t addr) {
+    uint2 e;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr));
+    return e;
 }
 
 // the fast wall loop: factor <= 1 and TS_TRUNC (every wall of an ordinary scene)
@@ -431,15 +460,16 @@ __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra,
     // pays a 33-bit add with carry per texel instead of a single IMAD.WIDE.U32 (u * 2 + base)
     const uint16_t *__restrict__ col = texels + ra.z;
     asm("" : "+l"(col));
-    const uint32_t K = ra.w - 0x4b000000u;
+    const float magic = __uint_as_float(rd.w);
     const int yb8 = yb - TILE_LPG;
     int y = ya + t.li;
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
 #pragma unroll 2
     for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
         uint32_t t0, t1;
-        wall_texels2<POW2, true>(rb, rc, K, rd.z, hF, yt, t.one, col, t0, t1);
-        const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(t0), factor), rgb1 = lit_rgb_unit_p(pal_fetch(t1), factor);
+        wall_texels2_trunc<POW2>(rb, rc, magic, rd.z, hF, yt, t.one, col, t0, t1);
+        uint32_t rgb0, rgb1;
+        lit_rgb_unit_2(pal_fetch_raw(t0), pal_fetch_raw(t1), factor, factor, rgb0, rgb1);
         if (!HOLES || t0 != t.hole) sts_u32(addr, rgb0);
         if (y <= yb8 && (!HOLES || t1 != t.hole)) sts_u32(addr + ROW8, rgb1);
     }
@@ -457,8 +487,8 @@ __device__ __noinline__ void tile_wall_span_any(TileCtx t, uint4 ra, uint4 rb, u
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
     for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
         uint32_t t0, t1;
-        if (pow2) wall_texels2<true, false>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
-        else wall_texels2<false, false>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
+        if (pow2) wall_texels2<true>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
+        else wall_texels2<false>(rb, rc, ra.w, rd.z, hF, yt, t.one, col, t0, t1);
         if (!holes || t0 != t.hole) sts_u32(addr, lit_rgb_any(pal_fetch(t0), factor));
         if (y <= yb8 && (!holes || t1 != t.hole)) sts_u32(addr + ROW8, lit_rgb_any(pal_fetch(t1), factor));
     }
@@ -512,7 +542,8 @@ __device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView 
         // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
         fac.x = fmaxf(fac.x, 0.0f);
         fac.y = fmaxf(fac.y, 0.0f);
-        const uint32_t rgb0 = lit_rgb_unit_p(pal_fetch(t.pal + t0 * PAL_ENTRY), fac.x), rgb1 = lit_rgb_unit_p(pal_fetch(t.pal + t1 * PAL_ENTRY), fac.y);
+        uint32_t rgb0, rgb1;
+        lit_rgb_unit_2(pal_fetch_raw(t.pal + t0 * PAL_ENTRY), pal_fetch_raw(t.pal + t1 * PAL_ENTRY), fac.x, fac.y, rgb0, rgb1);
         sts_u32(addr, rgb0);
         if (y <= yb8) sts_u32(addr + ROW8, rgb1);
     }
@@ -597,7 +628,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     // texel pool holds absolute shared addresses of palette entries.
     if ((uint32_t)__cvta_generic_to_shared(s_dyn) != a.pal_base) __trap();
     const uint32_t pal = a.pal_base + SM_PAL, bar = a.pal_base + SM_BAR, tile = a.pal_base + SM_TILE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // (the shuffle tells ptxas it is warp-uniform)
     const int grp = lane >> 3, li = lane & 7;
     const uint16_t *__restrict__ texels = a.texels;
     const uint8_t *__restrict__ flats = a.flats;
