@@ -172,6 +172,7 @@ struct Knobs {
     int submit_chunks = 0;       // DRR_SUBMIT_CHUNKS: upload chunks of drr_submit (default: ~4 MB of lists each, at most 8)
     int submit_one_stream = 0;   // DRR_SUBMIT_ONE_STREAM: all chunks on the context's stream
     int submit_trace = 0;        // DRR_SUBMIT_TRACE: per-chunk time line on stderr
+    int tile_max_rows = 0;       // DRR_TILE_MAX_ROWS: rows per tile band (default 400; A/B runs)
     int fe_trace = 0;            // DRR_FE_TRACE: host-side time line of drr_fe_emit_views on stderr
     int fe_two_pass = 0;         // DRR_FE_TWO_PASS: count pass + emit pass instead of slabs + compaction
     int fe_slab_div = 0;         // DRR_FE_SLAB_DIV: shrink the per-view slabs (tests: provoke the fallback)
@@ -180,7 +181,7 @@ struct Knobs {
     static const Name *table(size_t *n) {
         static const Name t[] = {{"DRR_DBG", "dbg", &Knobs::dbg}, {"DRR_SUBMIT_CHUNKS", "submit_chunks", &Knobs::submit_chunks},
                                  {"DRR_SUBMIT_ONE_STREAM", "submit_one_stream", &Knobs::submit_one_stream}, {"DRR_SUBMIT_TRACE", "submit_trace", &Knobs::submit_trace},
-                                 {"DRR_FE_TRACE", "fe_trace", &Knobs::fe_trace}, {"DRR_FE_TWO_PASS", "fe_two_pass", &Knobs::fe_two_pass},
+                                 {"DRR_TILE_MAX_ROWS", "tile_max_rows", &Knobs::tile_max_rows}, {"DRR_FE_TRACE", "fe_trace", &Knobs::fe_trace}, {"DRR_FE_TWO_PASS", "fe_two_pass", &Knobs::fe_two_pass},
                                  {"DRR_FE_SLAB_DIV", "fe_slab_div", &Knobs::fe_slab_div}, {"DRR_FE_CAP_RENDERS", "fe_cap_renders", &Knobs::fe_cap_renders},
                                  {"DRR_FE_CAP_DSEGS", "fe_cap_dsegs", &Knobs::fe_cap_dsegs}, {"DRR_FE_CAP_ALLCOLS_PER_W", "fe_cap_allcols_per_w", &Knobs::fe_cap_allcols_per_w}};
         *n = sizeof(t) / sizeof(t[0]);
@@ -890,7 +891,7 @@ static int reserve_device_lists(drr_ctx *ctx) {
     CU(ctx, ctx->d_planes.reserve(std::max<size_t>(ctx->planes.n, 1)));
     CU(ctx, ctx->d_parr.reserve(std::max<size_t>(ctx->parr.n, 1)));
     int nbands, band_rows;
-    tile_bands(ctx->H, &nbands, &band_rows);
+    tile_bands(ctx->H, ctx->knobs.tile_max_rows, &nbands, &band_rows);
     const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1; // one span list per (column, row band)
     if (ctx->rec_cap * nlists > 0xffffffffull) return fail(ctx, DRR_E_INVALID, "batch too large: more than 2^32 record slots");
     CU(ctx, ctx->d_colidx.reserve(nf * (size_t)ctx->W * nlists));
@@ -952,7 +953,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.W = ctx->W;
     a.H = ctx->H;
     a.nframes = (int)nframes;
-    tile_bands(ctx->H, &a.nbands, &a.band_rows);
+    tile_bands(ctx->H, ctx->knobs.tile_max_rows, &a.nbands, &a.band_rows);
     a.CFX = ctx->CFX;
     a.CFY = ctx->CFY;
     a.GCFX = ctx->GCFX;
@@ -1566,7 +1567,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         ctx->slot_to_frame[first_view_idx + (int)i] = b.frame;
     }
     int nbands, band_rows;
-    tile_bands(ctx->H, &nbands, &band_rows);
+    tile_bands(ctx->H, ctx->knobs.tile_max_rows, &nbands, &band_rows);
     const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
     if (reccap * nlists > 0xffffffffull || cols > 0xffffffffull || parr > 0xffffffffull || ops > 0x7fffffffull) {
         ctx->clear_lists();
@@ -1779,7 +1780,7 @@ int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out)
     if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
     if (!colidx_out || !recs_out || ctx->uploaded_frames == 0) return fail(ctx, DRR_E_STATE, "drr_test_device_bins: nothing drawn");
     int nbands, band_rows;
-    tile_bands(ctx->H, &nbands, &band_rows);
+    tile_bands(ctx->H, ctx->knobs.tile_max_rows, &nbands, &band_rows);
     const size_t nlists = nbands <= MAX_LIST_BANDS ? (size_t)nbands : 1;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaMemcpy(colidx_out, ctx->d_colidx.p, ctx->uploaded_frames * nlists * (size_t)ctx->W * sizeof(ColIdx), cudaMemcpyDeviceToHost));
@@ -1790,7 +1791,7 @@ int drr_test_device_bins(drr_ctx *ctx, uint32_t *colidx_out, uint32_t *recs_out)
 // how the tile kernel cuts this context's columns into row bands, and how many span lists per column the bin kernel writes
 int drr_test_tile_bands(drr_ctx *ctx, int *nbands, int *band_rows, int *nlists) {
     if (!ctx || !nbands || !band_rows || !nlists) return DRR_E_INVALID;
-    tile_bands(ctx->H, nbands, band_rows);
+    tile_bands(ctx->H, ctx->knobs.tile_max_rows, nbands, band_rows);
     *nlists = *nbands <= MAX_LIST_BANDS ? *nbands : 1;
     return DRR_OK;
 }

@@ -74,7 +74,7 @@ cudaError_t probe_shared_base(uint32_t *base); // shared window address of a CTA
 cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
 cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
 void tile_config(int W, int H, int *tc, int *lpg);
-void tile_bands(int H, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (equal bands of at most 400 rows, a multiple of 8 when H is)
+void tile_bands(int H, int max_rows, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (equal bands of at most 400 rows, a multiple of 8 when H is)
 static constexpr int MAX_LIST_BANDS = 8;             // up to this many bands the bin kernel writes one span list per (column, band)
 // ---- device front-end (drr_frontend.cu / drr_frontend.cuh) ----------------------------------------------------------
 namespace fe {

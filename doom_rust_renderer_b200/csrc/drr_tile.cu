@@ -31,7 +31,8 @@
 
 namespace drr {
 
-// Decoded span record, 64 bytes.  Word layout (a.x .. d.w):
+// Decoded span record, 64 bytes, stored as the four 16-byte words a, c, d, b: a flat needs a and c, a wall a, c and d (b only
+// when its texture height is not a power of two), so the words a span needs first share a 32-byte sector.  Word layout:
 //   all kinds : a.x = y0 | y1 << 16     a.y = kind | flags << 8      a.z = texel index / flat byte offset of the column
 //   wall kinds: a.w = K1   d.z = mask   b.y = K2   b.z = magic   b.w = -h      (ty = ((tyr + K1) & mask) + K2, then mod h;
 //                                                                              word b is only read when h is not a power of two)
@@ -100,7 +101,7 @@ __device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, i
 
 // Decoded record of a visplane column: the per-plane and per-column constants of draw_visplane / draw_sky
 __device__ __forceinline__ Rec plane_record(const DrawArgs &a, const PlaneRec &p, const View &vw, int x, int ya, int yb) {
-    uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rc = make_uint4(0u, 0u, 0u, 0u);
+    uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rc = make_uint4(0u, 0u, 0u, 0u), rd = rc;
     if (p.kind == KIND_FLAT) {
         // visplanes.rs:112  wz = visplane.height as f32 - player.floor_height - PLAYER_EYE_HEIGHT
         const float wz = __fsub_rn(__fsub_rn((float)p.height, vw.floor_height), 41.0f);
@@ -130,7 +131,7 @@ __device__ __forceinline__ Rec plane_record(const DrawArgs &a, const PlaneRec &p
         ra.z = a.sky_base + ((uint32_t)tx << 7);
         ra.y = kind;
     }
-    return Rec{ra, make_uint4(0u, 0u, 0u, 0u), rc, make_uint4(0u, 0u, 0u, 0u), ra.y & 0xffu};
+    return Rec{ra, make_uint4(0u, 0u, 0u, 0u), rc, rd, ra.y & 0xffu};
 }
 
 // Walk the ops of frame f in call order and visit what each of them draws in screen column x.  EMIT = false only counts;
@@ -222,9 +223,9 @@ struct ColOut {
                 if (i == b) k = n[i]++;
             uint4 *out = recs + ((size_t)first + (size_t)b * cap + k) * 4;
             out[0] = r.a;
-            out[1] = r.b;
-            out[2] = r.c;
-            out[3] = r.d;
+            out[1] = r.c;
+            out[2] = r.d;
+            out[3] = r.b;
         }
     }
 };
@@ -538,7 +539,8 @@ __device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView 
         const uint32_t t0 = ldg_u8(flat + o0), t1 = ldg_u8(flat + o1);
         // diminish_color :191-201: light/255 - dist * (1/4096), clamped below at 0
         const float2 dist = f2((float)sat_i16(wx.x), (float)sat_i16(wx.y));
-        float2 fac = add2_nofuse(__fmul2_rn(dist, f2(-0.000244140625f)), f2(lf), t.one);
+        // (dist is an integer below 2^15, so dist / 4096 is exact and one fused multiply-add rounds like the reference's two steps)
+        float2 fac = __ffma2_rn(dist, f2(-0.000244140625f), f2(lf));
         // `if factor < 0.0 { factor = 0.0 }`: fmaxf turns -0.0 into +0.0, which changes nothing once multiplied and cast to u8
         fac.x = fmaxf(fac.x, 0.0f);
         fac.y = fmaxf(fac.y, 0.0f);
@@ -656,6 +658,17 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     ColIdx ci;
     ci.first = 0; ci.n = 0;
     if (x < a.W) ci = a.colidx[((size_t)f * nlists + lband) * a.W + x];
+    int left = DBG(16) ? 0 : (int)(ci.n & ~COL_COVERED); // spans of the column still to draw
+    uint32_t rec = ci.first;                             // record of the next one
+    const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams);
+    // The next span's first word is fetched while the current one is drawn: into registers where the budget allows (MINB 4),
+    // otherwise only into L1 (four registers kept across the pixel loops would spill at 40)
+    constexpr bool HEAD_IN_REGS = MINB <= 4;
+    uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
+    if (left > 0) {
+        if (HEAD_IN_REGS) ra_next = P[(size_t)rec * 4]; // the first span's head: in flight while the palette arrives
+        else asm volatile("prefetch.global.L1 [%0];" ::"l"(P + (size_t)rec * 4));
+    }
     __syncthreads(); // the barrier's initialisation is visible to every thread
     mbar_wait(bar, 0);
 
@@ -673,9 +686,6 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         fv.sin_a = vw.sin_a;
         fv.px16 = sat_i16(vw.pos_x); // visplanes.rs:119-120 `player.position.x as i16`
         fv.py16 = sat_i16(vw.pos_y);
-        int left = DBG(16) ? 0 : (int)(ci.n & ~COL_COVERED); // spans of the column still to draw
-        uint32_t rec = ci.first;                             // record of the next one
-        const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams);
         // shared address of row r (of the band) of this lane group's column, tile_offset(c, r): the tile base is 128-byte
         // aligned, so the row's slot (bits 4..6, swizzled with bit 2 of the quad = warp) goes in with an exclusive or
         const uint32_t colx = (tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2)) ^ (((uint32_t)warp & 4u) << 4);
@@ -686,32 +696,34 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
             uint32_t addr = row_addr(li);
             for (int r = li; r <= b1 - b0; r += TILE_LPG, addr += ROW8) sts_u32(addr, 0u);
         }
-        uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
-        if (left > 0) ra_next = P[(size_t)rec * 4];
         while (__any_sync(0xffffffffu, left > 0)) {
             __syncwarp(); // a span may overwrite what another lane of the group stored for an earlier span of the column
             if (left > 0) {
-                const uint4 ra = ra_next;
                 const uint4 *__restrict__ R = P + (size_t)rec * 4;
+                const uint4 ra = HEAD_IN_REGS ? ra_next : R[0];
                 ++rec;
-                if (--left > 0) ra_next = R[4]; // the next span's first words are fetched while this one is drawn
+                if (--left > 0) { // the next span's first word is fetched while this one is drawn (word c arrives in L1 with it) ...
+                    if (HEAD_IN_REGS) ra_next = R[4];
+                    else asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 4));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 6)); // ... and so is the sector with words d and b
+                }
                 const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
                 const uint32_t kind = ra.y & 0xffu;
                 if (ya <= yb && kind != KIND_NONE) {
                     const uint32_t addr = row_addr(ya + li - b0);
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
-                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, R[2], ya, yb, addr, flats);
-                        else tile_flat_span_any(t, fv, ra, R[2], ya, yb, addr, flats);
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, R[1], ya, yb, addr, flats);
+                        else tile_flat_span_any(t, fv, ra, R[1], ya, yb, addr, flats);
                     } else if (kind <= KIND_WALL_HOLES) {
-                        const uint4 rc = R[2], rd = R[3];
-                        if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, R[1], rc, rd, ya, yb, addr, texels);
+                        const uint4 rc = R[1], rd = R[2];
+                        if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, R[3], rc, rd, ya, yb, addr, texels);
                         else if (kind == KIND_WALL) {
                             if (ra.y & TS_POW2) tile_wall_span<false, true>(t, ra, ra, rc, rd, ya, yb, addr, texels);
-                            else tile_wall_span<false, false>(t, ra, R[1], rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<false, false>(t, ra, R[3], rc, rd, ya, yb, addr, texels);
                         } else {
                             if (ra.y & TS_POW2) tile_wall_span<true, true>(t, ra, ra, rc, rd, ya, yb, addr, texels);
-                            else tile_wall_span<true, false>(t, ra, R[1], rc, rd, ya, yb, addr, texels);
+                            else tile_wall_span<true, false>(t, ra, R[3], rc, rd, ya, yb, addr, texels);
                         }
                     } else if (kind == KIND_SKY || kind == KIND_SKY_HOLES) {
                         tile_sky_span(t, ra, ya, yb, addr, a.sky_rows, texels);
@@ -830,10 +842,14 @@ cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-void tile_bands(int H, int *nbands, int *band_rows) {
-    // rows per band: at most 400 (a tile is then 51 KB: four CTAs per SM), equal bands; a multiple of 8 rows when H is, so that
-    // every band is whole 8-row blocks (the TMA write-out's box).  The bin kernel writes one span list per (column, band).
-    const int max_rows = 400;
+void tile_bands(int H, int max_rows, int *nbands, int *band_rows) {
+    // rows per band: equal bands, a multiple of 8 rows when H is, so that every band is whole 8-row blocks (the TMA write-out's
+    // box).  Up to 800 rows: bands of at most 400 rows (a tile is then 51 KB: four CTAs per SM; five CTAs of 272 rows were
+    // measured equal at 1280x800, and cutting a 400-row screen in two costs 6 %).  Taller screens: at most 328 rows, so that
+    // five CTAs fit (1920x1200: 0.798 -> 0.724 ms per 128 frames of the stress map).  The bin kernel writes one span list
+    // per (column, band); max_rows > 0 overrides (A/B runs: DRR_TILE_MAX_ROWS).
+    if (max_rows <= 0) max_rows = H > 800 ? 328 : 400;
+    max_rows = std::max(8, std::min(max_rows, 400)) / 8 * 8;
     *nbands = (H + max_rows - 1) / max_rows;
     *band_rows = (H + *nbands - 1) / *nbands;
     if (H % 8 == 0) *band_rows = (*band_rows + 7) / 8 * 8;
@@ -878,7 +894,7 @@ cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0,
     if ((long long)gpf * a.nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t dyn = SM_TILE + (size_t)((a.band_rows + 7) / 8) * 1024; // whole 8-row blocks
     const bool fast = fbmap && a.W % TILE_COLS == 0 && a.H % 8 == 0 && a.band_rows % 8 == 0;
-    const bool small = dyn <= 36 * 1024; // six CTAs per SM fit: 40 registers; else four: 56
+    const bool small = dyn <= 36 * 1024; // six CTAs per SM fit: 40 registers; else five (up to 44 KB) or four: 48 registers
     cudaError_t e;
     if (fast) {
         e = small ? launch_tile_t<6, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);

@@ -1,11 +1,14 @@
 #!/bin/bash
-# A/B run-time knobs (run under gpurun): tools/sweep_env.sh walk1280 "DRR_TILE_SMEM_PAD_KB=0" "DRR_TILE_SMEM_PAD_KB=20" ...
-wl=$1; shift
-for kv in "$@"; do
-  env $kv python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --secondary= > /tmp/s.json 2>/tmp/s.err || { tail -3 /tmp/s.err; continue; }
-  python - $wl "$kv" <<'PY'
+# A/B run-time knobs (run under gpurun): tools/sweep_env.sh "walk1280 walk320" "DRR_TILE_MAX_ROWS=400" "DRR_TILE_MAX_ROWS=272" ...
+# prints bin / tile kernel ms per step and the roofline fraction for every (workload, setting)
+WLS=$1; shift
+for wl in $WLS; do
+  for setting in "$@"; do
+    env $setting python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --secondary= > /tmp/s.json 2>/tmp/s.err || { tail -3 /tmp/s.err; continue; }
+    python - "$wl" "$setting" <<'P'
 import json, sys
-d = json.loads(open("/tmp/s.json").read().strip().splitlines()[-1])
-print("%-9s %-40s step %.4f ms value %.0f | bin %.4f tile %.4f ms frac %.4f e2e %.0f" % (sys.argv[1], sys.argv[2], d["ms_per_step"], d["value"], d["roofline"]["setup_ms"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
-PY
+d = json.load(open("/tmp/s.json")); r = d["roofline"]
+print("%-10s %-40s bin %.4f tile %.4f ms frac %.4f step %.4f" % (sys.argv[1], sys.argv[2], r["setup_ms"], r["kernel_ms"], r["frac"], d["ms_per_step"]))
+P
+  done
 done
