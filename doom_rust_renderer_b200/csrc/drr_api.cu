@@ -1656,6 +1656,8 @@ int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms) {
 }
 int drr_fe_last_mode(drr_ctx *ctx) { return ctx ? (ctx->fes.single_pass ? 1 : 2) : DRR_E_INVALID; }
 
+// ==== test infrastructure: compiled only into libdrr_test.so (-DDRR_TESTING), never into the product library ===============
+#ifdef DRR_TESTING
 // Test infrastructure: the per-view front-end code of drr_frontend.cuh run on the CPU into the context's host lists
 // (works in a recording-only context), so that tests/ can compare it list by list with the host front-end.
 int drr_test_fe_emit_views_host(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status) {
@@ -1868,5 +1870,7 @@ int drr_test_fastdiv(drr_ctx *ctx, int mode, long long n0, long long n1, float C
     cudaFree(d_first);
     return DRR_OK;
 }
+
+#endif // DRR_TESTING
 
 } // extern "C"

@@ -11,7 +11,18 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrr.so")
+LIB_PATH = os.path.join(_HERE, "libdrr.so")            # the product
+TEST_LIB_PATH = os.path.join(_HERE, "libdrr_test.so")  # the product's objects + the drr_test_* accessors (-DDRR_TESTING)
+_USE_TEST_LIBRARY = False
+
+
+def use_test_library():
+    """tests/conftest.py: load libdrr_test.so instead of libdrr.so (must be called before the first call into the library)."""
+    global _USE_TEST_LIBRARY
+    if _LIB is not None and not _USE_TEST_LIBRARY:
+        raise RuntimeError("libdrr.so is already loaded")
+    _USE_TEST_LIBRARY = True
+
 
 PHASES_WALLS, PHASES_PLANES, PHASES_MASKED, PHASES_ALL = 1, 2, 4, 7
 PHASE_WALL, PHASE_MASKED = 0, 2
@@ -59,10 +70,11 @@ _LIB = None
 def _lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError("libdrr.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                              "(or `make -C doom_rust_renderer_b200/csrc`). There is no fallback implementation.")
-        L = C.CDLL(LIB_PATH)
+        path = TEST_LIB_PATH if _USE_TEST_LIBRARY else LIB_PATH
+        if not os.path.exists(path):
+            raise ImportError("%s is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(or `make -C doom_rust_renderer_b200/csrc`). There is no fallback implementation." % os.path.basename(path))
+        L = C.CDLL(path)
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         sig = {
             "drr_ctx_create": (i, [i, i, i, i, C.POINTER(vp)]), "drr_ctx_destroy": (None, [vp]),
@@ -101,6 +113,8 @@ def _lib() -> C.CDLL:
             "drr_test_fastdiv": (i, [vp, i, C.c_longlong, C.c_longlong, f, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong), vp]),
         }
         for name, (res, args) in sig.items():
+            if name.startswith("drr_test_") and not _USE_TEST_LIBRARY:
+                continue  # not in the product library
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -132,16 +146,7 @@ def checksum_host(frame: np.ndarray) -> int:
     return int(_lib().drr_checksum_host(_ptr(a), a.size))
 
 
-def checksum_numpy(frame: np.ndarray) -> int:
-    """Same checksum in numpy (drr.h: sum of w_i * ((i+1)*0x9E3779B1 mod 2^32) mod 2^64 over LE u32 words)."""
-    b = np.ascontiguousarray(frame, np.uint8).reshape(-1)
-    pad = (-b.size) % 4
-    if pad:
-        b = np.concatenate([b, np.zeros(pad, np.uint8)])
-    w = b.view("<u4").astype(np.uint64)
-    k = (np.arange(1, w.size + 1, dtype=np.uint64) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)
-    with np.errstate(over="ignore"):
-        return int((w * k).sum(dtype=np.uint64))
+from .checksum import checksum_numpy  # noqa: E402,F401  (pure numpy; lives apart so that CPU-only tools need not import this module)
 
 
 class Context:
@@ -258,9 +263,9 @@ class Context:
         return t.value, s.value, m.value
 
     def kernel_name(self) -> str:
-        tc, lpg = C.c_int(), C.c_int()
-        self._ck(self.L.drr_test_tile_config(self.h, C.byref(tc), C.byref(lpg)))
-        return "drr_tile_kernel<%d,%d>" % (tc.value, lpg.value)
+        """The dominant kernel (csrc/drr_tile.cu): 32-column tiles, 8 lanes per span; <resident CTAs per SM the register
+        budget is set for, TMA write-out>."""
+        return "drr_tile_kernel<4|6, true>"
 
     def tile_bands(self):
         """(nbands, band_rows, nlists): the row bands of a tile and the number of span lists per column the bin kernel writes."""

@@ -1,8 +1,12 @@
 """Multi-GPU sharding of viewpoint batches.
 
 Frames are independent units (the reference rebuilds Renderer and Pixels per frame, src/game.rs:505-519), so a batch
-shards by contiguous viewpoint ranges, one process / context per GPU, assets replicated, NO collective on the draw path.
-The only exchange is a host-side gather of the per-frame checksums (8 bytes per frame), off the timed path.
+shards by viewpoint, one process / context per GPU, assets replicated, NO collective on the draw path.  The only exchange
+is a host-side gather of the per-frame checksums (8 bytes per frame), off the timed path.
+
+Assignment is STRIDED (`shard_indices`: rank r owns viewpoints r, r + G, r + 2G, ...): consecutive viewpoints of a walk
+path see the same rooms and cost the same, so every GPU gets the same mix.  Contiguous ranges (`shard_range`, round 1) gave
+each GPU a different part of the map, and the slowest range set the step time (8 GPUs: 0.907 of linear).
 """
 from __future__ import annotations
 
@@ -14,6 +18,25 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     if world <= 0 or not 0 <= rank < world:
         raise ValueError("bad rank/world")
     return (rank * n_total) // world, ((rank + 1) * n_total) // world
+
+
+def shard_indices(n_total: int, rank: int, world: int) -> np.ndarray:
+    """Viewpoint indices owned by `rank`: rank, rank + world, rank + 2*world, ... (< n_total)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return np.arange(rank, n_total, world, dtype=np.int64)
+
+
+def unshard(parts: list[np.ndarray], n_total: int) -> np.ndarray:
+    """Inverse of shard_indices: parts[r] holds the values of rank r's viewpoints in its own order."""
+    world = len(parts)
+    out = np.zeros(n_total, np.asarray(parts[0]).dtype)
+    for r, p in enumerate(parts):
+        idx = shard_indices(n_total, r, world)
+        if len(p) != len(idx):
+            raise ValueError("rank %d: %d values for %d viewpoints" % (r, len(p), len(idx)))
+        out[idx] = p
+    return out
 
 
 def gather_checksums(local: np.ndarray, device=None) -> np.ndarray:

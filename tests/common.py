@@ -11,6 +11,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from doom_rust_renderer_b200 import lib as drr  # noqa: E402
+drr.use_test_library()  # the suite (and the processes it spawns) runs against libdrr_test.so: product objects + drr_test_* accessors
 from doom_rust_renderer_b200 import synth_wad  # noqa: E402
 from oracle import orc  # noqa: E402
 

@@ -1,4 +1,4 @@
-"""World-size-2 test of the multi-GPU host logic on CPU (gloo): contiguous viewpoint sharding, per-rank draw-list
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): strided viewpoint sharding, per-rank draw-list
 recording, and the host-side gather of per-frame checksums.  No collective touches the draw path."""
 from __future__ import annotations
 
@@ -38,10 +38,12 @@ def _worker(rank, world, port, path, views, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = shard.shard_range(len(views), rank, world)
-    local = _frame_sums(path, views[lo:hi])
-    allsums = shard.gather_checksums(local)
-    np.save(os.path.join(out_dir, "rank%d.npy" % rank), allsums)
+    mine = shard.shard_indices(len(views), rank, world)
+    local = _frame_sums(path, views[mine])
+    allsums = shard.gather_checksums(local)  # rank order: rank 0's viewpoints, then rank 1's, ...
+    counts = [len(shard.shard_indices(len(views), r, world)) for r in range(world)]
+    parts = np.split(allsums, np.cumsum(counts)[:-1])
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), shard.unshard(parts, len(views)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,6 +57,18 @@ def test_shard_ranges_partition_the_batch():
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
     with pytest.raises(ValueError):
         shard.shard_range(10, 2, 2)
+
+
+def test_strided_shards_partition_the_batch():
+    for n in (0, 1, 7, 4096, 65537):
+        for world in (1, 2, 3, 8):
+            parts = [shard.shard_indices(n, k, world) for k in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            if n:
+                assert (shard.unshard([p * 3 for p in parts], n) == np.arange(n) * 3).all()
+    with pytest.raises(ValueError):
+        shard.shard_indices(10, 2, 2)
 
 
 def test_two_rank_sharding_gathers_the_same_checksums(tmp_path):

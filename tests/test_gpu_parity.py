@@ -469,3 +469,111 @@ def test_fast_division_flats_sampled(H):
     for lo in (0x00000000, 0x80000000, 0x3F800000 - (1 << 24), 0x12345678):
         bad, first = ctx.test_fastdiv(1, 1 << 23, H, H / 2.0, lo, 255)
         assert bad == 0, (H, lo, first)
+
+
+# ---- contexts side by side: several devices in one process, large tiles in any order, recording while a batch uploads -----
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _draw_and_check(ctx, scene, game, views, what):
+    assert scene.emit_views(ctx, views) == []
+    ctx.submit()
+    ctx.sync()
+    crcs = ctx.read_checksums(0, len(views))
+    for k, v in enumerate(views):
+        ref = game.render(float(v[0]), float(v[1]), float(v[2]))
+        _compare(ctx, k, ref, "%s view %d" % (what, k))
+        assert int(crcs[k]) == drr.checksum_numpy(ref)
+
+
+def test_two_devices_in_one_process():
+    """drr.h: "distinct contexts may be driven from distinct threads, one per GPU".  Two contexts on two devices at 1280x800 (a
+    tile needs more than the default 48 KB of dynamic shared memory: the opt-in is per device), driven interleaved from one
+    thread -- every entry point binds its context's device -- and then from one thread each."""
+    if _device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+    path, gm = common.wad("e1m1")
+    W, H, n = 1280, 800, 3
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::331], 2 * n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    ctxs = [drr.Context(W, H, d, n) for d in (0, 1)]
+    for c in ctxs:
+        scene.upload_assets(c)
+    # one thread, calls interleaved
+    for d, c in enumerate(ctxs):
+        assert scene.emit_views(c, views[d * n:(d + 1) * n]) == []
+    for c in ctxs:
+        c.submit()
+    for d, c in enumerate(ctxs):
+        c.sync()
+        for k in range(n):
+            v = views[d * n + k]
+            _compare(c, k, game.render(float(v[0]), float(v[1]), float(v[2])), "device %d view %d (one thread)" % (d, k))
+    # one thread per context
+    errors = []
+
+    def work(d):
+        try:
+            c = ctxs[d]
+            g = orc.Game(path, "E1M1", W, H)
+            for rep in range(3):
+                c.reset()
+                _draw_and_check(c, drr.Scene(path, "E1M1", W, H), g, views[(1 - d) * n:(2 - d) * n], "device %d (own thread, pass %d)" % (d, rep))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
+def test_large_tiles_of_both_store_paths_in_one_process():
+    """1280x800 (TMA write-out) and 1000x800 (width no multiple of 32: bytewise write-out), both with tiles above 48 KB, in
+    either order on the same device: the shared-memory opt-in is kept per kernel instantiation."""
+    path, gm = common.wad("e1m1")
+    for order in ((1280, 1000), (1000, 1280)):
+        for W in order:
+            H, n = 800, 2
+            game = orc.Game(path, "E1M1", W, H)
+            views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::577], n)
+            ctx = drr.Context(W, H, 0, n)
+            scene = drr.Scene(path, "E1M1", W, H)
+            scene.upload_assets(ctx)
+            _draw_and_check(ctx, scene, game, views, "%dx%d" % (W, H))
+            ctx.close()
+
+
+def test_recording_the_next_batch_while_the_previous_uploads():
+    """drr_submit returns while its copies out of the pinned host lists may still run; resetting and recording the next
+    batch right away must not disturb them (the library waits for the copies before it touches the lists)."""
+    path, gm = common.wad("e1m1")
+    W, H, n = 320, 200, 256
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::7], 2 * n)
+    ctx = drr.Context(W, H, 0, 2 * n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    ctx.set_knob("submit_chunks", 8)
+    for rep in range(3):
+        ctx.reset()
+        assert scene.emit_views(ctx, views[:n], first_slot=0) == []
+        ctx.submit()                                   # asynchronous: copies + kernels queued
+        ctx.reset()                                    # ... and the lists are reused at once
+        assert scene.emit_views(ctx, views[n:], first_slot=n) == []
+        ctx.submit()
+        ctx.sync()
+        crcs = ctx.read_checksums(0, 2 * n)  # (a draw zeroes every slot's checksum first: only the second batch's are left)
+        for k in range(n, 2 * n, 5):
+            v = views[k]
+            assert int(crcs[k]) == drr.checksum_numpy(game.render(float(v[0]), float(v[1]), float(v[2]))), (rep, k)
+        for k in range(0, n, 17):  # the first batch's frames are still in their slots
+            v = views[k]
+            _compare(ctx, k, game.render(float(v[0]), float(v[1]), float(v[2])), "first batch, pass %d, view %d" % (rep, k))

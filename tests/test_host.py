@@ -23,6 +23,14 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(drr.EXPORTED_SYMBOLS) <= declared
     assert len(declared) >= 30
+    # the product library carries no test infrastructure; the test build is the same library plus the accessors
+    import subprocess
+    def exported(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+        return {line.split()[-1] for line in out.splitlines() if line.strip()}
+    prod, test = exported(drr.LIB_PATH), exported(drr.TEST_LIB_PATH)
+    assert not [s for s in prod if "drr_test_" in s or "fastdiv" in s], "test infrastructure in the product library"
+    assert any(s.startswith("drr_test_") for s in test) and declared <= test
 
 
 def test_struct_layouts_match_header():

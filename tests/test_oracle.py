@@ -182,3 +182,112 @@ def test_trace_replay_closure_on_cpu():
                 leaf.visplane(img, game.flat(t["asset"]), sky, t["top"], t["bottom"], t["is_sky"], t["height"], t["light_level"],
                               t["left"], t["right"], x, y, fh, a)
         assert (img == ref).all()
+
+
+# ---- hand-derived known-answer tests (the derivation is in each docstring; nothing here is computed by code under test) ------
+def test_kat_diminish_color():
+    """bitmap_render.rs:190-208.  factor = light/255 - distance/4096, clamped below at 0 only; `as u8` saturates at 255.
+      (200,100,50), light 300, dist 0     : factor 1.17647   -> 235.29, 117.65, 58.82  -> (235, 117, 58)
+      (200,100,50), light 400, dist 0     : factor 1.56863   -> 313.7 (saturates), 156.86, 78.43 -> (255, 156, 78)
+      (200,100,50), light 255, dist -4096 : factor 1 + 1 = 2 -> 400 (saturates), 200, 100 -> (255, 200, 100)
+      (200,100,50), light 128, dist 1024  : factor 0.50196 - 0.25 = 0.25196 -> 50.39, 25.19, 12.59 -> (50, 25, 12)
+      (200,100,50), light 0,   dist 100   : factor -0.0244 -> 0 -> (0, 0, 0)
+      (255,255,255), light 255, dist 0    : factor exactly 1 -> (255, 255, 255)"""
+    assert orc.diminish_color((200, 100, 50), 300, 0) == (235, 117, 58)
+    assert orc.diminish_color((200, 100, 50), 400, 0) == (255, 156, 78)
+    assert orc.diminish_color((200, 100, 50), 255, -4096) == (255, 200, 100)
+    assert orc.diminish_color((200, 100, 50), 128, 1024) == (50, 25, 12)
+    assert orc.diminish_color((200, 100, 50), 0, 100) == (0, 0, 0)
+    assert orc.diminish_color((255, 255, 255), 255, 0) == (255, 255, 255)
+
+
+def _grey_palette():
+    return np.repeat(np.arange(256, dtype=np.uint8), 3)  # colour i = (i, i, i)
+
+
+def test_kat_sky_texture_column_for_negative_and_large_angles():
+    """visplanes.rs:54-66 at 320x200, screen column x = 100: tx = (100 * 256 / 320) as i16 = 80, then (80 + tx_offset) % 256 with
+    tx_offset = (-256 * angle / (pi/2)) as i16 + 256, wrapped up by whole textures when negative:
+      angle -pi/4 : -256 * -0.5 = 128          -> 128 + 256 = 384                                   -> (80 + 384) % 256 = 208
+      angle  pi   : -256 * 2 = -512            -> -256 < 0 -> += 256 * (1 - (-256 / 256)) = +512    -> 256 -> (80 + 256) % 256 = 80
+      angle 3pi/4 : -256 * 1.5 = -384          -> -128 < 0 -> += 256 * (1 - (-128 / 256 = 0)) = +256 -> 128 -> (80 + 128) % 256 = 208
+      angle  0    : 0                          -> 256                                               -> (80 + 256) % 256 = 80
+    (f32(pi)/4, f32(pi)/2 and f32(pi) are exact binary multiples of each other, so the quotients are exact.)
+    Row y = 150: ty = (150 * 128 * 2 / 200) as i16 = 192, % 128 = 64.  The sky texture encodes tx in one test and ty in the other."""
+    W, H = 320, 200
+    leaf = orc.Leaf(W, H, _grey_palette())
+    tex_tx = np.tile(np.arange(256, dtype=np.int16), (128, 1))            # texel = tx
+    tex_ty = np.tile(np.arange(128, dtype=np.int16)[:, None], (1, 256))   # texel = ty
+    top, bottom = np.full(W, 150, np.int16), np.full(W, 150, np.int16)
+    pi = np.float32(np.pi)
+    for angle, want_tx in ((-pi / 4, 208), (pi, 80), (3 * pi / 4, 208), (np.float32(0), 80)):
+        img = np.zeros((H, W, 3), np.uint8)
+        leaf.visplane(img, None, tex_tx, top, bottom, 1, 0, 255, 100, 100, 0.0, 0.0, 0.0, angle)
+        assert img[150, 100].tolist() == [want_tx] * 3, (float(angle), img[150, 100])
+        assert img.sum() == 3 * want_tx  # nothing else was drawn
+    img = np.zeros((H, W, 3), np.uint8)
+    leaf.visplane(img, None, tex_ty, top, bottom, 1, 0, 255, 100, 100, 0.0, 0.0, 0.0, 0.0)
+    assert img[150, 100].tolist() == [64] * 3
+
+
+def test_kat_texture_row_of_a_zero_height_column():
+    """bitmap_render.rs:253-265 when bottom_y == top_y (a zero-height sector, e.g. sector 16 of E1M1): ay = (y - top_y) / 0 is NaN
+    (y == top_y) or +-inf, (1 - ay) * 0.0 is NaN either way, the sum is NaN and `NaN as i16` is 0; so every drawn row takes
+    texture row (0 + offset_y) mod height.  Texture 16 rows high whose texel = its row, offset_y = 5 -> palette entry 5;
+    offset_y = -3 -> ty = -3 < 0 -> += 16 * (1 - (-3 / 16 = 0)) = 13 -> entry 13.  Light 255 at depth 0 -> factor 1."""
+    W, H = 64, 48
+    leaf = orc.Leaf(W, H, _grey_palette())
+    tex = np.tile(np.arange(16, dtype=np.int16)[:, None], (1, 8))
+    line = (np.float32(0.0), np.float32(10.0), np.float32(0.0), np.float32(-10.0))  # uz0 = uz1 = 0: z = (1 / (0/0 ...)) -> NaN -> 0
+    for oy, want in ((5, 5), (-3, 13)):
+        img = np.zeros((H, W, 3), np.uint8)
+        leaf.column(img, tex, 255, line, np.float32(0.0), 0, 10, np.float32(0.0), np.float32(64.0), 0, oy, 5, 22, 18, 20, 20)
+        assert [img[y, 5, 0] for y in range(18, 23)] == [want] * 5, (oy, img[16:25, 5, 0])
+
+
+# ---- the front-end's stateless half, pinned by an independent restatement written from the Rust ---------------------------------
+@pytest.mark.parametrize("kind,W,H,step", [("e1m1", 320, 200, 409), ("e1m1", 1280, 800, 1021), ("stress", 640, 400, 3)])
+def test_oracle_wall_calls_carry_the_arguments_an_independent_restatement_derives(kind, W, H, step):
+    """tests/ref_frontend.py restates, from src/renderer/misc.rs, segs.rs and src/map/*.rs, how a seg becomes the arguments of
+    render_vertical_bitmap_line (own WAD reader, view transform, clip_to_viewport, make_sidedef_non_vertical_line, the parts
+    of process_seg, the per-column bottom_y / top_y).  Every immediate wall call in the oracle's trace must carry, bit for
+    bit, the arguments derived there for some part of some seg, and its rows must obey process_sidedef's clipping rules."""
+    import ref_frontend as rf
+    path, gm = common.wad(kind)
+    game = orc.Game(path, "E1M1", W, H)
+    m = rf.MapLumps(path)
+    k = rf.Constants(W, H)
+    allv = synth_wad.walk_viewpoints(gm, 4096)[::step] if kind == "e1m1" else synth_wad.scatter_viewpoints(gm, 64)[::step]
+    views = common.usable_views(game, allv, 10 if (kind, W) == ("e1m1", 320) else 4)
+    checked = masked = 0
+    bits = lambda v: np.float32(v).view(np.uint32).item()  # noqa: E731
+    for v in views:
+        x, y, a = (np.float32(t) for t in v)
+        game.render(float(x), float(y), float(a), trace=True)
+        fh = game.floor_height_at(float(x), float(y))
+        cands = {}
+        for seg in m.segs:
+            for p in rf.seg_parts(k, m, seg, x, y, a, fh):
+                key = tuple(bits(t) for t in p["line"]) + (bits(p["start_offset"]), p["start_x"], p["end_x"], bits(p["bottom_height"]),
+                                                           bits(p["top_height"]), p["offset_x"], p["offset_y"], p["light_level"])
+                cands[key] = p
+        for t in game.trace():
+            if t["kind"] != 0:
+                continue
+            key = tuple(bits(q) for q in t["line"]) + (bits(t["start_offset"]), t["start_x"], t["end_x"], bits(t["bottom_height"]),
+                                                       bits(t["top_height"]), t["offset_x"], t["offset_y"], t["light_level"])
+            p = cands.get(key)
+            if t["phase"] != 0:  # drawn late: a masked mid-texture (must be a two-sided middle part) or a sprite (not a seg at all)
+                masked += p is not None and p["flags"] == "two_sided_middle"
+                continue
+            assert p is not None, ("no seg part yields this wall call", v, t)
+            assert p["flags"] in ("solid", "lower", "upper"), p["flags"]
+            assert p["start_x"] <= t["x"] <= p["end_x"]
+            assert p["column"](t["x"]) == (t["bottom_y"], t["top_y"]), (v, t, p["column"](t["x"]))
+            # segs.rs:189-200: clipped to the occlusion arrays and the screen, drawn only when not empty
+            assert t["clipped_bottom_y"] <= min(H - 1, t["bottom_y"]) and t["clipped_top_y"] >= max(0, t["top_y"])
+            assert t["clipped_bottom_y"] >= t["clipped_top_y"]
+            checked += 1
+    assert checked > 50 * len(views), checked
+    if (kind, W) == ("e1m1", 320):
+        assert masked > 0  # (one of these viewpoints looks through the grates)
