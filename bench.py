@@ -206,28 +206,28 @@ def build_oracle():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
 
 
-def cpu_baseline(path, used, crc_dev, W, H, phases):
+def cpu_baseline(name, path, used, crc_dev, W, H, phases):
     """The oracle on the GPU box's host cores, on a bounded sample of the same batch: one process per core and
-    single-threaded; every sampled frame's checksum is compared with the device's (outside the timed passes)."""
+    single-threaded.  The timing IS the reference arm (`bench.py --impl reference`, run here as a child process so that it
+    meets the same conditions as when the driver runs it: no CUDA context, no other threads of this process in its way);
+    every sampled frame's checksum is compared with the device's in a separate, untimed pass."""
     build_oracle()
     cores = os.cpu_count() or 1
-    scale = 64000.0 / (W * H)
-    nm = int(max(cores, min(len(used), cores * max(4, int(FRAMES_PER_WORKER * scale)))))
-    n1 = int(max(4, min(len(used), max(4, int(FRAMES_PER_WORKER * scale)))))
+
+    def arm(procs, steps):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", str(steps), "--warmup", "1", "--ref-procs", str(procs)]
+        return json.loads(subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+
+    multi, single = arm(cores, 3), arm(1, 1)
+    nm = int(max(cores, min(len(used), multi["frames_per_step"])))
     pool = CpuPool(path, W, H, cores)
-    pool.render(used[:nm], phases)  # warm-up
-    tm = min(pool.render(used[:nm], phases)[0] for _ in range(3))
     _, sums = pool.render(used[:nm], phases, want_sums=True)
     pool.close()
-    one = CpuPool(path, W, H, 1)
-    one.render(used[:n1], phases)
-    t1 = min(one.render(used[:n1], phases)[0] for _ in range(2))
-    one.close()
     ok = all(int(crc_dev[i]) == s for i, s in enumerate(sums))
-    return {"value": W * H * nm / tm / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-            "sample": "%d frames of the same batch per pass, one oracle process per core (%d), best of 3 passes; oracle = literal C++ restatement, g++ -O2 -ffp-contract=off" % (nm, cores),
-            "frames_per_s": nm / tm, "single_thread_value": W * H * n1 / t1 / 1e6, "single_thread_frames_per_s": n1 / t1,
-            "single_thread_sample": "%d frames" % n1, "parity_checked_frames": nm, "parity_ok": bool(ok)}
+    return {"value": multi["value"], "unit": "Mpixel/s", "cores": cores, "kind": "port",
+            "sample": multi["cpu_baseline"]["sample"] + "; 3 steps after 1 warm-up; oracle = literal C++ restatement, g++ -O2 -ffp-contract=off",
+            "frames_per_s": multi["frames_per_s"], "single_thread_value": single["value"], "single_thread_frames_per_s": single["frames_per_s"],
+            "single_thread_sample": "%d frames" % single["frames_per_step"], "parity_checked_frames": nm, "parity_ok": bool(ok)}
 
 
 def parity_sample(path, used, crc_dev, W, H, phases, n=16):
@@ -250,7 +250,7 @@ def run_reference(args, rank):
     if args.views:
         n_views = args.views
     content = Content(kind)
-    cores = os.cpu_count() or 1
+    cores = args.ref_procs or os.cpu_count() or 1
     scale = 64000.0 / (W * H)
     per_step = cores * max(4, int(FRAMES_PER_WORKER * scale))
     pool = CpuPool(content.path, W, H, cores)
@@ -271,7 +271,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "textured Mpixels/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": make_config(args.workload, n_views, passes, content.source),
-        "frames_per_s": len(good) / (ms * 1e-3),
+        "frames_per_s": len(good) / (ms * 1e-3), "frames_per_step": len(good),
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "the Rust reference cannot be compiled here (no rustc/cargo/SDL2); this is the literal C++ restatement in oracle/"},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -469,6 +469,7 @@ def main():
     ap.add_argument("--views", type=int, default=0, help="override viewpoints per GPU of the headline workload")
     ap.add_argument("--secondary", default="walk1280,walls1280,flats1280,things640,stress1920", help="extra workloads reported under 'secondary'; '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = one per host core)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -506,7 +507,7 @@ def main():
     }
     if rank == 0 and not args.no_cpu_baseline:
         if world == 1:
-            out["cpu_baseline"] = cpu_baseline(*ctxinfo)
+            out["cpu_baseline"] = cpu_baseline(args.workload, *ctxinfo)
         else:
             out["parity_sample"] = parity_sample(*ctxinfo)
     sec = []

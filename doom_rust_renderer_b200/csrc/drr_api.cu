@@ -1152,6 +1152,21 @@ int drr_read_checksums(drr_ctx *ctx, int first, int count, uint64_t *out) {
     return DRR_OK;
 }
 
+int drr_read_crc32(drr_ctx *ctx, int first, int count, uint32_t *out) {
+    CTX_DEV(ctx);
+    if (ctx->host_only) return fail(ctx, DRR_E_CUDA, "recording-only test context");
+    if (!out || first < 0 || count < 0 || first + count > ctx->max_views) return fail(ctx, DRR_E_INVALID, "drr_read_crc32: bad range");
+    if (count == 0) return DRR_OK;
+    const uint64_t nbytes = (uint64_t)ctx->W * ctx->H * 3;
+    DevBuf<uint32_t> scratch, result;
+    CU(ctx, scratch.reserve(crc32_scratch_words(nbytes, count)));
+    CU(ctx, result.reserve((size_t)count));
+    CU(ctx, launch_crc32(ctx->d_frames, ctx->frame_stride, nbytes, first, count, scratch.p, result.p, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, result.p, sizeof(uint32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DRR_OK;
+}
+
 uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes) {
     uint64_t acc = 0;
     const uint64_t nwords = (nbytes + 3) / 4;

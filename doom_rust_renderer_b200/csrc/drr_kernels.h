@@ -72,6 +72,10 @@ cudaError_t launch_bin(const DrawArgs &a, int frame0, int nframes, cudaStream_t 
 cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0, int nframes, cudaStream_t st, int *launches);
 cudaError_t probe_shared_base(uint32_t *base); // shared window address of a CTA's dynamic shared memory on the current device
 cudaError_t launch_sky_rows(uint8_t *rows, int H, cudaStream_t st);
+// CRC-32 (zlib polynomial) of nframes resident framebuffers starting at slot `first`: out[k] = crc32 of frames + (first + k) * stride
+cudaError_t launch_crc32(const uint8_t *frames, uint64_t frame_stride, uint64_t nbytes, int first, int nframes, uint32_t *chunk_scratch,
+                         uint32_t *out, cudaStream_t st);
+size_t crc32_scratch_words(uint64_t nbytes, int nframes);
 cudaError_t launch_checksum_pass(const DrawArgs &a, int frame0, int nframes, cudaStream_t st, int *launches);
 void tile_config(int W, int H, int *tc, int *lpg);
 void tile_bands(int H, int max_rows, int *nbands, int *band_rows); // how the tile kernel cuts a column into row bands (equal bands of at most 400 rows, a multiple of 8 when H is)

@@ -85,7 +85,7 @@ def _lib() -> C.CDLL:
             "drr_emit_columns": (i, [vp, C.POINTER(DrrSegHdr), vp, i]),
             "drr_emit_visplane": (i, [vp, C.POINTER(DrrVisplaneHdr), vp, vp]), "drr_frame_end": (i, [vp]), "drr_frame_abort": (i, [vp]),
             "drr_upload_lists": (i, [vp]), "drr_draw": (i, [vp]), "drr_submit": (i, [vp]), "drr_sync": (i, [vp]),
-            "drr_read_framebuffer": (i, [vp, i, vp]), "drr_read_checksums": (i, [vp, i, i, vp]),
+            "drr_read_framebuffer": (i, [vp, i, vp]), "drr_read_checksums": (i, [vp, i, i, vp]), "drr_read_crc32": (i, [vp, i, i, vp]),
             "drr_checksum_host": (C.c_uint64, [vp, C.c_uint64]), "drr_get_stats": (i, [vp, C.POINTER(DrrStats)]),
             "drr_time_draw": (i, [vp, i, C.POINTER(f), C.POINTER(f), C.POINTER(f)]),
             "drr_profile_begin": (i, [vp, i]), "drr_profile_end": (i, [vp, C.POINTER(i), C.POINTER(f), C.POINTER(f)]),
@@ -126,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "drr_ctx_create", "drr_ctx_destroy", "drr_last_error", "drr_error_name", "drr_set_stream", "drr_get_stream", "drr_set_knob",
     "drr_upload_palette", "drr_upload_bitmap", "drr_upload_flat", "drr_set_sky", "drr_reset", "drr_frame_begin",
     "drr_emit_columns", "drr_emit_visplane", "drr_frame_end", "drr_frame_abort", "drr_upload_lists", "drr_draw", "drr_submit", "drr_sync",
-    "drr_read_framebuffer", "drr_read_checksums", "drr_checksum_host", "drr_get_stats", "drr_time_draw",
+    "drr_read_framebuffer", "drr_read_checksums", "drr_read_crc32", "drr_checksum_host", "drr_get_stats", "drr_time_draw",
     "drr_profile_begin", "drr_profile_end",
     "drr_scene_load", "drr_scene_free", "drr_scene_last_error", "drr_scene_upload_assets", "drr_scene_player_start",
     "drr_scene_emit_view", "drr_scene_emit_views",
@@ -250,6 +250,12 @@ class Context:
     def read_checksums(self, first: int, count: int) -> np.ndarray:
         out = np.zeros(count, np.uint64)
         self._ck(self.L.drr_read_checksums(self.h, first, count, _ptr(out)))
+        return out
+
+    def read_crc32(self, first: int, count: int) -> np.ndarray:
+        """zlib.crc32 of each resident frame's W*H*3 bytes, computed on the device (export side)."""
+        out = np.zeros(count, np.uint32)
+        self._ck(self.L.drr_read_crc32(self.h, first, count, _ptr(out)))
         return out
 
     def stats(self) -> dict:

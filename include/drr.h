@@ -134,6 +134,9 @@ int drr_recorder_frame_abort(drr_recorder *rec);
 int drr_append(drr_ctx *ctx, drr_recorder *rec);
 
 /* ---- execution ---------------------------------------------------------------------------------------------- */
+/* drr_upload_lists and drr_submit return while their copies out of the context's pinned host lists may still be running; the
+ * library waits for them itself before the lists are touched again (drr_reset, drr_frame_begin, drr_append), so recording
+ * the next batch right after a submit is safe. */
 int drr_upload_lists(drr_ctx *ctx); /* async H2D of everything recorded since drr_reset (from pinned staging) */
 int drr_draw(drr_ctx *ctx);         /* async: render every uploaded frame into its framebuffer (+ per-frame checksum) */
 int drr_submit(drr_ctx *ctx);       /* drr_upload_lists + drr_draw */
@@ -143,6 +146,13 @@ int drr_read_checksums(drr_ctx *ctx, int first_view, int count, uint64_t *out);
 /* Per-frame checksum: sum over little-endian u32 words w_i of the frame of  w_i * ((i+1)*0x9E3779B1 mod 2^32),
  * mod 2^64.  drr_checksum_host computes the same on a host buffer. */
 uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes);
+/* Export side (the reference presents Pixels.pixels through SDL, src/game.rs:500-533): the framebuffer
+ * drr_read_framebuffer returns is what an SDL RGB24 streaming texture takes as is (pitch = width*3), and drr_read_crc32 gives
+ * the standard CRC-32 (zlib / PNG polynomial 0xEDB88320, as zlib.crc32 of the frame's width*height*3 bytes) of the resident
+ * frames, computed on the device by a separate kernel -- chunk CRCs folded with the usual GF(2) shift -- so frames can be
+ * compared with files without copying them back.  (The fused per-frame checksum above stays the cheap one: it rides on the
+ * write-out's registers; a CRC cannot, its chunks combine in order.) */
+int drr_read_crc32(drr_ctx *ctx, int first_view, int count, uint32_t *out);
 
 /* ---- introspection for benchmarks ----------------------------------------------------------------------------- */
 typedef struct {

@@ -577,3 +577,49 @@ def test_recording_the_next_batch_while_the_previous_uploads():
         for k in range(0, n, 17):  # the first batch's frames are still in their slots
             v = views[k]
             _compare(ctx, k, game.render(float(v[0]), float(v[1]), float(v[2])), "first batch, pass %d, view %d" % (rep, k))
+
+
+# ---- presentation / export (the reference presents Pixels.pixels, src/game.rs:500-533) ----------------------------
+@pytest.mark.parametrize("W,H", [(320, 200), (324, 203), (1280, 800)])
+def test_export_png_and_crc32_of_device_frames(W, H, tmp_path):
+    """A device frame through the export path: drr_read_framebuffer -> PNG file -> decoded == the oracle's frame, byte for
+    byte; and the device-side CRC-32 of the resident frames == zlib.crc32 of the oracle's frames (324x203: a frame whose size
+    is no multiple of the CRC chunk or of 16 bytes)."""
+    import zlib
+    from doom_rust_renderer_b200 import png
+    path, gm = common.wad("e1m1")
+    game = orc.Game(path, "E1M1", W, H)
+    n = 5
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::700], n)
+    ctx = drr.Context(W, H, 0, n + 2)
+    scene = drr.Scene(path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    assert scene.emit_views(ctx, views, first_slot=1) == []  # slots 0 and n+1 stay untouched: all-zero frames
+    ctx.submit()
+    ctx.sync()
+    refs = [game.render(float(v[0]), float(v[1]), float(v[2])) for v in views]
+    crcs = ctx.read_crc32(0, n + 2)
+    assert int(crcs[0]) == int(crcs[n + 1]) == zlib.crc32(bytes(W * H * 3))
+    for k, ref in enumerate(refs):
+        assert int(crcs[k + 1]) == zlib.crc32(ref.tobytes()), k
+    f = tmp_path / "frame.png"
+    f.write_bytes(png.encode_png(ctx.read_framebuffer(3)))
+    assert (png.decode_png(f.read_bytes()) == refs[2]).all()
+    assert (ctx.read_crc32(2, 1) == crcs[2:3]).all()
+
+
+def test_real_wad_if_supplied():
+    """BASELINE.md:47: with DRR_WAD=<doom1.wad> the E1M1-class workloads use the real IWAD (src/wad.rs:86-109 is the format).
+    Skipped when the variable is not set (no WAD ships in the image); with it, frames of a tour over the map's thing positions
+    are compared with the oracle like every other workload."""
+    from doom_rust_renderer_b200 import workloads
+    if not workloads.real_wad():
+        pytest.skip("DRR_WAD not set")
+    content = workloads.Content("e1m1")
+    W, H, n = 320, 200, 24
+    game = orc.Game(content.path, "E1M1", W, H)
+    views = common.usable_views(game, content.viewpoints(4 * n), n)
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(content.path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    _draw_and_check(ctx, scene, game, views, "real WAD")

@@ -257,3 +257,24 @@ def test_png_export_roundtrip():
     assert (png.decode_png(png.encode_png(noise)) == noise).all()
     with pytest.raises(ValueError):
         png.encode_png(np.zeros((4, 4), np.uint8))
+
+
+def test_workload_content_and_real_wad_switch(tmp_path, monkeypatch):
+    """workloads.Content: synthetic by default; DRR_WAD points the E1M1-class workloads at a real IWAD, whose THINGS lump
+    (read with the module's own directory walk) gives the viewpoint tour.  The synthetic WAD stands in for the real one here."""
+    from doom_rust_renderer_b200 import workloads
+    monkeypatch.delenv("DRR_WAD", raising=False)
+    c = workloads.Content("e1m1", cache_dir=str(tmp_path))
+    assert c.real is None and "synthetic" in c.source and len(c.viewpoints(7)) == 7
+    things = workloads.wad_things(c.path)
+    assert things.shape[1] == 5 and len(things) >= 100 and (things[:, 3] == 1).sum() == 1  # one Player1Start
+    monkeypatch.setenv("DRR_WAD", c.path)
+    r = workloads.Content("e1m1")
+    assert r.real == c.path and r.path == c.path and "real IWAD" in r.source
+    v = r.viewpoints(2 * len(things) + 3)
+    assert v.shape == (2 * len(things) + 3, 3) and (v[:len(things), :2] == things[:, :2]).all()
+    assert not np.allclose(v[0, 2], v[len(things), 2])  # the second round looks elsewhere
+    assert workloads.Content("stress").real is None     # only the E1M1-class workloads switch
+    monkeypatch.setenv("DRR_WAD", str(tmp_path / "missing.wad"))
+    with pytest.raises(FileNotFoundError):
+        workloads.Content("e1m1")
