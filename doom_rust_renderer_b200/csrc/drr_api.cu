@@ -131,6 +131,11 @@ struct FeState {
     DevBuf<int32_t> d_dseg_part;
     std::vector<fe::Node> nodes;
     std::vector<fe::SubSector> ssectors;
+    std::vector<fe::NodeUp> node_up; // empty when the node lump is not a proper tree
+    std::vector<int32_t> ss_up;
+    int nord = 0;
+    DevBuf<fe::NodeUp> d_node_up;
+    DevBuf<int32_t> d_ss_up;
     std::vector<fe::Seg> segs;
     std::vector<fe::Line> lines;
     std::vector<fe::Side> sides;
@@ -150,6 +155,8 @@ struct FeState {
     DevBuf<int16_t> d_focl, d_cocl;
     DevBuf<uint32_t> d_rows;
     DevBuf<int32_t> d_order;
+    DevBuf<fe::SegPre> d_pre; // the stateless kernel's records and codes, nsegs per viewpoint
+    DevBuf<uint8_t> d_pre_code;
     PinnedVec<fe::ViewIn> h_views_in;
     PinnedVec<fe::Counts> h_counts;
     PinnedVec<fe::Bases> h_bases;
@@ -1275,6 +1282,44 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
         }
     S.nodes.assign(reinterpret_cast<const fe::Node *>(m->nodes), reinterpret_cast<const fe::Node *>(m->nodes) + m->n_nodes);
     S.ssectors.assign(reinterpret_cast<const fe::SubSector *>(m->subsectors), reinterpret_cast<const fe::SubSector *>(m->subsectors) + m->n_subsectors);
+    // The tree seen from below, for the closed-form seg order (drr_frontend.cuh: Frame::run).  Only when the lump is a proper
+    // tree: every node but the root and every subsector is the child of exactly one node, and no seg is listed twice.
+    {
+        const int nn = m->n_nodes, ns = m->n_subsectors;
+        S.node_up.assign((size_t)nn, fe::NodeUp{-1, 0, 0});
+        S.ss_up.assign((size_t)ns, -2);
+        std::vector<int> refs((size_t)nn, 0);
+        std::vector<int32_t> total((size_t)nn, 0); // segs under the node
+        bool tree = true;
+        int64_t nord = 0;
+        for (int i = 0; i < ns; i++) nord += m->subsectors[i].count;
+        for (int i = 0; i < nn && tree; i++) { // children come before their parents (checked above)
+            for (int side = 0; side < 2; side++) {
+                const int32_t ch = side ? m->nodes[i].left : m->nodes[i].right;
+                const int32_t up = (int32_t)((uint32_t)i << 1) | side;
+                int32_t under;
+                if (ch < 0) {
+                    if (S.ss_up[(size_t)~ch] != -2) tree = false;
+                    S.ss_up[(size_t)~ch] = up;
+                    under = m->subsectors[~ch].count;
+                } else {
+                    if (++refs[(size_t)ch] > 1) tree = false;
+                    S.node_up[(size_t)ch].up = up;
+                    under = total[(size_t)ch];
+                }
+                (side ? S.node_up[(size_t)i].left : S.node_up[(size_t)i].right) = under;
+                total[(size_t)i] += under;
+            }
+        }
+        for (int i = 0; i + 1 < nn; i++) tree = tree && refs[(size_t)i] == 1;
+        for (int i = 0; i < ns; i++) tree = tree && S.ss_up[(size_t)i] != -2;
+        tree = tree && nord <= m->n_segs && total[(size_t)nn - 1] == nord;
+        if (!tree) {
+            S.node_up.clear();
+            S.ss_up.clear();
+        }
+        S.nord = (int)std::min<int64_t>(nord, m->n_segs);
+    }
     S.segs.assign(reinterpret_cast<const fe::Seg *>(m->segs), reinterpret_cast<const fe::Seg *>(m->segs) + m->n_segs);
     S.lines.assign(reinterpret_cast<const fe::Line *>(m->linedefs), reinterpret_cast<const fe::Line *>(m->linedefs) + m->n_linedefs);
     S.sides.assign(reinterpret_cast<const fe::Side *>(m->sidedefs), reinterpret_cast<const fe::Side *>(m->sidedefs) + m->n_sidedefs);
@@ -1306,6 +1351,8 @@ int drr_fe_upload_map(drr_ctx *ctx, const drr_fe_map *m) {
         CU(ctx, cudaStreamSynchronize(ctx->stream)); // a previous batch's front-end may still read the old tables
         CU(ctx, up(S.d_nodes, S.nodes));
         CU(ctx, up(S.d_ssectors, S.ssectors));
+        CU(ctx, up(S.d_node_up, S.node_up));
+        CU(ctx, up(S.d_ss_up, S.ss_up));
         CU(ctx, up(S.d_segs, S.segs));
         CU(ctx, up(S.d_lines, S.lines));
         CU(ctx, up(S.d_sides, S.sides));
@@ -1326,6 +1373,11 @@ static fe::Map fe_make_map(const drr_ctx *ctx, bool device, int phases) {
     fe::Map m;
     m.nodes = device ? S.d_nodes.p : S.nodes.data();
     m.ssectors = device ? S.d_ssectors.p : S.ssectors.data();
+    m.node_up = S.node_up.empty() ? nullptr : device ? S.d_node_up.p : S.node_up.data();
+    m.ss_up = S.ss_up.empty() ? nullptr : device ? S.d_ss_up.p : S.ss_up.data();
+    m.nssectors = (int)S.ssectors.size();
+    m.nord = S.nord;
+    m.side_words = ((int)S.nodes.size() + 31) / 32;
     m.segs = device ? S.d_segs.p : S.segs.data();
     m.lines = device ? S.d_lines.p : S.lines.data();
     m.sides = device ? S.d_sides.p : S.sides.data();
@@ -1430,7 +1482,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             CU(ctx, S.d_mos.reserve(N * cap_mos));
             CU(ctx, S.d_mo_order.reserve(N * cap_mos));
         }
-        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
+        scr = FeScratch{S.d_hor.p, S.d_focl.p, S.d_cocl.p, S.d_rows.p, S.d_order.p, S.d_pre.p, S.d_pre_code.p, S.d_renders.p, S.d_allcols.p, S.d_dsegs.p, S.d_mos.p, S.d_mo_order.p,
                         S.d_dseg_part.p, cap_renders, cap_allcols, cap_dsegs, cap_mos};
         return DRR_OK;
     };
@@ -1439,7 +1491,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         hs_focl.resize(W);
         hs_cocl.resize(W);
         hs_rows.resize(2 * W);
-        hs_order.resize(S.segs.size());
+        hs_order.resize(S.segs.size() + (S.nodes.size() + 31) / 32); // the seg order, then the node side bits
     } else {
         int rc = upload_assets(ctx);
         if (rc) return rc;
@@ -1450,7 +1502,9 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         CU(ctx, S.d_focl.reserve(N * W));
         CU(ctx, S.d_cocl.reserve(N * W));
         CU(ctx, S.d_rows.reserve(N * W * 2));
-        CU(ctx, S.d_order.reserve(N * S.segs.size()));
+        CU(ctx, S.d_order.reserve(N * (S.segs.size() + (S.nodes.size() + 31) / 32))); // per view: the seg order, then the node side bits
+        CU(ctx, S.d_pre.reserve(N * S.segs.size()));
+        CU(ctx, S.d_pre_code.reserve(N * S.segs.size()));
         CU(ctx, cudaMemcpyAsync(S.d_views_in.p, S.h_views_in.p, N * sizeof(fe::ViewIn), cudaMemcpyHostToDevice, ctx->stream));
     }
     {
@@ -1472,7 +1526,8 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
                 if (b.frame < 0) continue;
             }
             fe::Frame<EMIT> fr(m);
-            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data(), hs_renders.data(),
+            fr.sc = fe::Scratch{hs_hor.data(), hs_focl.data(), hs_cocl.data(), {hs_rows.data(), hs_rows.data() + W}, hs_order.data(),
+                                reinterpret_cast<uint32_t *>(hs_order.data() + S.segs.size()), nullptr, nullptr, hs_renders.data(),
                                 hs_allcols.data(), hs_dsegs.data(), hs_mos.data(), hs_mo_order.data(), hs_dseg_part.data(), cap_renders, cap_allcols, cap_dsegs, cap_mos};
             fr.out = out;
             fr.cap = cap;
@@ -1482,6 +1537,14 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
     };
     fe::Slabs sl{};
     sl.cap = slab;
+    bool pre_done = false;
+    auto pre_once = [&]() -> int { // the stateless (viewpoint, seg) kernel: once per batch, in front of the first front-end launch (and inside its timing)
+        if (pre_done) return DRR_OK;
+        pre_done = true;
+        CU(ctx, launch_fe_pre(fe_make_map(ctx, true, phases), S.d_views_in.p, n, scr, ctx->stream));
+        ctx->stats.kernel_launches++;
+        return DRR_OK;
+    };
     for (int attempt = 0;; attempt++) { // again when a view outgrew its slab (then two-pass) or the masked phase's working arrays (then larger ones)
         if (single) {
             if (on_host) {
@@ -1502,6 +1565,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
                 CU(ctx, S.d_sl_parr.reserve(N * slab.parr));
                 sl.out = fe::Out{S.d_sl_views.p, S.d_sl_ops.p, S.d_sl_segs.p, reinterpret_cast<ColRec *>(S.d_sl_cols.p), S.d_sl_planes.p, S.d_sl_parr.p};
                 CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+                if (int rc = pre_once()) return rc;
                 CU(ctx, launch_frontend(true, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, sl.out, slab, ctx->stream));
                 ctx->stats.kernel_launches++;
                 CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -1510,6 +1574,7 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
             host_pass(std::false_type{}, fe::Out{}, false);
         } else {
             CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+            if (int rc = pre_once()) return rc;
             CU(ctx, launch_frontend(false, fe_make_map(ctx, true, phases), S.d_views_in.p, nullptr, S.d_counts.p, n, scr, fe::Out{}, nocap, ctx->stream));
             ctx->stats.kernel_launches++;
             CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -10,6 +10,7 @@
 // straight into the arrays drr_bin_kernel reads -- no draw list ever crosses PCIe.
 #include "drr_frontend.cuh"
 #include "drr_kernels.h"
+#include <algorithm>
 
 namespace drr {
 
@@ -17,7 +18,9 @@ namespace drr {
 // Slabs) and leaves its counts; drr_fe_compact_kernel then makes the lists dense.
 template <bool EMIT>
 __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel(const __grid_constant__ fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
-                                                                                 fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab) {
+                                                                                 fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab,
+                                                                                 int smem_mode, uint32_t smem_per_view) {
+    extern __shared__ __align__(16) uint8_t fe_smem[];
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
     fe::Bases b = fe::Bases{0, 0, 0, 0, 0, 0, {0, 0}};
@@ -39,7 +42,24 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     fr.sc.ceil_ocl = s.ceil_ocl + o;
     fr.sc.rows[0] = s.rows + 2 * o;
     fr.sc.rows[1] = s.rows + 2 * o + m.W;
-    fr.sc.order = s.order + (size_t)v * (size_t)m.nsegs;
+    fr.sc.order = s.order + (size_t)v * (size_t)(m.nsegs + m.side_words);
+    fr.sc.side = reinterpret_cast<uint32_t *>(fr.sc.order + m.nsegs);
+    // The per-view state the column loops hammer on goes to shared memory when it fits with every warp of the SM resident
+    // (launch_frontend picks the mode): 1 = the three occlusion arrays and the side bits, 2 = also the two visplane row buffers.
+    if (smem_mode >= 1) {
+        uint8_t *base = fe_smem + (size_t)(threadIdx.x >> 5) * smem_per_view;
+        const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15;
+        fr.sc.hor_ocl = base;
+        fr.sc.floor_ocl = reinterpret_cast<int16_t *>(base + Wp);
+        fr.sc.ceil_ocl = reinterpret_cast<int16_t *>(base + 3 * Wp);
+        fr.sc.side = reinterpret_cast<uint32_t *>(base + 5 * Wp);
+        if (smem_mode >= 2) {
+            fr.sc.rows[0] = reinterpret_cast<uint32_t *>(base + 5 * Wp + 4 * (size_t)((m.side_words + 3) & ~3));
+            fr.sc.rows[1] = fr.sc.rows[0] + Wp;
+        }
+    }
+    fr.sc.pre = s.pre ? static_cast<const fe::SegPre *>(s.pre) + (size_t)v * (size_t)m.nsegs : nullptr;
+    fr.sc.pre_code = s.pre_code ? s.pre_code + (size_t)v * (size_t)m.nsegs : nullptr;
     fr.sc.renders = static_cast<fe::RenderRec *>(s.renders) + (size_t)v * s.cap_renders;
     fr.sc.allcols = static_cast<ColRec *>(s.allcols) + (size_t)v * s.cap_allcols;
     fr.sc.dsegs = static_cast<SegRec *>(s.dsegs) + (size_t)v * s.cap_dsegs;
@@ -56,6 +76,21 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     if ((!EMIT || slab.ops) && (threadIdx.x & 31u) == 0u) counts[v] = fr.n;
 }
 
+// One thread per (viewpoint, seg): the part of process_seg that needs neither order nor state.  Consecutive threads take
+// consecutive segs of one viewpoint, so the records and codes go out coalesced; ~85 % of the pairs end at the field-of-view clip.
+__global__ void __launch_bounds__(256) drr_fe_pre_kernel(const __grid_constant__ fe::Map m, const fe::ViewIn *__restrict__ views, int n, fe::SegPre *__restrict__ pre,
+                                                         uint8_t *__restrict__ code) {
+    const int s = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (s >= m.nsegs) return;
+    for (int v = (int)blockIdx.y; v < n; v += (int)gridDim.y) {
+        const fe::ViewIn vi = views[v];
+        const fe::SegPre p = fe::seg_pre_of(m, fe::V2{vi.x, vi.y}, vi.cos_n, vi.sin_n, m.segs[s]);
+        const size_t at = (size_t)v * (size_t)m.nsegs + (size_t)s;
+        code[at] = (uint8_t)p.code;
+        if (p.code) pre[at] = p;
+    }
+}
+
 __global__ void __launch_bounds__(128) drr_fe_compact_kernel(fe::Slabs sl, const fe::Counts *__restrict__ counts, const fe::Bases *__restrict__ bases, int n, fe::Out dst) {
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
@@ -69,10 +104,23 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     if (n <= 0) return cudaSuccess;
     const int vpb = FE_THREADS / 32; // viewpoints per CTA
     const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
+    // shared memory per viewpoint: occlusion arrays 5 bytes per column + side bits (mode 1), + 8 bytes per column of visplane
+    // rows (mode 2); taken when 32 viewpoints (every warp the register budget allows on an SM) fit in ~200 KB
+    const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15, side_bytes = 4 * (size_t)((m.side_words + 3) & ~3);
+    const size_t need1 = 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * vpb);
+    const int mode = need2 <= budget ? 2 : need1 <= budget ? 1 : 0;
+    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : 0, dyn = per_view * vpb;
     if (emit)
-        drr_frontend_kernel<true><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out, slab);
+        drr_frontend_kernel<true><<<blocks, FE_THREADS, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
     else
-        drr_frontend_kernel<false><<<blocks, FE_THREADS, 0, st>>>(m, views, bases, counts, n, s, out, slab);
+        drr_frontend_kernel<false><<<blocks, FE_THREADS, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fe_pre(const fe::Map &m, const fe::ViewIn *views, int n, const FeScratch &s, cudaStream_t st) {
+    if (n <= 0 || !s.pre || !s.pre_code) return cudaSuccess;
+    const dim3 grid((unsigned)((m.nsegs + 255) / 256), (unsigned)std::min(n, 65535));
+    drr_fe_pre_kernel<<<grid, 256, 0, st>>>(m, views, n, static_cast<fe::SegPre *>(s.pre), s.pre_code);
     return cudaGetLastError();
 }
 

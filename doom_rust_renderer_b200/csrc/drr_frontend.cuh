@@ -78,9 +78,17 @@ struct Thing { // a non-null map object at tic 0 (map_objects.rs:25-50), everyth
     int32_t bitmap[8];   // index into Map::bitmaps per rotation (entry 0 when !rotate)
     int16_t top_offset[8];
 };
+struct NodeUp { // the BSP tree seen from below (drr_fe_upload_map builds it when the node lump is a proper tree)
+    int32_t up;          // (parent node << 1) | (1 when this is the parent's LEFT child), -1 at the root
+    int32_t left, right; // segs under the left / right child (node entries only)
+};
 struct Map {
     const Node *nodes;
     const SubSector *ssectors;
+    const NodeUp *node_up; // [nnodes], null when the lump is not a tree (the walk then runs serially with a stack)
+    const int32_t *ss_up;  // [nssectors] NodeUp::up of every subsector
+    int nssectors, nord;   // nord = segs the walk lists = sum of the subsectors' counts
+    int side_words;        // (nnodes + 31) / 32: words of the per-view "player is left of the node's line" bit set
     const Seg *segs;
     const Line *lines;
     const Side *sides;
@@ -148,12 +156,16 @@ struct MoRec { // 16 bytes
     int32_t dseg;  // its header in Scratch::dsegs (-1: no column)
 };
 
+struct SegPre;
 // per-viewpoint scratch (global memory)
 struct Scratch {
     uint8_t *hor_ocl;              // W entries each: segs.rs:97-99
     int16_t *floor_ocl, *ceil_ocl;
     uint32_t *rows[2]; // W (top, bottom) pairs of the visplane being accumulated: 0 = bottom (floor), 1 = top (ceiling)
     int32_t *order;    // nsegs entries: the map's segs in this view's BSP order
+    uint32_t *side;    // Map::side_words words: bit i = the player is on the left of node i's partition line
+    const SegPre *pre;       // nsegs records of drr_fe_pre_kernel for this view (valid where the code is not 0), or null
+    const uint8_t *pre_code; // nsegs codes
     // masked phase only
     RenderRec *renders; // the parts that can clip sprites or are drawn late, in creation order
     ColRec *allcols;    // their columns, and the sprites' columns
@@ -295,6 +307,48 @@ FE_NOINLINE int sector_at(const Map &m, V2 p) { // renderer/bsp.rs:9-44
         }
         return -1;
     }
+}
+
+// The part of process_seg that touches no per-view state (segs.rs:353-460): the view transform, the clip against the
+// field of view, the screen x of the ends, the back-face test.  On the device it runs for every (viewpoint, seg) pair in a
+// kernel of its own (drr_fe_pre_kernel: one thread per pair, no order, no state), which leaves one 32-byte record per pair
+// that survives and a code byte per pair; the per-view walk then only looks the codes up in BSP order.  Without those arrays
+// (CPU test harness) the walk evaluates it in place, 32 segs at a time.
+struct SegPre { // 32 bytes
+    float csx, csy, cex, cey, so; // ClippedLine
+    int32_t sx, ex;               // screen x of its ends
+    int32_t code;                 // 0 draws nothing, 1 go on, 2 panics ("Clipped line x < -0.01"), 4 go on and nothing in its
+                                  // sidedef can panic (no unknown texture, no missing flat): may be skipped when occluded
+};
+FE_NOINLINE SegPre seg_pre_of(const Map &m, V2 ppos, float cos_n, float sin_n, const Seg &sg) {
+    SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
+    const Line ld = m.lines[sg.line];
+    const int fi = sg.dir ? ld.back : ld.front;
+    if (fi == -1) return p;
+    const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
+    const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
+    Seg2 cl;
+    float so;
+    if (!clip_fov(view, &cl, &so)) return p;
+    p.csx = cl.s.x;
+    p.csy = cl.s.y;
+    p.cex = cl.e.x;
+    p.cey = cl.e.y;
+    p.so = so;
+    if (cl.s.x < -0.01f) {
+        p.code = 2;
+        return p;
+    }
+    const ScreenX sx = project_x(m, cl);
+    p.sx = sx.sx;
+    p.ex = sx.ex;
+    p.code = sx.sx > sx.ex ? 0 : 1; // back faces draw nothing
+    if (p.code == 1 && sx.sx >= 0) {
+        const Side sd = m.sides[fi];
+        const Sector sec = m.sectors[sd.sector];
+        if (sd.upper != -2 && sd.lower != -2 && sd.middle != -2 && sec.floor_flat >= 0 && sec.ceil_flat >= 0) p.code = 4;
+    }
+    return p;
 }
 
 // ---- one viewpoint = one warp ---------------------------------------------------------------------------------------
@@ -1031,45 +1085,7 @@ struct Frame {
         }) == 0xffffffffu;
     }
 
-    // The part of process_seg that touches no per-view state (segs.rs:353-460): the view transform, the clip against the
-    // field of view, the screen x of the ends, the back-face test.  Evaluated for up to 32 segs of a subsector at once
-    // (one per lane); the segs that survive go through seg() in order with these values.
-    struct SegPre {
-        float csx, csy, cex, cey, so; // ClippedLine
-        int32_t sx, ex;               // screen x of its ends
-        int32_t code;                 // 0 draws nothing, 1 go on, 2 panics ("Clipped line x < -0.01"), 4 go on and nothing in its
-                                      // sidedef can panic (no unknown texture, no missing flat): may be skipped when occluded
-    };
-    FE_NOINLINE SegPre seg_pre(const Seg &sg) const {
-        SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
-        const Line ld = m.lines[sg.line];
-        const int fi = sg.dir ? ld.back : ld.front;
-        if (fi == -1) return p;
-        const V2 v1 = {sg.v1x, sg.v1y}, v2 = {sg.v2x, sg.v2y};
-        const Seg2 view = {rot(sub(v1, ppos), cos_n, sin_n), rot(sub(v2, ppos), cos_n, sin_n)};
-        Seg2 cl;
-        float so;
-        if (!clip_fov(view, &cl, &so)) return p;
-        p.csx = cl.s.x;
-        p.csy = cl.s.y;
-        p.cex = cl.e.x;
-        p.cey = cl.e.y;
-        p.so = so;
-        if (cl.s.x < -0.01f) {
-            p.code = 2;
-            return p;
-        }
-        const ScreenX sx = project_x(m, cl);
-        p.sx = sx.sx;
-        p.ex = sx.ex;
-        p.code = sx.sx > sx.ex ? 0 : 1; // back faces draw nothing
-        if (p.code == 1 && sx.sx >= 0) {
-            const Side sd = m.sides[fi];
-            const Sector sec = m.sectors[sd.sector];
-            if (sd.upper != -2 && sd.lower != -2 && sd.middle != -2 && sec.floor_flat >= 0 && sec.ceil_flat >= 0) p.code = 4;
-        }
-        return p;
-    }
+    FE_HD SegPre seg_pre(const Seg &sg) const { return seg_pre_of(m, ppos, cos_n, sin_n, sg); }
 
     // process_seg, segs.rs:353-590 (after seg_pre)
     FE_NOINLINE void seg(const Seg &sg, const SegPre &pre) {
@@ -1159,12 +1175,44 @@ struct Frame {
         // walk itself only decides the ORDER in which the segs are processed (the reference does no occlusion culling in
         // the tree), so it first lists the segs in that order; they are then taken 32 at a time: one lane per seg for the
         // stateless part (seg_pre), the survivors in order through seg().
-        int stack[64];
-        int sp = 0, nord = 0;
-        stack[sp++] = m.nnodes - 1;
-        int32_t *const order = sc.order; // (locals: the walk is the hottest uniform loop of the kernel)
+        int nord = 0;
+        int32_t *const order = sc.order;
         const Node *const nodes = m.nodes;
         const SubSector *const ssectors = m.ssectors;
+        if (m.node_up) {
+            // The order in closed form.  The walk visits, at every node, the child on the player's side first; so a
+            // subsector's position in the list is the number of segs under the first-visited siblings along its path to the
+            // root.  The 32 lanes evaluate the side test of 32 nodes at a time (one bit each), then every lane climbs from
+            // its own subsector to the root adding up -- instead of one lane-uniform pointer chase through every node.
+            uint32_t *const side = sc.side;
+            for (int i0 = 0; i0 < m.nnodes; i0 += 32) {
+                const uint32_t bits = ballot([&](int l) {
+                    if (i0 + l >= m.nnodes) return false;
+                    const Node nd = nodes[i0 + l];
+                    return left_of(ppos, V2{nd.x, nd.y}, V2{nd.x + nd.dx, nd.y + nd.dy});
+                });
+                FE_LEADER { side[i0 >> 5] = bits; }
+            }
+            FE_SYNC();
+            FE_LANES(l) {
+                for (int si = l; si < m.nssectors; si += 32) {
+                    int rank = 0;
+                    for (int32_t up = m.ss_up[si]; up >= 0;) {
+                        const int a = up >> 1;
+                        const bool under_left = (up & 1) != 0, is_left = ((side[a >> 5] >> (a & 31)) & 1u) != 0u;
+                        const NodeUp nu = m.node_up[a];
+                        if (under_left != is_left) rank += under_left ? nu.right : nu.left; // the sibling is visited first
+                        up = nu.up;
+                    }
+                    const SubSector ss = ssectors[si];
+                    for (int i = 0; i < ss.count; i++) order[rank + i] = ss.first + i;
+                }
+            }
+            nord = m.nord;
+        } else {
+        int stack[64];
+        int sp = 0;
+        stack[sp++] = m.nnodes - 1;
         const int nsegs = m.nsegs;
         while (sp > 0) {
             const int node = stack[--sp];
@@ -1191,6 +1239,7 @@ struct Frame {
             stack[sp++] = is_left ? nd.right : nd.left; // visited second
             stack[sp++] = is_left ? nd.left : nd.right; // visited first
         }
+        }
         FE_SYNC();
         for (int c0 = 0; c0 < nord && n.status == FE_OK; c0 += 32) {
             PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
@@ -1200,7 +1249,8 @@ struct Frame {
                 int si = 0;
                 if (c0 + l < nord) {
                     si = sc.order[c0 + l];
-                    p = seg_pre(m.segs[si]);
+                    if (!sc.pre) p = seg_pre(m.segs[si]);
+                    else if (sc.pre_code[si]) p = sc.pre[si]; // the stateless kernel's record: every survivor of the batch fetches its own at once
                 }
                 p_seg[l] = si;
                 p_csx[l] = p.csx;

@@ -99,7 +99,9 @@ struct FeScratch {                    // per-viewpoint working state of the fron
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;
     uint32_t *rows;                   // 2 * W per viewpoint: the (top, bottom) rows of the two visplanes being accumulated
-    int32_t *order;                   // nsegs per viewpoint: the segs in the view's BSP order
+    int32_t *order;                   // nsegs per viewpoint: the segs in the view's BSP order (then the node side bits)
+    void *pre;                        // nsegs records (fe::SegPre, 32 bytes) per viewpoint, written by drr_fe_pre_kernel; null = evaluate in the walk
+    uint8_t *pre_code;                // nsegs codes per viewpoint
     // masked phase only (null otherwise); per viewpoint: cap_* entries each, cap_dsegs part indices, cap_mos draw-order entries
     void *renders, *allcols, *dsegs, *mos;
     int32_t *mo_order;
@@ -108,6 +110,8 @@ struct FeScratch {                    // per-viewpoint working state of the fron
 };
 // emit == false: count pass (writes counts[0..n)); emit == true: writes the lists at the offsets in bases[0..n), or -- when
 // slab.ops != 0, single-pass mode -- into per-view slabs of those capacities, leaving counts[0..n) for launch_fe_compact
+// the stateless part of process_seg for every (viewpoint, seg) pair: fills s.pre / s.pre_code
+cudaError_t launch_fe_pre(const fe::Map &m, const fe::ViewIn *views, int n, const FeScratch &s, cudaStream_t st);
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
                             const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st);
 cudaError_t launch_fe_compact(const fe::Slabs &sl, const fe::Counts *counts, const fe::Bases *bases, int n, const fe::Out &dst, cudaStream_t st);
