@@ -522,6 +522,9 @@ __device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView 
     int y = ya + t.li;
     // rows y and y + 8 of this lane together (visplanes.rs:109-128, twice)
     float2 vy = f2(__fsub_rn(v.CFY, (float)y), __fsub_rn(v.CFY, (float)(y + TILE_LPG)));
+#ifdef DRR_FLAT_UNROLL2
+#pragma unroll 2
+#endif
     for (; y <= yb; y += 2 * TILE_LPG, vy = __fadd2_rn(vy, f2((float)(-2 * TILE_LPG))), addr += ROW16) {
         float2 r0;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
@@ -622,6 +625,9 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // MINB = resident CTAs per SM the register budget is set for (6: tiles of up to ~224 rows; 4: up to 400 rows)
 // FAST = W % 32 == 0 and every band a multiple of 8 rows: TMA write-out with the checksum fused; otherwise a bytewise
 //        write-out and a separate checksum pass
+#ifndef DRR_TILE_MINB_SMALL
+#define DRR_TILE_MINB_SMALL 6 // resident CTAs per SM the small-tile build is compiled for (A/B: 5 = 48 registers)
+#endif
 template <int MINB, bool FAST>
 __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __grid_constant__ DrawArgs a, const __grid_constant__ CUtensorMap fbmap, int frame0) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams);
     // The next span's first word is fetched while the current one is drawn: into registers where the budget allows (MINB 4),
     // otherwise only into L1 (four registers kept across the pixel loops would spill at 40)
-    constexpr bool HEAD_IN_REGS = MINB <= 4;
+    constexpr bool HEAD_IN_REGS = MINB <= 5;
     uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
     if (left > 0) {
         if (HEAD_IN_REGS) ra_next = P[(size_t)rec * 4]; // the first span's head: in flight while the palette arrives
@@ -897,10 +903,10 @@ cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0,
     const bool small = dyn <= 36 * 1024; // six CTAs per SM fit: 40 registers; else five (up to 44 KB) or four: 48 registers
     cudaError_t e;
     if (fast) {
-        e = small ? launch_tile_t<6, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);
+        e = small ? launch_tile_t<DRR_TILE_MINB_SMALL, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);
     } else {
         static const CUtensorMap none = {};
-        e = small ? launch_tile_t<6, false>(a, none, frame0, nframes, dyn, st, launches) : launch_tile_t<4, false>(a, none, frame0, nframes, dyn, st, launches);
+        e = small ? launch_tile_t<DRR_TILE_MINB_SMALL, false>(a, none, frame0, nframes, dyn, st, launches) : launch_tile_t<4, false>(a, none, frame0, nframes, dyn, st, launches);
         if (e == cudaSuccess) e = launch_checksum_pass(a, frame0, nframes, st, launches);
     }
     return e;

@@ -623,3 +623,78 @@ def test_real_wad_if_supplied():
     scene = drr.Scene(content.path, "E1M1", W, H)
     scene.upload_assets(ctx)
     _draw_and_check(ctx, scene, game, views, "real WAD")
+
+
+# ---- BASELINE configs [2], [3], [4] at (or near) their stated sizes ----------------------------------------------------------------
+def _oracle_checksums(path, W, H, phases, views, procs=8):
+    """Per-frame checksums of the oracle's frames of `views`, several oracle processes side by side."""
+    import bench  # the CPU pool of bench.py (oracle worker processes)
+    pool = bench.CpuPool(path, W, H, min(procs, len(views)))
+    try:
+        return pool.render(np.asarray(views, np.float32), phases, want_sums=True)[1]
+    finally:
+        pool.close()
+
+
+def _device_batch(kind, W, H, n, phases):
+    """n viewpoints of the workload through the device front-end (nudging what the reference would panic on, like bench.py)."""
+    import bench
+    from doom_rust_renderer_b200 import workloads
+    content = workloads.Content(kind, cache_dir=common.CACHE)
+    ctx = drr.Context(W, H, 0, n)
+    scene = drr.Scene(content.path, "E1M1", W, H)
+    scene.upload_assets(ctx)
+    used = bench.settle_views_device(scene, ctx, content.viewpoints(n), phases)
+    ctx.draw()
+    ctx.sync()
+    return content.path, ctx, scene, used
+
+
+@pytest.mark.parametrize("phases,what", [(1, "walls only"), (2, "flats and sky only")])
+def test_config2_phase_isolation_at_1280x800(phases, what):
+    """BASELINE configs[2]: the column / span isolation at the resolution it is quoted on; 256 viewpoints, every 4th frame
+    against the oracle (64 frames, checksums), six of them byte for byte."""
+    W, H, n = 1280, 800, 256
+    path, ctx, scene, used = _device_batch("e1m1", W, H, n, phases)
+    crcs = ctx.read_checksums(0, n)
+    idx = np.arange(0, n, 4)
+    want = _oracle_checksums(path, W, H, phases, used[idx])
+    assert [int(crcs[k]) for k in idx] == want, what
+    game = orc.Game(path, "E1M1", W, H)
+    for k in idx[::11]:
+        v = used[k]
+        _compare(ctx, int(k), game.render(float(v[0]), float(v[1]), float(v[2]), phases=phases), "%s, view %d" % (what, k))
+
+
+def test_config3_things_and_masked_at_4096_viewpoints():
+    """BASELINE configs[3] at its full size: 640x400, all phases (things, masked mid-textures, sector light), 4096 viewpoints;
+    96 seeded frames against the oracle by checksum, and drawing the batch again from host-recorded lists gives the same 4096
+    checksums (device front-end == host front-end at full size)."""
+    W, H, n = 640, 400, 4096
+    path, ctx, scene, used = _device_batch("e1m1", W, H, n, 7)
+    crcs = ctx.read_checksums(0, n)
+    idx = np.sort(np.random.default_rng(0xD00D1993).choice(n, 96, replace=False))
+    assert [int(crcs[k]) for k in idx] == _oracle_checksums(path, W, H, 7, used[idx])
+    ctx.reset()
+    assert scene.emit_views(ctx, used, 0.0, 7) == []
+    ctx.submit()
+    ctx.sync()
+    assert (ctx.read_checksums(0, n) == crcs).all()
+
+
+def test_config4_stress_map_at_1024_viewpoints():
+    """BASELINE configs[4]: the stress map at 1920x1200 (three row bands per tile column, hundreds of sprites per view), 1024
+    viewpoints of one GPU's share; 64 seeded frames against the oracle by checksum, two byte for byte; a second draw of the
+    resident lists changes nothing."""
+    W, H, n = 1920, 1200, 1024
+    path, ctx, scene, used = _device_batch("stress", W, H, n, 7)
+    crcs = ctx.read_checksums(0, n)
+    idx = np.sort(np.random.default_rng(0xD00D1993).choice(n, 64, replace=False))
+    assert [int(crcs[k]) for k in idx] == _oracle_checksums(path, W, H, 7, used[idx], procs=16)
+    game = orc.Game(path, "E1M1", W, H)
+    for k in idx[:2]:
+        v = used[k]
+        _compare(ctx, int(k), game.render(float(v[0]), float(v[1]), float(v[2])), "stress view %d" % k)
+    ctx.draw()
+    ctx.sync()
+    assert (ctx.read_checksums(0, n) == crcs).all()

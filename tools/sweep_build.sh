@@ -1,9 +1,10 @@
 #!/bin/bash
-# Rebuild the whole library with different compile-time knobs and time the draw path on several workloads (run under gpurun):
-#   tools/sweep_build.sh "walk320 walk1280" "" "-DDRR_PAL8"
-wls=$1; shift
-for knob in "$@"; do
-  make -s -C doom_rust_renderer_b200/csrc clean > /dev/null; make -s -C doom_rust_renderer_b200/csrc EXTRA="$knob" > /dev/null || continue
-  for wl in $wls; do ./tools/sweep_env.sh $wl "KNOB=[$knob]" | sed "s/^/$knob /"; done
+# A/B compile-time flags of the tile kernel (run under gpurun): tools/sweep_build.sh "walk320 things640" "" "-DDRR_TILE_MINB_SMALL=5" ...
+WLS=$1; shift
+for flags in "$@"; do
+  touch doom_rust_renderer_b200/csrc/drr_tile.cu
+  make -s -j4 -C doom_rust_renderer_b200/csrc EXTRA="$flags" > /dev/null 2>&1 || { echo "build failed: $flags"; continue; }
+  grep -A2 "tile_kernelILi[0-9]ELb1" doom_rust_renderer_b200/csrc/build/ptxas_tile.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo
+  ./tools/sweep_env.sh "$WLS" "FLAGS=${flags:-default}"
 done
-make -s -C doom_rust_renderer_b200/csrc clean > /dev/null; make -s -C doom_rust_renderer_b200/csrc > /dev/null
+touch doom_rust_renderer_b200/csrc/drr_tile.cu; make -s -j4 -C doom_rust_renderer_b200/csrc > /dev/null 2>&1
