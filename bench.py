@@ -215,17 +215,17 @@ def cpu_baseline(name, path, used, crc_dev, W, H, phases):
     cores = os.cpu_count() or 1
 
     def arm(procs, steps):
-        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", str(steps), "--warmup", "1", "--ref-procs", str(procs)]
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", str(steps), "--warmup", "2", "--ref-procs", str(procs)]
         return json.loads(subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
 
-    multi, single = arm(cores, 3), arm(1, 1)
+    multi, single = arm(cores, 6), arm(1, 1)
     nm = int(max(cores, min(len(used), multi["frames_per_step"])))
     pool = CpuPool(path, W, H, cores)
     _, sums = pool.render(used[:nm], phases, want_sums=True)
     pool.close()
     ok = all(int(crc_dev[i]) == s for i, s in enumerate(sums))
     return {"value": multi["value"], "unit": "Mpixel/s", "cores": cores, "kind": "port",
-            "sample": multi["cpu_baseline"]["sample"] + "; 3 steps after 1 warm-up; oracle = literal C++ restatement, g++ -O2 -ffp-contract=off",
+            "sample": multi["cpu_baseline"]["sample"] + "; 6 steps after 2 warm-ups; oracle = literal C++ restatement, g++ -O2 -ffp-contract=off",
             "frames_per_s": multi["frames_per_s"], "single_thread_value": single["value"], "single_thread_frames_per_s": single["frames_per_s"],
             "single_thread_sample": "%d frames" % single["frames_per_step"], "parity_checked_frames": nm, "parity_ok": bool(ok)}
 

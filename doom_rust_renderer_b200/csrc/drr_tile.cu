@@ -512,7 +512,9 @@ struct FlatView { // per-frame constants of the flat loops
     int px16, py16;
 };
 
-// the fast flat loop: TS_FASTDIV and TS_UNIT (the span does not touch the horizon row, factor <= 1 on every row)
+// the fast flat loop: TS_FASTDIV and TS_UNIT (the span does not touch the horizon row, factor <= 1 on every row).  UNROLL = 2
+// in the 48-register build of the tall tiles (measured: -1.2 % at 1280x800, +2.7 % in the 40-register build at 320x200).
+template <int UNROLL>
 __device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView &v, const uint4 ra, const uint4 rc, int ya, int yb, uint32_t addr,
                                                const uint8_t *__restrict__ flats) {
     const float wzvx = __uint_as_float(rc.x), gwz = __uint_as_float(rc.y), lf = __uint_as_float(rc.z);
@@ -522,9 +524,7 @@ __device__ __forceinline__ void tile_flat_span(const TileCtx &t, const FlatView 
     int y = ya + t.li;
     // rows y and y + 8 of this lane together (visplanes.rs:109-128, twice)
     float2 vy = f2(__fsub_rn(v.CFY, (float)y), __fsub_rn(v.CFY, (float)(y + TILE_LPG)));
-#ifdef DRR_FLAT_UNROLL2
-#pragma unroll 2
-#endif
+#pragma unroll UNROLL
     for (; y <= yb; y += 2 * TILE_LPG, vy = __fadd2_rn(vy, f2((float)(-2 * TILE_LPG))), addr += ROW16) {
         float2 r0;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(vy.x));
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                     const uint32_t addr = row_addr(ya + li - b0);
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
-                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span(t, fv, ra, R[1], ya, yb, addr, flats);
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span<(MINB <= 4 ? 2 : 1)>(t, fv, ra, R[1], ya, yb, addr, flats);
                         else tile_flat_span_any(t, fv, ra, R[1], ya, yb, addr, flats);
                     } else if (kind <= KIND_WALL_HOLES) {
                         const uint4 rc = R[1], rd = R[2];

@@ -8,7 +8,7 @@ for wl in $WLS; do
     python - "$wl" "$setting" <<'P'
 import json, sys
 d = json.load(open("/tmp/s.json")); r = d["roofline"]
-print("%-10s %-40s bin %.4f tile %.4f ms frac %.4f step %.4f" % (sys.argv[1], sys.argv[2], r["setup_ms"], r["kernel_ms"], r["frac"], d["ms_per_step"]))
+print("%-10s %-40s bin %.4f tile %.4f ms frac %.4f pass %.4f e2e %.4f" % (sys.argv[1], sys.argv[2], r["bin_kernel_ms"], r["kernel_ms"], r["frac"], d["ms_per_pass"], d["e2e"]["ms_per_pass"]))
 P
   done
 done
