@@ -40,7 +40,11 @@ namespace drr {
 //               d.x = bitmap.height as f32 (NaN when bottom_y == top_y)   d.y = light factor   d.w = 2^23 + offset_y (f32, TS_TRUNC)
 //   flat      : c.x = wz * vx   c.y = GCFX * wz   c.z = light / 255
 static constexpr uint32_t COL_COVERED = 0x80000000u; // ColIdx.n flag: the column's always-writing spans cover every row
-enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11, TS_TRUNC = 1u << 12 };
+enum : uint32_t { TS_POW2 = 1u << 8, TS_BRIGHT = 1u << 9, TS_FASTDIV = 1u << 10, TS_UNIT = 1u << 11, TS_TRUNC = 1u << 12, TS_RUNS = 1u << 13 };
+#ifndef DRR_RUN_ROWS
+#define DRR_RUN_ROWS 6
+#endif
+static constexpr int RUN_ROWS = DRR_RUN_ROWS; // consecutive rows a lane takes in the texel-run wall loop (even: rows are evaluated in pairs)
 
 // Decoded record of a wall / sprite column (everything of render_vertical_bitmap_line that depends on the column only)
 struct Rec { // a decoded record in registers
@@ -94,6 +98,12 @@ __device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, i
         const float lo = fminf(sa, sb), hi = fmaxf(sa, sb); // (a NaN fails the comparisons below through sa / sb themselves)
         if (sa >= 0.0f && sb >= 0.0f && hi <= 32767.0f && __fadd_rz(lo, off) >= 0.0f && truncf(hi) + off <= 32767.0f) flags |= TS_TRUNC;
         rd.w = __float_as_uint(8388608.0f + off);
+        // Magnified walls: when RUN_ROWS consecutive rows advance the texture row by less than one (|uy1| * (RUN_ROWS - 1) <
+        // |den|, with a margin for the roundings of the sum), they show at most two different texels, the first row's and the
+        // last row's; the texel-run loop then lights two texels per RUN_ROWS pixels instead of one per pixel.
+        if ((flags & (TS_TRUNC | TS_BRIGHT)) == TS_TRUNC && yb - ya + 1 >= 2 * RUN_ROWS &&
+            fabsf(wc.uy1) * (float)(RUN_ROWS - 1) <= 0.98f * fabsf(denF))
+            flags |= TS_RUNS;
     }
     ra.y = kind | flags;
     return Rec{ra, rb, rc, rd, kind};
@@ -476,6 +486,67 @@ __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra,
     }
 }
 
+// The texel-run wall loop (TS_RUNS: a magnified wall, see wall_record).  A lane takes RUN_ROWS CONSECUTIVE rows; along them the
+// texture row v is monotonic and moves by at most one, so they show the texel of the first row (A) or of the last row (B): two
+// texel fetches, two palette lookups and one packed lighting per RUN_ROWS pixels; every row still evaluates v (the reference's
+// own expression, bit for bit, two rows per packed instruction) to pick A's colour or B's.  The 8 lanes of a group cover
+// 8 * RUN_ROWS rows per iteration (RUN_ROWS blocks of the tile).
+template <bool HOLES, bool POW2>
+__device__ __forceinline__ void tile_wall_span_runs(const TileCtx &t, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0,
+                                                    uint32_t colx, const uint16_t *__restrict__ texels) {
+    constexpr int K = RUN_ROWS;
+    static_assert(K % 2 == 0 && K >= 4, "rows are evaluated in pairs");
+    const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y), magic = __uint_as_float(rd.w);
+    const float2 nden = f2(__uint_as_float(rc.y)), rden = f2(__uint_as_float(rc.z)), uy1 = f2(__uint_as_float(rc.w));
+    const uint32_t mask = rd.z;
+    const uint16_t *__restrict__ col = texels + ra.z;
+    asm("" : "+l"(col));
+    int y = ya + K * t.li;
+    uint32_t addr[K]; // shared addresses of the lane's rows: K rows anywhere in the block structure, all K blocks further per iteration
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const uint32_t r = (uint32_t)(y + j - b0);
+        addr[j] = (colx ^ ((r & 7u) << 4)) + ((r >> 3) << 10);
+    }
+    float2 yt01 = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + 1), __uint_as_float(rc.x))); // (y - top_y) as f32 of rows 0, 1
+    const float yt_last = __fadd_rn((float)yb, __uint_as_float(rc.x));                                              // ... of the span's last row
+    auto vbits = [&](float2 ytp) { // 0x4b000000 + v of two rows (wall_texels2_trunc without the mask)
+        const float2 ay = fast_div2(ytp, nden, rden);
+        const float2 sum = add2_nofuse(__fmul2_rn(ay, uy1), f2(hF), t.one);
+        return __fadd2_rz(sum, f2(magic));
+    };
+    for (; y <= yb; y += 8 * K, yt01 = __fadd2_rn(yt01, f2((float)(8 * K)))) {
+        float2 v[K / 2];
+        float2 ytp = yt01;
+#pragma unroll
+        for (int p = 0; p < K / 2; ++p) {
+            // the run's last row is A's partner B; when the run sticks out of the span, B is the span's last row instead (the rows
+            // of the run that are inside the span lie between the two)
+            if (p == K / 2 - 1) ytp.y = fminf(ytp.y, yt_last);
+            v[p] = vbits(ytp);
+            ytp = __fadd2_rn(ytp, f2(2.0f));
+        }
+        const uint32_t bitsA = __float_as_uint(v[0].x);
+        uint32_t uA = bitsA & mask, uB = __float_as_uint(v[K / 2 - 1].y) & mask;
+        if (!POW2) {
+            uA = __umulhi(uA, rb.z) * rb.w + uA;
+            uB = __umulhi(uB, rb.z) * rb.w + uB;
+        }
+        const uint32_t tA = ldg_u16(col + uA), tB = ldg_u16(col + uB);
+        uint32_t cA, cB;
+        lit_rgb_unit_2(pal_fetch_raw(tA), pal_fetch_raw(tB), factor, factor, cA, cB);
+        if (!HOLES || tA != t.hole) sts_u32(addr[0], cA);
+#pragma unroll
+        for (int j = 1; j < K - 1; ++j) {
+            const bool isA = __float_as_uint(j & 1 ? v[j / 2].y : v[j / 2].x) == bitsA;
+            if (y + j <= yb && (!HOLES || (isA ? tA : tB) != t.hole)) sts_u32(addr[j], isA ? cA : cB);
+        }
+        if (y + K - 1 <= yb && (!HOLES || tB != t.hole)) sts_u32(addr[K - 1], cB);
+#pragma unroll
+        for (int j = 0; j < K; ++j) addr[j] += (uint32_t)K * ROW8;
+    }
+}
+
 // every other wall span (light level above 255, negative depth, texture rows outside 0..32767, NaN geometry): same
 // arithmetic with the saturating conversions spelled out
 __device__ __noinline__ void tile_wall_span_any(TileCtx t, uint4 ra, uint4 rb, uint4 rc, uint4 rd, int ya, int yb, uint32_t addr,
@@ -670,6 +741,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     // The next span's first word is fetched while the current one is drawn: into registers where the budget allows (MINB 4),
     // otherwise only into L1 (four registers kept across the pixel loops would spill at 40)
     constexpr bool HEAD_IN_REGS = MINB <= 5;
+#ifdef DRR_RUNS_ALWAYS
+    constexpr bool RUNS = true;
+#elif defined(DRR_RUNS_NEVER)
+    constexpr bool RUNS = false;
+#else
+    constexpr bool RUNS = MINB <= 5; // the texel-run wall loop: in the 48 / 56 register builds of the tall tiles (spills at 40)
+#endif
     uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
     if (left > 0) {
         if (HEAD_IN_REGS) ra_next = P[(size_t)rec * 4]; // the first span's head: in flight while the palette arrives
@@ -719,11 +797,20 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                     const uint32_t addr = row_addr(ya + li - b0);
                     if (kind == KIND_FLAT) {
                         // a span clipped to a band stays inside the rows its flags were computed for
-                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span<(MINB <= 4 ? 2 : 1)>(t, fv, ra, R[1], ya, yb, addr, flats);
+                        if ((ra.y & (TS_UNIT | TS_FASTDIV)) == (TS_UNIT | TS_FASTDIV)) tile_flat_span<(MINB <= 5 ? 2 : 1)>(t, fv, ra, R[1], ya, yb, addr, flats);
                         else tile_flat_span_any(t, fv, ra, R[1], ya, yb, addr, flats);
                     } else if (kind <= KIND_WALL_HOLES) {
                         const uint4 rc = R[1], rd = R[2];
                         if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, R[3], rc, rd, ya, yb, addr, texels);
+                        else if (RUNS && (ra.y & TS_RUNS)) {
+                            if (kind == KIND_WALL) {
+                                if (ra.y & TS_POW2) tile_wall_span_runs<false, true>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
+                                else tile_wall_span_runs<false, false>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
+                            } else {
+                                if (ra.y & TS_POW2) tile_wall_span_runs<true, true>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
+                                else tile_wall_span_runs<true, false>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
+                            }
+                        }
                         else if (kind == KIND_WALL) {
                             if (ra.y & TS_POW2) tile_wall_span<false, true>(t, ra, ra, rc, rd, ya, yb, addr, texels);
                             else tile_wall_span<false, false>(t, ra, R[3], rc, rd, ya, yb, addr, texels);
@@ -900,13 +987,17 @@ cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0,
     if ((long long)gpf * a.nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const size_t dyn = SM_TILE + (size_t)((a.band_rows + 7) / 8) * 1024; // whole 8-row blocks
     const bool fast = fbmap && a.W % TILE_COLS == 0 && a.H % 8 == 0 && a.band_rows % 8 == 0;
-    const bool small = dyn <= 36 * 1024; // six CTAs per SM fit: 40 registers; else five (up to 44 KB) or four: 48 registers
+    // resident CTAs per SM by tile size: six (40 registers) up to 36 KB, five (48 registers) up to 44 KB, else four (56 registers,
+    // with the texel-run wall loop)
+    const int minb = dyn <= 36 * 1024 ? DRR_TILE_MINB_SMALL : dyn <= 44 * 1024 ? 5 : 4;
     cudaError_t e;
     if (fast) {
-        e = small ? launch_tile_t<DRR_TILE_MINB_SMALL, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);
+        e = minb == DRR_TILE_MINB_SMALL ? launch_tile_t<DRR_TILE_MINB_SMALL, true>(a, *fbmap, frame0, nframes, dyn, st, launches)
+            : minb == 5 ? launch_tile_t<5, true>(a, *fbmap, frame0, nframes, dyn, st, launches) : launch_tile_t<4, true>(a, *fbmap, frame0, nframes, dyn, st, launches);
     } else {
         static const CUtensorMap none = {};
-        e = small ? launch_tile_t<DRR_TILE_MINB_SMALL, false>(a, none, frame0, nframes, dyn, st, launches) : launch_tile_t<4, false>(a, none, frame0, nframes, dyn, st, launches);
+        e = minb == DRR_TILE_MINB_SMALL ? launch_tile_t<DRR_TILE_MINB_SMALL, false>(a, none, frame0, nframes, dyn, st, launches)
+            : minb == 5 ? launch_tile_t<5, false>(a, none, frame0, nframes, dyn, st, launches) : launch_tile_t<4, false>(a, none, frame0, nframes, dyn, st, launches);
         if (e == cudaSuccess) e = launch_checksum_pass(a, frame0, nframes, st, launches);
     }
     return e;
