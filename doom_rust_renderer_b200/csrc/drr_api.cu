@@ -1176,12 +1176,17 @@ int drr_read_crc32(drr_ctx *ctx, int first, int count, uint32_t *out) {
 
 uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes) {
     uint64_t acc = 0;
-    const uint64_t nwords = (nbytes + 3) / 4;
-    for (uint64_t i = 0; i < nwords; i++) {
-        uint32_t w = 0;
-        for (int k = 0; k < 4; k++)
-            if (i * 4 + k < nbytes) w |= (uint32_t)rgb24[i * 4 + k] << (8 * k);
-        acc += checksum_term(w, i);
+    const uint64_t ngroups = (nbytes + 4 * CK_GROUP - 1) / (4 * CK_GROUP);
+    for (uint64_t g = 0; g < ngroups; g++) {
+        uint32_t sum = 0;
+        for (int j = 0; j < CK_GROUP; j++) {
+            const uint64_t i = g * CK_GROUP + j;
+            uint32_t w = 0;
+            for (int k = 0; k < 4; k++)
+                if (i * 4 + k < nbytes) w |= (uint32_t)rgb24[i * 4 + k] << (8 * k);
+            sum += w * checksum_word_weight(j);
+        }
+        acc += checksum_group_term(sum, g);
     }
     return acc;
 }

@@ -122,10 +122,17 @@ __device__ __forceinline__ uint32_t lit_rgb(float4 pal, float factor) {
     return r | (g << 8) | (b << 16);
 }
 
-// Position-weighted linear checksum (drr.h: drr_read_checksums)
-__host__ __device__ __forceinline__ uint64_t checksum_term(uint32_t word, uint64_t index) {
-    uint32_t k = (uint32_t)(index + 1u) * 0x9E3779B1u; // never 0 for index + 1 < 2^32 (the multiplier is odd)
-    return (uint64_t)word * (uint64_t)k;
+// Position-weighted linear checksum (drr.h: drr_read_checksums).  The frame's little-endian u32 words (zero-padded) are taken
+// in groups of 12 (48 bytes = 16 pixels): s_g = sum_j w[12g + j] * ((2j + 1) * C) mod 2^32, checksum = sum_g s_g * ((g + 1) * C
+// mod 2^32) mod 2^64, C = 0x9E3779B1.  Every multiplier is odd, so any change of a single word changes the sum.  (A lane of the
+// tile kernel's write-out holds exactly one group: twelve 32-bit multiply-adds and one wide one, where a weight per word cost
+// twelve wide ones.)
+static constexpr uint32_t CK_C = 0x9E3779B1u;
+static constexpr int CK_GROUP = 12;
+__host__ __device__ __forceinline__ uint32_t checksum_word_weight(int j) { return (uint32_t)(2 * j + 1) * CK_C; }
+__host__ __device__ __forceinline__ uint64_t checksum_group_term(uint32_t s, uint64_t group) {
+    const uint32_t k = (uint32_t)(group + 1u) * CK_C; // never 0 for group + 1 < 2^32 (the multiplier is odd)
+    return (uint64_t)s * (uint64_t)k;
 }
 
 } // namespace drr

@@ -712,13 +712,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     const uint16_t *__restrict__ texels = a.texels;
     const uint8_t *__restrict__ flats = a.flats;
 
-    // grid: x = column group (times the row band when the column is cut into bands), y = frame of this launch
-    int g = (int)blockIdx.x, band = 0;
-    if (a.nbands > 1) {
-        g = (int)(blockIdx.x / (unsigned)a.nbands);
-        band = (int)blockIdx.x - g * a.nbands;
-    }
-    const int f = frame0 + (int)blockIdx.y;
+    // grid: x = column group, y = row band, z = frame of this launch
+    const int g = (int)blockIdx.x, band = (int)blockIdx.y;
+    const int f = frame0 + (int)blockIdx.z;
     const int b0 = band * a.band_rows, b1 = min(a.H, b0 + a.band_rows) - 1;
     const int nlists = a.nbands <= MAX_LIST_BANDS ? a.nbands : 1, lband = a.nbands <= MAX_LIST_BANDS ? band : 0; // the bin kernel's list of this band
     // the palette image: one bulk copy, completion on an mbarrier
@@ -838,11 +834,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         const int nblk = nrows >> 3;
         const uint32_t src_off = ((uint32_t)(rr >> 3) << 10) + ((uint32_t)h << 9) + ((((uint32_t)rr & 7u) ^ ((uint32_t)h << 2)) << 4);
         const uint32_t dst_off = (uint32_t)rr * 96u + (uint32_t)h * 48u;
-        const uint32_t C = 0x9E3779B1u; // checksum weight of word i is (i + 1) * C mod 2^32 (drr.h)
-        const uint32_t pw = (uint32_t)a.W * 3u / 4u; // framebuffer row pitch in words
-        // weight of this lane's first word in step s: k0 + s * kstep
-        uint32_t k0 = ((uint32_t)(b0 + 16 * warp + rr) * pw + (uint32_t)g * (TILE_COLS * 3 / 4) + 12u * (uint32_t)h + 1u) * C;
-        const uint32_t kstep = 16u * (TILE_THREADS / 32) * pw * C;
+        // checksum (drr_device.cuh): this lane's twelve words of a step are one 48-byte group of the frame, number
+        // row * (row pitch / 48) + 2 * column group + half; its weight in step s is k0 + s * kstep
+        const uint32_t gpr = (uint32_t)a.W / 16u; // groups per framebuffer row
+        uint32_t k0 = ((uint32_t)(b0 + 16 * warp + rr) * gpr + 2u * (uint32_t)g + (uint32_t)h + 1u) * CK_C;
+        const uint32_t kstep = 16u * (TILE_THREADS / 32) * gpr * CK_C;
         uint64_t acc = 0;
         if (!DBG(8))
         for (int s = warp; 2 * s < nblk; s += TILE_THREADS / 32, k0 += kstep) {
@@ -872,10 +868,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                 bulk_commit();
             }
             if (!DBG(4)) { // (an inactive lane's words are zero)
-                uint32_t k = k0;
-                acc += (uint64_t)v0.x * k; k += C; acc += (uint64_t)v0.y * k; k += C; acc += (uint64_t)v0.z * k; k += C; acc += (uint64_t)v0.w * k; k += C;
-                acc += (uint64_t)v1.x * k; k += C; acc += (uint64_t)v1.y * k; k += C; acc += (uint64_t)v1.z * k; k += C; acc += (uint64_t)v1.w * k; k += C;
-                acc += (uint64_t)v2.x * k; k += C; acc += (uint64_t)v2.y * k; k += C; acc += (uint64_t)v2.z * k; k += C; acc += (uint64_t)v2.w * k;
+                uint32_t sum = v0.x * checksum_word_weight(0);
+                sum += v0.y * checksum_word_weight(1); sum += v0.z * checksum_word_weight(2); sum += v0.w * checksum_word_weight(3);
+                sum += v1.x * checksum_word_weight(4); sum += v1.y * checksum_word_weight(5); sum += v1.z * checksum_word_weight(6); sum += v1.w * checksum_word_weight(7);
+                sum += v2.x * checksum_word_weight(8); sum += v2.y * checksum_word_weight(9); sum += v2.z * checksum_word_weight(10); sum += v2.w * checksum_word_weight(11);
+                acc += (uint64_t)sum * k0;
             }
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -972,8 +969,8 @@ static cudaError_t launch_tile_t(const DrawArgs &a, const CUtensorMap &map, int 
     const int gpf = (a.W + TILE_COLS - 1) / TILE_COLS;
     cudaError_t e = allow_big_tiles(reinterpret_cast<const void *>(&drr_tile_kernel<MINB, FAST>));
     if (e != cudaSuccess) return e;
-    for (int f0 = 0; f0 < nframes; f0 += 65535) { // gridDim.y limit
-        const dim3 grid((unsigned)(gpf * a.nbands), (unsigned)std::min(65535, nframes - f0));
+    for (int f0 = 0; f0 < nframes; f0 += 65535) { // gridDim.z limit
+        const dim3 grid((unsigned)gpf, (unsigned)a.nbands, (unsigned)std::min(65535, nframes - f0));
         drr_tile_kernel<MINB, FAST><<<grid, TILE_THREADS, dyn, st>>>(a, map, frame0 + f0);
         ++*launches;
     }
@@ -984,7 +981,7 @@ cudaError_t launch_tile(const DrawArgs &a, const CUtensorMap *fbmap, int frame0,
     *launches = 0;
     if (nframes <= 0) return cudaSuccess;
     const int gpf = (a.W + TILE_COLS - 1) / TILE_COLS;
-    if ((long long)gpf * a.nbands > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    if (a.nbands > 65535) return cudaErrorInvalidConfiguration; // gridDim.y limit
     const size_t dyn = SM_TILE + (size_t)((a.band_rows + 7) / 8) * 1024; // whole 8-row blocks
     const bool fast = fbmap && a.W % TILE_COLS == 0 && a.H % 8 == 0 && a.band_rows % 8 == 0;
     // resident CTAs per SM by tile size: six (40 registers) up to 36 KB, five (48 registers) up to 44 KB, else four (56 registers,

@@ -143,8 +143,10 @@ int drr_submit(drr_ctx *ctx);       /* drr_upload_lists + drr_draw */
 int drr_sync(drr_ctx *ctx);
 int drr_read_framebuffer(drr_ctx *ctx, int view_idx, uint8_t *out_rgb24);    /* width*height*3 bytes, row-major RGB24 == Pixels.pixels */
 int drr_read_checksums(drr_ctx *ctx, int first_view, int count, uint64_t *out);
-/* Per-frame checksum: sum over little-endian u32 words w_i of the frame of  w_i * ((i+1)*0x9E3779B1 mod 2^32),
- * mod 2^64.  drr_checksum_host computes the same on a host buffer. */
+/* Per-frame checksum.  The frame's little-endian u32 words (zero-padded) are taken in groups of 12 (48 bytes = 16 pixels):
+ *   s_g = sum_j w[12g + j] * ((2j + 1) * C) mod 2^32,   checksum = sum_g s_g * ((g + 1) * C mod 2^32) mod 2^64,   C = 0x9E3779B1
+ * (every multiplier is odd: a change of any single word changes the sum).  drr_checksum_host computes the same on a host
+ * buffer. */
 uint64_t drr_checksum_host(const uint8_t *rgb24, uint64_t nbytes);
 /* Export side (the reference presents Pixels.pixels through SDL, src/game.rs:500-533): the framebuffer
  * drr_read_framebuffer returns is what an SDL RGB24 streaming texture takes as is (pitch = width*3), and drr_read_crc32 gives
