@@ -11,6 +11,7 @@
 #include "drr_frontend.cuh"
 #include "drr_kernels.h"
 #include <algorithm>
+#include <new>
 
 namespace drr {
 
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
                                                                                  fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab,
                                                                                  int smem_mode, uint32_t smem_per_view) {
     extern __shared__ __align__(16) uint8_t fe_smem[];
+    constexpr size_t frame_bytes = (sizeof(fe::Frame<EMIT>) + 15) & ~(size_t)15;
     const int v = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); // one warp per viewpoint
     if (v >= n) return;
     fe::Bases b = fe::Bases{0, 0, 0, 0, 0, 0, {0, 0}};
@@ -35,7 +37,11 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
             if (b.frame < 0) return; // the reference panics on this viewpoint: no frame
         }
     }
-    fe::Frame<EMIT> fr(m);
+    // The per-view state (fe::Frame: cursors, counts, pointers, open visplanes, the occlusion bit masks) is ONE object per warp in
+    // shared memory.  As a local variable it is replicated per lane (it is handed to non-inlined member functions, so it lives
+    // in local memory): 32 KB per warp, 900 KB per SM with every warp resident -- a third of the loads of uniform state then
+    // missed L1.  Every lane executes the same uniform updates on the same shared word.
+    fe::Frame<EMIT> &fr = *new (fe_smem + (size_t)(threadIdx.x >> 5) * smem_per_view) fe::Frame<EMIT>(m);
     const size_t o = (size_t)v * (size_t)m.W;
     fr.sc.hor_ocl = s.hor_ocl + o;
     fr.sc.floor_ocl = s.floor_ocl + o;
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel
     // The per-view state the column loops hammer on goes to shared memory when it fits with every warp of the SM resident
     // (launch_frontend picks the mode): 1 = the three occlusion arrays and the side bits, 2 = also the two visplane row buffers.
     if (smem_mode >= 1) {
-        uint8_t *base = fe_smem + (size_t)(threadIdx.x >> 5) * smem_per_view;
+        uint8_t *base = fe_smem + (size_t)(threadIdx.x >> 5) * smem_per_view + frame_bytes;
         const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15;
         fr.sc.hor_ocl = base;
         fr.sc.floor_ocl = reinterpret_cast<int16_t *>(base + Wp);
@@ -107,9 +113,10 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     // shared memory per viewpoint: occlusion arrays 5 bytes per column + side bits (mode 1), + 8 bytes per column of visplane
     // rows (mode 2); taken when 32 viewpoints (every warp the register budget allows on an SM) fit in ~200 KB
     const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15, side_bytes = 4 * (size_t)((m.side_words + 3) & ~3);
-    const size_t need1 = 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * vpb);
+    const size_t frame_bytes = (std::max(sizeof(fe::Frame<true>), sizeof(fe::Frame<false>)) + 15) & ~(size_t)15; // the per-view state itself: always
+    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * vpb);
     const int mode = need2 <= budget ? 2 : need1 <= budget ? 1 : 0;
-    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : 0, dyn = per_view * vpb;
+    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes, dyn = per_view * vpb;
     if (emit)
         drr_frontend_kernel<true><<<blocks, FE_THREADS, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
     else

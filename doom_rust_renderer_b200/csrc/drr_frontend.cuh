@@ -359,9 +359,11 @@ FE_NOINLINE SegPre seg_pre_of(const Map &m, V2 ppos, float cos_n, float sin_n, c
 // are appended in x order; a visplane runs from its first point to the next flush) are resolved from ballots.
 // On the host (CPU test harness) the 32 lanes are emulated by loops: FE_LANES(l) { ... } runs its body once per lane.
 #if defined(__CUDA_ARCH__)
-#define FE_LANES(l) for (int l = (int)(threadIdx.x & 31u), l##_1 = 1; l##_1; l##_1 = 0)
+// (the __syncwarp at the end of a per-lane block: the per-view state lives in ONE copy per warp in shared memory, so the uniform
+// code after the block must find every lane back in step before it reads and updates that state)
+#define FE_LANES(l) for (int l = (int)(threadIdx.x & 31u), l##_1 = 1; l##_1; l##_1 = 0, __syncwarp())
 #define FE_SYNC() __syncwarp()
-#define FE_LEADER if ((threadIdx.x & 31u) == 0u)
+#define FE_LEADER for (int ld_1 = 1; ld_1; ld_1 = 0, __syncwarp()) if ((threadIdx.x & 31u) == 0u)
 template <class T>
 struct PerLane { // a value every lane holds its own copy of
     T v;
@@ -377,6 +379,11 @@ struct PerLane {
     T &operator[](int l) { return v[l]; }
 };
 #endif
+template <class T>
+struct LaneArr { // one value per lane inside the per-view state (which is one object per warp)
+    T v[32];
+    FE_HD T &operator[](int l) { return v[l]; }
+};
 template <class F>
 FE_HD uint32_t ballot(F f) { // bit l = f(l)
 #if defined(__CUDA_ARCH__)
@@ -421,6 +428,13 @@ FE_HD int highest(uint32_t v) { // index of the highest set bit, v != 0
     return i;
 }
 FE_HD uint32_t below(int l) { return (uint32_t)((1ull << l) - 1ull); } // bits of the lanes < l, 0 <= l <= 32
+FE_HD void prefetch_l1(const void *p) { // a hint: the line is on its way while the warp works on something else
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 template <bool EMIT>
 struct Frame {
@@ -443,7 +457,7 @@ struct Frame {
     // Which screen columns are fully occluded (hor_ocl), as a bit mask spread over the lanes: word w (columns 32w .. 32w+31)
     // lives on lane w % 32, slot w / 32.  A seg all of whose columns are occluded can only re-occlude them and flush
     // visplanes that are not open (segs.rs:186-330): it is skipped without touching memory.
-    PerLane<uint32_t> occ[4];
+    LaneArr<uint32_t> occ[4];
     bool occ_on; // W <= 4096
 
     FE_HD Frame(const Map &map) : m(map) {}
@@ -621,9 +635,13 @@ struct Frame {
                 if (m_occ) {
                     const int w0 = c0 >> 5, sh = c0 & 31;
                     const uint32_t lo_bits = m_occ << sh, hi_bits = sh ? m_occ >> (32 - sh) : 0u;
-                    FE_LANES(l) {
-                        if ((w0 & 31) == l) occ[(w0 >> 5) & 3][l] |= lo_bits;
-                        if (((w0 + 1) & 31) == l && hi_bits) occ[((w0 + 1) >> 5) & 3][l] |= hi_bits;
+                    FE_LANES(l) { // (constant slot indices: the masks stay in registers)
+                        const uint32_t a = (w0 & 31) == l ? lo_bits : 0u, b = ((w0 + 1) & 31) == l ? hi_bits : 0u;
+                        const int sa = (w0 >> 5) & 3, sb = ((w0 + 1) >> 5) & 3;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                        for (int s4 = 0; s4 < 4; s4++) occ[s4][l] |= (sa == s4 ? a : 0u) | (sb == s4 ? b : 0u);
                     }
                 }
             }
@@ -1075,10 +1093,14 @@ struct Frame {
         const int nslots = (m.W + 1023) >> 10;
         return ballot([&](int l) {
             uint32_t miss = 0;
-            for (int s = 0; s < nslots; s++) { // branch-free per word: the columns of [xs, xe] inside this lane's word of slot s
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int s = 0; s < 4; s++) { // (constant slot indices: the masks stay in registers)
+                // the columns of [xs, xe] inside this lane's word of slot s: bits from .. to, none when from > to
                 const int lo = ((s << 5) + l) << 5;
-                const int from = xs - lo > 0 ? xs - lo : 0, to = xe - lo < 31 ? xe - lo : 31; // empty when from > to
-                const uint32_t upto = (uint32_t)((2ull << (to < 0 ? 0 : to)) - 1ull), want = from <= to ? upto & ~((1u << (from > 31 ? 31 : from)) - 1u) : 0u;
+                const int from = xs - lo > 0 ? xs - lo : 0, to = xe - lo < 31 ? xe - lo : 31;
+                const uint32_t want = s < nslots && from <= to ? (0xffffffffu >> (31 - to)) & (0xffffffffu << from) : 0u;
                 miss |= want & ~occ[s][l];
             }
             return miss == 0u;
@@ -1241,18 +1263,31 @@ struct Frame {
         }
         }
         FE_SYNC();
+        // The seg numbers are read one batch ahead, and the stateless kernel's code and record of the NEXT batch's segs are
+        // requested (prefetch) while this batch's survivors are processed: otherwise every batch starts with three dependent
+        // global loads (order -> code -> record).
+        PerLane<int32_t> s_cur, s_nxt;
+        FE_LANES(l) {
+            s_cur[l] = l < nord ? sc.order[l] : -1;
+            s_nxt[l] = 32 + l < nord ? sc.order[32 + l] : -1;
+        }
         for (int c0 = 0; c0 < nord && n.status == FE_OK; c0 += 32) {
             PerLane<float> p_csx, p_csy, p_cex, p_cey, p_so;
             PerLane<int32_t> p_sx, p_ex, p_code, p_seg;
             FE_LANES(l) {
                 SegPre p{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0, 0, 0};
-                int si = 0;
-                if (c0 + l < nord) {
-                    si = sc.order[c0 + l];
+                const int si = s_cur[l], sn = s_nxt[l];
+                if (sn >= 0 && sc.pre) {
+                    prefetch_l1(sc.pre_code + sn);
+                    prefetch_l1(sc.pre + sn);
+                }
+                if (si >= 0) {
                     if (!sc.pre) p = seg_pre(m.segs[si]);
                     else if (sc.pre_code[si]) p = sc.pre[si]; // the stateless kernel's record: every survivor of the batch fetches its own at once
                 }
-                p_seg[l] = si;
+                s_cur[l] = sn;
+                s_nxt[l] = c0 + 64 + l < nord ? sc.order[c0 + 64 + l] : -1;
+                p_seg[l] = si >= 0 ? si : 0;
                 p_csx[l] = p.csx;
                 p_csy[l] = p.csy;
                 p_cex[l] = p.cex;

@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         for (int s = warp; 2 * s < nblk; s += TILE_THREADS / 32, k0 += kstep) {
             const uint32_t region = tile + ((uint32_t)s << 11);
             const bool act = 2 * s + (rr >> 3) < nblk; // (the last step of a band of 8 * odd rows has one block only)
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0;
+            uint4 v0, v1, v2;
             if (act) {
                 const uint4 q0 = lds_u128(region + src_off), q1 = lds_u128(region + src_off + 128u);
                 const uint4 q2 = lds_u128(region + src_off + 256u), q3 = lds_u128(region + src_off + 384u);
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                 if (2 * s + 1 < nblk) tma_store_box(&fbmap, region + 768u, g * (TILE_COLS * 3), b0 + 16 * s + 8, (int)slot);
                 bulk_commit();
             }
-            if (!DBG(4)) { // (an inactive lane's words are zero)
+            if (act && !DBG(4)) {
                 uint32_t sum = v0.x * checksum_word_weight(0);
                 sum += v0.y * checksum_word_weight(1); sum += v0.z * checksum_word_weight(2); sum += v0.w * checksum_word_weight(3);
                 sum += v1.x * checksum_word_weight(4); sum += v1.y * checksum_word_weight(5); sum += v1.z * checksum_word_weight(6); sum += v1.w * checksum_word_weight(7);
