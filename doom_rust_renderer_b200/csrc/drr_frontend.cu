@@ -17,8 +17,8 @@ namespace drr {
 
 // slab.ops != 0: single-pass mode -- no count pass ran, view v writes into its own slab of every array (drr_frontend.cuh:
 // Slabs) and leaves its counts; drr_fe_compact_kernel then makes the lists dense.
-template <bool EMIT>
-__global__ void __launch_bounds__(FE_THREADS, FE_MIN_BLOCKS) drr_frontend_kernel(const __grid_constant__ fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
+template <bool EMIT, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) drr_frontend_kernel(const __grid_constant__ fe::Map m, const fe::ViewIn *__restrict__ views, const fe::Bases *__restrict__ bases,
                                                                                  fe::Counts *__restrict__ counts, int n, FeScratch s, fe::Out out, fe::Caps slab,
                                                                                  int smem_mode, uint32_t smem_per_view) {
     extern __shared__ __align__(16) uint8_t fe_smem[];
@@ -108,19 +108,30 @@ __global__ void __launch_bounds__(128) drr_fe_compact_kernel(fe::Slabs sl, const
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
                             const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    const int vpb = FE_THREADS / 32; // viewpoints per CTA
-    const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
-    // shared memory per viewpoint: occlusion arrays 5 bytes per column + side bits (mode 1), + 8 bytes per column of visplane
-    // rows (mode 2); taken when 32 viewpoints (every warp the register budget allows on an SM) fit in ~200 KB
+    // shared memory per viewpoint: the per-view state itself (always), + occlusion arrays 5 bytes per column + side bits (mode 1),
+    // + 8 bytes per column of visplane rows (mode 2); taken when every warp the register budget allows on an SM fits in ~200 KB
     const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15, side_bytes = 4 * (size_t)((m.side_words + 3) & ~3);
-    const size_t frame_bytes = (std::max(sizeof(fe::Frame<true>), sizeof(fe::Frame<false>)) + 15) & ~(size_t)15; // the per-view state itself: always
-    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * vpb);
-    const int mode = need2 <= budget ? 2 : need1 <= budget ? 1 : 0;
-    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes, dyn = per_view * vpb;
-    if (emit)
-        drr_frontend_kernel<true><<<blocks, FE_THREADS, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
-    else
-        drr_frontend_kernel<false><<<blocks, FE_THREADS, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+    const size_t frame_bytes = (std::max(sizeof(fe::Frame<true>), sizeof(fe::Frame<false>)) + 15) & ~(size_t)15;
+    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * FE_WARPS);
+    // (mode 1 only up to 8 KB per viewpoint: at 1920 columns 16 viewpoints' arrays would take 170 KB of the SM and leave the
+    // global scratch of the masked phase no L1 to speak of -- measured on the stress map: 64.0 ms against 56.1 ms in mode 0)
+    const int mode = need2 <= budget ? 2 : need1 <= std::min(budget, (size_t)8192) ? 1 : 0;
+    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes;
+    // mode 0 (the arrays in global scratch): the build with the smaller register budget and twice the resident warps
+    const int vpb = mode == 0 ? FE_WARPS_GLOBAL : FE_WARPS; // viewpoints per CTA
+    const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
+    const size_t dyn = per_view * vpb;
+    if (mode == 0) {
+        if (emit)
+            drr_frontend_kernel<true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+        else
+            drr_frontend_kernel<false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+    } else {
+        if (emit)
+            drr_frontend_kernel<true, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+        else
+            drr_frontend_kernel<false, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+    }
     return cudaGetLastError();
 }
 

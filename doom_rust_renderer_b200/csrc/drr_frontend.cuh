@@ -1097,10 +1097,11 @@ struct Frame {
 #pragma unroll
 #endif
             for (int s = 0; s < 4; s++) { // (constant slot indices: the masks stay in registers)
+                if (s >= nslots) break; // uniform: a 320-column screen has one slot
                 // the columns of [xs, xe] inside this lane's word of slot s: bits from .. to, none when from > to
                 const int lo = ((s << 5) + l) << 5;
                 const int from = xs - lo > 0 ? xs - lo : 0, to = xe - lo < 31 ? xe - lo : 31;
-                const uint32_t want = s < nslots && from <= to ? (0xffffffffu >> (31 - to)) & (0xffffffffu << from) : 0u;
+                const uint32_t want = from <= to ? (0xffffffffu >> (31 - to)) & (0xffffffffu << from) : 0u;
                 miss |= want & ~occ[s][l];
             }
             return miss == 0u;

@@ -90,11 +90,26 @@ struct Out;
 struct Caps;
 struct Slabs;
 } // namespace fe
-#ifndef DRR_FE_MIN_BLOCKS
-#define DRR_FE_MIN_BLOCKS 16
+// Shape of the front-end kernel (one warp per viewpoint): warps per CTA and resident CTAs per SM the register budget is set for.
+// The kernel wants ~146 registers.  Measured per 4096 viewpoints of walk320, two warps per CTA: 16 CTAs per SM (64 registers,
+// spills) 0.834 ms, 12 (80) 0.736, 10 (96) 0.697, 8 (128) 0.644, 6 (146) 0.720 -- fewer, fatter warps win as long as the per-view
+// arrays sit in shared memory; four warps per CTA at the same 128 registers (neighbouring viewpoints walk the same part of the
+// map: they share L1) 0.618 ms, things640 1.90 -> 1.79 ms.  With the arrays in global scratch (wide screens: the stress map at
+// 1920x1200) more warps hide more than the spills cost: 64 registers 56.1 ms, 128 registers 60.5 ms per 8192 viewpoints.
+#ifndef DRR_FE_WARPS
+#define DRR_FE_WARPS 4
 #endif
-static constexpr int FE_MIN_BLOCKS = DRR_FE_MIN_BLOCKS; // resident CTAs per SM the register budget is set for (16 x 2 warps: 64 registers)
-static constexpr int FE_THREADS = 64; // one warp per viewpoint, two viewpoints per CTA: a few thousand viewpoints spread over every SM
+#ifndef DRR_FE_MIN_BLOCKS
+#define DRR_FE_MIN_BLOCKS 4
+#endif
+#ifndef DRR_FE_WARPS_GLOBAL
+#define DRR_FE_WARPS_GLOBAL 2
+#endif
+#ifndef DRR_FE_MIN_BLOCKS_GLOBAL
+#define DRR_FE_MIN_BLOCKS_GLOBAL 16
+#endif
+static constexpr int FE_WARPS = DRR_FE_WARPS, FE_MIN_BLOCKS = DRR_FE_MIN_BLOCKS;                             // per-view arrays in shared memory
+static constexpr int FE_WARPS_GLOBAL = DRR_FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL = DRR_FE_MIN_BLOCKS_GLOBAL; // ... in global scratch
 struct FeScratch {                    // per-viewpoint working state of the front-end, W entries per viewpoint each
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;

@@ -462,6 +462,10 @@ __device__ __forceinline__ uint2 pal_fetch_raw(uint32_t addr) {
     return e;
 }
 
+#ifndef DRR_WALL_UNROLL
+#define DRR_WALL_UNROLL 2
+#endif
+static constexpr int WALL_UNROLL = DRR_WALL_UNROLL; // iterations of the wall loop in flight (A/B: 1, 3, 4)
 // the fast wall loop: factor <= 1 and TS_TRUNC (every wall of an ordinary scene)
 template <bool HOLES, bool POW2>
 __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb,
@@ -475,7 +479,7 @@ __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra,
     const int yb8 = yb - TILE_LPG;
     int y = ya + t.li;
     float2 yt = f2(__fadd_rn((float)y, __uint_as_float(rc.x)), __fadd_rn((float)(y + TILE_LPG), __uint_as_float(rc.x)));
-#pragma unroll 2
+#pragma unroll WALL_UNROLL
     for (; y <= yb; y += 2 * TILE_LPG, yt = __fadd2_rn(yt, f2((float)(2 * TILE_LPG))), addr += ROW16) {
         uint32_t t0, t1;
         wall_texels2_trunc<POW2>(rb, rc, magic, rd.z, hF, yt, t.one, col, t0, t1);
