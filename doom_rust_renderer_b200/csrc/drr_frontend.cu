@@ -52,17 +52,20 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) drr_frontend_kernel(const __
     fr.sc.side = reinterpret_cast<uint32_t *>(fr.sc.order + m.nsegs);
     // The per-view state the column loops hammer on goes to shared memory when it fits with every warp of the SM resident
     // (launch_frontend picks the mode): 1 = the three occlusion arrays and the side bits, 2 = also the two visplane row buffers.
-    if (smem_mode >= 1) {
+    if ((smem_mode & 3) >= 1) {
         uint8_t *base = fe_smem + (size_t)(threadIdx.x >> 5) * smem_per_view + frame_bytes;
         const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15;
         fr.sc.hor_ocl = base;
         fr.sc.floor_ocl = reinterpret_cast<int16_t *>(base + Wp);
         fr.sc.ceil_ocl = reinterpret_cast<int16_t *>(base + 3 * Wp);
         fr.sc.side = reinterpret_cast<uint32_t *>(base + 5 * Wp);
-        if (smem_mode >= 2) {
-            fr.sc.rows[0] = reinterpret_cast<uint32_t *>(base + 5 * Wp + 4 * (size_t)((m.side_words + 3) & ~3));
+        uint8_t *end = base + 5 * Wp + 4 * (size_t)((m.side_words + 3) & ~3);
+        if ((smem_mode & 3) >= 2) {
+            fr.sc.rows[0] = reinterpret_cast<uint32_t *>(end);
             fr.sc.rows[1] = fr.sc.rows[0] + Wp;
+            end += 8 * Wp;
         }
+        if (smem_mode & 4) fr.sc.order = reinterpret_cast<int32_t *>(end); // the seg order too (written once, read once, by this warp)
     }
     fr.sc.pre = s.pre ? static_cast<const fe::SegPre *>(s.pre) + (size_t)v * (size_t)m.nsegs : nullptr;
     fr.sc.pre_code = s.pre_code ? s.pre_code + (size_t)v * (size_t)m.nsegs : nullptr;
@@ -116,21 +119,24 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     // (mode 1 only up to 8 KB per viewpoint: at 1920 columns 16 viewpoints' arrays would take 170 KB of the SM and leave the
     // global scratch of the masked phase no L1 to speak of -- measured on the stress map: 64.0 ms against 56.1 ms in mode 0)
     const int mode = need2 <= budget ? 2 : need1 <= std::min(budget, (size_t)8192) ? 1 : 0;
-    const size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes;
+    size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes;
+    const size_t order_bytes = (4 * (size_t)m.nsegs + 15) & ~(size_t)15;
+    const bool order_too = mode >= 1 && per_view + order_bytes <= budget;
+    if (order_too) per_view += order_bytes;
     // mode 0 (the arrays in global scratch): the build with the smaller register budget and twice the resident warps
     const int vpb = mode == 0 ? FE_WARPS_GLOBAL : FE_WARPS; // viewpoints per CTA
     const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
     const size_t dyn = per_view * vpb;
     if (mode == 0) {
         if (emit)
-            drr_frontend_kernel<true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+            drr_frontend_kernel<true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
         else
-            drr_frontend_kernel<false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+            drr_frontend_kernel<false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
     } else {
         if (emit)
-            drr_frontend_kernel<true, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+            drr_frontend_kernel<true, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
         else
-            drr_frontend_kernel<false, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode, (uint32_t)per_view);
+            drr_frontend_kernel<false, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
     }
     return cudaGetLastError();
 }

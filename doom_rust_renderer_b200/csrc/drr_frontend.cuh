@@ -1108,6 +1108,18 @@ struct Frame {
         }) == 0xffffffffu;
     }
 
+    // The same question asked by ONE lane for its own seg (the masks are shared memory of the warp): a batch's 32 segs are
+    // tested at once before they are taken one by one, so the hidden ones cost nothing serial.  0 <= xs <= xe < W <= 4096.
+    FE_HD bool range_occluded(int xs, int xe) {
+        for (int w = xs >> 5; w <= (xe >> 5); w++) {
+            const int lo = w << 5;
+            const int from = xs - lo > 0 ? xs - lo : 0, to = xe - lo < 31 ? xe - lo : 31;
+            const uint32_t want = (0xffffffffu >> (31 - to)) & (0xffffffffu << from);
+            if (want & ~occ[(w >> 5) & 3].v[w & 31]) return false;
+        }
+        return true;
+    }
+
     FE_HD SegPre seg_pre(const Seg &sg) const { return seg_pre_of(m, ppos, cos_n, sin_n, sg); }
 
     // process_seg, segs.rs:353-590 (after seg_pre)
@@ -1299,6 +1311,9 @@ struct Frame {
                 p_code[l] = p.code;
             }
             uint32_t live = ballot([&](int l) { return p_code[l] != 0; });
+            // what is hidden already (and cannot panic) drops out here, every lane testing its own seg; occlusion only grows, so
+            // this is the serial test below asked early -- which remains for what the batch's own earlier segs come to hide
+            if (occ_on && live) live &= ~ballot([&](int l) { return p_code[l] == 4 && range_occluded(p_sx[l], p_ex[l]); });
             for (; live && n.status == FE_OK; live &= live - 1) {
                 const int src = lowest(live);
                 const SegPre p{from_lane(p_csx, src), from_lane(p_csy, src), from_lane(p_cex, src), from_lane(p_cey, src), from_lane(p_so, src),
