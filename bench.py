@@ -14,7 +14,10 @@ long enough for an 8-process max-over-ranks; every figure is per pixel / per fra
            the reference covers (src/renderer/mod.rs:118-136: front-end + draw): every pass uploads the viewpoints (12 B each),
            runs the device front-end (drr_fe_emit_views), bins, draws and reads the checksums back (8 B per frame); the
            framebuffers stay in HBM (north_star: "at most a host-side gather of per-frame CRCs").  This is the pair of the
-           CPU arm, which also walks the BSP.
+           CPU arm, which also walks the BSP.  Measured with TWO batches in flight (two contexts with their own stream and
+           framebuffers, one host thread each: the second batch's kernels fill the GPU while the first one's counts are
+           turned into offsets on the host and its checksums are read back); `e2e.one_batch_in_flight` is the strictly
+           sequential figure.  (The stress map's 8192 frames of 1920x1200 are 57 GB: one batch in flight there.)
   e2e_host_lists : the draw path alone through its C-ABI boundary: the HOST front-end's recorded lists go up every pass
            (pinned H2D, chunked and overlapped), are drawn, and the checksums come back.
   N > 1  : viewpoints shard across GPUs by stride (rank r draws viewpoints r, r+N, ...: the same mix of the walk on every GPU),
@@ -399,6 +402,49 @@ def run_workload(name, args, rank, world, local_rank, dist, torch, headline):
     fe_mode = ctx.fe_last_mode()
     assert (ctx.read_checksums(0, n_views) == crc_dev).all(), "end-to-end pass drew different frames"
 
+    # ---- the same with TWO batches in flight: a second context (own stream, own framebuffers) driven by a second host thread.
+    # One batch alone leaves the GPU idle while the host turns the front-end's counts into offsets, launches and reads back,
+    # and the front-end kernel's last wave runs at a fraction of the machine; a second batch fills both.  Every pass still
+    # uploads its viewpoints, runs the front-end, bins, draws and reads its checksums back.  (Not when two sets of framebuffers
+    # would take more than 60 GB: the stress map's 8192 x 1920x1200 frames.)
+    ms_fe2 = None
+    if 2 * 3 * W * H * n_views <= 60e9:
+        import threading
+        ctx2 = drr.Context(W, H, local_rank, n_views)
+        scene2 = drr.Scene(content.path, "E1M1", W, H)
+        scene2.upload_assets(ctx2)
+        stream2 = torch.cuda.Stream(device=local_rank)
+        ctx2.set_stream(stream2.cuda_stream)
+
+        def pass_fe2():
+            ctx2.reset()
+            scene2.emit_views_device(ctx2, used, 0.0, phases)
+            ctx2.draw()
+            return ctx2.read_checksums(0, n_views)
+
+        assert (pass_fe2() == crc_dev).all(), "second context drew different frames"
+        half = max(1, steps * passes // 2)
+
+        def pair():
+            ta = threading.Thread(target=lambda: [pass_fe() for _ in range(half)])
+            tb = threading.Thread(target=lambda: [pass_fe2() for _ in range(half)])
+            ta.start(); tb.start(); ta.join(); tb.join()
+
+        pair()  # warm-up
+        barrier()
+        e0.record(stream)
+        pair()
+        done2 = torch.cuda.Event()
+        done2.record(stream2)
+        stream.wait_event(done2)
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms_fe2 = max_over_ranks(e0.elapsed_time(e1) / (2 * half))
+        assert (ctx.read_checksums(0, n_views) == crc_dev).all() and (ctx2.read_checksums(0, n_views) == crc_dev).all(), "pipelined passes drew different frames"
+        ctx2.close()
+        scene2.close()
+
     frames_total, px_total = n_views * world, W * H * n_views * world
     peak, peak_src = measured_peak()
     alg_bytes = 3 * W * H * n_views + st["drawlist_bytes_algorithmic"]  # per GPU per launch
@@ -409,10 +455,13 @@ def run_workload(name, args, rank, world, local_rank, dist, torch, headline):
         "config": make_config(name, n_views, passes, content.source), "steps": steps,
         "value": px_total / (ms_pass * 1e-3) / 1e6, "frames_per_s": frames_total / (ms_pass * 1e-3), "ms_per_pass": ms_pass,
         "ms_per_step": ms_pass * passes, "gpu_launches": launches, "clocks": clocks,
-        "e2e": {"value": px_total / (ms_fe * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": 28 * n_views * passes,
-                "d2h_bytes_per_step": (40 + 8) * n_views * passes, "ms_per_step": ms_fe * passes, "ms_per_pass": ms_fe,
-                "frames_per_s": frames_total / (ms_fe * 1e-3),
-                "path": "viewpoints -> drr_fe_emit_views (front-end kernel, counts to the host, compaction) -> bin -> tile -> per-frame checksums; no draw list crosses PCIe, framebuffers stay resident in HBM",
+        "e2e": {"value": px_total / ((ms_fe2 or ms_fe) * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": 28 * n_views * passes,
+                "d2h_bytes_per_step": (40 + 8) * n_views * passes, "ms_per_step": (ms_fe2 or ms_fe) * passes, "ms_per_pass": ms_fe2 or ms_fe,
+                "frames_per_s": frames_total / ((ms_fe2 or ms_fe) * 1e-3),
+                "batches_in_flight": 2 if ms_fe2 else 1,
+                "path": "viewpoints -> drr_fe_emit_views (front-end kernel, counts to the host, compaction) -> bin -> tile -> per-frame checksums; no draw list crosses PCIe, framebuffers stay resident in HBM"
+                        + ("; two batches in flight (two contexts, two host threads, one stream each)" if ms_fe2 else ""),
+                "one_batch_in_flight": {"value": px_total / (ms_fe * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_pass": ms_fe, "frames_per_s": frames_total / (ms_fe * 1e-3)},
                 "front_end_kernel_ms": fe_kernel_ms, "compaction_or_count_ms": fe_front_ms,
                 "mode": "single pass: per-view slabs, then compaction" if fe_mode == 1 else "two passes: count, then emit"},
         "roofline": {"bound": "issue", "roof": "hbm", "kernel": ctx.kernel_name(), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

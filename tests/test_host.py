@@ -197,6 +197,25 @@ def test_checksum_definitions_agree():
         assert drr.checksum_host(b) == drr.checksum_numpy(b)
 
 
+def test_checksum_known_answer():
+    """Hand-derived value of the checksum of include/drr.h.  Frame = 52 bytes = the little-endian words 1, 2, ..., 13: two groups
+    of 12 words, the second zero-padded.  With C = 0x9E3779B1 = 2654435761:
+      s_0 = sum_{j=0..11} (j + 1) (2 j + 1) C = (2 * 506 + 3 * 66 + 12) C = 1222 C = 3243720499942 = 755 * 2^32 + 1020191462
+      s_1 = 13 * 1 * C = 34507664893 = 8 * 2^32 + 147926525
+      weights of the groups: 1 * C = 2654435761,  2 * C mod 2^32 = 5308871522 - 2^32 = 1013904226
+      checksum = 1020191462 * 2654435761 + 147926525 * 1013904226 mod 2^64 = 2858016028634667232"""
+    b = np.arange(1, 14, dtype="<u4").view(np.uint8)
+    assert b.size == 52
+    assert drr.checksum_numpy(b) == 2858016028634667232
+    assert drr.checksum_host(b) == 2858016028634667232
+    assert drr.checksum_numpy(np.zeros(48, np.uint8)) == 0
+    # a change of any single word changes the sum (every multiplier is odd)
+    for i in range(13):
+        c = b.copy()
+        c[4 * i] ^= 1
+        assert drr.checksum_numpy(c) != 2858016028634667232
+
+
 def test_threaded_front_end_records_the_same_lists():
     """drr_scene_emit_views (worker threads, one recorder each, appended in view order) records byte for byte what calling
     drr_scene_emit_view view by view records; a recorder refuses what a context refuses; appending twice the same view fails."""

@@ -10,9 +10,9 @@ for path in sys.argv[1:]:
     for r in rows:
         rf, e = r["roofline"], r["e2e"]
         spread = [p["ms_per_pass"] for p in r.get("per_rank", [])]
-        print("  %-11s %5d views  pass %.4f ms  tile %.4f  bin %.4f  frac %.4f | e2e %.3f ms (fe kernel %.3f) %.0f Mpix/s | value %.0f Mpix/s%s%s" % (
+        print("  %-11s %5d views  pass %.4f ms  tile %.4f  bin %.4f  frac %.4f | e2e %.3f ms [%d in flight; one: %.3f] (fe kernel %.3f) %.0f Mpix/s | value %.0f Mpix/s%s%s" % (
             r["workload"], r["config"]["views_per_gpu"], r["ms_per_pass"], rf["kernel_ms"], rf["bin_kernel_ms"], rf["frac"], e["ms_per_pass"],
-            e["front_end_kernel_ms"], e["value"], r["value"],
+            e.get("batches_in_flight", 1), e.get("one_batch_in_flight", e)["ms_per_pass"], e["front_end_kernel_ms"], e["value"], r["value"],
             "  ranks %.4f..%.4f" % (min(spread), max(spread)) if len(spread) > 1 else "",
             "  parity %s" % r["parity_sample"]["ok"] if "parity_sample" in r else ""))
     if "cpu_baseline" in d:
