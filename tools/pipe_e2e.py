@@ -14,7 +14,7 @@ def make():
     ctx = drr.Context(W, H, 0, n); scene = drr.Scene(path, 'E1M1', W, H); scene.upload_assets(ctx)
     st = torch.cuda.Stream(); ctx.set_stream(st.cuda_stream)
     return ctx, scene, st
-A, B = make(), make()
+C4 = [make() for _ in range(4)]; A, B = C4[0], C4[1]
 def one(ctx, scene):
     ctx.reset(); scene.emit_views_device(ctx, views, 0.0, phases); ctx.draw(); return ctx.read_checksums(0, n)
 ref = one(*A[:2]); assert (one(*B[:2]) == ref).all()
@@ -32,3 +32,12 @@ for mode in ("one", "two", "one", "two"):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     assert all((x == ref).all() for x in o)
     print("%s in flight: %.4f ms per batch of %d views (%dx%d)" % (mode, dt / K * 1e3, n, W, H))
+for k in (3, 4):
+    for c in C4[:k]: assert (one(*c[:2]) == ref).all()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    outs = [[] for _ in range(k)]
+    per = 96 // k
+    ts = [threading.Thread(target=loop, args=(C4[i], per, outs[i])) for i in range(k)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print("%d in flight: %.4f ms per batch" % (k, dt / (per * k) * 1e3))
