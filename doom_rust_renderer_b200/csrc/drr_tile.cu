@@ -51,11 +51,11 @@ struct Rec { // a decoded record in registers
     uint4 a, b, c, d;
     uint32_t kind;
 };
-__device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, int x, int ya, int yb, int top_y, int bottom_y) {
+__device__ __forceinline__ Rec wall_record(const DrawArgs &a, const SegRec &g, const SegConst &kc, int x, int ya, int yb, int top_y, int bottom_y) {
     const uint32_t h = (uint32_t)g.tex_h;
     uint32_t kind = g.tex_opaque ? KIND_WALL : KIND_WALL_HOLES;
     uint4 ra = make_uint4((uint32_t)ya | ((uint32_t)yb << 16), 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u), rc = rb, rd = rb;
-    const WallColumn wc = wall_column(g, g.tex_w, x);
+    const WallColumn wc = wall_column(g, kc, g.tex_w, x);
     if (wc.tx < 0) kind = KIND_NONE; // reference: negative index -> panic
     const uint32_t lp = ilog2_ceil(h); // column-major texel pool: one texture column = 1 << lp consecutive texels
     ra.z = g.tex_base + ((uint32_t)(wc.tx < 0 ? 0 : wc.tx) << lp);
@@ -240,7 +240,7 @@ struct ColOut {
     }
 };
 
-__device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, ColOut &out, Cover *cover) {
+__device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, const SegConst *s_kc, ColOut &out, Cover *cover) {
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
     for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t k) {
         if (x >= a.W || x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) return; // (Pixels::set ignores x >= W)
@@ -273,7 +273,8 @@ __device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, con
             const ColRec c = a.cols[cols_first + i];
             const int ya = max((int)c.clipped_top_y, 0), yb = min((int)c.clipped_bottom_y, a.H - 1);
             if (ya > yb) return;
-            const Rec r = wall_record(a, *gp, x, ya, yb, c.top_y, c.bottom_y);
+            // the seg's part of the column math: once per op for the staged ones (s_kc), else here
+            const Rec r = wall_record(a, *gp, k < (uint32_t)BIN_REC ? s_kc[k] : seg_const(*gp), x, ya, yb, c.top_y, c.bottom_y);
             if (r.kind == KIND_WALL) cover->add(ya, yb);
             out.put(r, ya, yb);
         }
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kerne
     const int nthreads = (int)blockDim.x;
     __shared__ uint2 s_tab[BIN_TAB];
     __shared__ uint4 s_rec[BIN_REC * 5]; // the first BIN_REC ops' records: the walk then depends on one global load (the column record) only
+    __shared__ SegConst s_kc[BIN_REC];
     const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
     const int x = (int)(blockIdx.x % (unsigned)bpf) * nthreads + (int)threadIdx.x;
     const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
@@ -301,6 +303,10 @@ __global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kerne
             s_rec[i] = reinterpret_cast<const uint4 *>(a.segs + op)[part];
         }
     }
+    __syncthreads();
+    // what of the column math depends on the seg only (length, four quotients, light / 255: a square root and five divisions): once per staged op
+    for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_REC); k += nthreads)
+        if (!(s_tab[k].y & 0x80000000u)) s_kc[k] = seg_const(*reinterpret_cast<const SegRec *>(s_rec + 5 * k));
     __syncthreads();
     if ((x & ~31) >= a.W) return; // whole warps only: the candidate walk is a warp-wide operation
     const bool live = x < a.W;
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kerne
     if (cap) out.first += atomicAdd(a.frame_cursor + f, cap * (uint32_t)nlists);
     Cover cover;
     // (a dead lane of a partly live warp, x >= W, visits nothing: it only takes part in the ballots)
-    walk_column(a, f, x, vw, s_tab, s_rec, out, &cover);
+    walk_column(a, f, x, vw, s_tab, s_rec, s_kc, out, &cover);
     if (live) {
         for (int b = 0; b < nlists; ++b) {
             uint32_t nb = 0;
@@ -748,10 +754,24 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
 #else
     constexpr bool RUNS = MINB <= 5; // the texel-run wall loop: in the 48 / 56 register builds of the tall tiles (spills at 40)
 #endif
+    // ... and the record REC_AHEAD spans further on is requested into L1 (64 bytes each, consecutive per column).  Measured (tile
+    // kernel ms, 1 / 2 / 3 / 4 ahead): walk1280 0.8124 / 0.8049 / 0.8064 / 0.8073, things640 1.878 / 1.834 / 1.839 / 1.842, stress1920
+    // 41.99 / 40.77 / 41.04 / 40.96 -- but walk320 (no head in registers, 40 registers) 0.5282 / 0.5304 / 0.5321 / 0.5333.
+#ifdef DRR_REC_AHEAD
+    constexpr int REC_AHEAD = DRR_REC_AHEAD;
+#else
+    constexpr int REC_AHEAD = HEAD_IN_REGS ? 2 : 1;
+#endif
     uint4 ra_next = make_uint4(0u, 0u, 0u, 0u);
     if (left > 0) {
         if (HEAD_IN_REGS) ra_next = P[(size_t)rec * 4]; // the first span's head: in flight while the palette arrives
         else asm volatile("prefetch.global.L1 [%0];" ::"l"(P + (size_t)rec * 4));
+#pragma unroll
+        for (int k = 1; k < REC_AHEAD; ++k)
+            if (left > k) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(P + ((size_t)rec + k) * 4));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(P + ((size_t)rec + k) * 4 + 2));
+            }
     }
     __syncthreads(); // the barrier's initialisation is visible to every thread
     mbar_wait(bar, 0);
@@ -788,8 +808,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                 ++rec;
                 if (--left > 0) { // the next span's first word is fetched while this one is drawn (word c arrives in L1 with it) ...
                     if (HEAD_IN_REGS) ra_next = R[4];
-                    else asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 4));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 6)); // ... and so is the sector with words d and b
+                    if (REC_AHEAD == 1) {
+                        if (!HEAD_IN_REGS) asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 4));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 6)); // ... and so is the sector with words d and b
+                    } else if (left >= REC_AHEAD) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 4 * REC_AHEAD));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(R + 4 * REC_AHEAD + 2));
+                    }
                 }
                 const int ya = max((int)(ra.x & 0xffff), b0), yb = min((int)(ra.x >> 16), b1);
                 const uint32_t kind = ra.y & 0xffu;
