@@ -6,6 +6,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -188,6 +189,34 @@ def test_sass_keeps_products_and_sums_apart():
         assert not re.search(r"FFMA2 [^;]*, 1, ", k), name
         assert "UBLKCP" in k and "SYNCS" in k, name                       # palette image: bulk copy on an mbarrier
         assert ("UTMASTG" in k) == ("ELb1E" in name), name               # TMA write-out in the fast-store kernels only
+
+
+def test_front_end_ptx_has_no_fused_multiply_add():
+    """drr_frontend.cuh is plain C++ shared with the host compiler: its f32 expressions are only bit-equal to the host front-end's
+    (and the reference's) when nvcc does not contract a*b+c.  Compile the translation unit to PTX with the Makefile's flags and
+    look: no fma.rn.f32 of the compiler's making (IEEE division and square root stay div.rn / sqrt.rn in PTX)."""
+    import shutil, tempfile
+    if not shutil.which("nvcc"):
+        pytest.skip("no nvcc")
+    src = os.path.join(common.ROOT, "doom_rust_renderer_b200", "csrc")
+    flags = re.search(r"^NVFLAGS\s*=\s*(.*)$", open(os.path.join(src, "Makefile")).read(), re.M).group(1)
+    assert "-fmad=false" in flags and "-prec-div=true" in flags and "-ftz=false" in flags
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "fe.ptx")
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=compute_100a", "-O3", "-std=c++17", "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+                        "-ftz=false", "-ptx", os.path.join(src, "drr_frontend.cu"), "-o", out], check=True, capture_output=True)
+        ptx = open(out).read()
+    assert "drr_frontend_kernel" in ptx and "div.rn.f32" in ptx
+    # the only fma allowed is inside CUDA's fmodf (exact by definition: the remainder is computed with fma on purpose), which
+    # mo_pre calls twice (map_objects.rs:44-58): 8 per call, in the two instantiations of Frame::mo_pre
+    func, where = "?", {}
+    for line in ptx.splitlines():
+        m = re.match(r"\.(?:visible |weak )?(?:entry|func)\s.*?(_Z\w+)", line)
+        if m:
+            func = m.group(1)
+        if re.search(r"\bfma\.", line):
+            where[func] = where.get(func, 0) + 1
+    assert where and all("mo_pre" in f and n == 16 for f, n in where.items()), where
 
 
 def test_checksum_definitions_agree():
