@@ -580,6 +580,45 @@ def test_recording_the_next_batch_while_the_previous_uploads():
 
 
 # ---- presentation / export (the reference presents Pixels.pixels, src/game.rs:500-533) ----------------------------
+@pytest.mark.parametrize("W,H,phases", [(320, 200, 3), (640, 400, 7)])
+def test_two_batches_in_flight_on_one_device(W, H, phases):
+    """The throughput pattern of INTEGRATION.md 6 and of bench.py's `e2e`: two contexts on ONE device (own stream, own framebuffers),
+    each driven by its own host thread through reset -> device front-end -> draw -> checksums, several passes over different
+    viewpoint sets, concurrently.  Every checksum must equal the oracle's frame, whatever the other context is doing."""
+    import threading
+    path, gm = common.wad("e1m1")
+    n = 48
+    game = orc.Game(path, "E1M1", W, H)
+    views = common.usable_views(game, synth_wad.walk_viewpoints(gm, 4096)[::41], 2 * n)
+    want = [drr.checksum_numpy(game.render(float(v[0]), float(v[1]), float(v[2]), phases=phases)) for v in views]
+    errors = []
+
+    def work(d):
+        try:
+            ctx = drr.Context(W, H, 0, n)
+            scene = drr.Scene(path, "E1M1", W, H)
+            scene.upload_assets(ctx)
+            for rep in range(6):
+                half = (d + rep) % 2  # the two threads swap viewpoint sets every pass
+                ctx.reset()
+                assert scene.emit_views_device(ctx, views[half * n:(half + 1) * n], 0.0, phases) == []
+                ctx.draw()
+                got = ctx.read_checksums(0, n)
+                assert [int(x) for x in got] == want[half * n:(half + 1) * n], "thread %d pass %d" % (d, rep)
+            ctx.close()
+            scene.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
 @pytest.mark.parametrize("W,H", [(320, 200), (324, 203), (1280, 800)])
 def test_export_png_and_crc32_of_device_frames(W, H, tmp_path):
     """A device frame through the export path: drr_read_framebuffer -> PNG file -> decoded == the oracle's frame, byte for
