@@ -792,7 +792,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
         fv.py16 = sat_i16(vw.pos_y);
         // shared address of row r (of the band) of this lane group's column, tile_offset(c, r): the tile base is 128-byte
         // aligned, so the row's slot (bits 4..6, swizzled with bit 2 of the quad = warp) goes in with an exclusive or
-        const uint32_t colx = (tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2)) ^ (((uint32_t)warp & 4u) << 4);
+        uint32_t colx = (tile + ((uint32_t)warp << 7) + ((uint32_t)grp << 2)) ^ (((uint32_t)warp & 4u) << 4);
+#ifndef DRR_NO_PIN
+        // (opaque to ptxas: otherwise the 40-register build re-derives it from SR_TID.X -- ~18 instructions -- in front of every span
+        // instead of keeping one register)
+        if (MINB >= 6) asm volatile("" : "+r"(colx), "+r"(t.li));
+#endif
         auto row_addr = [&](int r) { return (colx ^ (((uint32_t)r & 7u) << 4)) + (((uint32_t)r >> 3) << 10); };
         // uncovered pixels are (0,0,0) like the reference's zero-initialised Pixels::new (pixels.rs:10-14); a column whose
         // always-writing spans cover every row (the normal case, flagged by the bin kernel) needs no clearing
