@@ -49,8 +49,9 @@ from doom_rust_renderer_b200.workloads import WORKLOADS, Content  # noqa: E402  
 
 # what binds the tile kernel, from the committed ncu captures (profiles/r2_final_tile_*.txt): not HBM
 LIMITER = {
-    "what": "instruction issue and the FMA / ALU pipes, not HBM: the per-pixel f32 arithmetic the reference prescribes",
-    "source": "profiles/r2_final_tile_1280x800.txt, profiles/r2_final_tile_320x200.txt (ncu --set full)",
+    "what": "instruction issue (68-72 % of the slots busy) together with the L1/shared pipe (61-73 %), not HBM (DRAM 22 %): the per-pixel f32 "
+            "arithmetic the reference prescribes; 38.8 issue slots per screen pixel at 1280x800, 53 at 320x200",
+    "source": "profiles/r2b_final_tile_1280x800.txt, profiles/r2b_final_tile_320x200.txt (ncu --set full)",
 }
 
 

@@ -501,11 +501,10 @@ __device__ __forceinline__ void tile_wall_span(const TileCtx &t, const uint4 ra,
 // texel fetches, two palette lookups and one packed lighting per RUN_ROWS pixels; every row still evaluates v (the reference's
 // own expression, bit for bit, two rows per packed instruction) to pick A's colour or B's.  The 8 lanes of a group cover
 // 8 * RUN_ROWS rows per iteration (RUN_ROWS blocks of the tile).
-template <bool HOLES, bool POW2>
+template <bool HOLES, bool POW2, int K>
 __device__ __forceinline__ void tile_wall_span_runs(const TileCtx &t, const uint4 ra, const uint4 rb, const uint4 rc, const uint4 rd, int ya, int yb, int b0,
                                                     uint32_t colx, const uint16_t *__restrict__ texels) {
-    constexpr int K = RUN_ROWS;
-    static_assert(K % 2 == 0 && K >= 4, "rows are evaluated in pairs");
+    static_assert(K % 2 == 0 && K >= 4 && K <= RUN_ROWS, "rows are evaluated in pairs; the span's flag is proven for runs of RUN_ROWS rows");
     const float hF = __uint_as_float(rd.x), factor = __uint_as_float(rd.y), magic = __uint_as_float(rd.w);
     const float2 nden = f2(__uint_as_float(rc.y)), rden = f2(__uint_as_float(rc.z)), uy1 = f2(__uint_as_float(rc.w));
     const uint32_t mask = rd.z;
@@ -754,6 +753,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
 #else
     constexpr bool RUNS = MINB <= 5; // the texel-run wall loop: in the 48 / 56 register builds of the tall tiles (spills at 40)
 #endif
+    // rows per run: RUN_ROWS, or 4 in the 40-register build (no spill there; a span flagged for runs of RUN_ROWS rows qualifies for shorter ones)
+    constexpr int RUN_K = MINB >= 6 ? 4 : RUN_ROWS;
     // ... and the record REC_AHEAD spans further on is requested into L1 (64 bytes each, consecutive per column).  Measured (tile
     // kernel ms, 1 / 2 / 3 / 4 ahead): walk1280 0.8124 / 0.8049 / 0.8064 / 0.8073, things640 1.878 / 1.834 / 1.839 / 1.842, stress1920
     // 41.99 / 40.77 / 41.04 / 40.96 -- but walk320 (no head in registers, 40 registers) 0.5282 / 0.5304 / 0.5321 / 0.5333.
@@ -834,11 +835,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                         if ((ra.y & (TS_TRUNC | TS_BRIGHT)) != TS_TRUNC) tile_wall_span_any(t, ra, R[3], rc, rd, ya, yb, addr, texels);
                         else if (RUNS && (ra.y & TS_RUNS)) {
                             if (kind == KIND_WALL) {
-                                if (ra.y & TS_POW2) tile_wall_span_runs<false, true>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
-                                else tile_wall_span_runs<false, false>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
+                                if (ra.y & TS_POW2) tile_wall_span_runs<false, true, RUN_K>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
+                                else tile_wall_span_runs<false, false, RUN_K>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
                             } else {
-                                if (ra.y & TS_POW2) tile_wall_span_runs<true, true>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
-                                else tile_wall_span_runs<true, false>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
+                                if (ra.y & TS_POW2) tile_wall_span_runs<true, true, RUN_K>(t, ra, ra, rc, rd, ya, yb, b0, colx, texels);
+                                else tile_wall_span_runs<true, false, RUN_K>(t, ra, R[3], rc, rd, ya, yb, b0, colx, texels);
                             }
                         }
                         else if (kind == KIND_WALL) {
