@@ -186,19 +186,29 @@ struct Out { // where the emit pass writes (pointers are the batch's arrays; ind
 };
 
 // ---- Rust scalar semantics (the same helpers as csrc/host/drr_scene.cpp) ------------------------------------------
+// (on the device one conversion instruction each: cvt.rzi saturates and turns NaN into 0, which is Rust's `as`)
 FE_HD int16_t as_i16(float f) {
+#if defined(__CUDA_ARCH__)
+    return (int16_t)sat_i16(f);
+#endif
     if (f != f) return 0;
     if (f <= -32768.0f) return (int16_t)-32768;
     if (f >= 32767.0f) return (int16_t)32767;
     return (int16_t)f;
 }
 FE_HD int32_t as_i32(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rz(f);
+#endif
     if (f != f) return 0;
     if (f <= -2147483648.0f) return (int32_t)0x80000000;
     if (f >= 2147483648.0f) return 0x7fffffff;
     return (int32_t)f;
 }
 FE_HD uint8_t as_u8(float f) {
+#if defined(__CUDA_ARCH__)
+    return (uint8_t)sat_u8(f);
+#endif
     if (f != f || f <= 0.0f) return 0;
     if (f >= 255.0f) return 255;
     return (uint8_t)f;
@@ -427,7 +437,12 @@ FE_HD int highest(uint32_t v) { // index of the highest set bit, v != 0
     while (!((v >> i) & 1u)) i--;
     return i;
 }
-FE_HD uint32_t below(int l) { return (uint32_t)((1ull << l) - 1ull); } // bits of the lanes < l, 0 <= l <= 32
+FE_HD uint32_t below(int l) { // bits of the lanes < l, 0 <= l <= 32
+#if defined(__CUDA_ARCH__)
+    return l >= 32 ? 0xffffffffu : (1u << l) - 1u;
+#endif
+    return (uint32_t)((1ull << l) - 1ull);
+}
 FE_HD void prefetch_l1(const void *p) { // a hint: the line is on its way while the warp works on something else
 #if defined(__CUDA_ARCH__)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
