@@ -115,7 +115,8 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     // + 8 bytes per column of visplane rows (mode 2); taken when every warp the register budget allows on an SM fits in ~200 KB
     const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15, side_bytes = 4 * (size_t)((m.side_words + 3) & ~3);
     const size_t frame_bytes = (std::max(sizeof(fe::Frame<true>), sizeof(fe::Frame<false>)) + 15) & ~(size_t)15;
-    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = 200 * 1024 / (FE_MIN_BLOCKS * FE_WARPS);
+    // (at most 48 KB per CTA: the default limit of dynamic shared memory, no opt-in needed)
+    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = std::min<size_t>(200 * 1024 / (FE_MIN_BLOCKS * FE_WARPS), 48 * 1024 / FE_WARPS);
     // (mode 1 only up to 8 KB per viewpoint: at 1920 columns 16 viewpoints' arrays would take 170 KB of the SM and leave the
     // global scratch of the masked phase no L1 to speak of -- measured on the stress map: 64.0 ms against 56.1 ms in mode 0)
     const int mode = need2 <= budget ? 2 : need1 <= std::min(budget, (size_t)8192) ? 1 : 0;

@@ -253,7 +253,9 @@ def test_device_front_end_two_pass_and_overflow_fallback(env, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,W,H,n,phases", [("e1m1", 320, 200, 24, 3), ("e1m1", 1280, 800, 4, 3), ("stress", 640, 400, 6, 3), ("e1m1", 320, 200, 32, 7),
-                                               ("e1m1", 640, 400, 8, 7), ("stress", 1920, 1200, 2, 7)])
+                                               ("e1m1", 640, 400, 8, 7), ("stress", 1920, 1200, 2, 7),
+                                               # widths around the edges of the front-end's shared-memory modes (all arrays / occlusion arrays only / none)
+                                               ("e1m1", 896, 504, 6, 7), ("e1m1", 928, 520, 6, 3), ("e1m1", 1600, 400, 4, 7)])
 def test_device_front_end_frames_match_oracle(kind, W, H, n, phases):
     """viewpoints -> device front-end -> bin kernel -> tile kernel == the oracle's frames (no list ever touches the host)."""
     path, gm = common.wad(kind)
