@@ -370,7 +370,7 @@ def run_workload(name, args, rank, world, local_rank, dist, torch, headline):
 
     def pass_fe():
         ctx.reset()
-        scene.emit_views_device(ctx, used, 0.0, phases)  # 12 B per viewpoint up; front-end kernel, counts to the host, compaction
+        scene.emit_views_device(ctx, used, 0.0, phases)  # 12 B per viewpoint up; front-end kernel, counts to the host (offsets of the record slots), the draw kernels read the per-view slabs
         ctx.draw()
         ctx.read_checksums(0, n_views)
 
@@ -461,11 +461,11 @@ def run_workload(name, args, rank, world, local_rank, dist, torch, headline):
                 "d2h_bytes_per_step": (40 + 8) * n_views * passes, "ms_per_step": (ms_fe2 or ms_fe) * passes, "ms_per_pass": ms_fe2 or ms_fe,
                 "frames_per_s": frames_total / ((ms_fe2 or ms_fe) * 1e-3),
                 "batches_in_flight": 2 if ms_fe2 else 1,
-                "path": "viewpoints -> drr_fe_emit_views (front-end kernel, counts to the host, compaction) -> bin -> tile -> per-frame checksums; no draw list crosses PCIe, framebuffers stay resident in HBM"
+                "path": "viewpoints -> drr_fe_emit_views (front-end kernel into per-view slabs, counts to the host) -> bin (reads the slabs) -> tile -> per-frame checksums; no draw list crosses PCIe, framebuffers stay resident in HBM"
                         + ("; two batches in flight (two contexts, two host threads, one stream each)" if ms_fe2 else ""),
                 "one_batch_in_flight": {"value": px_total / (ms_fe * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_pass": ms_fe, "frames_per_s": frames_total / (ms_fe * 1e-3)},
                 "front_end_kernel_ms": fe_kernel_ms, "compaction_or_count_ms": fe_front_ms,
-                "mode": "single pass: per-view slabs, then compaction" if fe_mode == 1 else "two passes: count, then emit"},
+                "mode": "single pass: per-view slabs, read in place by the draw kernels" if fe_mode == 1 else "two passes: count, then emit"},
         "roofline": {"bound": "issue", "roof": "hbm", "kernel": ctx.kernel_name(), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": traffic,
                      "traffic_source": "profiles/r2_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of one tile-kernel launch over this batch" if traffic else None,

@@ -166,6 +166,13 @@ struct FeState {
     DevBuf<uint16_t> d_sl_cols;
     DevBuf<PlaneRec> d_sl_planes;
     bool single_pass = false; // how the last batch ran
+    // slab draw: the last batch's lists are still the per-view slabs (the draw kernels index them through d_slab_meta); dense lists
+    // exist only after compact_now() (the test accessor that downloads them)
+    bool slab_draw = false, dense_valid = false;
+    fe::Slabs sl_last{};
+    int n_last = 0, first_last = 0;
+    PinnedVec<uint32_t> h_slab_meta; // [nf + 1] first op of each frame in the slab array, then [nf] its op count
+    DevBuf<uint32_t> d_slab_meta;
     uint32_t scratch_boost = 1; // x4 whenever a batch outgrew the masked phase's working arrays
     uint32_t slab_boost = 1;  // doubled (up to 8) whenever a batch outgrew its slabs: the next batch of the context gets more room
     float count_ms = 0.0f, emit_ms = 0.0f;
@@ -182,13 +189,14 @@ struct Knobs {
     int tile_max_rows = 0;       // DRR_TILE_MAX_ROWS: rows per tile band (default 400; A/B runs)
     int fe_trace = 0;            // DRR_FE_TRACE: host-side time line of drr_fe_emit_views on stderr
     int fe_two_pass = 0;         // DRR_FE_TWO_PASS: count pass + emit pass instead of slabs + compaction
+    int fe_compact = 0;          // DRR_FE_COMPACT: copy the slabs into dense lists before drawing (default: the draw kernels read the slabs)
     int fe_slab_div = 0;         // DRR_FE_SLAB_DIV: shrink the per-view slabs (tests: provoke the fallback)
     int fe_cap_renders = 0, fe_cap_dsegs = 0, fe_cap_allcols_per_w = 0; // DRR_FE_CAP_*: masked phase working arrays
     struct Name { const char *env, *name; int Knobs::*field; };
     static const Name *table(size_t *n) {
         static const Name t[] = {{"DRR_DBG", "dbg", &Knobs::dbg}, {"DRR_SUBMIT_CHUNKS", "submit_chunks", &Knobs::submit_chunks},
                                  {"DRR_SUBMIT_ONE_STREAM", "submit_one_stream", &Knobs::submit_one_stream}, {"DRR_SUBMIT_TRACE", "submit_trace", &Knobs::submit_trace},
-                                 {"DRR_TILE_MAX_ROWS", "tile_max_rows", &Knobs::tile_max_rows}, {"DRR_FE_TRACE", "fe_trace", &Knobs::fe_trace}, {"DRR_FE_TWO_PASS", "fe_two_pass", &Knobs::fe_two_pass},
+                                 {"DRR_TILE_MAX_ROWS", "tile_max_rows", &Knobs::tile_max_rows}, {"DRR_FE_TRACE", "fe_trace", &Knobs::fe_trace}, {"DRR_FE_TWO_PASS", "fe_two_pass", &Knobs::fe_two_pass}, {"DRR_FE_COMPACT", "fe_compact", &Knobs::fe_compact},
                                  {"DRR_FE_SLAB_DIV", "fe_slab_div", &Knobs::fe_slab_div}, {"DRR_FE_CAP_RENDERS", "fe_cap_renders", &Knobs::fe_cap_renders},
                                  {"DRR_FE_CAP_DSEGS", "fe_cap_dsegs", &Knobs::fe_cap_dsegs}, {"DRR_FE_CAP_ALLCOLS_PER_W", "fe_cap_allcols_per_w", &Knobs::fe_cap_allcols_per_w}};
         *n = sizeof(t) / sizeof(t[0]);
@@ -724,6 +732,7 @@ int drr_reset(drr_ctx *ctx) {
     if (int rc = lists_writable(ctx)) return rc;
     ctx->clear_lists();
     ctx->device_lists = false;
+    ctx->fes.slab_draw = false;
     ctx->t_spans.clear();
     ctx->t_colidx.clear();
     ctx->uploaded_frames = 0;
@@ -972,6 +981,7 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.views = ctx->d_views.p;
     a.ops = ctx->d_ops.p;
     a.frame_op_base = ctx->d_frame_op_base.p;
+    a.frame_nops = nullptr;
     a.frame_rec_base = ctx->d_frame_rec_base.p;
     a.frame_slot = ctx->d_frame_slot.p;
     a.segs = ctx->d_segs.p;
@@ -991,6 +1001,16 @@ static int make_args(drr_ctx *ctx, DrawArgs &a, size_t nframes) {
     a.frames = ctx->d_frames;
     a.frame_stride = ctx->frame_stride;
     a.crc = ctx->d_crc;
+    if (ctx->device_lists && ctx->fes.slab_draw) { // the front-end's per-view slabs as they are: every index in them is an index into the slab arrays
+        const FeState &S = ctx->fes;
+        a.ops = S.sl_last.out.ops;
+        a.segs = S.sl_last.out.segs;
+        a.cols = S.sl_last.out.cols;
+        a.planes = S.sl_last.out.planes;
+        a.parr = S.sl_last.out.parr;
+        a.frame_op_base = S.d_slab_meta.p;
+        a.frame_nops = S.d_slab_meta.p + nframes + 1;
+    }
     return DRR_OK;
 }
 
@@ -1688,8 +1708,47 @@ static int fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int
         }
         return DRR_OK;
     }
-    // the dense device lists: sized from the counts
     mark("offsets computed");
+    S.slab_draw = false;
+    S.dense_valid = true;
+    if (single && !ctx->knobs.fe_compact) {
+        // No compaction: the draw kernels read the slabs (the ops, SegRec::cols_first and PlaneRec::arr_first in them are indices into
+        // the slab arrays already).  What they need per frame: where its ops start and how many there are, its record slots, its
+        // framebuffer slot, and its View in an array indexed by frame.
+        if (!S.h_slab_meta.reserve(2 * nf + 1)) return fail(ctx, DRR_E_NOMEM, "alloc");
+        size_t f = 0;
+        for (size_t i = 0; i < N; i++)
+            if (S.h_bases.p[i].frame >= 0) {
+                S.h_slab_meta.p[f] = (uint32_t)i * slab.ops;
+                S.h_slab_meta.p[nf + 1 + f] = S.h_counts.p[i].nops;
+                f++;
+            }
+        S.h_slab_meta.p[nf] = 0u;
+        CU(ctx, ctx->d_views.reserve(nf));
+        CU(ctx, S.d_slab_meta.reserve(2 * nf + 1));
+        CU(ctx, ctx->d_frame_rec_base.reserve(nf + 1));
+        CU(ctx, ctx->d_frame_slot.reserve(nf));
+        CU(ctx, ctx->d_frame_cursor.reserve(nf));
+        CU(ctx, ctx->d_colidx.reserve(nf * W * nlists));
+        CU(ctx, ctx->d_tparams.reserve(std::max<uint64_t>(reccap, 1) * 4 * nlists));
+        CU(ctx, cudaMemcpyAsync(S.d_slab_meta.p, S.h_slab_meta.p, (2 * nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->d_frame_rec_base.p, ctx->frame_rec_base.p, (nf + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->d_frame_slot.p, ctx->frame_slot.p, nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        CU(ctx, launch_fe_gather_views(sl.out.views, ctx->d_frame_slot.p, first_view_idx, (int)nf, ctx->d_views.p, ctx->stream));
+        ctx->stats.kernel_launches++;
+        CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+        S.slab_draw = true;
+        S.dense_valid = false;
+        S.sl_last = sl;
+        S.n_last = n;
+        S.first_last = first_view_idx;
+        ctx->device_lists = true;
+        ctx->uploaded_frames = nf;
+        mark("views gathered, slabs handed to the draw kernels");
+        return DRR_OK;
+    }
+    // the dense device lists: sized from the counts
     CU(ctx, ctx->d_views.reserve(nf));
     CU(ctx, ctx->d_ops.reserve(std::max<uint64_t>(ops, 1)));
     CU(ctx, ctx->d_frame_op_base.reserve(nf + 1));
@@ -1759,6 +1818,18 @@ int drr_test_fe_download_lists(drr_ctx *ctx) {
     if (!ctx->views.reserve(nf) || !ctx->ops.reserve(ops) || !ctx->segs.reserve(segs) || !ctx->cols.reserve(cols) || !ctx->planes.reserve(planes) ||
         !ctx->parr.reserve(parr))
         return fail(ctx, DRR_E_NOMEM, "alloc");
+    FeState &S = ctx->fes;
+    if (S.slab_draw && !S.dense_valid) { // the batch was drawn from its slabs: make the dense lists now (what DRR_FE_COMPACT=1 does in line)
+        CU(ctx, ctx->d_ops.reserve(std::max<size_t>(ops, 1)));
+        CU(ctx, ctx->d_segs.reserve(std::max<size_t>(segs, 1)));
+        CU(ctx, ctx->d_cols.reserve(std::max<size_t>(cols, 1) * 5));
+        CU(ctx, ctx->d_planes.reserve(std::max<size_t>(planes, 1)));
+        CU(ctx, ctx->d_parr.reserve(std::max<size_t>(parr, 1)));
+        CU(ctx, cudaMemcpyAsync(S.d_bases.p, S.h_bases.p, (size_t)S.n_last * sizeof(fe::Bases), cudaMemcpyHostToDevice, ctx->stream));
+        const fe::Out out{ctx->d_views.p, ctx->d_ops.p, ctx->d_segs.p, reinterpret_cast<ColRec *>(ctx->d_cols.p), ctx->d_planes.p, ctx->d_parr.p};
+        CU(ctx, launch_fe_compact(S.sl_last, S.d_counts.p, S.d_bases.p, S.n_last, out, ctx->stream));
+        S.dense_valid = true;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaMemcpy(ctx->views.p, ctx->d_views.p, nf * sizeof(View), cudaMemcpyDeviceToHost));
     if (ops) CU(ctx, cudaMemcpy(ctx->ops.p, ctx->d_ops.p, ops * 4, cudaMemcpyDeviceToHost));

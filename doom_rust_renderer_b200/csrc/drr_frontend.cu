@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(128) drr_fe_compact_kernel(fe::Slabs sl, const
     fe::compact_view(sl, (uint32_t)v, counts[v], b, dst);
 }
 
+__global__ void __launch_bounds__(256) drr_fe_gather_views_kernel(const View *__restrict__ slab_views, const uint32_t *__restrict__ frame_slot, int first_view_idx, int nframes,
+                                                                  View *__restrict__ dst) {
+    const int f = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (f < nframes) dst[f] = slab_views[(int)frame_slot[f] - first_view_idx];
+}
+
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
                             const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -146,6 +152,12 @@ cudaError_t launch_fe_pre(const fe::Map &m, const fe::ViewIn *views, int n, cons
     if (n <= 0 || !s.pre || !s.pre_code) return cudaSuccess;
     const dim3 grid((unsigned)((m.nsegs + 255) / 256), (unsigned)std::min(n, 65535));
     drr_fe_pre_kernel<<<grid, 256, 0, st>>>(m, views, n, static_cast<fe::SegPre *>(s.pre), s.pre_code);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fe_gather_views(const View *slab_views, const uint32_t *frame_slot, int first_view_idx, int nframes, View *dst, cudaStream_t st) {
+    if (nframes <= 0) return cudaSuccess;
+    drr_fe_gather_views_kernel<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(slab_views, frame_slot, first_view_idx, nframes, dst);
     return cudaGetLastError();
 }
 

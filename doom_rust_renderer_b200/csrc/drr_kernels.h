@@ -43,6 +43,7 @@ struct DrawArgs {
     const View *views;               // [nframes]
     const uint32_t *ops;             // per frame, in call order: bit 31 = visplane, low bits = index into planes[] / segs[]
     const uint32_t *frame_op_base;   // [nframes + 1]
+    const uint32_t *frame_nops;      // [nframes] ops of each frame when the lists are the front-end's per-view slabs (null: frame_op_base[f + 1] - frame_op_base[f])
     const uint32_t *frame_rec_base;  // [nframes + 1] first record slot of each frame (one slot per emitted column: an upper bound)
     const uint32_t *frame_slot;      // framebuffer slot (view index) of each recorded frame
     const SegRec *segs;
@@ -130,6 +131,8 @@ cudaError_t launch_fe_pre(const fe::Map &m, const fe::ViewIn *views, int n, cons
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
                             const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st);
 cudaError_t launch_fe_compact(const fe::Slabs &sl, const fe::Counts *counts, const fe::Bases *bases, int n, const fe::Out &dst, cudaStream_t st);
+// frame f's View out of the slab array (indexed by viewpoint = frame_slot[f] - first_view_idx) into the dense one the draw kernels index by frame
+cudaError_t launch_fe_gather_views(const View *slab_views, const uint32_t *frame_slot, int first_view_idx, int nframes, View *dst, cudaStream_t st);
 
 cudaError_t launch_fastdiv_check(int mode, long long n0, long long n1, float CFY, int H, uint32_t lo, uint32_t stride,
                                  unsigned long long *d_bad, float *d_first, cudaStream_t st);

@@ -241,7 +241,7 @@ struct ColOut {
 };
 
 __device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, const View &vw, const uint2 *s_tab, const uint4 *s_rec, const SegConst *s_kc, ColOut &out, Cover *cover) {
-    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
+    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_nops ? a.frame_nops[f] : a.frame_op_base[f + 1] - o0;
     for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t k) {
         if (x >= a.W || x < (int)(short)(e.x & 0xffffu) || x > (int)(short)(e.x >> 16)) return; // (Pixels::set ignores x >= W)
         const uint32_t op = e.y;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kerne
     __shared__ SegConst s_kc[BIN_REC];
     const int f = frame0 + (int)(blockIdx.x / (unsigned)bpf);
     const int x = (int)(blockIdx.x % (unsigned)bpf) * nthreads + (int)threadIdx.x;
-    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_op_base[f + 1] - o0;
+    const uint32_t o0 = a.frame_op_base[f], nops = a.frame_nops ? a.frame_nops[f] : a.frame_op_base[f + 1] - o0;
     for (uint32_t k = threadIdx.x; k < min(nops, (uint32_t)BIN_TAB); k += nthreads) s_tab[k] = op_range(a, a.ops[o0 + k]);
     for (uint32_t i = threadIdx.x; i < min(nops, (uint32_t)BIN_REC) * 5; i += nthreads) {
         const uint32_t k = i / 5, part = i % 5, op = a.ops[o0 + k];

@@ -316,13 +316,13 @@ class Context:
         return [first_slot + int(k) for k in np.nonzero(status == -7)[0]]
 
     def fe_last_times(self):
-        """(count_ms, emit_ms) of the last fe_emit_views; in single-pass mode (fe_last_mode() == 1) the first is the compaction kernel."""
+        """(count_ms, emit_ms) of the last fe_emit_views; in single-pass mode (fe_last_mode() == 1) the first is the gather of the frames' View records (the compaction kernel with DRR_FE_COMPACT=1)."""
         a, b = C.c_float(), C.c_float()
         self._ck(self.L.drr_fe_last_times(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def fe_last_mode(self) -> int:
-        """1 = single pass (per-view slabs + compaction), 2 = count pass + emit pass."""
+        """1 = single pass (per-view slabs, read in place by the draw kernels), 2 = count pass + emit pass."""
         return int(self.L.drr_fe_last_mode(self.h))
 
     def fe_download_lists(self):

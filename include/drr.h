@@ -220,9 +220,10 @@ uint32_t drr_fe_map_id(drr_ctx *ctx); /* 0 = no map; otherwise a number that cha
  * (may be NULL) = DRR_OK or DRR_E_PANIC (the reference would have panicked on that viewpoint: it gets no frame). */
 int drr_fe_emit_views(drr_ctx *ctx, int first_view_idx, const float *xya, int n, int phases, int *status);
 /* How the last drr_fe_emit_views ran and its device times in ms (CUDA events on the context's stream).  Mode 1 = single
- * pass: every view writes into its own slab, then a compaction kernel makes the lists dense (emit_ms = the front-end
- * kernel, count_ms = the compaction).  Mode 2 = two passes (a view outgrew its slab, or DRR_FE_TWO_PASS is set): count
- * pass, then emit pass straight into the dense lists.  Both modes write the same bytes. */
+ * pass: every view writes into its own slab, and the draw kernels read the slabs in place (emit_ms = the front-end
+ * kernels, count_ms = the gather of the frames' View records; DRR_FE_COMPACT=1 copies the slabs into dense lists first,
+ * count_ms is then that copy).  Mode 2 = two passes (a view outgrew its slab, or DRR_FE_TWO_PASS is set): count pass,
+ * then emit pass straight into dense lists.  Dense lists hold the same bytes in both modes. */
 int drr_fe_last_times(drr_ctx *ctx, float *count_ms, float *emit_ms);
 int drr_fe_last_mode(drr_ctx *ctx);
 
