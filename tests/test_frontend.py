@@ -252,6 +252,42 @@ def test_device_front_end_two_pass_and_overflow_fallback(env, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("compact", [False, True])
+def test_device_front_end_slabs_drawn_in_place_or_compacted_first(compact, monkeypatch):
+    """Single-pass mode: by default the draw kernels read the front-end's per-view slabs in place, DRR_FE_COMPACT=1 copies them into
+    dense lists first.  Either way the frames are the same (checksums equal to the host lists' frames), drawing twice changes
+    nothing, and the dense lists -- made on demand in the first case, AFTER the draw -- are byte for byte the host front-end's."""
+    W, H, n = 320, 200, 90
+    path, gm = common.wad("e1m1")
+    views = _views("e1m1", gm, n)
+    scene = drr.Scene(path, "E1M1", W, H)
+    a = drr.Context(W, H, 0, n, _host_only=True)
+    scene.upload_assets(a)
+    skipped = scene.emit_views(a, views, phases=7)
+    ref = drr.Context(W, H, 0, n)
+    scene.upload_assets(ref)
+    assert scene.emit_views(ref, views, phases=7) == skipped
+    ref.submit()
+    want = ref.read_checksums(0, n)
+    if compact:
+        monkeypatch.setenv("DRR_FE_COMPACT", "1")
+    b = drr.Context(W, H, 0, n)
+    scene.upload_assets(b)
+    assert scene.emit_views_device(b, views, phases=7) == skipped
+    assert b.fe_last_mode() == 1
+    b.draw()
+    got = b.read_checksums(0, n)
+    b.draw()
+    assert (b.read_checksums(0, n) == got).all()
+    keep = [k for k in range(n) if k not in skipped]
+    assert (got[keep] == want[keep]).all()
+    b.fe_download_lists()
+    _assert_same_lists(a, b, "compact=%s" % compact)
+    b.draw()  # and the slabs are still what the draw kernels read
+    assert (b.read_checksums(0, n) == got).all()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("kind,W,H,n,phases", [("e1m1", 320, 200, 24, 3), ("e1m1", 1280, 800, 4, 3), ("stress", 640, 400, 6, 3), ("e1m1", 320, 200, 32, 7),
                                                ("e1m1", 640, 400, 8, 7), ("stress", 1920, 1200, 2, 7),
                                                # widths around the edges of the front-end's shared-memory modes (all arrays / occlusion arrays only / none)
