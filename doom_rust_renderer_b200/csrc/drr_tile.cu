@@ -201,15 +201,17 @@ struct Cover {
 // Visit, in call order, the ops of the frame whose x range touches the warp's 32 columns [wx0, wx0 + 31]: 32 table
 // entries are tested at a time (one per lane), the survivors are handed to every lane through a ballot.  All 32 lanes of
 // the warp must call it together.
-template <class F>
-__device__ __forceinline__ void for_each_candidate(const DrawArgs &a, uint32_t o0, uint32_t nops, int wx0, const uint2 *s_tab, F visit) {
+template <class F, class P>
+__device__ __forceinline__ void for_each_candidate(const DrawArgs &a, uint32_t o0, uint32_t nops, int wx0, const uint2 *s_tab, F visit, P ahead) {
     const int lane = threadIdx.x & 31;
     for (uint32_t base = 0; base < nops; base += 32) {
         const uint32_t k = base + (uint32_t)lane;
         uint2 e = make_uint2(1u, 0u); // empty range
         if (k < nops) e = k < (uint32_t)BIN_TAB ? s_tab[k] : op_range(a, a.ops[o0 + k]);
         const int ex0 = (int)(short)(e.x & 0xffffu), ex1 = (int)(short)(e.x >> 16);
-        uint32_t m = __ballot_sync(0xffffffffu, ex0 <= ex1 && ex1 >= wx0 && ex0 <= wx0 + 31);
+        const bool cand = ex0 <= ex1 && ex1 >= wx0 && ex0 <= wx0 + 31;
+        if (cand) ahead(e, k); // the lane that holds a candidate asks for what the warp's 32 columns will read of it, before the serial visits
+        uint32_t m = __ballot_sync(0xffffffffu, cand);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
@@ -278,6 +280,25 @@ __device__ __forceinline__ void walk_column(const DrawArgs &a, int f, int x, con
             if (r.kind == KIND_WALL) cover->add(ya, yb);
             out.put(r, ya, yb);
         }
+    }, [&](uint2 e, uint32_t k) {
+        // what the warp's columns [wx0, wx0 + 31] read of this op first: their (top, bottom) pairs of the visplane (4 bytes per column)
+        // or their column records of the seg (10 bytes per column, when the records are dense in x) -- requested into L1 now
+        const int wx0 = x & ~31, lo = max(wx0, (int)(short)(e.x & 0xffffu)), hi = min(wx0 + 31, (int)(short)(e.x >> 16));
+        const uint32_t op = e.y;
+        if (op & 0x80000000u) {
+            const PlaneRec p = k < (uint32_t)BIN_REC ? *reinterpret_cast<const PlaneRec *>(s_rec + 5 * k) : a.planes[op & 0x7fffffffu];
+            const uint32_t *q = a.parr + p.arr_first + (uint32_t)(lo - p.left);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (hi - lo)));
+        } else {
+            const SegRec *gp = k < (uint32_t)BIN_REC ? reinterpret_cast<const SegRec *>(s_rec + 5 * k) : a.segs + op;
+            if ((uint32_t)(gp->x1 - gp->x0) + 1u == gp->n) {
+                const ColRec *q = a.cols + gp->cols_first + (uint32_t)(lo - gp->x0);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (hi - lo) / 2));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (hi - lo)));
+            }
+        }
     });
 }
 
@@ -316,7 +337,7 @@ __global__ void __launch_bounds__(BIN_THREADS, DRR_BIN_MIN_BLOCKS) drr_bin_kerne
     uint32_t cap = 0;
     for_each_candidate(a, o0, nops, x & ~31, s_tab, [&](uint2 e, uint32_t) {
         cap += (live && x >= (int)(short)(e.x & 0xffffu) && x <= (int)(short)(e.x >> 16)) ? 1u : 0u;
-    });
+    }, [](uint2, uint32_t) {});
     // one list of `cap` slots per row band (a single list when the column is not cut into bands, or into too many)
     const int nlists = a.nbands <= MAX_LIST_BANDS ? a.nbands : 1;
     ColOut out;
