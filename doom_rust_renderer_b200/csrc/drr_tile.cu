@@ -760,7 +760,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
     const int c = warp * 4 + grp, x = g * TILE_COLS + c; // a warp owns four adjacent columns, a lane group one of them
     ColIdx ci;
     ci.first = 0; ci.n = 0;
-    if (x < a.W) ci = a.colidx[((size_t)f * nlists + lband) * a.W + x];
+    // (frame * (lists per frame * W) as ONE 32 x 32 -> 64 bit multiply-add: nlists * W < 2^18, lband * W + x too)
+    if (x < a.W) ci = a.colidx[(size_t)(uint32_t)f * (uint32_t)(nlists * a.W) + (uint32_t)(lband * a.W + x)];
     int left = DBG(16) ? 0 : (int)(ci.n & ~COL_COVERED); // spans of the column still to draw
     uint32_t rec = ci.first;                             // record of the next one
     const uint4 *__restrict__ P = reinterpret_cast<const uint4 *>(a.tparams);
