@@ -932,7 +932,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) drr_tile_kernel(const __gr
                 acc += (uint64_t)sum * k0;
             }
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        // the warp's sum mod 2^64 through three REDUX instead of five rounds of 64-bit shuffles: 22-bit limbs, so that 32 of them add
+        // up without a carry out of 32 bits
+        {
+            const uint32_t l0 = (uint32_t)acc & 0x3fffffu, l1 = (uint32_t)(acc >> 22) & 0x3fffffu, l2 = (uint32_t)(acc >> 44);
+            const uint32_t s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1), s2 = __reduce_add_sync(0xffffffffu, l2);
+            acc = (uint64_t)s0 + ((uint64_t)s1 << 22) + ((uint64_t)s2 << 44);
+        }
         if (lane == 0) {
             if (acc) atomicAdd(reinterpret_cast<unsigned long long *>(a.crc + slot), (unsigned long long)acc);
             bulk_wait_read_all(); // the copy engine has read this warp's boxes: the CTA's shared memory may be handed on
