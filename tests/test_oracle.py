@@ -291,3 +291,72 @@ def test_oracle_wall_calls_carry_the_arguments_an_independent_restatement_derive
     assert checked > 50 * len(views), checked
     if (kind, W) == ("e1m1", 320):
         assert masked > 0  # (one of these viewpoints looks through the grates)
+
+
+def test_oracle_late_draw_order_obeys_the_reference_rules():
+    """The order of what is drawn late (map objects and masked mid-textures), checked against rules read off the Rust, not off
+    the C++ oracle: draw_map_objects sorts the sprites by `clipped_line.line.start.x as i16` and reverses (map_objects.rs:216-217,
+    Ord for BitmapRender bitmap_render.rs:167-173), and before a sprite is drawn every not yet drawn two-sided seg for which
+    is_behind_vertex(midpoint of the sprite's line) holds is drawn (map_objects.rs:219-239, bitmap_render.rs:137-165).  So in
+    the oracle's trace (1) the sprites' keys never increase, and (2) whenever a masked mid-texture M is behind the midpoint of a
+    sprite S, M's columns come before S's.  Masked mid-textures are told from sprites by tests/ref_frontend.py (a late call
+    that carries the arguments of a two-sided middle part of some seg)."""
+    import ref_frontend as rf
+    W, H = 320, 200
+    path, gm = common.wad("e1m1")
+    game = orc.Game(path, "E1M1", W, H)
+    m = rf.MapLumps(path)
+    k = rf.Constants(W, H)
+    f32 = np.float32
+    bits = lambda v: np.float32(v).view(np.uint32).item()  # noqa: E731
+
+    def as_i16(v):  # Rust `as i16`
+        v = float(v)
+        return 0 if v != v else int(max(-32768.0, min(32767.0, np.trunc(v))))
+
+    def is_behind_vertex(line, v):  # bitmap_render.rs:137-165, line = (sx, sy, ex, ey) in view space
+        sx, sy, ex, ey = (f32(t) for t in line)
+        min_x, max_x = min(sx, ex), max(sx, ex)
+        if min_x > v[0]:
+            return True
+        return bool(max_x > v[0] and not rf.is_left_of_line(v, ((sx, sy), (ex, ey))))
+
+    allv = synth_wad.walk_viewpoints(gm, 4096)
+    # (the stretches of the walk from which the map's grates -- its masked mid-textures -- are in view, and a sample of the rest)
+    views = common.usable_views(game, np.concatenate([allv[3320:3440:3], allv[3560:3704:3], allv[::173]]), 110)
+    pairs = behind_pairs = sprites_seen = mids_seen = 0
+    for v in views:
+        x, y, a = (f32(t) for t in v)
+        game.render(float(x), float(y), float(a), trace=True)
+        fh = game.floor_height_at(float(x), float(y))
+        mids_args = set()
+        for seg in m.segs:
+            for p in rf.seg_parts(k, m, seg, x, y, a, fh):
+                if p["flags"] == "two_sided_middle":
+                    mids_args.add(tuple(bits(t) for t in p["line"]) + (bits(p["start_offset"]), p["start_x"], p["end_x"], bits(p["bottom_height"]),
+                                                                       bits(p["top_height"]), p["offset_x"], p["offset_y"], p["light_level"]))
+        late = []  # BitmapRenders in draw order: (is_mid, line)
+        last = None
+        for t in game.trace():
+            if t["kind"] != 0 or t["phase"] != 2:
+                continue
+            key = tuple(bits(q) for q in t["line"]) + (bits(t["start_offset"]), t["start_x"], t["end_x"], bits(t["bottom_height"]),
+                                                       bits(t["top_height"]), t["offset_x"], t["offset_y"], t["light_level"])
+            if (key, t["asset"]) != last:  # a BitmapRender draws its columns in one go (bitmap_render.rs:107-128)
+                late.append((key in mids_args, tuple(f32(q) for q in t["line"])))
+                last = (key, t["asset"])
+        spr = [(i, line) for i, (is_mid, line) in enumerate(late) if not is_mid]
+        mid = [(i, line) for i, (is_mid, line) in enumerate(late) if is_mid]
+        sprites_seen += len(spr)
+        mids_seen += len(mid)
+        keys = [as_i16(line[0]) for _, line in spr]
+        assert all(keys[i] >= keys[i + 1] for i in range(len(keys) - 1)), ("sprites not in descending key order", v, keys)
+        for si, sl in spr:
+            mp = (f32(f32(sl[0] + sl[2]) / f32(2.0)), f32(f32(sl[1] + sl[3]) / f32(2.0)))
+            for mi, ml in mid:
+                pairs += 1
+                if is_behind_vertex(ml, mp):
+                    behind_pairs += 1
+                    assert mi < si, ("a masked mid-texture behind a sprite was drawn after it", v, ml, sl)
+    print("late-draw order: %d sprites, %d masked mid-textures, %d pairs, %d of them \"behind\"" % (sprites_seen, mids_seen, pairs, behind_pairs))
+    assert sprites_seen > 100 and mids_seen > 10 and behind_pairs > 10, (sprites_seen, mids_seen, pairs, behind_pairs)
