@@ -121,30 +121,41 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     // + 8 bytes per column of visplane rows (mode 2); taken when every warp the register budget allows on an SM fits in ~200 KB
     const size_t Wp = ((size_t)m.W + 15) & ~(size_t)15, side_bytes = 4 * (size_t)((m.side_words + 3) & ~3);
     const size_t frame_bytes = (std::max(sizeof(fe::Frame<true>), sizeof(fe::Frame<false>)) + 15) & ~(size_t)15;
+    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp;
+    // Eight warps per CTA when map objects are drawn (eight neighbouring viewpoints see the same sprites and masked parts: things640
+    // 1.56 -> 1.39 ms per 4096 viewpoints; without map objects four warps are 1-5 % faster) and their occlusion arrays fit.
+    const bool eight = (m.phases & 4) && m.nthings > 0 && need1 <= 48 * 1024 / FE_WARPS_THINGS;
+    const int warps = eight ? FE_WARPS_THINGS : FE_WARPS, minb = eight ? FE_MIN_BLOCKS_THINGS : FE_MIN_BLOCKS;
     // (at most 48 KB per CTA: the default limit of dynamic shared memory, no opt-in needed)
-    const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp, budget = std::min<size_t>(200 * 1024 / (FE_MIN_BLOCKS * FE_WARPS), 48 * 1024 / FE_WARPS);
+    const size_t budget = std::min<size_t>(200 * 1024 / (size_t)(minb * warps), 48 * 1024 / (size_t)warps);
     // (mode 1 only up to 8 KB per viewpoint: at 1920 columns 16 viewpoints' arrays would take 170 KB of the SM and leave the
     // global scratch of the masked phase no L1 to speak of -- measured on the stress map: 64.0 ms against 56.1 ms in mode 0)
+#ifdef DRR_FE_MAX_MODE // A/B: never more than this mode
+    const int mode = std::min(DRR_FE_MAX_MODE, need2 <= budget ? 2 : need1 <= std::min(budget, (size_t)8192) ? 1 : 0);
+#else
     const int mode = need2 <= budget ? 2 : need1 <= std::min(budget, (size_t)8192) ? 1 : 0;
+#endif
     size_t per_view = mode == 2 ? need2 : mode == 1 ? need1 : frame_bytes;
     const size_t order_bytes = (4 * (size_t)m.nsegs + 15) & ~(size_t)15;
     const bool order_too = mode >= 1 && per_view + order_bytes <= budget;
     if (order_too) per_view += order_bytes;
     // mode 0 (the arrays in global scratch): the build with the smaller register budget and twice the resident warps
-    const int vpb = mode == 0 ? FE_WARPS_GLOBAL : FE_WARPS; // viewpoints per CTA
+    const int vpb = mode == 0 ? FE_WARPS_GLOBAL : warps; // viewpoints per CTA
     const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
     const size_t dyn = per_view * vpb;
+    const int mflags = mode | (order_too ? 4 : 0);
+#define DRR_FE_LAUNCH(E, WARPS, MINB) drr_frontend_kernel<E, WARPS, MINB><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mflags, (uint32_t)per_view)
     if (mode == 0) {
-        if (emit)
-            drr_frontend_kernel<true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
-        else
-            drr_frontend_kernel<false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
+        if (emit) DRR_FE_LAUNCH(true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL);
+        else DRR_FE_LAUNCH(false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL);
+    } else if (eight) {
+        if (emit) DRR_FE_LAUNCH(true, FE_WARPS_THINGS, FE_MIN_BLOCKS_THINGS);
+        else DRR_FE_LAUNCH(false, FE_WARPS_THINGS, FE_MIN_BLOCKS_THINGS);
     } else {
-        if (emit)
-            drr_frontend_kernel<true, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
-        else
-            drr_frontend_kernel<false, FE_WARPS, FE_MIN_BLOCKS><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mode | (order_too ? 4 : 0), (uint32_t)per_view);
+        if (emit) DRR_FE_LAUNCH(true, FE_WARPS, FE_MIN_BLOCKS);
+        else DRR_FE_LAUNCH(false, FE_WARPS, FE_MIN_BLOCKS);
     }
+#undef DRR_FE_LAUNCH
     return cudaGetLastError();
 }
 

@@ -111,6 +111,7 @@ struct Slabs;
 #endif
 static constexpr int FE_WARPS = DRR_FE_WARPS, FE_MIN_BLOCKS = DRR_FE_MIN_BLOCKS;                             // per-view arrays in shared memory
 static constexpr int FE_WARPS_GLOBAL = DRR_FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL = DRR_FE_MIN_BLOCKS_GLOBAL; // ... in global scratch
+static constexpr int FE_WARPS_THINGS = 8, FE_MIN_BLOCKS_THINGS = 2;                                           // ... in shared memory, map objects drawn
 struct FeScratch {                    // per-viewpoint working state of the front-end, W entries per viewpoint each
     uint8_t *hor_ocl;
     int16_t *floor_ocl, *ceil_ocl;

@@ -151,7 +151,10 @@ __device__ __forceinline__ Rec plane_record(const DrawArgs &a, const PlaneRec &p
 // loaded on a hit.  Ops beyond the table's capacity are read from global memory.
 static constexpr int BIN_THREADS = 384; // upper bound of the CTA size; the launcher picks ceil(W / ceil(W / 192)) rounded up to a warp (the size hardly matters: tools/sweep_env.sh DRR_BIN_THREADS)
 static constexpr int BIN_TAB = 512;
-static constexpr int BIN_REC = 96; // ops whose whole record (80-byte SegRec / 16-byte PlaneRec) is staged in shared memory too
+#ifndef DRR_BIN_REC
+#define DRR_BIN_REC 96
+#endif
+static constexpr int BIN_REC = DRR_BIN_REC; // ops whose whole record (80-byte SegRec / 16-byte PlaneRec) is staged in shared memory too (A/B: 160 -> walk320 bin 0.191 -> ?)
 
 __device__ __forceinline__ uint2 op_range(const DrawArgs &a, uint32_t op) { // (x0 | x1 << 16, op); an empty op gets x0 > x1
     if (op & 0x80000000u) {
