@@ -428,9 +428,19 @@ def run_workload(name, args, rank, world, local_rank, dist, torch, headline):
         half = max(1, steps * passes // 2)
 
         def pair():
-            ta = threading.Thread(target=lambda: [pass_fe() for _ in range(half)])
-            tb = threading.Thread(target=lambda: [pass_fe2() for _ in range(half)])
+            errors = []
+
+            def loop(body):
+                try:
+                    for _ in range(half):
+                        body()
+                except BaseException as ex:  # noqa: BLE001 -- re-raised below, on the main thread
+                    errors.append(ex)
+
+            ta, tb = threading.Thread(target=loop, args=(pass_fe,)), threading.Thread(target=loop, args=(pass_fe2,))
             ta.start(); tb.start(); ta.join(); tb.join()
+            if errors:
+                raise errors[0]
 
         pair()  # warm-up
         barrier()
