@@ -11,10 +11,7 @@
 #include "drr_frontend.cuh"
 #include "drr_kernels.h"
 #include <algorithm>
-#include <mutex>
 #include <new>
-#include <set>
-#include <utility>
 
 namespace drr {
 
@@ -117,21 +114,6 @@ __global__ void __launch_bounds__(256) drr_fe_gather_views_kernel(const View *__
     if (f < nframes) dst[f] = slab_views[(int)frame_slot[f] - first_view_idx];
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which (device, kernel) pairs have it
-static constexpr size_t FE_MAX_DYN = 96 * 1024; // dynamic shared memory a front-end CTA may ask for (opt-in above 48 KB)
-static cudaError_t allow_big_fe(const void *kernel) {
-    static std::mutex mu;
-    static std::set<std::pair<int, const void *>> done;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    std::lock_guard<std::mutex> lock(mu);
-    if (done.count({dev, kernel})) return cudaSuccess;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FE_MAX_DYN);
-    if (e == cudaSuccess) done.insert({dev, kernel});
-    return e;
-}
-
 cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views, const fe::Bases *bases, fe::Counts *counts, int n,
                             const FeScratch &s, const fe::Out &out, const fe::Caps &slab, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -142,10 +124,10 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp;
     // Eight warps per CTA when map objects are drawn (eight neighbouring viewpoints see the same sprites and masked parts: things640
     // 1.56 -> 1.39 ms per 4096 viewpoints; without map objects four warps are 1-5 % faster) and their occlusion arrays fit.
-    const bool eight = (m.phases & 4) && m.nthings > 0 && need1 <= FE_MAX_DYN / FE_WARPS_THINGS && need1 <= 8192;
+    const bool eight = (m.phases & 4) && m.nthings > 0 && need1 <= 48 * 1024 / FE_WARPS_THINGS;
     const int warps = eight ? FE_WARPS_THINGS : FE_WARPS, minb = eight ? FE_MIN_BLOCKS_THINGS : FE_MIN_BLOCKS;
-    // (at most FE_MAX_DYN per CTA: above 48 KB the kernel is opted in, per device, before the launch)
-    const size_t budget = std::min<size_t>(200 * 1024 / (size_t)(minb * warps), FE_MAX_DYN / (size_t)warps);
+    // (at most 48 KB per CTA: the default limit of dynamic shared memory, no opt-in needed)
+    const size_t budget = std::min<size_t>(200 * 1024 / (size_t)(minb * warps), 48 * 1024 / (size_t)warps);
     // (mode 1 only up to 8 KB per viewpoint: at 1920 columns 16 viewpoints' arrays would take 170 KB of the SM and leave the
     // global scratch of the masked phase no L1 to speak of -- measured on the stress map: 64.0 ms against 56.1 ms in mode 0)
 #ifdef DRR_FE_MAX_MODE // A/B: never more than this mode
@@ -162,14 +144,7 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     const unsigned blocks = (unsigned)((n + vpb - 1) / vpb);
     const size_t dyn = per_view * vpb;
     const int mflags = mode | (order_too ? 4 : 0);
-#define DRR_FE_LAUNCH(E, WARPS, MINB)                                                                                                           \
-    do {                                                                                                                                       \
-        if (dyn > 48 * 1024) {                                                                                                                 \
-            const cudaError_t e = allow_big_fe(reinterpret_cast<const void *>(&drr_frontend_kernel<E, WARPS, MINB>));                          \
-            if (e != cudaSuccess) return e;                                                                                                    \
-        }                                                                                                                                      \
-        drr_frontend_kernel<E, WARPS, MINB><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mflags, (uint32_t)per_view); \
-    } while (0)
+#define DRR_FE_LAUNCH(E, WARPS, MINB) drr_frontend_kernel<E, WARPS, MINB><<<blocks, 32 * vpb, dyn, st>>>(m, views, bases, counts, n, s, out, slab, mflags, (uint32_t)per_view)
     if (mode == 0) {
         if (emit) DRR_FE_LAUNCH(true, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL);
         else DRR_FE_LAUNCH(false, FE_WARPS_GLOBAL, FE_MIN_BLOCKS_GLOBAL);
