@@ -124,7 +124,11 @@ cudaError_t launch_frontend(bool emit, const fe::Map &m, const fe::ViewIn *views
     const size_t need1 = frame_bytes + 5 * Wp + side_bytes, need2 = need1 + 8 * Wp;
     // Eight warps per CTA when map objects are drawn (eight neighbouring viewpoints see the same sprites and masked parts: things640
     // 1.56 -> 1.39 ms per 4096 viewpoints; without map objects four warps are 1-5 % faster) and their occlusion arrays fit.
+#ifdef DRR_FE_EIGHT_ALWAYS // A/B: whenever they fit
+    const bool eight = need1 <= 48 * 1024 / FE_WARPS_THINGS;
+#else
     const bool eight = (m.phases & 4) && m.nthings > 0 && need1 <= 48 * 1024 / FE_WARPS_THINGS;
+#endif
     const int warps = eight ? FE_WARPS_THINGS : FE_WARPS, minb = eight ? FE_MIN_BLOCKS_THINGS : FE_MIN_BLOCKS;
     // (at most 48 KB per CTA: the default limit of dynamic shared memory, no opt-in needed)
     const size_t budget = std::min<size_t>(200 * 1024 / (size_t)(minb * warps), 48 * 1024 / (size_t)warps);
